@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the dmesh2_renderer hot path on B200.
+
+Metric (BASELINE.json): fwd+bwd frames/s, 1M triangles @ 1024x1024 (cfg2), reported at 1/2/4/8 GPUs,
+plus the fraction of the measured HBM roofline of the dominant kernel.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # this implementation
+    python bench.py --impl reference --gpus 1 --steps 20 --warmup 5   # the unmodified reference
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # one rank per GPU (weak scaling)
+
+A "step" is one optimisation step of one view per GPU: Renderer.forward + loss + backward through
+the public API (and, for N > 1, ONE NCCL allreduce of [dverts | dverts_color | dfaces_opacity]).
+`value` is measured with the scene parameters resident in HBM; `e2e` additionally copies the step's
+inputs (verts, colours, opacity, intensity) from pinned host memory and reads the loss back.
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--faces", type=int, default=1_000_000)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-patch", type=int, default=512)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(stage, B, P, F, H, W, R):
+    """SURVEY.md section 8d; see DESIGN.md 'Algorithmic bytes'."""
+    G = 16 * F + 24 * P + B * (20 * P + 28 * F) + 24 * B * H * W
+    grads = 24 * P + 4 * F + B * (12 * P + 28 * F)
+    table = {
+        "raster_forward": G + 28 * B * H * W + 4 * R,
+        "raster_backward": G + 28 * B * H * W + 4 * R + grads,
+        "radix_sort": 24 * R,
+        "preprocess_pack": G - 24 * B * H * W + 16 * B * F,
+        "emit_keys": 12 * R + 16 * B * F,
+        "scan": 8 * B * F,
+        "tile_ranges": 8 * R,
+    }
+    return table.get(stage)
+
+
+def make_scene(args, rank):
+    from dmesh2_renderer_b200 import scenes
+    if args.faces == 1_000_000 and args.size == 1024:
+        sc = scenes.cfg2()
+    else:
+        sc = scenes.cfg2(n_faces=args.faces, size=args.size)
+    if rank > 0:      # weak scaling: rank r renders the same scene from Fibonacci-sphere camera r
+        import numpy as np
+        eye = scenes.fibonacci_eyes(64)[rank % 64]
+        sc.mv = np.stack([scenes.look_at(tuple(eye))]).astype("float32")
+    return sc
+
+
+def cpu_baseline(args, sc):
+    """The CPU oracle (kind 'port': the reference has no CPU path) on a bounded sample of the workload:
+    a centred patch of the frame, forward+backward, scaled by the pixel ratio."""
+    import numpy as np
+    import torch
+    from dmesh2_renderer_b200 import Renderer
+    from oracle import oracle as orc
+    ps = min(args.cpu_sample_patch, sc.width, sc.height)
+    x0, y0 = (sc.width - ps) // 2, (sc.height - ps) // 2
+    t = torch.from_numpy
+    r = Renderer(t(sc.mv), t(sc.proj), sc.width, sc.height, "cpu")
+    a = r.prepare_inputs([0], torch.tensor([[x0, y0]], dtype=torch.int32), ps, ps, t(sc.verts), t(sc.faces),
+                         t(sc.verts_color), t(sc.faces_opacity), t(sc.faces_intense), t(sc.background), 1.0)
+    names = ["background", "patch_min", "pw", "ph", "verts", "faces", "verts_color", "faces_opacity", "verts_ndc",
+             "verts_image", "faces_intense", "tau", "aa_face_verts", "aa_face_edges", "aa_face_edges_iszero",
+             "aa_face_edges_recip", "aa_face_edges_normal", "aa_face_edges_normal_c", "K", "image_ray_o", "image_ray_d"]
+    d = {n: (v.numpy() if isinstance(v, torch.Tensor) else v) for n, v in zip(names, a)}
+    wc = sc.w_color[:1, y0:y0 + ps, x0:x0 + ps]
+    wd = sc.w_depth[:1, y0:y0 + ps, x0:x0 + ps]
+    cores = orc.hardware_threads()
+    t0 = time.perf_counter()
+    orc.render(d, ps, ps, 1.0, K=0, nthreads=cores, backward=True, dL_dcolor=wc, dL_ddepth=wd)
+    dt = time.perf_counter() - t0
+    scale = (sc.width * sc.height) / float(ps * ps)
+    return {"value": 1.0 / (dt * scale), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"C++ oracle fwd+bwd on the centred {ps}x{ps} patch of the workload ({dt:.2f} s), "
+                      f"scaled by {scale:.0f}x pixels"}
+
+
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference" and not torch.cuda.is_available():
+        # no GPU: the only runnable stand-in is the CPU oracle port
+        if rank == 0:
+            sc = make_scene(args, 0)
+            cb = cpu_baseline(args, sc)
+            print(json.dumps({"impl": "reference", "metric": "fwd+bwd frames/s", "value": cb["value"],
+                              "unit": "frames/s", "n_gpus": 0, "steps": 1, "warmup": 0, "higher_is_better": True,
+                              "cpu_baseline": cb, "config": {"workload": sc.name},
+                              "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sc = make_scene(args, rank)
+    W, H = sc.width, sc.height
+    t = lambda a: torch.from_numpy(a)
+
+    if args.impl == "reference":
+        ref_dir = os.path.join(ROOT, "baseline", "_ref")
+        if not os.path.isdir(os.path.join(ref_dir, "dmesh2_renderer")):
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not built (baseline/build_ref.sh)"}))
+            return
+        sys.path.insert(0, ref_dir)
+        import dmesh2_renderer as pkg          # the UNMODIFIED reference package
+        prof = None
+    else:
+        import dmesh2_renderer_b200 as pkg
+        from dmesh2_renderer_b200 import _lib as prof
+        pkg.load_library()
+
+    renderer = pkg.Renderer(t(sc.mv).to(dev), t(sc.proj).to(dev), W, H, dev)
+    faces = t(sc.faces).to(dev)
+    background = t(sc.background).to(dev)
+    patch_min = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    wc, wd = t(sc.w_color).to(dev), t(sc.w_depth).to(dev)
+    host = {k: t(getattr(sc, k)).pin_memory() for k in ("verts", "verts_color", "faces_opacity", "faces_intense")}
+    params = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
+    P, F = sc.verts.shape[0], sc.faces.shape[0]
+    bucket = torch.zeros(3 * P + 3 * P + F, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(e2e):
+        if e2e:
+            with torch.no_grad():
+                for k in params:
+                    params[k].copy_(host[k], non_blocking=True)
+        for p in params.values():
+            p.grad = None
+        color, depth = renderer([0], patch_min, W, H, params["verts"], faces, params["verts_color"],
+                                params["faces_opacity"], params["faces_intense"], background)
+        loss = (color * wc).sum() + (depth * wd).sum()
+        loss.backward()
+        if world > 1:
+            # one allreduce per optimisation step over the flat [dverts | dverts_color | dfaces_opacity] bucket
+            torch.cat((params["verts"].grad.reshape(-1), params["verts_color"].grad.reshape(-1),
+                       params["faces_opacity"].grad.reshape(-1)), out=bucket)
+            dist.all_reduce(bucket)
+        if e2e:
+            return float(loss.item())
+        return None
+
+    def timed(n, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            step(e2e)
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if prof:
+        prof.profile_reset()
+        prof.profile_enable(True)
+        prof.launch_count(reset=True)
+    ms_total = timed(args.steps, False)
+    launches = prof.launch_count() if prof else None
+    stages = prof.profile_report() if prof else {}
+    if prof:
+        prof.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step(True)
+    ms_e2e = timed(args.steps, True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = world * 1000.0 / ms_step
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    out = {
+        "metric": "fwd+bwd frames/s, 1M tris @1024^2", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{sc.name}: Renderer fwd+bwd, {F} random semi-transparent triangles, {W}x{H}, "
+                               f"1 view per GPU (SURVEY 8d cfg2, seed 2, sigma 0.0115, aa_temperature 1.0)",
+                   "views_per_step": world, "parallelism": f"view-sharded dp{world}, 1 NCCL allreduce/step" if world > 1 else "single GPU",
+                   "l2": "working set (packed face records 256 MB + inputs ~190 MB) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": world * 1000.0 * args.steps / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "clocks": clocks,
+    }
+    if args.impl == "reference":
+        out["impl"] = "reference"
+        out["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
+                               "sample": "the reference has no CPU path: this arm runs its own CUDA extension "
+                                         "(baseline/_ref, unmodified, built for sm_100a) through its public "
+                                         "Renderer API on the same GPU, same scene, same harness"}
+        out["gpu_launches"] = None
+    else:
+        out["gpu_launches"] = launches
+        R = None
+        try:
+            R = int(renderer_num_rendered(pkg, renderer, patch_min, W, H, params, faces, background))
+        except Exception:
+            pass
+        peak, peak_src = peaks()
+        if stages and R is not None:
+            dom = max(stages, key=lambda k: stages[k][0])
+            dom_ms = stages[dom][0] / max(stages[dom][1], 1)
+            ab = algorithmic_bytes(dom, 1, P, F, H, W, R)
+            achieved = ab / (dom_ms * 1e-3) / 1e9 if ab else None
+            out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                               "frac": (achieved / peak) if achieved else None, "traffic": None,
+                               "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": dom_ms,
+                               "note": "kernel is issue/latency bound, not HBM bound (see profiles/ and DESIGN.md)"}
+            out["stages_ms_per_step"] = {k: v[0] / args.steps for k, v in stages.items()}
+            out["num_rendered"] = R
+            sort_ms = stages.get("radix_sort", (0, 0))[0] / args.steps
+            if sort_ms > 0:
+                out["sort_keys_per_s"] = R / (sort_ms * 1e-3)
+        if not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(args, make_scene(args, 0))
+            except Exception as ex:
+                out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port",
+                                       "sample": f"failed: {ex}"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def renderer_num_rendered(pkg, renderer, patch_min, W, H, params, faces, background):
+    import torch
+    with torch.no_grad():
+        a = renderer.prepare_inputs([0], patch_min, W, H, params["verts"], faces, params["verts_color"],
+                                    params["faces_opacity"], params["faces_intense"], background, 1.0)
+        return pkg._C.render_forward_cuda(*a)[0]
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,485 @@
+// dm2_binning.cu — per-face preprocess + record packing, prefix scan, key emission,
+// stable LSD radix sort, tile ranges.  Replaces reference cuda_impl/forward.cu:16-137
+// (preprocessFaceCUDA), cuda_impl/renderer.cu:165-218, 415-492 and the two CUB calls.
+#include "dm2_common.cuh"
+
+namespace dm2 {
+
+// torch.min / torch.max over the 3 triangle vertices propagate NaN (reference forward.cu:480-481)
+__device__ __forceinline__ float nanmin(float a, float b) { return (a != a || a < b) ? a : b; }
+__device__ __forceinline__ float nanmax(float a, float b) { return (a != a || a > b) ? a : b; }
+
+// ------------------------------------------------------------------ preprocess (shared part)
+struct PreOut { bool live; int x0, y0, x1, y1; float depth, dmin, dmax; };
+
+__device__ __forceinline__ PreOut preprocess_face(int b, int P, int v0, int v1, int v2,
+                                                  const float* __restrict__ verts_ndc,
+                                                  const float* __restrict__ verts_image,
+                                                  uint32_t pmx, uint32_t pmy, int gx, int gy) {
+    // reference forward.cu:41-107.  SASS of the reference shows no FMA in this chain.
+    PreOut o; o.live = false; o.x0 = o.y0 = o.x1 = o.y1 = 0; o.depth = o.dmin = o.dmax = 0.f;
+    const size_t vb = (size_t)b * P;
+    const float z0 = verts_ndc[(vb + v0) * 3 + 2];
+    const float z1 = verts_ndc[(vb + v1) * 3 + 2];
+    const float z2 = verts_ndc[(vb + v2) * 3 + 2];
+    const float2 i0 = *reinterpret_cast<const float2*>(verts_image + (vb + v0) * 2);
+    const float2 i1 = *reinterpret_cast<const float2*>(verts_image + (vb + v1) * 2);
+    const float2 i2 = *reinterpret_cast<const float2*>(verts_image + (vb + v2) * 2);
+    float max_z = fmaxf(fmaxf(z0, z1), z2);
+    float min_z = fminf(fminf(z0, z1), z2);
+    float depth = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, z0), z1), z2);
+    depth = __fdiv_rn(depth, 3.0f);
+    if (max_z < -1.0f || min_z > 1.0f) return o;
+    patch_rect(pmx, pmy, i0.x, i0.y, i1.x, i1.y, i2.x, i2.y, gx, gy, o.x0, o.y0, o.x1, o.y1);
+    if ((uint32_t)(o.x1 - o.x0) * (uint32_t)(o.y1 - o.y0) == 0u) return o;
+    o.live = true;
+    o.depth = clamp01_depth(depth);
+    o.dmin = clamp01_depth(min_z);
+    o.dmax = clamp01_depth(max_z);
+    return o;
+}
+
+// ------------------------------------------------------------------ render preprocess + pack
+__global__ void __launch_bounds__(256)
+k_render_preprocess(DM2RenderInputs in, int gx, int gy, float* __restrict__ depths,
+                    float* __restrict__ min_depths, float* __restrict__ max_depths,
+                    uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
+                    float* __restrict__ records) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long BF = (long long)in.B * in.F;
+    if (idx >= BF) return;
+    const int b = (int)(idx / in.F), f = (int)(idx % in.F);
+    const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
+    const uint32_t pmx = (uint32_t)in.patch_min[2 * b], pmy = (uint32_t)in.patch_min[2 * b + 1];
+    const PreOut o = preprocess_face(b, in.P, v0, v1, v2, in.verts_ndc, in.verts_image, pmx, pmy, gx, gy);
+    if (!o.live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return; }
+    tiles_touched[idx] = (uint32_t)(o.y1 - o.y0) * (uint32_t)(o.x1 - o.x0);
+    rects[idx] = make_uint2((uint32_t)o.x0 | ((uint32_t)o.y0 << 16), (uint32_t)o.x1 | ((uint32_t)o.y1 << 16));
+    depths[idx] = o.depth; min_depths[idx] = o.dmin; max_depths[idx] = o.dmax;
+
+    // ---- packed record (layout: dm2_common.cuh) ----
+    float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * kRecWords);
+    const float* av = in.aa_face_verts + (size_t)idx * 6;
+    const float* ae = in.aa_face_edges + (size_t)idx * 6;
+    const float* ar = in.aa_face_edges_recip + (size_t)idx * 6;
+    const float* an = in.aa_face_edges_normal + (size_t)idx * 6;
+    const float* ac = in.aa_face_edges_normal_c + (size_t)idx * 3;
+    const uint8_t* az = in.aa_face_edges_iszero + (size_t)idx * 6;
+    float a[6], e[6], r[6], n[6];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float2 t;
+        t = *reinterpret_cast<const float2*>(av + 2 * k); a[2 * k] = t.x; a[2 * k + 1] = t.y;
+        t = *reinterpret_cast<const float2*>(ae + 2 * k); e[2 * k] = t.x; e[2 * k + 1] = t.y;
+        t = *reinterpret_cast<const float2*>(ar + 2 * k); r[2 * k] = t.x; r[2 * k + 1] = t.y;
+        t = *reinterpret_cast<const float2*>(an + 2 * k); n[2 * k] = t.x; n[2 * k + 1] = t.y;
+    }
+    const float c0 = ac[0], c1 = ac[1], c2 = ac[2];
+    uint32_t flags = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) flags |= (az[k] ? 1u : 0u) << k;
+    const float txmin = nanmin(nanmin(a[0], a[2]), a[4]), txmax = nanmax(nanmax(a[0], a[2]), a[4]);
+    const float tymin = nanmin(nanmin(a[1], a[3]), a[5]), tymax = nanmax(nanmax(a[1], a[3]), a[5]);
+    const float* p0 = in.verts + 3 * (size_t)v0;
+    const float* p1 = in.verts + 3 * (size_t)v1;
+    const float* p2 = in.verts + 3 * (size_t)v2;
+    const float* q0 = in.verts_color + 3 * (size_t)v0;
+    const float* q1 = in.verts_color + 3 * (size_t)v1;
+    const float* q2 = in.verts_color + 3 * (size_t)v2;
+    const size_t vb = (size_t)b * in.P;
+    const float z0 = in.verts_ndc[(vb + v0) * 3 + 2];
+    const float z1 = in.verts_ndc[(vb + v1) * 3 + 2];
+    const float z2 = in.verts_ndc[(vb + v2) * 3 + 2];
+    rec[0]  = make_float4(txmin, txmax, tymin, tymax);
+    rec[1]  = make_float4(n[0], n[1], n[2], n[3]);
+    rec[2]  = make_float4(n[4], n[5], c0, c1);
+    rec[3]  = make_float4(c2, in.faces_opacity[f], in.faces_intense[idx], __uint_as_float(flags));
+    rec[4]  = make_float4(p0[0], p0[1], p0[2], z0);
+    rec[5]  = make_float4(p1[0], p1[1], p1[2], z1);
+    rec[6]  = make_float4(p2[0], p2[1], p2[2], z2);
+    rec[7]  = make_float4(q0[0], q0[1], q0[2], q1[0]);
+    rec[8]  = make_float4(q1[1], q1[2], q2[0], q2[1]);
+    rec[9]  = make_float4(q2[2], __int_as_float(v0), __int_as_float(v1), __int_as_float(v2));
+    rec[10] = make_float4(a[0], a[1], a[2], a[3]);
+    rec[11] = make_float4(a[4], a[5], e[0], e[1]);
+    rec[12] = make_float4(e[2], e[3], e[4], e[5]);
+    rec[13] = make_float4(r[0], r[1], r[2], r[3]);
+    rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
+}
+
+int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    ProfScope _ps("preprocess_pack", s);
+    k_render_preprocess<<<cdiv(BF, 256), 256, 0, s>>>(in, gx, gy, fw.depths, fw.min_depths, fw.max_depths,
+                                                      fw.tiles_touched, fw.rects, fw.records);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ layered preprocess + pack
+__global__ void __launch_bounds__(256)
+k_layers_preprocess(DM2LayerInputs in, int gx, int gy, float* __restrict__ depths,
+                    float* __restrict__ min_depths, float* __restrict__ max_depths,
+                    uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
+                    float* __restrict__ records) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long BF = (long long)in.B * in.F;
+    if (idx >= BF) return;
+    const int b = (int)(idx / in.F), f = (int)(idx % in.F);
+    const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
+    const PreOut o = preprocess_face(b, in.P, v0, v1, v2, in.verts_ndc, in.verts_image, 0u, 0u, gx, gy);
+    if (!o.live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return; }
+    tiles_touched[idx] = (uint32_t)(o.y1 - o.y0) * (uint32_t)(o.x1 - o.x0);
+    rects[idx] = make_uint2((uint32_t)o.x0 | ((uint32_t)o.y0 << 16), (uint32_t)o.x1 | ((uint32_t)o.y1 << 16));
+    depths[idx] = o.depth; min_depths[idx] = o.dmin; max_depths[idx] = o.dmax;
+    float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * kLRecWords);
+    const float* p0 = in.verts + 3 * (size_t)v0;
+    const float* p1 = in.verts + 3 * (size_t)v1;
+    const float* p2 = in.verts + 3 * (size_t)v2;
+    rec[0] = make_float4(p0[0], p0[1], p0[2], p1[0]);
+    rec[1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
+    rec[2] = make_float4(p2[2], o.dmin, o.dmax, __int_as_float(f));
+}
+
+int launch_layers_preprocess(const DM2LayerInputs& in, const FaceWs& fw, cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    ProfScope _ps("layers_preprocess", s);
+    k_layers_preprocess<<<cdiv(BF, 256), 256, 0, s>>>(in, gx, gy, fw.depths, fw.min_depths, fw.max_depths,
+                                                      fw.tiles_touched, fw.rects, fw.records);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ inclusive u32 scan
+// reduce-then-scan: (1) per-block sums, (2) one block scans the sums, (3) per-block scan + base.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+long long scan_partials_count(long long n) { return (n + kScanTile - 1) / kScanTile + 1; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix,
+// total in `total`.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t& total) {
+    __shared__ uint32_t wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = warp_incl_scan(v, lane);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { uint32_t s = wsum[i]; if (i < w) base += s; tot += s; }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_reduce(const uint32_t* __restrict__ in, long long n, uint32_t* __restrict__ partials) {
+    const long long base = (long long)blockIdx.x * kScanTile;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        long long j = base + (long long)i * kScanThreads + threadIdx.x;
+        if (j < n) s += in[j];
+    }
+    uint32_t tot;
+    block_excl_scan(s, tot);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_partials(uint32_t* __restrict__ partials, int nblocks) {
+    // exclusive scan in place; partials[nblocks] receives the grand total
+    uint32_t carry = 0;
+    for (int base = 0; base < nblocks; base += kScanThreads) {
+        int j = base + threadIdx.x;
+        uint32_t v = (j < nblocks) ? partials[j] : 0u;
+        uint32_t tot;
+        uint32_t ex = block_excl_scan(v, tot);
+        if (j < nblocks) partials[j] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) partials[nblocks] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long n,
+             const uint32_t* __restrict__ partials) {
+    // each thread owns kScanItems consecutive elements
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) { v[i] = (base + i < n) ? in[base + i] : 0u; s += v[i]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(s, tot) + partials[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) { ex += v[i]; if (base + i < n) out[base + i] = ex; }
+}
+
+int launch_scan(const uint32_t* in, uint32_t* out, long long n, uint32_t* partials, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int nb = cdiv(n, kScanTile);
+    ProfScope _ps("scan", s);
+    k_scan_reduce<<<nb, kScanThreads, 0, s>>>(in, n, partials);
+    DM2_LAUNCH_CHECK();
+    k_scan_partials<<<1, kScanThreads, 0, s>>>(partials, nb);
+    DM2_LAUNCH_CHECK();
+    k_scan_apply<<<nb, kScanThreads, 0, s>>>(in, out, n, partials);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ key emission
+// reference renderer.cu:415-465.  key = (tile + tiles*view) << 32 | bits(depth); value = face id.
+// Faces covering more than 16 tiles are emitted cooperatively by the whole warp so that one huge
+// triangle does not serialise 2 000 stores behind a single lane.
+__global__ void __launch_bounds__(256)
+k_emit_keys(long long BF, int F, int gx, int gy, const float* __restrict__ key_depths,
+            const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
+            const uint2* __restrict__ rects, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t n = 0, off = 0, x0 = 0, y0 = 0, w = 1, dbits = 0, fid = 0, tbase = 0;
+    if (idx < BF) {
+        n = tiles_touched[idx];
+        if (n) {
+            off = (idx == 0) ? 0u : offsets[idx - 1];
+            const uint2 r = rects[idx];
+            x0 = r.x & 0xffffu; y0 = r.x >> 16;
+            w = (r.y & 0xffffu) - x0;
+            dbits = __float_as_uint(key_depths[idx]);
+            fid = (uint32_t)(idx % F);
+            tbase = (uint32_t)(idx / F) * (uint32_t)(gx * gy);
+        }
+    }
+    if (n && n <= 16) {
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t y = y0 + i / w, x = x0 + i % w;
+            keys[off + i] = ((uint64_t)(y * gx + x + tbase) << 32) | dbits;
+            vals[off + i] = fid;
+        }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, n > 16);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t sn = __shfl_sync(0xffffffffu, n, src), so = __shfl_sync(0xffffffffu, off, src);
+        const uint32_t sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src);
+        const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sd = __shfl_sync(0xffffffffu, dbits, src);
+        const uint32_t sf = __shfl_sync(0xffffffffu, fid, src), st = __shfl_sync(0xffffffffu, tbase, src);
+        for (uint32_t i = lane; i < sn; i += 32) {
+            uint32_t y = sy + i / sw, x = sx + i % sw;
+            keys[so + i] = ((uint64_t)(y * gx + x + st) << 32) | sd;
+            vals[so + i] = sf;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stable LSD radix sort
+// 8-bit digits, 4096 keys per block.  Per pass: per-block digit histogram -> digit-major
+// exclusive scan -> stable scatter (warp-level match_any ranking).  Replaces
+// cub::DeviceRadixSort::SortPairs (reference renderer.cu:202-207): sorts on key bits
+// [0, end_bit) only and keeps the input order of equal keys.
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096
+constexpr int kRadix = 256;
+
+size_t sort_temp_bytes(long long n) {
+    const long long nblk = (n + kSortTile - 1) / kSortTile;
+    return align_up((size_t)(nblk * kRadix + 1) * sizeof(uint32_t), 256);
+}
+
+__device__ __forceinline__ void warp_rank_digit(uint32_t* wc /*this warp's 256 counters*/, bool valid,
+                                                uint32_t d, int lane, uint32_t& rank_out) {
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const unsigned peers = __match_any_sync(vm, d);
+        const int leader = __ffs(peers) - 1;
+        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+        uint32_t prev = 0;
+        if (lane == leader) { prev = wc[d]; wc[d] = prev + __popc(peers); }
+        prev = __shfl_sync(peers, prev, leader);
+        rank_out = prev + below;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t mask,
+             uint32_t* __restrict__ counts, int nblk) {
+    __shared__ uint32_t wc[8][kRadix];
+    for (int i = threadIdx.x; i < 8 * kRadix; i += kSortThreads) (&wc[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * kSortTile + w * (kSortItems * 32);
+#pragma unroll 4
+    for (int it = 0; it < kSortItems; it++) {
+        const uint32_t i = base + it * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? (uint32_t)(keys[i] >> shift) & mask : 0u;
+        uint32_t r;
+        warp_rank_digit(wc[w], valid, d, lane, r);
+    }
+    __syncthreads();
+    const int d = threadIdx.x;
+    uint32_t c = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ww++) c += wc[ww][d];
+    counts[(size_t)d * nblk + blockIdx.x] = c;
+}
+
+// exclusive scan over the digit-major count matrix (single block, 1024 threads)
+__global__ void __launch_bounds__(1024)
+k_radix_scan(uint32_t* __restrict__ counts, uint32_t total) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t per = (total + 1023u) / 1024u;
+    const uint32_t lo = min(threadIdx.x * per, total), hi = min(lo + per, total);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += counts[i];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = warp_incl_scan(s, lane);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) { uint32_t v = wsum[lane]; uint32_t iv = warp_incl_scan(v, lane); wsum[lane] = iv - v; }
+    __syncthreads();
+    uint32_t run = wsum[w] + inc - s;
+    for (uint32_t i = lo; i < hi; i++) { uint32_t c = counts[i]; counts[i] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                uint64_t* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n, int shift,
+                uint32_t mask, const uint32_t* __restrict__ gbase, int nblk) {
+    __shared__ uint32_t wc[8][kRadix];
+    for (int i = threadIdx.x; i < 8 * kRadix; i += kSortThreads) (&wc[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * kSortTile + w * (kSortItems * 32);
+    uint64_t k[kSortItems];
+    uint32_t r[kSortItems];
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+        const uint32_t i = base + it * 32 + lane;
+        k[it] = (i < n) ? kin[i] : 0ull;
+    }
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+        const uint32_t i = base + it * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = (uint32_t)(k[it] >> shift) & mask;
+        r[it] = 0;
+        warp_rank_digit(wc[w], valid, d, lane, r[it]);
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;
+        uint32_t run = gbase[(size_t)d * nblk + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < 8; ww++) { uint32_t c = wc[ww][d]; wc[ww][d] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {
+        const uint32_t i = base + it * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (uint32_t)(k[it] >> shift) & mask;
+            const uint32_t dst = wc[w][d] + r[it];
+            kout[dst] = k[it];
+            vout[dst] = vin[i];
+        }
+    }
+}
+
+int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
+                      long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s) {
+    if (n <= 0) return 0;
+    DM2_REQUIRE(n < (1ll << 31), "dm2_sort_pairs: n must be < 2^31");
+    DM2_REQUIRE(end_bit >= 0 && end_bit <= 64, "dm2_sort_pairs: end_bit out of range");
+    DM2_REQUIRE(temp_bytes >= sort_temp_bytes(n), "dm2_sort_pairs: temp buffer too small");
+    const int nblk = cdiv(n, kSortTile);
+    const int passes = (end_bit + 7) / 8;
+    ProfScope _ps("radix_sort", s);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(temp);
+    if (passes == 0) {
+        DM2_CHECK(cudaMemcpyAsync(kout, kin, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        DM2_CHECK(cudaMemcpyAsync(vout, vin, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    // ping-pong between (kin,vin) and (kout,vout); the input buffers are clobbered when passes > 1.
+    // With an even number of passes the first hop goes through a copy so that the result lands in
+    // (kout, vout).
+    uint64_t* ka = const_cast<uint64_t*>(kin); uint32_t* va = const_cast<uint32_t*>(vin);
+    uint64_t* kb = kout;                       uint32_t* vb = vout;
+    if (passes % 2 == 0) {
+        DM2_CHECK(cudaMemcpyAsync(kout, kin, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        DM2_CHECK(cudaMemcpyAsync(vout, vin, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        ka = kout; va = vout; kb = const_cast<uint64_t*>(kin); vb = const_cast<uint32_t*>(vin);
+    }
+    for (int p = 0; p < passes; p++) {
+        const int shift = 8 * p;
+        const int bits = min(8, end_bit - shift);
+        const uint32_t mask = (1u << bits) - 1u;
+        k_radix_hist<<<nblk, kSortThreads, 0, s>>>(ka, (uint32_t)n, shift, mask, counts, nblk);
+        DM2_LAUNCH_CHECK();
+        k_radix_scan<<<1, 1024, 0, s>>>(counts, (uint32_t)(nblk * kRadix));
+        DM2_LAUNCH_CHECK();
+        k_radix_scatter<<<nblk, kSortThreads, 0, s>>>(ka, va, kb, vb, (uint32_t)n, shift, mask, counts, nblk);
+        DM2_LAUNCH_CHECK();
+        uint64_t* tk = ka; ka = kb; kb = tk;
+        uint32_t* tv = va; va = vb; vb = tv;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ tile ranges
+// reference renderer.cu:470-492 (+ the memset at :211)
+__global__ void __launch_bounds__(256)
+k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R) return;
+    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    if (idx == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+    }
+    if (idx == R - 1) ranges[cur].y = R;
+}
+
+int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, cudaStream_t s) {
+    DM2_CHECK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
+    if (R > 0) {
+        ProfScope _ps("tile_ranges", s);
+        k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges);
+        DM2_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int launch_emit_keys(long long BF, int F, int gx, int gy, const float* key_depths,
+                           const uint32_t* tiles_touched, const uint32_t* offsets, const uint2* rects,
+                           uint64_t* keys, uint32_t* vals, cudaStream_t s) {
+    if (BF == 0) return 0;
+    ProfScope _ps("emit_keys", s);
+    k_emit_keys<<<cdiv(BF, 256), 256, 0, s>>>(BF, F, gx, gy, key_depths, tiles_touched, offsets, rects, keys, vals);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dm2

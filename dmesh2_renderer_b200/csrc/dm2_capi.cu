@@ -1,0 +1,342 @@
+// dm2_capi.cu — the extern "C" surface declared in include/dm2_renderer.h: argument validation
+// (mirrors the AT_ERROR checks of reference render.cu:62-118, 247-303, 397-429 that can be done
+// without torch shapes), workspace carving (reference state.h / renderer.cu:40-76, 499-507) and
+// kernel sequencing (reference renderer.cu:78-269, 271-392, 509-674) — on the caller's stream,
+// with a single stream wait for the num_rendered read-back and no cudaDeviceSynchronize.
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+#include "dm2_common.cuh"
+
+namespace dm2 {
+
+static thread_local char g_err[1024] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches++; }
+
+// ---- optional per-stage timing (CUDA events on the launching stream) -------------------------
+struct ProfEntry { const char* name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::map<std::string, std::pair<double, long long>> g_prof_acc;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(const char* name, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfEntry p{name, prof_event(), prof_event()};
+    cudaEventRecord(p.a, s);
+    g_prof_pending.push_back(p);
+}
+void prof_end(cudaStream_t s) {
+    if (!g_prof_on || g_prof_pending.empty()) return;
+    // scopes do not nest in this library: the last pending entry is the open one
+    cudaEventRecord(g_prof_pending.back().b, s);
+}
+static void prof_collect() {
+    for (auto& p : g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            auto& acc = g_prof_acc[p.name];
+            acc.first += ms; acc.second += 1;
+        }
+        g_prof_pool.push_back(p.a); g_prof_pool.push_back(p.b);
+    }
+    g_prof_pending.clear();
+}
+
+static uint32_t higher_msb(uint32_t n) {          // reference renderer.cu:396-411
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+static void face_layout(long long BF, bool layered, DM2FaceLayout* L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L->depths        = take((size_t)BF * 4);
+    L->min_depths    = take((size_t)BF * 4);
+    L->max_depths    = take((size_t)BF * 4);
+    L->tiles_touched = take((size_t)BF * 4);
+    L->face_offsets  = take((size_t)BF * 4);
+    L->scan_partials = take((size_t)scan_partials_count(BF) * 4);
+    L->rects         = take((size_t)BF * 8);
+    L->record_stride = layered ? (size_t)kLRecWords * 4 : (size_t)kRecBytes;
+    L->records       = take((size_t)BF * L->record_stride);
+    L->total         = off + 256;
+}
+
+static void image_layout(long long B, int H, int W, bool layered, DM2ImageLayout* L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const long long tiles = (long long)cdiv(W, kTile) * cdiv(H, kTile);
+    const size_t npix = (size_t)B * H * W;
+    L->ranges = take((size_t)B * tiles * 8);
+    if (layered) {
+        L->final_T = L->final_prev_T = L->n_contrib = 0;
+        L->first_face = take(npix * 4);
+        L->first_tet  = take(npix * 4);
+    } else {
+        L->final_T      = take(npix * 4);
+        L->final_prev_T = take(npix * 4);
+        L->n_contrib    = take(npix * 4);
+        L->first_face = L->first_tet = 0;
+    }
+    L->total = off + 256;
+}
+
+static void binning_layout(long long R, DM2BinningLayout* L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L->keys_unsorted = take((size_t)R * 8);
+    L->vals_unsorted = take((size_t)R * 4);
+    L->keys          = take((size_t)R * 8);
+    L->vals          = take((size_t)R * 4);
+    L->sort_temp     = take(sort_temp_bytes(R));
+    L->total         = off + 256;
+}
+
+static FaceWs carve_face(void* ws, long long BF, bool layered) {
+    DM2FaceLayout L; face_layout(BF, layered, &L);
+    char* p = reinterpret_cast<char*>(ws);
+    FaceWs f;
+    f.depths = (float*)(p + L.depths); f.min_depths = (float*)(p + L.min_depths);
+    f.max_depths = (float*)(p + L.max_depths); f.tiles_touched = (uint32_t*)(p + L.tiles_touched);
+    f.face_offsets = (uint32_t*)(p + L.face_offsets); f.scan_partials = (uint32_t*)(p + L.scan_partials);
+    f.rects = (uint2*)(p + L.rects); f.records = (float*)(p + L.records); f.record_stride = L.record_stride;
+    return f;
+}
+static ImageWs carve_image(void* ws, long long B, int H, int W, bool layered) {
+    DM2ImageLayout L; image_layout(B, H, W, layered, &L);
+    char* p = reinterpret_cast<char*>(ws);
+    ImageWs i;
+    i.ranges = (uint2*)(p + L.ranges); i.final_T = (float*)(p + L.final_T);
+    i.final_prev_T = (float*)(p + L.final_prev_T); i.n_contrib = (uint32_t*)(p + L.n_contrib);
+    i.first_face = (int*)(p + L.first_face); i.first_tet = (int*)(p + L.first_tet);
+    return i;
+}
+static BinWs carve_bin(void* ws, long long R) {
+    DM2BinningLayout L; binning_layout(R, &L);
+    char* p = reinterpret_cast<char*>(ws);
+    BinWs b;
+    b.keys_unsorted = (uint64_t*)(p + L.keys_unsorted); b.vals_unsorted = (uint32_t*)(p + L.vals_unsorted);
+    b.keys = (uint64_t*)(p + L.keys); b.vals = (uint32_t*)(p + L.vals);
+    b.sort_temp = p + L.sort_temp; b.sort_temp_bytes = sort_temp_bytes(R);
+    return b;
+}
+
+static int check_render_inputs(const DM2RenderInputs* in) {
+    DM2_REQUIRE(in != nullptr, "inputs must not be null");
+    DM2_REQUIRE(in->B >= 0 && in->P >= 0 && in->F >= 0 && in->H >= 0 && in->W >= 0, "negative dimension");
+    DM2_REQUIRE(in->aa_temperature >= 0.0f && in->aa_temperature <= 1.0f, "aa_temperature must be in the range [0, 1]");
+    DM2_REQUIRE(in->len_oarea_buffer >= 0, "len_oarea_buffer must be non-negative");
+    DM2_REQUIRE((long long)in->B * in->F < (1ll << 31), "B*F must be < 2^31");
+    DM2_REQUIRE((long long)in->B * in->H * in->W < (1ll << 31), "B*H*W must be < 2^31");
+    DM2_REQUIRE(cdiv(in->W, kTile) < 65536 && cdiv(in->H, kTile) < 65536, "patch too large");
+    return 0;
+}
+
+// shared tail of both preprocess entry points: scan + read-back of num_rendered
+static int scan_and_count(const FaceWs& fw, long long BF, int64_t* num_rendered_host, cudaStream_t s) {
+    *num_rendered_host = 0;
+    if (BF == 0) return 0;
+    if (launch_scan(fw.tiles_touched, fw.face_offsets, BF, fw.scan_partials, s)) return 1;
+    uint32_t r = 0;
+    DM2_CHECK(cudaMemcpyAsync(&r, fw.face_offsets + BF - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    DM2_CHECK(cudaStreamSynchronize(s));
+    *num_rendered_host = (int64_t)r;
+    return 0;
+}
+
+// shared middle of both pipelines: keys -> sort -> ranges
+static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* key_depths, const FaceWs& fw,
+                     const BinWs& bw, const ImageWs& iw, long long R, cudaStream_t s) {
+    const int num_tiles = B * gx * gy;
+    if (R > 0) {
+        if (launch_emit_keys(BF, F, gx, gy, key_depths, fw.tiles_touched, fw.face_offsets, fw.rects,
+                             bw.keys_unsorted, bw.vals_unsorted, s)) return 1;
+        const int bit = (int)higher_msb((uint32_t)num_tiles);
+        if (launch_sort_pairs(bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, R, 32 + bit, bw.sort_temp,
+                              bw.sort_temp_bytes, s)) return 1;
+    }
+    return launch_tile_ranges(bw.keys, R, iw.ranges, num_tiles, s);
+}
+
+}  // namespace dm2
+
+using namespace dm2;
+
+extern "C" {
+
+const char* dm2_last_error(void) { return g_err; }
+int dm2_abi_version(void) { return DM2_ABI_VERSION; }
+uint32_t dm2_higher_msb(uint32_t n) { return higher_msb(n); }
+void dm2_profile_enable(int32_t on) {
+    prof_collect();
+    g_prof_on = on != 0;
+}
+void dm2_profile_reset(void) { prof_collect(); g_prof_acc.clear(); }
+// Writes "name total_ms count\n" lines into buf; returns the number of bytes needed.
+int64_t dm2_profile_report(char* buf, int64_t cap) {
+    prof_collect();
+    std::string out;
+    char line[256];
+    for (auto& kv : g_prof_acc) {
+        snprintf(line, sizeof(line), "%s %.6f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap > 0) { size_t n = std::min((size_t)cap - 1, out.size()); memcpy(buf, out.data(), n); buf[n] = 0; }
+    return (int64_t)out.size() + 1;
+}
+int64_t dm2_launch_count(int32_t reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+
+int dm2_face_layout(int32_t B, int32_t F, int32_t layered, DM2FaceLayout* out) {
+    DM2_REQUIRE(out && B >= 0 && F >= 0, "dm2_face_layout: bad arguments");
+    face_layout((long long)B * F, layered != 0, out);
+    return 0;
+}
+int dm2_image_layout(int32_t B, int32_t H, int32_t W, int32_t layered, DM2ImageLayout* out) {
+    DM2_REQUIRE(out && B >= 0 && H >= 0 && W >= 0, "dm2_image_layout: bad arguments");
+    image_layout(B, H, W, layered != 0, out);
+    return 0;
+}
+int dm2_binning_layout(int64_t num_rendered, DM2BinningLayout* out) {
+    DM2_REQUIRE(out && num_rendered >= 0 && num_rendered < (1ll << 31), "dm2_binning_layout: bad arguments");
+    binning_layout(num_rendered, out);
+    return 0;
+}
+
+int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream) {
+    if (check_render_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && num_rendered_host, "dm2_render_preprocess: null workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    *num_rendered_host = 0;
+    if (in->P == 0 || BF == 0) return 0;                       // reference render.cu:149
+    FaceWs fw = carve_face(face_ws, BF, false);
+    if (launch_render_preprocess(*in, fw, s)) return 1;
+    return scan_and_count(fw, BF, num_rendered_host, s);
+}
+
+int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                       int64_t num_rendered, float* out_color, float* out_depth, void* stream) {
+    if (check_render_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && binning_ws && image_ws && out_color && out_depth, "dm2_render_forward: null buffer");
+    DM2_REQUIRE(num_rendered >= 0 && num_rendered < (1ll << 31), "dm2_render_forward: bad num_rendered");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+    FaceWs fw = carve_face(face_ws, BF, false);
+    BinWs bw = carve_bin(binning_ws, num_rendered);
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
+    if (in->P == 0) {                                          // reference render.cu:128-129, 149: zeros
+        const size_t npix = (size_t)in->B * in->H * in->W;
+        DM2_CHECK(cudaMemsetAsync(out_color, 0, npix * 3 * sizeof(float), s));
+        DM2_CHECK(cudaMemsetAsync(out_depth, 0, npix * sizeof(float), s));
+        return 0;
+    }
+    const long long R = num_rendered;
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, s)) return 1;
+    return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, s);
+}
+
+int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
+                        const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
+                        const float* dL_dout_depth, const DM2RenderGrads* grads, void* stream) {
+    if (check_render_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads,
+                "dm2_render_backward: null buffer");
+    DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dverts_ndc &&
+                grads->dL_dfaces_intense && grads->dL_daa_face_verts, "dm2_render_backward: null gradient buffer");
+    if (in->F == 0 || num_rendered == 0) return 0;             // reference render.cu:320
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
+    BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
+    ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
+    return launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, *grads, s);
+}
+
+static int check_layer_inputs(const DM2LayerInputs* in) {
+    DM2_REQUIRE(in != nullptr, "inputs must not be null");
+    DM2_REQUIRE(in->B >= 0 && in->P >= 0 && in->F >= 0 && in->T >= 0 && in->H >= 0 && in->W >= 0, "negative dimension");
+    DM2_REQUIRE(in->num_layers >= 0, "num_layers must be non-negative");
+    DM2_REQUIRE((long long)in->B * in->F < (1ll << 31), "B*F must be < 2^31");
+    DM2_REQUIRE((long long)in->B * in->H * in->W < (1ll << 31), "B*H*W must be < 2^31");
+    return 0;
+}
+
+int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream) {
+    if (check_layer_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && num_rendered_host, "dm2_layers_preprocess: null workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    *num_rendered_host = 0;
+    if (BF == 0) return 0;
+    FaceWs fw = carve_face(face_ws, BF, true);
+    if (launch_layers_preprocess(*in, fw, s)) return 1;
+    return scan_and_count(fw, BF, num_rendered_host, s);
+}
+
+int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes) {
+    DM2_REQUIRE(bytes && F >= 0 && T >= 0, "dm2_layers_geo_bytes: bad arguments");
+    *bytes = layers_geo_bytes(F, T);
+    return 0;
+}
+
+int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                               void* geo_ws, int64_t num_rendered, int32_t* render_layers,
+                               int32_t* render_layers_cnt, void* stream) {
+    if (check_layer_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && binning_ws && image_ws && geo_ws && render_layers_cnt, "dm2_generate_render_layers: null buffer");
+    DM2_REQUIRE(render_layers || in->num_layers == 0, "dm2_generate_render_layers: null render_layers");
+    DM2_REQUIRE(num_rendered >= 0 && num_rendered < (1ll << 31), "dm2_generate_render_layers: bad num_rendered");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+    FaceWs fw = carve_face(face_ws, BF, true);
+    BinWs bw = carve_bin(binning_ws, num_rendered);
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
+    // key = min depth (reference renderer.cu:603)
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, s)) return 1;
+    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, s);
+}
+
+int dm2_sort_temp_bytes(int64_t n, size_t* bytes) {
+    DM2_REQUIRE(bytes && n >= 0, "dm2_sort_temp_bytes: bad arguments");
+    *bytes = sort_temp_bytes(n);
+    return 0;
+}
+int dm2_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
+                   int64_t n, int32_t end_bit, void* temp, size_t temp_bytes, void* stream) {
+    DM2_REQUIRE(n == 0 || (keys_in && vals_in && keys_out && vals_out && temp), "dm2_sort_pairs: null buffer");
+    return launch_sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, temp_bytes, (cudaStream_t)stream);
+}
+int dm2_scan_partials_count(int64_t n, int64_t* count) {
+    DM2_REQUIRE(count && n >= 0, "dm2_scan_partials_count: bad arguments");
+    *count = scan_partials_count(n);
+    return 0;
+}
+int dm2_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* partials, void* stream) {
+    DM2_REQUIRE(n == 0 || (in && out && partials), "dm2_inclusive_scan_u32: null buffer");
+    return launch_scan(in, out, n, partials, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// dm2_common.cuh — shared declarations for libdm2_b200 (sm_100a only).
+//
+// Numerics policy.  Everything that feeds a discrete decision the reference makes (tile bbox,
+// depth keys, AA inside/clip tests, ray/triangle hits, tet-walk sign tests, early termination)
+// is written with explicit round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fmaf_rn, IEEE
+// division and sqrt) so that the instruction sequence is fixed by the source, not by the
+// optimiser.  The sequences follow the FMA-contraction pattern nvcc 12.9 produces for the
+// reference's expressions on sm_100a:
+//      a*b - c*d          ->  fma(a, b, -rn(c*d))
+//      a*b + c*d          ->  fma(a, b,  rn(c*d))
+//      a*b + c*d + e*f    ->  fma(e, f, fma(a, b, rn(c*d)))
+//      x + a*b            ->  fma(a, b, x)
+// The CPU oracle (oracle/dm2_oracle.cpp) restates the same sequences with fmaf().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/dm2_renderer.h"
+
+namespace dm2 {
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_error(const char* fmt, ...);
+void count_launch();
+// optional per-kernel timing with CUDA events on the launching stream (dm2_profile_* in the C-ABI)
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+    cudaStream_t s;
+    ProfScope(const char* name, cudaStream_t st) : s(st) { prof_begin(name, st); }
+    ~ProfScope() { prof_end(s); }
+};
+#define DM2_CHECK(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            dm2::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,           \
+                           cudaGetErrorString(_e));                                       \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+#define DM2_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        dm2::count_launch();                                                              \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            dm2::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,       \
+                           cudaGetErrorString(_e));                                       \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+#define DM2_REQUIRE(cond, msg)                                                            \
+    do {                                                                                  \
+        if (!(cond)) { dm2::set_error("%s", msg); return 2; }                             \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+constexpr int kTile = DM2_TILE;
+constexpr float kTEps = 1e-4f;           // T_EPS, reference cuda_impl/auxiliary.h:9
+
+// ---------------------------------------------------------------- packed face record (render)
+// One 256-byte record per (view, face), written once by the preprocess kernel and staged into
+// shared memory by the tile kernels with 16-byte loads.  Word offsets (32-bit words):
+constexpr int kRecWords   = 64;
+constexpr int kRecBytes   = kRecWords * 4;
+constexpr int R_BBOX      = 0;    // txmin txmax tymin tymax      (min/max of aa_face_verts)
+constexpr int R_N01       = 4;    // n0.x n0.y n1.x n1.y          (aa_face_edges_normal)
+constexpr int R_N2C       = 8;    // n2.x n2.y c0 c1              (…, aa_face_edges_normal_c)
+constexpr int R_MISC      = 12;   // c2, opacity, intense, flags (bits 0..5: edges_iszero[e][k] at bit 2e+k)
+constexpr int R_P0        = 16;   // p0.xyz (world), z0 (ndc)
+constexpr int R_P1        = 20;
+constexpr int R_P2        = 24;
+constexpr int R_COL       = 28;   // c0.rgb c1.rgb c2.rgb  (9 words: 28..36)
+constexpr int R_VID       = 37;   // vertex ids (3 ints: 37..39)
+constexpr int R_AAV       = 40;   // aa_face_verts   3 x (x,y)   40..45
+constexpr int R_AAE       = 46;   // aa_face_edges   3 x (x,y)   46..51
+constexpr int R_AAR       = 52;   // aa_face_edges_recip         52..57
+constexpr int R_FID       = 58;   // face id (int)
+
+// packed record of the layered path: 12 words = 48 bytes per (view, face)
+constexpr int kLRecWords  = 12;   // p0.xyz p1.xyz p2.xyz min_depth max_depth face_id
+
+// ---------------------------------------------------------------- device math
+struct f3 { float x, y, z; };
+
+__device__ __forceinline__ f3 sub3(const f3& a, const f3& b) {
+    return { __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z) };
+}
+// helper_math cross(): (a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x)
+__device__ __forceinline__ f3 cross3(const f3& a, const f3& b) {
+    return { __fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)),
+             __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+             __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)) };
+}
+// helper_math dot(): a.x*b.x + a.y*b.y + a.z*b.z
+__device__ __forceinline__ float dot3(const f3& a, const f3& b) {
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+}
+
+// Moller-Trumbore without rejection (reference cuda_impl/auxiliary.h:212-243).
+// Returns false iff denom == 0.  tuv = (t, u, v).
+__device__ __forceinline__ bool ray_tri(const f3& o, const f3& d, const f3& p0, const f3& p1,
+                                        const f3& p2, float& t, float& u, float& v) {
+    f3 T  = sub3(o, p0);
+    f3 E1 = sub3(p1, p0);
+    f3 E2 = sub3(p2, p0);
+    f3 Pv = cross3(d, E2);
+    f3 Q  = cross3(T, E1);
+    float denom = dot3(Pv, E1);
+    if (denom == 0.0f) return false;
+    float inv = __fdiv_rn(1.0f, denom);
+    t = __fmul_rn(dot3(Q, E2), inv);
+    u = __fmul_rn(dot3(Pv, T), inv);
+    v = __fmul_rn(dot3(Q, d), inv);
+    return true;
+}
+
+// 7-region barycentric clamp (reference cuda_impl/auxiliary.h:292-329).
+__device__ __forceinline__ void clamp_bary(float u, float v, float& uc, float& vc, int& code) {
+    if (u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f) { uc = u; vc = v; code = 0; }
+    else if (u <= 0.0f && v <= 0.0f) { uc = 0.0f; vc = 0.0f; code = 1; }
+    else if ((u >= 1.0f && v <= 0.0f) || (v >= 0.0f && v <= __fsub_rn(u, 1.0f))) { uc = 1.0f; vc = 0.0f; code = 2; }
+    else if ((u <= 0.0f && v >= 1.0f) || (u >= 0.0f && v >= __fadd_rn(u, 1.0f))) { uc = 0.0f; vc = 1.0f; code = 3; }
+    else if (u <= 0.0f && v <= 1.0f && v >= 0.0f) { uc = 0.0f; vc = v; code = 4; }
+    else if (u <= 1.0f && u >= 0.0f && v <= 0.0f) { uc = u; vc = 0.0f; code = 5; }
+    else {
+        uc = __fmul_rn(__fsub_rn(__fadd_rn(1.0f, u), v), 0.5f);
+        vc = __fmul_rn(__fadd_rn(__fsub_rn(1.0f, u), v), 0.5f);
+        code = 6;
+    }
+}
+
+// getPatchRectFromTri (reference cuda_impl/auxiliary.h:72-92).  No FMA in this chain.
+__device__ __forceinline__ void patch_rect(uint32_t pmx, uint32_t pmy, float p0x, float p0y, float p1x,
+                                           float p1y, float p2x, float p2y, int gx, int gy,
+                                           int& x0, int& y0, int& x1, int& y1) {
+    float fpx = (float)pmx, fpy = (float)pmy;          // float - uint  ->  uint converted to float
+    float min_x = __fsub_rn(fminf(fminf(p0x, p1x), p2x), fpx);
+    float min_y = __fsub_rn(fminf(fminf(p0y, p1y), p2y), fpy);
+    float max_x = __fsub_rn(fmaxf(fmaxf(p0x, p1x), p2x), fpx);
+    float max_y = __fsub_rn(fmaxf(fmaxf(p0y, p1y), p2y), fpy);
+    int ix0 = (int)floorf(__fmul_rn(min_x, 0.0625f));
+    int iy0 = (int)floorf(__fmul_rn(min_y, 0.0625f));
+    int ix1 = (int)ceilf(__fmul_rn(max_x, 0.0625f));
+    int iy1 = (int)ceilf(__fmul_rn(max_y, 0.0625f));
+    x0 = min(gx, max(0, ix0));
+    y0 = min(gy, max(0, iy0));
+    x1 = min(gx, max(0, ix1));
+    y1 = min(gy, max(0, iy1));
+}
+
+__device__ __forceinline__ float clamp01_depth(float z) {
+    float d = __fmul_rn(__fadd_rn(z, 1.0f), 0.5f);
+    if (d < 0.0f) d = 0.0f;
+    if (d > 1.0f) d = 1.0f;
+    return d;
+}
+
+// ---------------------------------------------------------------- internal launchers
+struct FaceWs {
+    float* depths; float* min_depths; float* max_depths;
+    uint32_t* tiles_touched; uint32_t* face_offsets; uint32_t* scan_partials;
+    uint2* rects;                 // packed tile bbox per (view,face): x = x0 | y0<<16, y = x1 | y1<<16
+    float* records; size_t record_stride;
+};
+struct ImageWs {
+    uint2* ranges; float* final_T; float* final_prev_T; uint32_t* n_contrib;
+    int* first_face; int* first_tet;
+};
+struct BinWs {
+    uint64_t* keys_unsorted; uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
+    void* sort_temp; size_t sort_temp_bytes;
+};
+
+int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaStream_t s);
+int launch_layers_preprocess(const DM2LayerInputs& in, const FaceWs& fw, cudaStream_t s);
+int launch_scan(const uint32_t* in, uint32_t* out, long long n, uint32_t* partials, cudaStream_t s);
+long long scan_partials_count(long long n);
+int launch_emit_keys(long long BF, int F, int gx, int gy, const float* key_depths,
+                     const uint32_t* tiles_touched, const uint32_t* offsets, const uint2* rects,
+                     uint64_t* keys, uint32_t* vals, cudaStream_t s);
+int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
+                      long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
+size_t sort_temp_bytes(long long n);
+int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, cudaStream_t s);
+int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
+                          const ImageWs& iw, float* out_color, float* out_depth, cudaStream_t s);
+int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
+                           const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
+                           const DM2RenderGrads& g, cudaStream_t s);
+int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
+                  void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, cudaStream_t s);
+size_t layers_geo_bytes(int F, int T);
+
+}  // namespace dm2

@@ -1,0 +1,226 @@
+// dm2_layers.cu — LayeredRenderer hot path: per-pixel first hit over the min-depth-sorted tile
+// list, choice of the entry tetrahedron, then the per-ray walk through the tet mesh recording the
+// first L existing faces.  Behaviour of reference cuda_impl/forward.cu:538-709
+// (firstIntersectCUDA), :744-1000 (generateRenderLayersCUDA) and auxiliary.h:382-431
+// (tet_face_outward_normal); re-designed:
+//   * unit face normals and tet centroids are computed once per call into 48-byte / 32-byte
+//     records instead of being rebuilt from 21 scattered vertex loads at every walk step;
+//   * first hit and walk run in ONE kernel (first_face/first_tet stay in registers; they are still
+//     written out as debug taps);
+//   * out-of-image threads are bounds-checked (the reference writes first_face[-1..] for them when
+//     W or H is not a multiple of 16, forward.cu:565-585).
+// All sign/hit decisions use the fixed FMA sequences of dm2_common.cuh, so layer ids are
+// reproducible bit-for-bit against the reference and the CPU oracle.
+#include "dm2_common.cuh"
+
+namespace dm2 {
+
+constexpr int kLStage = 256;
+constexpr int kFGeoWords = 12;     // p0.xyz p1.xyz p2.xyz n.xyz   (n: unit normal, not yet oriented)
+constexpr int kTGeoWords = 8;      // centroid.xyz, pad, tet_faces[4]
+
+size_t layers_geo_bytes(int F, int T) {
+    return align_up((size_t)F * kFGeoWords * 4, 256) + align_up((size_t)T * kTGeoWords * 4, 256) + 256;
+}
+
+__global__ void __launch_bounds__(256)
+k_face_geo(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces, float* __restrict__ fgeo) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int v0 = faces[3 * (size_t)f], v1 = faces[3 * (size_t)f + 1], v2 = faces[3 * (size_t)f + 2];
+    const f3 p0{verts[3 * (size_t)v0], verts[3 * (size_t)v0 + 1], verts[3 * (size_t)v0 + 2]};
+    const f3 p1{verts[3 * (size_t)v1], verts[3 * (size_t)v1 + 1], verts[3 * (size_t)v1 + 2]};
+    const f3 p2{verts[3 * (size_t)v2], verts[3 * (size_t)v2 + 1], verts[3 * (size_t)v2 + 2]};
+    // auxiliary.h:403-408
+    f3 n = cross3(sub3(p1, p0), sub3(p2, p0));
+    float nn = __fsqrt_rn(dot3(n, n));
+    nn = fmaxf(nn, 0.0001f);
+    n = f3{__fdiv_rn(n.x, nn), __fdiv_rn(n.y, nn), __fdiv_rn(n.z, nn)};
+    float4* o = reinterpret_cast<float4*>(fgeo + (size_t)f * kFGeoWords);
+    o[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+    o[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+    o[2] = make_float4(p2.z, n.x, n.y, n.z);
+}
+
+__global__ void __launch_bounds__(256)
+k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ tets,
+          const int32_t* __restrict__ tet_faces, float* __restrict__ tgeo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int4 q = *reinterpret_cast<const int4*>(tets + 4 * (size_t)t);
+    const float* a = verts + 3 * (size_t)q.x;
+    const float* b = verts + 3 * (size_t)q.y;
+    const float* c = verts + 3 * (size_t)q.z;
+    const float* d = verts + 3 * (size_t)q.w;
+    // auxiliary.h:421: (q0 + q1 + q2 + q3) * 0.25f, left to right
+    const float sx = __fadd_rn(__fadd_rn(__fadd_rn(a[0], b[0]), c[0]), d[0]);
+    const float sy = __fadd_rn(__fadd_rn(__fadd_rn(a[1], b[1]), c[1]), d[1]);
+    const float sz = __fadd_rn(__fadd_rn(__fadd_rn(a[2], b[2]), c[2]), d[2]);
+    const int4 tf = *reinterpret_cast<const int4*>(tet_faces + 4 * (size_t)t);
+    float4* o = reinterpret_cast<float4*>(tgeo + (size_t)t * kTGeoWords);
+    o[0] = make_float4(sx, sy, sz, 0.0f);       // the *sum*; the 0.25 scale is fused below
+    o[1] = make_float4(__int_as_float(tf.x), __int_as_float(tf.y), __int_as_float(tf.z), __int_as_float(tf.w));
+}
+
+struct FGeo { f3 p0, p1, p2, n; };
+__device__ __forceinline__ FGeo load_fgeo(const float* __restrict__ fgeo, int f) {
+    const float4* p = reinterpret_cast<const float4*>(fgeo + (size_t)f * kFGeoWords);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    return FGeo{f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, f3{c.y, c.z, c.w}};
+}
+
+// dot(outward normal of `face` w.r.t. tet `tet`, ray_d)   (auxiliary.h:382-431 + the caller's dot)
+__device__ __forceinline__ float outward_dot(const FGeo& g, const float4 tsum, const f3& rd) {
+    // d = centroid - p0 with centroid = sum * 0.25  ->  fma(sum, 0.25, -p0)
+    const f3 d{__fmaf_rn(tsum.x, 0.25f, -g.p0.x), __fmaf_rn(tsum.y, 0.25f, -g.p0.y), __fmaf_rn(tsum.z, 0.25f, -g.p0.z)};
+    const float side = dot3(g.n, d);
+    const float nd = dot3(g.n, rd);
+    return (side > 0.0f) ? -nd : nd;     // dot(-n, rd) == -dot(n, rd) exactly
+}
+
+__device__ __forceinline__ bool hit_test(const f3& o, const f3& d, const FGeo& g) {
+    float t, u, v;
+    if (!ray_tri(o, d, g.p0, g.p1, g.p2, t, u, v)) return false;
+    return t >= 0.0f && u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f;
+}
+
+__global__ void __launch_bounds__(256)
+k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __restrict__ list,
+         const uint2* __restrict__ ranges, const float* __restrict__ fgeo, const float* __restrict__ tgeo,
+         int* __restrict__ first_face_out, int* __restrict__ first_tet_out, int32_t* __restrict__ layers,
+         int32_t* __restrict__ layers_cnt, int gx, int gy) {
+    __shared__ __align__(16) float srec[kLStage * kLRecWords];
+    const int tiles = gx * gy;
+    const int b = blockIdx.x / tiles, t_in = blockIdx.x % tiles;
+    const int tile_x = t_in % gx, tile_y = t_in / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
+    const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < in.W && py < in.H;
+    const size_t pix = inside ? ((size_t)b * in.H + py) * in.W + px : 0;
+    f3 ro{0, 0, 0}, rd{0, 0, 0};
+    if (inside) {
+        const float* o = in.image_ray_o + pix * 3;
+        const float* d = in.image_ray_d + pix * 3;
+        ro = f3{o[0], o[1], o[2]};
+        rd = f3{d[0], d[1], d[2]};
+    }
+    const uint2 range = ranges[blockIdx.x];
+    const int total = (int)(range.y - range.x);
+    const size_t view_base = (size_t)b * in.F;
+
+    // ---------------- first hit (forward.cu:603-681)
+    bool done = !inside;
+    float min_T = -1.0f, min_T_max_depth = -1.0f;
+    int first_face = -1;
+    for (int base = 0; base < total; base += kLStage) {
+        if (__syncthreads_count(done) == 256) break;
+        const int cnt = min(kLStage, total - base);
+        for (int q = threadIdx.x; q < cnt * 3; q += 256) {
+            const int slot = q / 3, chunk = q - slot * 3;
+            const uint32_t fid = list[(size_t)range.x + base + slot];
+            reinterpret_cast<float4*>(srec)[slot * 3 + chunk] =
+                __ldg(reinterpret_cast<const float4*>(lrec + (view_base + fid) * kLRecWords) + chunk);
+        }
+        __syncthreads();
+        for (int j = 0; j < cnt; j++) {
+            if (__all_sync(0xffffffffu, done)) break;
+            if (done) continue;
+            const float* r = srec + j * kLRecWords;
+            if (min_T >= 0.0f && r[9] > min_T_max_depth) { done = true; continue; }
+            float t, u, v;
+            if (!ray_tri(ro, rd, f3{r[0], r[1], r[2]}, f3{r[3], r[4], r[5]}, f3{r[6], r[7], r[8]}, t, u, v)) continue;
+            const bool hit = t >= 0.0f && u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f;
+            if (!hit) continue;
+            if (min_T < 0.0f || t < min_T) {
+                min_T = t;
+                min_T_max_depth = r[10];
+                first_face = __float_as_int(r[11]);
+            }
+        }
+    }
+    if (!inside) return;
+
+    // ---------------- entry tet (forward.cu:683-708)
+    int first_tet = -1;
+    if (first_face >= 0) {
+        const FGeo g = load_fgeo(fgeo, first_face);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int tet = in.face_tets[2 * (size_t)first_face + i];
+            if (tet < 0) continue;
+            const float4 ts = __ldg(reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords));
+            if (outward_dot(g, ts, rd) < 0.0f) first_tet = tet;
+        }
+    }
+    first_face_out[pix] = first_face;
+    first_tet_out[pix] = first_tet;
+
+    // ---------------- walk (forward.cu:842-999)
+    const int L = in.num_layers;
+    int curr_face = first_face, curr_tet = first_tet, n_done = 0;
+    bool wdone = (curr_face == -1 || curr_tet == -1);
+    long long guard = (long long)in.T + in.F + 16;          // safety net against cyclic walks
+    while (!wdone && guard-- > 0) {
+        if (in.face_existence[curr_face]) {
+            if (n_done < L) layers[pix * L + n_done] = curr_face;
+            n_done++;
+            if (n_done >= L) break;
+        }
+        if (curr_tet == -1) break;
+        const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)curr_tet * kTGeoWords);
+        const float4 ts = __ldg(tp);
+        const float4 tfw = __ldg(tp + 1);
+        const int tf[4] = {__float_as_int(tfw.x), __float_as_int(tfw.y), __float_as_int(tfw.z), __float_as_int(tfw.w)};
+        int others[4];
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (tf[i] != curr_face) { others[k < 3 ? k : 3] = tf[i]; k++; }
+        if (k != 3) break;
+        {
+            const FGeo g = load_fgeo(fgeo, curr_face);
+            if (outward_dot(g, ts, rd) >= 0.0f) break;
+        }
+        int next_face = -1, next_cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const FGeo g = load_fgeo(fgeo, others[i]);
+            float t, u, v;
+            if (!ray_tri(ro, rd, g.p0, g.p1, g.p2, t, u, v)) continue;
+            const bool hit = t >= 0.0f && u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f;
+            if (hit && outward_dot(g, ts, rd) > 0.0f) { next_face = others[i]; next_cnt++; }
+        }
+        if (next_cnt != 1) break;
+        int next_tet = -1;
+        const int ft0 = in.face_tets[2 * (size_t)next_face], ft1 = in.face_tets[2 * (size_t)next_face + 1];
+        if (ft0 != curr_tet) next_tet = ft0;
+        else if (ft1 != curr_tet) next_tet = ft1;
+        curr_face = next_face;
+        curr_tet = next_tet;
+    }
+    layers_cnt[pix] = n_done;
+}
+
+int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, void* geo_ws,
+                  int32_t* render_layers, int32_t* render_layers_cnt, cudaStream_t s) {
+    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    const long long nblk = (long long)in.B * gx * gy;
+    if (nblk == 0) return 0;
+    float* fgeo = reinterpret_cast<float*>(geo_ws);
+    float* tgeo = reinterpret_cast<float*>(reinterpret_cast<char*>(geo_ws) + align_up((size_t)in.F * kFGeoWords * 4, 256));
+    ProfScope _ps("layers_geo+first_hit+walk", s);
+    if (in.F > 0) {
+        k_face_geo<<<cdiv(in.F, 256), 256, 0, s>>>(in.F, in.verts, in.faces, fgeo);
+        DM2_LAUNCH_CHECK();
+    }
+    if (in.T > 0) {
+        k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.tet_faces, tgeo);
+        DM2_LAUNCH_CHECK();
+    }
+    k_layers<<<(unsigned)nblk, 256, 0, s>>>(in, fw.records, bw.vals, iw.ranges, fgeo, tgeo, iw.first_face,
+                                            iw.first_tet, render_layers, render_layers_cnt, gx, gy);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dm2

@@ -1,0 +1,177 @@
+"""``Renderer`` and ``LayeredRenderer``: drop-in replacements for the two classes of
+SonSang/dmesh2_renderer (reference dmesh2_renderer/__init__.py:179-380, 388-451).
+
+Constructor arguments, method names, argument order, defaults, tensor layouts and dtypes are the
+reference's.  The per-call host work (projection, CCW triangle set-up, ray selection) issues the
+same fp32 torch ops in the same order, so the tensors handed to ``RenderFunction`` are bit-identical
+to the reference's; everything below ``RenderFunction`` is libdm2_b200.so.
+"""
+from typing import List
+
+import torch
+
+from . import _C
+from .function import RenderFunction
+from .triangles import Triangles
+
+W_EPS = 1e-4      # |w| clamp of the projection (reference __init__.py:253-255)
+
+
+def _unproject_pixel_rays(mv, proj, width, height, device):
+    """One ray per pixel centre for every camera (reference __init__.py:198-237).
+
+    Origin: camera position (translation column of mv^-1).  Direction: normalised vector to the
+    pixel centre un-projected from NDC z = -1 *without* the homogeneous divide (upstream behaviour:
+    exact only when the near plane is at distance 1 or the projection is orthographic).
+    """
+    n_view = mv.shape[0]
+    inv_mv = torch.inverse(mv)
+    inv_proj = torch.inverse(proj)
+    origin = torch.zeros((n_view, height, width, 3), device=device)
+    for k in range(3):
+        origin[:, :, :, k] = inv_mv[:, k, 3].reshape(-1, 1, 1)
+
+    xs = torch.arange(width, device=device).float()
+    ys = torch.arange(height, device=device).float()
+    centre = torch.stack(torch.meshgrid([xs, ys], indexing="ij"), dim=-1).float() + 0.5      # [W, H, 2]
+    centre = centre.transpose(0, 1).unsqueeze(0).expand(n_view, -1, -1, -1)                  # [B, H, W, 2]
+    ndc = torch.zeros_like(centre)
+    ndc[:, :, :, 0] = (centre[:, :, :, 0] / width * 2) - 1
+    ndc[:, :, :, 1] = (centre[:, :, :, 1] / height * 2) - 1
+    near = -torch.ones_like(ndc[:, :, :, 0:1])
+    clip = torch.cat((ndc, near), dim=-1)
+    clip = torch.cat((clip, torch.ones_like(clip[:, :, :, 0:1])), dim=-1).unsqueeze(-2)      # [B, H, W, 1, 4]
+    view = torch.matmul(clip, inv_proj.transpose(1, 2).unsqueeze(1).unsqueeze(1))
+    world = torch.matmul(view, inv_mv.transpose(1, 2).unsqueeze(1).unsqueeze(1))
+    target = world[..., :3].squeeze(-2)                                                      # [B, H, W, 3]
+    direction = target - origin
+    length = torch.norm(direction, dim=-1, keepdim=True) + 1e-6
+    return origin, direction / length
+
+
+class Renderer(torch.nn.Module):
+    """Differentiable renderer with global (per-tile) depth ordering and anti-aliased coverage."""
+
+    def __init__(self, mv, proj, width, height, device, aa_grad_buffer_size=20):
+        super().__init__()
+        self._setup(mv, proj, width, height, device)
+        # kept for API parity; this implementation recomputes AA terms in the backward pass
+        self.aa_grad_buffer_size = aa_grad_buffer_size
+
+    def _setup(self, mv, proj, width, height, device):
+        self.mv = mv                  # [B, 4, 4]
+        self.proj = proj              # [B, 4, 4]
+        self.width = width
+        self.height = height
+        self.device = device
+        self.num_batch = self.mv.shape[0]
+        self.ray_o = None
+        self.ray_d = None
+        self._init_rays()
+
+    def _init_rays(self):
+        self.ray_o, self.ray_d = _unproject_pixel_rays(self.mv, self.proj, self.width, self.height, self.device)
+
+    def compute_verts_ndc_image(self, verts, mv, proj):
+        """verts [P,3], mv/proj [B,4,4] -> (verts_ndc [B,P,3], verts_image [B,P,2]) (reference :239-262)."""
+        hom = torch.cat((verts, torch.ones_like(verts[:, [0]])), dim=-1)           # [P, 4]
+        clip = torch.matmul(torch.matmul(hom, mv.transpose(1, 2)), proj.transpose(1, 2))   # [B, P, 4]
+        w = clip[..., [3]]
+        w = torch.where(torch.logical_and(w >= 0.0, w < W_EPS), torch.full_like(w, W_EPS), w)
+        w = torch.where(torch.logical_and(w < 0.0, w > -W_EPS), torch.full_like(w, -W_EPS), w)
+        ndc = clip[..., :3] / w
+        half = (ndc[..., :2] + 1) * 0.5
+        image = torch.stack((half[..., 0] * self.width, half[..., 1] * self.height), dim=-1)
+        return ndc, image
+
+    def select_rays(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height):
+        """Rays of a [patch_height, patch_width] window per selected view (reference :264-302)."""
+        all_o = self.ray_o[batch_mvp_idx]
+        all_d = self.ray_d[batch_mvp_idx]
+        x0 = batch_patch_min[:, 0]
+        y0 = batch_patch_min[:, 1]
+        assert (x0 + patch_width <= self.width).all(), "Some b_patch_max_x exceed self.width"
+        assert (y0 + patch_height <= self.height).all(), "Some b_patch_max_y exceed self.height"
+        n = all_o.shape[0]
+        dev = all_o.device
+        rows = (y0.view(n, 1, 1).to(dev) + torch.arange(patch_height, device=dev).view(1, patch_height, 1)).long()
+        cols = (x0.view(n, 1, 1).to(dev) + torch.arange(patch_width, device=dev).view(1, 1, patch_width)).long()
+        view = torch.arange(n, device=dev).view(n, 1, 1)
+        return all_o[view, rows, cols], all_d[view, rows, cols]
+
+    def forward(self,
+                batch_mvp_idx: List[int],           # [B,]
+                batch_patch_min: torch.Tensor,      # [B, 2]
+                patch_width: int,
+                patch_height: int,
+                verts: torch.Tensor,                # [P, 3]
+                faces: torch.Tensor,                # [F, 3]
+                verts_color: torch.Tensor,          # [P, 3]
+                faces_opacity: torch.Tensor,        # [F,]
+                faces_intense: torch.Tensor,        # [B, F]
+                background: torch.Tensor,           # [3]
+                aa_temperature: float = 1.0):
+        args = self.prepare_inputs(batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces,
+                                   verts_color, faces_opacity, faces_intense, background, aa_temperature)
+        color, depth = RenderFunction.apply(*args)
+        depth = 1.0 - (depth + 1.0) / 2.0        # NDC z -> [0, 1], near = 1 (reference :377-378)
+        return color, depth
+
+    def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
+                       faces_opacity, faces_intense, background, aa_temperature=1.0):
+        """The 21 positional inputs of ``RenderFunction`` for this call (reference :325-376)."""
+        n_view = len(batch_mvp_idx)
+        n_face = faces.shape[0]
+        verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])
+
+        corners = verts_image[:, faces.flatten()].view(-1, 3, 2)                  # [B*F, 3, 2]
+        tri = Triangles(corners[:, 0], corners[:, 1], corners[:, 2])
+        shape4 = (n_view, n_face, 3, 2)
+
+        ray_o, ray_d = self.select_rays(batch_mvp_idx, batch_patch_min, patch_width, patch_height)
+
+        f32 = torch.float32
+        return (
+            background.to(dtype=f32),
+            batch_patch_min.to(dtype=torch.int32), patch_width, patch_height,
+            verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
+            verts_ndc.to(dtype=f32), verts_image.to(dtype=f32), faces_intense.to(dtype=f32),
+            aa_temperature,
+            tri.verts.reshape(shape4).to(dtype=f32),
+            tri.edges.reshape(shape4).to(dtype=f32),
+            tri.edges_iszero.reshape(shape4).to(dtype=torch.bool),
+            tri.edges_recip.reshape(shape4).to(dtype=f32),
+            tri.edges_normal.reshape(shape4).to(dtype=f32),
+            tri.edges_normal_c.reshape((n_view, n_face, 3)).to(dtype=f32),
+            self.aa_grad_buffer_size,
+            ray_o.to(dtype=f32), ray_d.to(dtype=f32))
+
+
+class LayeredRenderer(Renderer):
+    """Per-ray, strictly depth-ordered layers of existing faces through a tetrahedral mesh.
+
+    Like the reference (dmesh2_renderer/__init__.py:388-402) the constructor does NOT initialise
+    ``torch.nn.Module``; the object only carries attributes and ``generate`` is not differentiable.
+    """
+
+    def __init__(self, mv, proj, width, height, device):
+        self._setup(mv, proj, width, height, device)
+
+    def generate(self,
+                 batch_mvp_idx: List[int],          # [B,]
+                 verts: torch.Tensor,               # [P, 3]
+                 faces: torch.Tensor,               # [F, 3]
+                 tets: torch.Tensor,                # [T, 4]
+                 face_tets: torch.Tensor,           # [F, 2]  (-1 = no tet on that side)
+                 tet_faces: torch.Tensor,           # [T, 4]
+                 faces_existence: torch.Tensor,     # [F,]
+                 num_layers: int):
+        verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])
+        ray_o, ray_d = self.ray_o[batch_mvp_idx], self.ray_d[batch_mvp_idx]
+        f32, i32 = torch.float32, torch.int32
+        return _C.generate_render_layers_cuda(
+            self.width, self.height,
+            verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),
+            tet_faces.to(dtype=i32), faces_existence.to(dtype=i32),
+            verts_ndc.to(dtype=f32), verts_image.to(dtype=f32), ray_o.to(dtype=f32), ray_d.to(dtype=f32),
+            num_layers)

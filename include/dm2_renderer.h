@@ -1,0 +1,193 @@
+/*
+ * dm2_renderer.h — C-ABI of libdm2_b200.so, the B200-native (sm_100a) replacement for the
+ * `dmesh2_renderer._C` torch extension of SonSang/dmesh2_renderer.
+ *
+ * Drop-in boundary.  The reference binds three pybind functions (reference ext.cpp:6-9):
+ *     render_forward_cuda          (reference render.h:12-45,  render.cu:28-195)
+ *     render_backward_cuda         (reference render.h:47-94,  render.cu:198-373)
+ *     generate_render_layers_cuda  (reference render.h:101-119, render.cu:378-476)
+ * called only from RenderFunction.forward/backward and LayeredRenderer.generate
+ * (reference dmesh2_renderer/__init__.py:78, :170, :432).  This header declares the plain-C
+ * entry points that replace them: raw device pointers, explicit sizes, an explicit CUDA
+ * stream, no torch types.  The host side (dmesh2_renderer_b200/) binds them with ctypes
+ * and keeps the reference's Python signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a densely packed (contiguous) array unless the
+ *     name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing in the
+ *     library calls cudaDeviceSynchronize — the only host wait is the one in
+ *     dm2_*_preprocess, which waits on `stream` for the 4-byte num_rendered read-back that
+ *     the reference also performs (reference cuda_impl/renderer.cu:174-179);
+ *   - workspaces are caller-allocated byte buffers (torch caching allocator on the host
+ *     side); their sizes come from the dm2_*_bytes functions and their internal layout from
+ *     DM2FaceLayout / DM2ImageLayout / DM2BinningLayout (used by the parity tests as the
+ *     "debug taps" of SURVEY.md §8b.5);
+ *   - every function returns 0 on success; on failure it returns non-zero and
+ *     dm2_last_error() returns a thread-local message (the Python wrapper raises
+ *     RuntimeError, mirroring AT_ERROR / CHECK_CUDA in the reference);
+ *   - gradient outputs of dm2_render_backward must be ZEROED by the caller (the reference
+ *     uses torch::zeros_like, render.cu:313-318); the kernels accumulate with atomics.
+ */
+#ifndef DM2_RENDERER_H_INCLUDED
+#define DM2_RENDERER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
+#define DM2_ABI_VERSION 3
+
+/* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
+typedef struct DM2RenderInputs {
+    int32_t B, P, F;             /* views in this call, vertices, faces                     */
+    int32_t H, W;                /* patch_height, patch_width                               */
+    float   aa_temperature;      /* in [0,1]                                                */
+    int32_t len_oarea_buffer;    /* K; accepted for parity, unused: AA is recomputed in bwd */
+    const float*   background;               /* (3)            */
+    const int32_t* patch_min;                /* (B,2)          */
+    const float*   verts;                    /* (P,3)          */
+    const int32_t* faces;                    /* (F,3)          */
+    const float*   verts_color;              /* (P,3)          */
+    const float*   faces_opacity;            /* (F)            */
+    const float*   verts_ndc;                /* (B,P,3)        */
+    const float*   verts_image;              /* (B,P,2)        */
+    const float*   faces_intense;            /* (B,F)          */
+    const float*   aa_face_verts;            /* (B,F,3,2)      */
+    const float*   aa_face_edges;            /* (B,F,3,2)      */
+    const uint8_t* aa_face_edges_iszero;     /* (B,F,3,2) bool */
+    const float*   aa_face_edges_recip;      /* (B,F,3,2)      */
+    const float*   aa_face_edges_normal;     /* (B,F,3,2)      */
+    const float*   aa_face_edges_normal_c;   /* (B,F,3)        */
+    const float*   image_ray_o;              /* (B,H,W,3)      */
+    const float*   image_ray_d;              /* (B,H,W,3)      */
+} DM2RenderInputs;
+
+/* Gradient outputs of render_backward_cuda (reference render.cu:313-318, 372). */
+typedef struct DM2RenderGrads {
+    float* dL_dverts;            /* (P,3)      */
+    float* dL_dverts_color;      /* (P,3)      */
+    float* dL_dfaces_opacity;    /* (F)        */
+    float* dL_dverts_ndc;        /* (B,P,3) — only channel 2 is written */
+    float* dL_dfaces_intense;    /* (B,F)      */
+    float* dL_daa_face_verts;    /* (B,F,3,2)  */
+} DM2RenderGrads;
+
+/* Inputs of generate_render_layers_cuda (reference render.h:101-119). */
+typedef struct DM2LayerInputs {
+    int32_t B, P, F, T;
+    int32_t H, W;                /* full frame; patch_min is 0 (reference renderer.cu:557-558) */
+    int32_t num_layers;          /* L */
+    const float*   verts;                    /* (P,3)   */
+    const int32_t* faces;                    /* (F,3)   */
+    const int32_t* tets;                     /* (T,4)   */
+    const int32_t* face_tets;                /* (F,2), -1 = none */
+    const int32_t* tet_faces;                /* (T,4)   */
+    const int32_t* face_existence;           /* (F)     */
+    const float*   verts_ndc;                /* (B,P,3) */
+    const float*   verts_image;              /* (B,P,2) */
+    const float*   image_ray_o;              /* (B,H,W,3) */
+    const float*   image_ray_d;              /* (B,H,W,3) */
+} DM2LayerInputs;
+
+/* Byte offsets inside the three workspaces (all 256-byte aligned).                         */
+typedef struct DM2FaceLayout {        /* per (view,face) state; reference FaceState, state.h:19-30 */
+    size_t depths;               /* f32[B*F]  clamp((mean z+1)/2,0,1); uninitialised if culled  */
+    size_t min_depths;           /* f32[B*F]                                                    */
+    size_t max_depths;           /* f32[B*F]                                                    */
+    size_t tiles_touched;        /* u32[B*F]                                                    */
+    size_t face_offsets;         /* u32[B*F]  inclusive prefix sum of tiles_touched             */
+    size_t scan_partials;        /* u32[...]  scan scratch                                      */
+    size_t rects;                /* uint2[B*F] tile bbox: x = x0 | y0<<16, y = x1 | y1<<16      */
+    size_t records;              /* packed per-(view,face) records staged by the tile kernels   */
+    size_t record_stride;        /* bytes per record                                            */
+    size_t total;
+} DM2FaceLayout;
+
+typedef struct DM2ImageLayout {       /* reference ImageState / ImageRenderLayerState, state.h:32-61 */
+    size_t ranges;               /* uint2[B*tiles] (x = first, y = last+1; (0,0) if empty)      */
+    size_t final_T;              /* f32[B*H*W]   (render)                                       */
+    size_t final_prev_T;         /* f32[B*H*W]   (render)                                       */
+    size_t n_contrib;            /* u32[B*H*W]   (render)                                       */
+    size_t first_face;           /* i32[B*H*W]   (layers)                                       */
+    size_t first_tet;            /* i32[B*H*W]   (layers)                                       */
+    size_t total;
+} DM2ImageLayout;
+
+typedef struct DM2BinningLayout {     /* reference BinningState, state.h:41-51 */
+    size_t keys_unsorted;        /* u64[R]  (tile + tiles*view) << 32 | float bits of depth     */
+    size_t vals_unsorted;        /* u32[R]  face id within the view                             */
+    size_t keys;                 /* u64[R]  sorted                                              */
+    size_t vals;                 /* u32[R]  sorted  (= reference face_list)                     */
+    size_t sort_temp;            /* radix-sort histograms                                       */
+    size_t total;
+} DM2BinningLayout;
+
+const char* dm2_last_error(void);
+int dm2_abi_version(void);
+
+/* ---- workspace sizing ------------------------------------------------------------------ */
+int dm2_face_layout   (int32_t B, int32_t F, int32_t layered, DM2FaceLayout* out);
+int dm2_image_layout  (int32_t B, int32_t H, int32_t W, int32_t layered, DM2ImageLayout* out);
+int dm2_binning_layout(int64_t num_rendered, DM2BinningLayout* out);
+
+/* ---- Renderer: replaces render_forward_cuda / render_backward_cuda ---------------------- */
+/* Stage 1 (reference renderer.cu:150-179): per-face depth / tile bbox / tiles_touched, the
+ * packed face records, the inclusive scan, and the num_rendered read-back (waits on stream). */
+int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws,
+                          int64_t* num_rendered_host, void* stream);
+/* Stage 2 (reference renderer.cu:181-266): key emission, stable radix sort on the low
+ * 32+bit key bits, tile ranges, then the forward tile compositor.  out_color (B,H,W,3) and
+ * out_depth (B,H,W) are fully overwritten.                                                   */
+int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                       int64_t num_rendered, float* out_color, float* out_depth, void* stream);
+/* reference renderer.cu:271-392 / backward.cu:17-532.                                       */
+int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
+                        const void* image_ws, int64_t num_rendered,
+                        const float* dL_dout_color, const float* dL_dout_depth,
+                        const DM2RenderGrads* grads, void* stream);
+
+/* ---- LayeredRenderer: replaces generate_render_layers_cuda ------------------------------- */
+int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws,
+                          int64_t* num_rendered_host, void* stream);
+/* render_layers (B,H,W,L) must be pre-filled with -1 and render_layers_cnt (B,H,W) with 0 by
+ * the caller (reference render.cu:437-438); geo_ws needs dm2_layers_geo_bytes(F,T) bytes.    */
+int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes);
+int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
+                               void* image_ws, void* geo_ws, int64_t num_rendered,
+                               int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
+
+/* ---- binning primitives exposed on their own (sort keys/s metric, parity tests) ---------- */
+/* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit).  Replaces
+ * cub::DeviceRadixSort::SortPairs (reference renderer.cu:202-207).  temp: sort_temp area.   */
+int dm2_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out,
+                   uint32_t* vals_out, int64_t n, int32_t end_bit, void* temp, size_t temp_bytes,
+                   void* stream);
+int dm2_sort_temp_bytes(int64_t n, size_t* bytes);
+/* Inclusive u32 prefix sum; replaces cub::DeviceScan::InclusiveSum (renderer.cu:165-171).   */
+int dm2_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* partials,
+                           void* stream);
+int dm2_scan_partials_count(int64_t n, int64_t* count);
+/* getHigherMsb of reference renderer.cu:396-411.                                            */
+uint32_t dm2_higher_msb(uint32_t n);
+
+/* number of kernels launched by this library on this thread since the last reset
+ * (bench.py's `gpu_launches`).                                                              */
+int64_t dm2_launch_count(int32_t reset);
+
+/* Optional per-stage device timing: CUDA events recorded on the launching stream around each
+ * stage (preprocess_pack, scan, emit_keys, radix_sort, tile_ranges, raster_forward,
+ * raster_backward, ...).  dm2_profile_report fills buf with "name total_ms count" lines
+ * (it waits for the recorded events) and returns the buffer size needed.                      */
+void dm2_profile_enable(int32_t on);
+void dm2_profile_reset(void);
+int64_t dm2_profile_report(char* buf, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM2_RENDERER_H_INCLUDED */

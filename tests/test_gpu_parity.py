@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the host mirror of the reference API)
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact for integer work (tiles_touched, keys, sorted list,
+tile ranges, n_contrib, first_face/first_tet, layer ids + counts); forward colour/depth within
+rel 1e-4; gradients within rel 1e-3 (atomic-order nondeterminism), both measured against the
+tensor's max magnitude, plus an element-wise outlier budget.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GRAD_NAMES, args_to_numpy, frac_outside, rel_err, render_args, scene_tensors
+
+pytestmark = pytest.mark.gpu
+
+FWD_RTOL = 1e-4
+BWD_RTOL = 1e-3
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _oracle_and_cuda(sc, tau=1.0, views=None, patch_min=None, patch_wh=None, K=0):
+    from dmesh2_renderer_b200 import _C, RenderFunction
+    from oracle import oracle as orc
+    dev = _dev()
+    r, st, args = render_args(sc, dev, views=views, patch_min=patch_min, patch_wh=patch_wh, tau=tau)
+    views = list(range(sc.mv.shape[0])) if views is None else list(views)
+    B = len(views)
+    pw, ph = args[2], args[3]
+    leaf_idx = [4, 6, 7, 8, 10, 12]
+    leaves = []
+    for i in leaf_idx:
+        args[i] = args[i].detach().clone().requires_grad_(True)
+        leaves.append(args[i])
+    color, depth = RenderFunction.apply(*args)
+    if patch_min is None and patch_wh is None:
+        wc, wd = st["w_color"][views], st["w_depth"][views]
+    else:
+        g = torch.Generator(device="cpu").manual_seed(5)
+        wc = (torch.rand((B, ph, pw, 3), generator=g) * 2 - 1).to(dev)
+        wd = (torch.rand((B, ph, pw), generator=g) * 2 - 1).to(dev)
+    loss = (color * wc).sum() + (depth * wd).sum()
+    loss.backward()
+    cuda = dict(color=color.detach().cpu().numpy(), depth=depth.detach().cpu().numpy())
+    for n, l in zip(GRAD_NAMES, leaves):
+        cuda[n] = l.grad.detach().cpu().numpy()
+    # taps: run the raw entry point once more to get at the scratch buffers
+    with torch.no_grad():
+        res = _C.render_forward_cuda(*[a.detach() if isinstance(a, torch.Tensor) else a for a in args])
+    R, _c, _d, _, _, _, _, fb, bb, ib = res
+    F = args[5].shape[0]
+    cuda["num_rendered"] = R
+    cuda.update({k: v.cpu().numpy() for k, v in _C.face_taps(fb, B, F).items()})
+    cuda.update({k: v.cpu().numpy() for k, v in _C.binning_taps(bb, R).items()})
+    cuda.update({k: v.cpu().numpy() for k, v in _C.image_taps(ib, B, ph, pw).items()})
+    assert np.array_equal(_c.cpu().numpy(), cuda["color"]), "forward is not run-to-run deterministic"
+    ref = orc.render(args_to_numpy(args), pw, ph, tau, K=K, backward=True, dL_dcolor=wc.cpu().numpy(),
+                     dL_ddepth=wd.cpu().numpy())
+    return cuda, ref
+
+
+def _check_ints(cuda, ref):
+    live = ref["tiles_touched"] > 0
+    assert np.array_equal(cuda["tiles_touched"].view(np.uint32), ref["tiles_touched"])
+    assert np.array_equal(cuda["face_offsets"].view(np.uint32), ref["face_offsets"])
+    assert cuda["num_rendered"] == ref["num_rendered"]
+    for k in ("depths", "min_depths", "max_depths"):
+        assert np.array_equal(cuda[k].view(np.uint32)[live], ref[k].view(np.uint32)[live]), k
+    assert np.array_equal(cuda["keys_unsorted"].view(np.uint64), ref["keys_unsorted"])
+    assert np.array_equal(cuda["vals_unsorted"].view(np.uint32), ref["vals_unsorted"])
+    assert np.array_equal(cuda["keys"].view(np.uint64), ref["keys"]), "sorted keys differ"
+    assert np.array_equal(cuda["vals"].view(np.uint32), ref["vals"]), "sorted face list differs"
+    assert np.array_equal(cuda["ranges"].view(np.uint32), ref["ranges"]), "tile ranges differ"
+    assert np.array_equal(cuda["n_contrib"].view(np.uint32), ref["n_contrib"]), "n_contrib differs"
+
+
+def _check_floats(cuda, ref):
+    for k in ("color", "depth", "final_T", "final_prev_T"):
+        assert rel_err(cuda[k], ref[k]) <= FWD_RTOL, (k, rel_err(cuda[k], ref[k]))
+        assert frac_outside(cuda[k], ref[k], FWD_RTOL, 1e-6) == 0.0, k
+    for k in GRAD_NAMES:
+        e = rel_err(cuda[k], ref[k])
+        assert e <= BWD_RTOL, (k, e)
+        assert frac_outside(cuda[k], ref[k], BWD_RTOL, BWD_RTOL * np.abs(ref[k]).max() + 1e-12) == 0.0, k
+
+
+@pytest.mark.parametrize("tau", [1.0, 0.5, 0.0])
+def test_render_small_scene(built, tau):
+    from dmesh2_renderer_b200 import scenes
+    cuda, ref = _oracle_and_cuda(scenes.small(n_faces=600, size=64), tau=tau)
+    _check_ints(cuda, ref)
+    _check_floats(cuda, ref)
+
+
+def test_render_multiview_ragged(built):
+    """3 views, image size not a multiple of 16, large triangles (long lists, big tile bboxes)."""
+    from dmesh2_renderer_b200 import scenes
+    sc = scenes.triangle_soup("ragged", 300, 72, 0.35, seed=9, eyes=[tuple(e) for e in scenes.fibonacci_eyes(64)[[3, 17, 40]]])
+    sc.height = 56
+    sc.w_color = sc.w_color[:, :56]
+    sc.w_depth = sc.w_depth[:, :56]
+    cuda, ref = _oracle_and_cuda(sc, views=[2, 0, 1])
+    _check_ints(cuda, ref)
+    _check_floats(cuda, ref)
+
+
+def test_render_patch_mode(built):
+    """Random sub-windows (patch_min != 0, patch smaller than the frame, not a multiple of 16)."""
+    from dmesh2_renderer_b200 import scenes
+    sc = scenes.small(n_faces=500, size=96, sigma=0.15, seed=13, n_views=2)
+    cuda, ref = _oracle_and_cuda(sc, views=[1, 0], patch_min=[[7, 20], [40, 3]], patch_wh=(50, 41))
+    _check_ints(cuda, ref)
+    _check_floats(cuda, ref)
+
+
+def test_render_matches_reference_cache_semantics(built):
+    """The oracle run WITH the reference's K=20 AA cache gives the same answer as the cache-free CUDA path."""
+    from dmesh2_renderer_b200 import scenes
+    cuda, ref = _oracle_and_cuda(scenes.small(n_faces=400, size=48, seed=3), K=20)
+    _check_ints(cuda, ref)
+    _check_floats(cuda, ref)
+
+
+def test_cfg1_vs_oracle(built):
+    """BASELINE config 0: 10k triangles at 256x256 (the oracle takes a few seconds)."""
+    from dmesh2_renderer_b200 import scenes
+    cuda, ref = _oracle_and_cuda(scenes.cfg1())
+    _check_ints(cuda, ref)
+    _check_floats(cuda, ref)
+
+
+def test_empty_and_degenerate(built):
+    from dmesh2_renderer_b200 import Renderer, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=50, size=32)
+    st = scene_tensors(sc, dev)
+    r = Renderer(st["mv"], st["proj"], 32, 32, dev)
+    pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    # everything behind the far plane: nothing rendered -> background, depth_ndc = 1 -> depth 0
+    far = st["verts"] * 0.01 + torch.tensor([0.0, 0.0, -50.0], device=dev)
+    color, depth = r([0], pm, 32, 32, far, st["faces"], st["verts_color"], st["faces_opacity"], st["faces_intense"],
+                     st["background"])
+    assert torch.all(color == 1.0) and torch.all(depth == 0.0)
+    # zero faces
+    f0 = st["faces"][:0]
+    color, depth = r([0], pm, 32, 32, st["verts"], f0, st["verts_color"], st["faces_opacity"][:0],
+                     st["faces_intense"][:, :0], st["background"])
+    assert torch.all(color == 1.0)
+    # degenerate (zero-area) triangles must not produce NaNs
+    deg = st["verts"].clone()
+    deg[1::3] = deg[0::3]
+    color, depth = r([0], pm, 32, 32, deg, st["faces"], st["verts_color"], st["faces_opacity"], st["faces_intense"],
+                     st["background"])
+    assert torch.isfinite(color).all() and torch.isfinite(depth).all()
+
+
+def test_error_behaviour(built):
+    from dmesh2_renderer_b200 import _C, scenes
+    dev = _dev()
+    _, _, args = render_args(scenes.small(n_faces=20, size=32), dev)
+    bad = list(args)
+    bad[11] = 1.5
+    with pytest.raises(RuntimeError, match="aa_temperature"):
+        _C.render_forward_cuda(*bad)
+    bad = list(args)
+    bad[0] = torch.ones(4, device=dev)
+    with pytest.raises(RuntimeError, match="background"):
+        _C.render_forward_cuda(*bad)
+    bad = list(args)
+    bad[7] = bad[7][:-1]
+    with pytest.raises(RuntimeError, match="face opacity"):
+        _C.render_forward_cuda(*bad)
+
+
+def test_sort_pairs_stable_and_bit_range(built):
+    from dmesh2_renderer_b200 import _C
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for n, end_bit in ((1, 40), (31, 33), (4096, 45), (4097, 45), (100_003, 47), (1_000_000, 45)):
+        keys = torch.randint(0, 2 ** 62, (n,), generator=g, dtype=torch.int64)
+        keys[::3] = keys[::3] & 0xFFFF        # lots of duplicates
+        vals = torch.arange(n, dtype=torch.int32)
+        kout, vout = _C.sort_pairs(keys.to(dev), vals.to(dev), end_bit)
+        mask = (1 << end_bit) - 1
+        order = np.argsort(keys.numpy() & mask, kind="stable")
+        assert np.array_equal(vout.cpu().numpy(), vals.numpy()[order]), (n, end_bit)
+        assert np.array_equal(kout.cpu().numpy(), keys.numpy()[order]), (n, end_bit)
+
+
+def test_inclusive_scan(built):
+    from dmesh2_renderer_b200 import _C
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for n in (1, 255, 2048, 2049, 1_000_003):
+        x = torch.randint(0, 50, (n,), generator=g, dtype=torch.int32)
+        out = _C.inclusive_scan_u32(x.to(dev))
+        assert np.array_equal(out.cpu().numpy().astype(np.int64), np.cumsum(x.numpy().astype(np.int64)))
+
+
+def _layers_both(sc, views=None):
+    from dmesh2_renderer_b200 import LayeredRenderer, _C
+    from oracle import oracle as orc
+    dev = _dev()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    views = list(range(sc.mv.shape[0])) if views is None else views
+    layers, cnt = lr.generate(views, t(sc.verts), t(sc.faces), t(sc.tets), t(sc.face_tets), t(sc.tet_faces),
+                              t(sc.face_existence), sc.num_layers)
+    ndc, img = lr.compute_verts_ndc_image(t(sc.verts), lr.mv[views], lr.proj[views])
+    ro, rd = lr.ray_o[views], lr.ray_d[views]
+    _l, _c, taps = _C.generate_render_layers_cuda(sc.width, sc.height, t(sc.verts), t(sc.faces), t(sc.tets),
+                                                  t(sc.face_tets), t(sc.tet_faces), t(sc.face_existence), ndc, img,
+                                                  ro, rd, sc.num_layers, return_taps=True)
+    assert torch.equal(_l, layers) and torch.equal(_c, cnt)
+    B = len(views)
+    img_t = _C.image_taps(taps["image_buffer"], B, sc.height, sc.width, layered=True)
+    bin_t = _C.binning_taps(taps["binning_buffer"], taps["num_rendered"])
+    ref = orc.layers(sc.verts, sc.faces, sc.tets, sc.face_tets, sc.tet_faces, sc.face_existence, ndc.cpu().numpy(),
+                     img.cpu().numpy(), ro.cpu().numpy(), rd.cpu().numpy(), sc.width, sc.height, sc.num_layers)
+    assert taps["num_rendered"] == ref["num_rendered"]
+    assert np.array_equal(bin_t["keys"].cpu().numpy().view(np.uint64), ref["keys"])
+    assert np.array_equal(bin_t["vals"].cpu().numpy().view(np.uint32), ref["vals"])
+    assert np.array_equal(img_t["ranges"].cpu().numpy().view(np.uint32), ref["ranges"])
+    assert np.array_equal(img_t["first_face"].cpu().numpy(), ref["first_face"])
+    assert np.array_equal(img_t["first_tet"].cpu().numpy(), ref["first_tet"])
+    assert np.array_equal(layers.cpu().numpy(), ref["render_layers"]), "layer ids differ"
+    assert np.array_equal(cnt.cpu().numpy(), ref["render_layers_cnt"]), "layer counts differ"
+    return layers, cnt
+
+
+def test_layers_small(built):
+    from dmesh2_renderer_b200 import scenes
+    layers, cnt = _layers_both(scenes.small_tets(n_points=300, size=64))
+    assert int(cnt.max()) > 0
+
+
+def test_layers_ragged_multiview(built):
+    from dmesh2_renderer_b200 import scenes
+    sc = scenes.delaunay_tets("tets_mv", 500, 80, seed=5, p_exist=0.3, num_layers=6,
+                              eyes=[tuple(e) for e in scenes.fibonacci_eyes(64)[[1, 30]]])
+    sc.height = 50
+    _layers_both(sc, views=[1, 0])
+
+
+def test_layers_properties(built):
+    """Size-independent properties: every recorded id exists, no id repeats along a ray, entries beyond cnt are -1."""
+    from dmesh2_renderer_b200 import scenes
+    sc = scenes.delaunay_tets("tets_prop", 3000, 256, seed=8, p_exist=0.2, num_layers=8)
+    layers, cnt = _layers_both(sc)
+    L = layers.cpu().numpy()
+    c = cnt.cpu().numpy()
+    k = np.arange(L.shape[-1])[None, None, None, :]
+    valid = k < np.minimum(c, L.shape[-1])[..., None]
+    assert np.all(L[~valid] == -1)
+    assert np.all(sc.face_existence[L[valid]] != 0)
+    Ls = np.sort(np.where(valid, L, -np.arange(1, L.shape[-1] + 1)[None, None, None, :]), axis=-1)
+    assert np.all(Ls[..., 1:] != Ls[..., :-1])
