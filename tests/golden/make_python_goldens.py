@@ -65,10 +65,12 @@ def make_aa(n=1500, seed=1234):
                 ok = False
                 break
             if isinstance(area, torch.Tensor) and area.requires_grad:
-                # gradient w.r.t. the CCW-ordered vertices handed to the kernel (Triangles.verts)
-                tris.verts.retain_grad()
+                # TOTAL derivative w.r.t. the three input points (edges / reciprocals are functions of
+                # them), re-ordered to the CCW order of Triangles.verts that the kernel sees
                 area.backward()
-                g = tris.verts.grad[0].numpy().copy() if tris.verts.grad is not None else np.zeros((3, 2), np.float32)
+                gl = [x.grad[0].numpy().copy() if x.grad is not None else np.zeros(2, np.float32) for x in p]
+                swapped = not np.array_equal(tris.verts[0, 1].detach().numpy(), tri[1])
+                g = np.stack([gl[0], gl[2], gl[1]] if swapped else gl)
                 a = float(area.detach())
             else:
                 g = np.zeros((3, 2), np.float32)
