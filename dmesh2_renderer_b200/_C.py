@@ -217,9 +217,12 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
         if s.F != 0:
             g = DM2RenderGrads(dL_dverts.data_ptr(), dL_dverts_color.data_ptr(), dL_dfaces_opacity.data_ptr(),
                                dL_dverts_ndc.data_ptr(), dL_dfaces_intense.data_ptr(), dL_daa_face_verts.data_ptr())
+            nb = C.c_size_t(0)
+            _lib.check(lib.dm2_backward_workspace_bytes(s.B, s.F, C.byref(nb)))
+            grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
             _lib.check(lib.dm2_render_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
                                                _ptr(image_buffer), int(num_rendered), _ptr(gc), _ptr(gd),
-                                               C.byref(g), _stream(dev)))
+                                               C.byref(g), _ptr(grad_ws), _stream(dev)))
     return dL_dverts, dL_dverts_color, dL_dfaces_opacity, dL_dverts_ndc, dL_dfaces_intense, dL_daa_face_verts
 
 

@@ -259,9 +259,9 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
 
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
                         const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
-                        const float* dL_dout_depth, const DM2RenderGrads* grads, void* stream) {
+                        const float* dL_dout_depth, const DM2RenderGrads* grads, void* grad_ws, void* stream) {
     if (check_render_inputs(in)) return 2;
-    DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads,
+    DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
                 "dm2_render_backward: null buffer");
     DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dverts_ndc &&
                 grads->dL_dfaces_intense && grads->dL_daa_face_verts, "dm2_render_backward: null gradient buffer");
@@ -271,7 +271,13 @@ int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const vo
     FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
     BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
     ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
-    return launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, *grads, s);
+    return launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, *grads, grad_ws, s);
+}
+
+int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes) {
+    DM2_REQUIRE(bytes && B >= 0 && F >= 0, "dm2_backward_workspace_bytes: bad arguments");
+    *bytes = backward_ws_bytes((long long)B * F);
+    return 0;
 }
 
 static int check_layer_inputs(const DM2LayerInputs* in) {

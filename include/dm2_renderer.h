@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 3
+#define DM2_ABI_VERSION 4
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -145,11 +145,13 @@ int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws,
  * out_depth (B,H,W) are fully overwritten.                                                   */
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
                        int64_t num_rendered, float* out_color, float* out_depth, void* stream);
-/* reference renderer.cu:271-392 / backward.cu:17-532.                                       */
+/* reference renderer.cu:271-392 / backward.cu:17-532.  grad_ws: scratch of
+ * dm2_backward_workspace_bytes(B, F) bytes (per-(view,face) gradient records; zeroed inside).  */
+int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes);
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
                         const void* image_ws, int64_t num_rendered,
                         const float* dL_dout_color, const float* dL_dout_depth,
-                        const DM2RenderGrads* grads, void* stream);
+                        const DM2RenderGrads* grads, void* grad_ws, void* stream);
 
 /* ---- LayeredRenderer: replaces generate_render_layers_cuda ------------------------------- */
 int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws,
