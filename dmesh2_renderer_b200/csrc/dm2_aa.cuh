@@ -57,32 +57,61 @@ __device__ __forceinline__ int aa_classify(const float* __restrict__ rec, float 
     return (m == 0xF) ? AA_FULL : AA_PART;
 }
 
+// inmask of a pixel already known to be AA_PART (same arithmetic as aa_classify, no early outs)
+__device__ __forceinline__ unsigned aa_inmask(const float* __restrict__ rec, float pxmin, float pymin) {
+    const float pxmax = __fadd_rn(pxmin, 1.0f);
+    const float pymax = __fadd_rn(pymin, 1.0f);
+    const float4 n01 = *reinterpret_cast<const float4*>(rec + R_N01);
+    const float4 n2c = *reinterpret_cast<const float4*>(rec + R_N2C);
+    const float c2 = rec[R_MISC];
+    const float nx[3] = {n01.x, n01.z, n2c.x};
+    const float ny[3] = {n01.y, n01.w, n2c.y};
+    const float cc[3] = {n2c.z, n2c.w, c2};
+    unsigned m = 0xF;
+#pragma unroll
+    for (int ti = 0; ti < 3; ti++) {
+        const float ylo = __fmul_rn(pymin, ny[ti]);
+        const float yhi = __fmul_rn(pymax, ny[ti]);
+        const bool i0 = __fsub_rn(__fmaf_rn(pxmin, nx[ti], ylo), cc[ti]) >= 0.0f;
+        const bool i1 = __fsub_rn(__fmaf_rn(pxmax, nx[ti], ylo), cc[ti]) >= 0.0f;
+        const bool i2 = __fsub_rn(__fmaf_rn(pxmax, nx[ti], yhi), cc[ti]) >= 0.0f;
+        const bool i3 = __fsub_rn(__fmaf_rn(pxmin, nx[ti], yhi), cc[ti]) >= 0.0f;
+        m &= (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
+    }
+    return m;
+}
+
+// Fan accumulator with PREDICATED pushes: every lane executes the same instruction stream whatever
+// its polygon looks like (the branchy formulation ran at 2-3 active lanes per instruction).
 struct FanAcc {
     int np = 0;
     float area = 0.0f;
-    float fx, fy, qx, qy;       // first and previous polygon vertex
-    // returns false on polygon overflow (aa.h:45-48) or negative fan-triangle area (aa.h:410-412)
-    __device__ __forceinline__ bool push(float x, float y) {
-        if (np >= 10) return false;
-        if (np == 0) { fx = x; fy = y; }
-        else if (np == 1) { qx = x; qy = y; }
-        else {
-            // _tri_area(first, prev, v), aa.h:88-94
-            const float ax = __fsub_rn(qx, fx), by = __fsub_rn(y, fy);
-            const float cx = __fsub_rn(x, fx),  dy = __fsub_rn(qy, fy);
-            const float s = __fmul_rn(0.5f, __fmaf_rn(ax, by, -__fmul_rn(cx, dy)));
-            if (s < 0.0f) return false;
-            area = __fadd_rn(area, s);
-            qx = x; qy = y;
-        }
-        np++;
-        return true;
+    float fx = 0.f, fy = 0.f, qx = 0.f, qy = 0.f;       // first and previous polygon vertex
+    bool bad = false;     // polygon overflow (aa.h:45-48) or negative fan-triangle area (aa.h:410-412)
+    __device__ __forceinline__ void push(bool cond, float x, float y) {
+        const bool is_first = cond && (np == 0);
+        const bool is_tri = cond && (np >= 2);
+        bad = bad || (cond && (np >= 10));
+        // _tri_area(first, prev, v), aa.h:88-94
+        const float ax = __fsub_rn(qx, fx), by = __fsub_rn(y, fy);
+        const float cx = __fsub_rn(x, fx),  dy = __fsub_rn(qy, fy);
+        const float s = __fmul_rn(0.5f, __fmaf_rn(ax, by, -__fmul_rn(cx, dy)));
+        bad = bad || (is_tri && (s < 0.0f));
+        area = is_tri ? __fadd_rn(area, s) : area;
+        fx = is_first ? x : fx;
+        fy = is_first ? y : fy;
+        const bool set_prev = cond && (np >= 1);
+        qx = set_prev ? x : qx;
+        qy = set_prev ? y : qy;
+        np += cond ? 1 : 0;
     }
 };
 
 // Step 4 of aa.h:446-504 (= aa.h:151-441) for a partially covered pixel.  Returns false if the face
 // must be skipped for this pixel (any reference error code, or zero overlap).  On true: area in
 // (0, 1] (or NaN, which the reference also lets through); g[6] = d area / d tri verts when GRAD.
+// Straight-line predicated code: errors are accumulated in a flag instead of returning early (every
+// reference error code has the same consequence - the face is skipped for this pixel).
 template <bool GRAD>
 __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxmin, float pymin, unsigned inmask,
                                         float& area_out, float* __restrict__ g) {
@@ -106,7 +135,7 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
 
         float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;     // up to two intersections, pixel-edge order
         float ta = 0.f, tb = 0.f;
-        int pa = -1, pb = -1, n = 0;
+        int pa = 0, pb = 0, n = 0;
 #pragma unroll
         for (int pi = 0; pi < 4; pi++) {
             const bool horiz = (pi == 0) || (pi == 2);               // pixel edge y = const
@@ -121,62 +150,55 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
             const float t  = __fmul_rn(__fsub_rn(cst, p0a0), ra0);   // aa.h:251
             const float i1 = __fmaf_rn(t, ea1, p0a1);                // aa.h:252
             const bool valid = (t >= 0.0f) && (t <= 1.0f) && (i1 >= lo1) && (i1 <= hi1) && !parallel;
-            if (!valid) continue;
-            if ((i1 == lo1) || (i1 == hi1)) return false;            // error 1: hits a pixel corner
-            if (n >= 2) return false;                                // error 2: more than 2 intersections
+            // error 1: hits a pixel corner; error 2: more than two intersections
+            fan.bad = fan.bad || (valid && ((i1 == lo1) || (i1 == hi1) || (n >= 2)));
             const float qx = horiz ? i1 : cst, qy = horiz ? cst : i1;
-            if (n == 0) { ax = qx; ay = qy; ta = t; pa = pi; } else { bx = qx; by = qy; tb = t; pb = pi; }
-            n++;
+            const bool is_a = valid && (n == 0), is_b = valid && (n == 1);
+            ax = is_a ? qx : ax; ay = is_a ? qy : ay; ta = is_a ? t : ta; pa = is_a ? pi : pa;
+            bx = is_b ? qx : bx; by = is_b ? qy : by; tb = is_b ? t : tb; pb = is_b ? pi : pb;
+            n += valid ? 1 : 0;
         }
-
-        int final_pedge = -1;
-        float t_in = 0.f, t_out = 0.f;        // part of the edge inside the pixel: [t_in, t_out]
-        bool covered = true;
-        if (n == 2) {
-            // sort by t (aa.h:308-328); strict '>' keeps pixel-edge order on ties
-            if (ta > tb) {
-                if (!fan.push(bx, by) || !fan.push(ax, ay)) return false;
-                final_pedge = pa; t_in = tb; t_out = ta;
-            } else {
-                if (!fan.push(ax, ay) || !fan.push(bx, by)) return false;
-                final_pedge = pb; t_in = ta; t_out = tb;
-            }
-        } else if (n == 1) {
-            if (!fan.push(ax, ay)) return false;
-            if (!in0 && in1) { if (!fan.push(p1.x, p1.y)) return false; t_in = ta; t_out = 1.0f; }
-            else if (in0 && !in1) { final_pedge = pa; t_in = 0.0f; t_out = ta; }
-            else return false;                                       // error 3
-        } else {
-            if (in0 && in1) { if (!fan.push(p1.x, p1.y)) return false; t_in = 0.0f; t_out = 1.0f; }
-            else if (in0 != in1) return false;                       // error 4
-            else covered = false;                                    // edge misses the pixel
+        // aa.h:299-400 as predicates
+        const bool two = (n >= 2), one = (n == 1), none = (n == 0);
+        const bool swap = two && (ta > tb);                          // sort by t; strict '>' keeps order on ties
+        const bool enter = one && !in0 && in1;                       // intersection, then the end point
+        const bool leave = one && in0 && !in1;                       // start point inside, intersection, corners
+        const bool whole = none && in0 && in1;                       // edge entirely inside the pixel
+        fan.bad = fan.bad || (one && (in0 == in1)) || (none && (in0 != in1));      // errors 3 and 4
+        fan.push(!none, swap ? bx : ax, swap ? by : ay);
+        fan.push(two || enter || whole, two ? (swap ? ax : bx) : p1.x, two ? (swap ? ay : by) : p1.y);
+        // run of inside pixel corners after the last-hit pixel edge (aa.h:359-379); a partially
+        // covered pixel has at most 3 inside corners
+        bool run = two || leave;
+        const int final_pedge = two ? (swap ? pa : pb) : pa;
+#pragma unroll
+        for (int pvi = 0; pvi < 3; pvi++) {
+            const int cur = (final_pedge + 1 + pvi) & 3;
+            run = run && ((inmask >> cur) & 1u);
+            fan.push(run, (cur == 1 || cur == 2) ? pxmax : pxmin, (cur >= 2) ? pymax : pymin);
         }
-        if (GRAD && covered) {
-            const float w1 = 0.5f * (t_out * t_out - t_in * t_in);
-            const float w0 = (t_out - t_in) - w1;
+        if (GRAD) {
+            // part of the edge inside the pixel: [t_in, t_out]
+            const bool covered = !none || whole;
+            const float t_in  = two ? (swap ? tb : ta) : (enter ? ta : 0.0f);
+            const float t_out = two ? (swap ? ta : tb) : (leave ? ta : 1.0f);
+            const float w1 = covered ? 0.5f * (t_out * t_out - t_in * t_in) : 0.0f;
+            const float w0 = covered ? (t_out - t_in) - w1 : 0.0f;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                if (k == ti) { gr[2 * k] += ed.y * w0; gr[2 * k + 1] -= ed.x * w0; }
-                if (k == tj) { gr[2 * k] += ed.y * w1; gr[2 * k + 1] -= ed.x * w1; }
-            }
-        }
-        if (final_pedge != -1) {
-            // run of inside pixel corners after the last-hit pixel edge (aa.h:359-379)
-            for (int pvi = 0; pvi < 4; pvi++) {
-                const int cur = (final_pedge + 1 + pvi) & 3;
-                if (!((inmask >> cur) & 1u)) break;
-                if (!fan.push((cur == 1 || cur == 2) ? pxmax : pxmin, (cur >= 2) ? pymax : pymin)) return false;
+                const float wk = (k == ti) ? w0 : ((k == tj) ? w1 : 0.0f);
+                gr[2 * k] += ed.y * wk;
+                gr[2 * k + 1] -= ed.x * wk;
             }
         }
     }
-    if (fan.area > 1.0f) return false;                               // error 6
-    if (fan.area == 0.0f) return false;                              // caller skips oarea == 0
+    const bool ok = !fan.bad && !(fan.area > 1.0f) && !(fan.area == 0.0f);   // error 6; caller skips oarea == 0
     area_out = fan.area;
     if (GRAD) {
 #pragma unroll
         for (int k = 0; k < 6; k++) g[k] = gr[k];
     }
-    return true;
+    return ok;
 }
 
 }  // namespace dm2

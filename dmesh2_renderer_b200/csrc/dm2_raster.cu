@@ -94,18 +94,80 @@ struct Shade {
     int code;
 };
 
-// cls/inmask: result of aa_classify (AA_FULL with area 0 when tau == 0).
+// Per-lane bit masks over the warp's candidate list: which candidates touch this lane's pixel, and
+// which of those only partially (need the polygon clip).  Popped lowest position first = list order.
+struct HitMasks {
+    uint32_t hit[kStage / 32], part[kStage / 32];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int ch = 0; ch < kStage / 32; ch++) hit[ch] = 0u;
+    }
+    __device__ __forceinline__ bool any() const {
+        uint32_t a = 0;
+#pragma unroll
+        for (int ch = 0; ch < kStage / 32; ch++) a |= hit[ch];
+        return a != 0;
+    }
+    __device__ __forceinline__ int pop(bool& is_part) {
+        int cpos = -1;
+        is_part = false;
+#pragma unroll
+        for (int ch = 0; ch < kStage / 32; ch++) {
+            if (cpos < 0 && hit[ch]) {
+                const int b = __ffs(hit[ch]) - 1;
+                cpos = ch * 32 + b;
+                is_part = (part[ch] >> b) & 1u;
+                hit[ch] &= hit[ch] - 1u;
+            }
+        }
+        return cpos;
+    }
+};
+
+// `limit`: candidates whose slot is >= limit are ignored (backward: behind the pixel's last contributor
+// after the slot -> list-position mapping has been applied by the caller through `slot_ok`).
+template <typename SlotOk>
+__device__ __forceinline__ void classify_candidates(const float* __restrict__ srec, const uint8_t* __restrict__ cand,
+                                                    int n_cand, bool use_aa, float pxmin, float pymin, bool lane_on,
+                                                    HitMasks& hm, SlotOk slot_ok) {
+#pragma unroll
+    for (int ch = 0; ch < kStage / 32; ch++) {
+        uint32_t h = 0u, p = 0u;
+        const int lim = min(32, n_cand - ch * 32);            // warp-uniform
+        for (int k = 0; k < lim; k++) {
+            const int j = cand[ch * 32 + k];                  // broadcast
+            int cls = AA_FULL;
+            unsigned inmask;
+            if (use_aa) cls = aa_classify(srec + j * kRecStride, pxmin, pymin, inmask);
+            const bool on = lane_on && (cls != AA_OUT) && slot_ok(j);
+            h |= (on ? 1u : 0u) << k;
+            p |= ((on && cls == AA_PART) ? 1u : 0u) << k;
+        }
+        hm.hit[ch] = h;
+        hm.part[ch] = p;
+    }
+}
+__device__ __forceinline__ void classify_candidates(const float* __restrict__ srec, const uint8_t* __restrict__ cand,
+                                                    int n_cand, bool use_aa, float pxmin, float pymin, bool lane_on,
+                                                    HitMasks& hm) {
+    classify_candidates(srec, cand, n_cand, use_aa, pxmin, pymin, lane_on, hm, [](int) { return true; });
+}
+
+// is_part: the pixel is only partially covered (aa_classify == AA_PART); ignored when tau == 0.
 template <bool GRAD>
-__device__ __forceinline__ bool shade(const float* __restrict__ rec, const PixelGeom& pg, float tau, int cls,
-                                      unsigned inmask, Shade& s, float* __restrict__ g) {
+__device__ __forceinline__ bool shade(const float* __restrict__ rec, const PixelGeom& pg, float tau, bool is_part,
+                                      Shade& s, float* __restrict__ g) {
     s.area = 0.0f;
     if (GRAD) {
 #pragma unroll
         for (int k = 0; k < 6; k++) g[k] = 0.0f;
     }
     if (tau > 0.0f) {
-        if (cls == AA_FULL) s.area = 1.0f;
-        else if (!aa_clip<GRAD>(rec, pg.pxmin, pg.pymin, inmask, s.area, g)) return false;
+        s.area = 1.0f;
+        if (is_part) {
+            const unsigned inmask = aa_inmask(rec, pg.pxmin, pg.pymin);
+            if (!aa_clip<GRAD>(rec, pg.pxmin, pg.pymin, inmask, s.area, g)) return false;
+        }
     }
     const float4 a0 = *reinterpret_cast<const float4*>(rec + R_P0);
     const float4 a1 = *reinterpret_cast<const float4*>(rec + R_P1);
@@ -202,28 +264,20 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;
         const int n_cand = build_candidates(srec, cnt, use_aa, tc.fx0, tc.fy0, cand, lane);
-        int c = 0;
+        // ---- classify: the warp walks its candidates in lock-step (broadcast smem reads, all lanes
+        //      busy); each lane keeps a private bit mask of the faces that touch ITS pixel
+        HitMasks hm;
+        classify_candidates(srec, cand, n_cand, use_aa, pg.pxmin, pg.pymin, !done, hm);
         for (;;) {
-            // ---- scan: advance this lane's cursor to the next face that touches its pixel
-            int jj = -1, cls = AA_FULL;
-            unsigned inmask = 0xF;
-            if (!done) {
-                while (c < n_cand) {
-                    const int j = cand[c++];
-                    if (use_aa) {
-                        cls = aa_classify(srec + j * kRecStride, pg.pxmin, pg.pymin, inmask);
-                        if (cls == AA_OUT) continue;
-                    }
-                    jj = j;
-                    break;
-                }
-            }
-            if (!__any_sync(0xffffffffu, jj >= 0)) break;
-            // ---- heavy part, lanes work on different faces
-            if (jj >= 0) {
+            // ---- every lane takes its own next hit (in list order); lanes work on different faces
+            bool is_part;
+            const int cpos = hm.pop(is_part);
+            if (!__any_sync(0xffffffffu, cpos >= 0)) break;
+            if (cpos >= 0) {
+                const int jj = cand[cpos];
                 const float* rec = srec + jj * kRecStride;
                 Shade s;
-                if (shade<false>(rec, pg, tau, cls, inmask, s, nullptr)) {
+                if (shade<false>(rec, pg, tau, is_part, s, nullptr)) {
                     // forward.cu:398-415
                     const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
                     const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
@@ -234,7 +288,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                     pT = T;
                     T = test_T;
                     last_contributor = (uint32_t)(base + jj + 1);
-                    if (T < kTEps) done = true;
+                    if (T < kTEps) { done = true; hm.clear(); }
                 }
             }
         }
@@ -391,33 +445,27 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         __syncthreads();
         int n_cand = 0;
         if (hi - cnt < warp_last) n_cand = build_candidates(sm.srec, cnt, use_aa, tc.fx0, tc.fy0, cand, lane);
-        int c = 0;
+        // lock-step classification; faces behind this pixel's last contributor are masked out
+        HitMasks hm;
+        classify_candidates(sm.srec, cand, n_cand, use_aa, pg.pxmin, pg.pymin, tc.inside, hm,
+                            [&](int j) { return hi - 1 - j < my_last; });
 
         for (;;) {        // alternate phase A (bounded) and phase B until the round is exhausted
             // ====================== phase A: pixel-sequential walk, queue the contributions
             int pushes = 0;
             for (;;) {
-                int jj = -1, cls = AA_FULL;
-                unsigned inmask = 0xF;
-                if (pushes < kMaxPush) {
-                    while (c < n_cand) {
-                        const int j = cand[c++];
-                        if (hi - 1 - j >= my_last) continue;          // behind this pixel's last contributor
-                        if (use_aa) {
-                            cls = aa_classify(sm.srec + j * kRecStride, pg.pxmin, pg.pymin, inmask);
-                            if (cls == AA_OUT) continue;
-                        }
-                        jj = j;
-                        break;
-                    }
-                }
-                if (!__any_sync(0xffffffffu, jj >= 0)) break;
+                bool is_part = false;
+                int cpos = -1;
+                if (pushes < kMaxPush) cpos = hm.pop(is_part);
+                if (!__any_sync(0xffffffffu, cpos >= 0)) break;
                 bool push = false;
                 float rec_T = 0.f, rec_g = 0.f;
-                if (jj >= 0) {
+                int jj = 0;
+                if (cpos >= 0) {
+                    jj = cand[cpos];
                     const float* rec = sm.srec + jj * kRecStride;
                     Shade s;
-                    if (shade<false>(rec, pg, tau, cls, inmask, s, nullptr)) {
+                    if (shade<false>(rec, pg, tau, is_part, s, nullptr)) {
                         const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
                         // backward.cu:340-348
                         if (!first_pass) T = T / (1.0f - alpha);
@@ -452,7 +500,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     qbase = __shfl_sync(0xffffffffu, qbase, __ffs(pm) - 1);
                     if (push) {
                         const int q = qbase + __popc(pm & ((1u << lane) - 1u));
-                        sm.q_meta[q] = (uint32_t)jj | ((uint32_t)tid << 8);
+                        sm.q_meta[q] = (uint32_t)jj | ((uint32_t)tid << 8) | ((is_part ? 1u : 0u) << 16);
                         sm.q_T[q] = rec_T;
                         sm.q_g[q] = rec_g;
                         atomicAdd(&sm.cnt[jj], 1);
@@ -460,7 +508,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     }
                 }
             }
-            const bool lane_more = c < n_cand;
+            const bool lane_more = hm.any();
             __syncthreads();
             const int qn = sm.qn;
             // ====================== phase B: counting sort by slot, one thread per contribution
@@ -498,7 +546,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                         const int i = sm.perm[p];
                         const uint32_t meta = sm.q_meta[i];
                         slot = (int)(meta & 0xffu);
-                        const int ptid = (int)(meta >> 8);
+                        const int ptid = (int)((meta >> 8) & 0xffu);
                         const float Tq = sm.q_T[i], dL_dalpha = sm.q_g[i];
                         const float* rec = sm.srec + slot * kRecStride;
                         const float* sp = sm.spix + ptid * kPixWords;
@@ -510,12 +558,10 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                         qg.o = f3{sp[0], sp[1], sp[2]};
                         qg.d = f3{sp[3], sp[4], sp[5]};
                         const float qdC[3] = {sp[6], sp[7], sp[8]}, qdD = sp[9];
-                        int cls = AA_FULL;
-                        unsigned inmask = 0xF;
-                        if (use_aa) cls = aa_classify(rec, qg.pxmin, qg.pymin, inmask);
+                        const bool is_part = (meta >> 16) & 1u;
                         Shade s;
                         float g[6];
-                        if (cls != AA_OUT && shade<true>(rec, qg, tau, cls, inmask, s, g)) {
+                        if (shade<true>(rec, qg, tau, is_part, s, g)) {
                             const float opacity = rec[R_MISC + 1], intense = rec[R_MISC + 2];
                             const float alpha = __fmul_rn(opacity, s.ratio);
                             float dL_diC[3];
