@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -23,6 +23,24 @@ class DM2RenderInputs(C.Structure):
         ("aa_face_edges", C.c_void_p), ("aa_face_edges_iszero", C.c_void_p), ("aa_face_edges_recip", C.c_void_p),
         ("aa_face_edges_normal", C.c_void_p), ("aa_face_edges_normal_c", C.c_void_p),
         ("image_ray_o", C.c_void_p), ("image_ray_d", C.c_void_p),
+        ("ray_view", C.c_void_p), ("ray_h", C.c_int32), ("ray_w", C.c_int32),
+    ]
+
+
+class DM2FusedInputs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("P", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("image_h", C.c_int32), ("image_w", C.c_int32), ("aa_temperature", C.c_float),
+        ("background", C.c_void_p), ("patch_min", C.c_void_p), ("verts", C.c_void_p), ("faces", C.c_void_p),
+        ("verts_color", C.c_void_p), ("faces_opacity", C.c_void_p), ("verts_proj", C.c_void_p),
+        ("faces_intense", C.c_void_p), ("ray_o", C.c_void_p), ("ray_d", C.c_void_p), ("ray_view", C.c_void_p),
+    ]
+
+
+class DM2FusedGrads(C.Structure):
+    _fields_ = [
+        ("dL_dverts", C.c_void_p), ("dL_dverts_color", C.c_void_p), ("dL_dfaces_opacity", C.c_void_p),
+        ("dL_dfaces_intense", C.c_void_p), ("dL_dverts_proj", C.c_void_p),
     ]
 
 
@@ -72,6 +90,11 @@ SYMBOLS = {
     "dm2_backward_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "dm2_render_backward": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_void_p, _P(DM2RenderGrads), C.c_void_p, C.c_void_p]),
+    "dm2_fused_preprocess": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, _P(C.c_int64), C.c_void_p]),
+    "dm2_fused_forward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dm2_fused_backward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, _P(DM2FusedGrads), C.c_void_p, C.c_void_p]),
     "dm2_layers_preprocess": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "dm2_layers_geo_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "dm2_generate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -118,6 +118,117 @@ int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaSt
     return 0;
 }
 
+// ------------------------------------------------------------------ fused host prep + preprocess + pack
+// Per-vertex part of Renderer.compute_verts_ndc_image (reference __init__.py:251-260) on one
+// clip-space vertex: w clamp to +-1e-4, perspective divide, NDC -> image.  Separately rounded IEEE
+// ops in torch's order, so the results are bit-identical to the torch tensors of the unfused path.
+struct ProjVert { float nx, ny, nz, ix, iy, w; bool clamped; };
+__device__ __forceinline__ ProjVert project_vertex(const float4 c, float img_w, float img_h) {
+    ProjVert o;
+    float w = c.w;
+    o.clamped = false;
+    if (w >= 0.0f && w < 1e-4f) { w = 1e-4f; o.clamped = true; }
+    if (w < 0.0f && w > -1e-4f) { w = -1e-4f; o.clamped = true; }
+    o.w = w;
+    o.nx = __fdiv_rn(c.x, w); o.ny = __fdiv_rn(c.y, w); o.nz = __fdiv_rn(c.z, w);
+    o.ix = __fmul_rn(__fmul_rn(__fadd_rn(o.nx, 1.0f), 0.5f), img_w);
+    o.iy = __fmul_rn(__fmul_rn(__fadd_rn(o.ny, 1.0f), 0.5f), img_h);
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths, float* __restrict__ min_depths,
+                   float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
+                   float* __restrict__ records) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long BF = (long long)in.B * in.F;
+    if (idx >= BF) return;
+    const int b = (int)(idx / in.F), f = (int)(idx % in.F);
+    const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
+    const uint32_t pmx = (uint32_t)in.patch_min[2 * b], pmy = (uint32_t)in.patch_min[2 * b + 1];
+    const float4* vp = reinterpret_cast<const float4*>(in.verts_proj) + (size_t)b * in.P;
+    const float fw = (float)in.image_w, fh = (float)in.image_h;
+    const ProjVert a0 = project_vertex(vp[v0], fw, fh);
+    const ProjVert a1 = project_vertex(vp[v1], fw, fh);
+    const ProjVert a2 = project_vertex(vp[v2], fw, fh);
+
+    // ---- preprocessFaceCUDA (reference forward.cu:41-107), same chain as preprocess_face()
+    const float max_z = fmaxf(fmaxf(a0.nz, a1.nz), a2.nz);
+    const float min_z = fminf(fminf(a0.nz, a1.nz), a2.nz);
+    float depth = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, a0.nz), a1.nz), a2.nz);
+    depth = __fdiv_rn(depth, 3.0f);
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    bool live = !(max_z < -1.0f || min_z > 1.0f);
+    if (live) {
+        patch_rect(pmx, pmy, a0.ix, a0.iy, a1.ix, a1.iy, a2.ix, a2.iy, gx, gy, x0, y0, x1, y1);
+        live = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) != 0u;
+    }
+    if (!live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return; }
+    tiles_touched[idx] = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
+    rects[idx] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+    depths[idx] = clamp01_depth(depth);
+    min_depths[idx] = clamp01_depth(min_z);
+    max_depths[idx] = clamp01_depth(max_z);
+
+    // ---- Triangles (reference pyrenderer.py:6-30, 521-535): CCW order, edges, flags, reciprocals, normals
+    const float p0x = a0.ix, p0y = a0.iy;
+    const float sarea = __fmul_rn(0.5f, __fsub_rn(__fmul_rn(__fsub_rn(a1.ix, p0x), __fsub_rn(a2.iy, p0y)),
+                                                  __fmul_rn(__fsub_rn(a2.ix, p0x), __fsub_rn(a1.iy, p0y))));
+    const bool flip = sarea < 0.0f;
+    const float p1x = flip ? a2.ix : a1.ix, p1y = flip ? a2.iy : a1.iy;
+    const float p2x = flip ? a1.ix : a2.ix, p2y = flip ? a1.iy : a2.iy;
+    const float e[6] = {__fsub_rn(p1x, p0x), __fsub_rn(p1y, p0y), __fsub_rn(p2x, p1x), __fsub_rn(p2y, p1y),
+                        __fsub_rn(p0x, p2x), __fsub_rn(p0y, p2y)};
+    float r[6];
+    uint32_t flags = flip ? 0x100u : 0u;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        r[k] = __fdiv_rn(1.0f, e[k]);
+        flags |= (fabsf(e[k]) < 1e-3f ? 1u : 0u) << k;
+    }
+    // n_k = (-e_k.y, e_k.x), c_k = n_k . anchor_k  (two rounded products, one add)
+    const float n[6] = {-e[1], e[0], -e[3], e[2], -e[5], e[4]};
+    const float c0 = __fadd_rn(__fmul_rn(n[0], p0x), __fmul_rn(n[1], p0y));
+    const float c1 = __fadd_rn(__fmul_rn(n[2], p1x), __fmul_rn(n[3], p1y));
+    const float c2 = __fadd_rn(__fmul_rn(n[4], p2x), __fmul_rn(n[5], p2y));
+    const float txmin = nanmin(nanmin(p0x, p1x), p2x), txmax = nanmax(nanmax(p0x, p1x), p2x);
+    const float tymin = nanmin(nanmin(p0y, p1y), p2y), tymax = nanmax(nanmax(p0y, p1y), p2y);
+
+    const float* w0 = in.verts + 3 * (size_t)v0;
+    const float* w1 = in.verts + 3 * (size_t)v1;
+    const float* w2 = in.verts + 3 * (size_t)v2;
+    const float* q0 = in.verts_color + 3 * (size_t)v0;
+    const float* q1 = in.verts_color + 3 * (size_t)v1;
+    const float* q2 = in.verts_color + 3 * (size_t)v2;
+    float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * kRecWords);
+    rec[0]  = make_float4(txmin, txmax, tymin, tymax);
+    rec[1]  = make_float4(n[0], n[1], n[2], n[3]);
+    rec[2]  = make_float4(n[4], n[5], c0, c1);
+    rec[3]  = make_float4(c2, in.faces_opacity[f], in.faces_intense[idx], __uint_as_float(flags));
+    rec[4]  = make_float4(w0[0], w0[1], w0[2], a0.nz);
+    rec[5]  = make_float4(w1[0], w1[1], w1[2], a1.nz);
+    rec[6]  = make_float4(w2[0], w2[1], w2[2], a2.nz);
+    rec[7]  = make_float4(q0[0], q0[1], q0[2], q1[0]);
+    rec[8]  = make_float4(q1[1], q1[2], q2[0], q2[1]);
+    rec[9]  = make_float4(q2[2], __int_as_float(v0), __int_as_float(v1), __int_as_float(v2));
+    rec[10] = make_float4(p0x, p0y, p1x, p1y);
+    rec[11] = make_float4(p2x, p2y, e[0], e[1]);
+    rec[12] = make_float4(e[2], e[3], e[4], e[5]);
+    rec[13] = make_float4(r[0], r[1], r[2], r[3]);
+    rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
+}
+
+int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    ProfScope _ps("preprocess_pack", s);
+    k_fused_preprocess<<<cdiv(BF, 256), 256, 0, s>>>(in, gx, gy, fw.depths, fw.min_depths, fw.max_depths,
+                                                     fw.tiles_touched, fw.rects, fw.records);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------ layered preprocess + pack
 __global__ void __launch_bounds__(256)
 k_layers_preprocess(DM2LayerInputs in, int gx, int gy, float* __restrict__ depths,

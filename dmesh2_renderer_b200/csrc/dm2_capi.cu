@@ -271,7 +271,69 @@ int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const vo
     FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
     BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
     ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
-    return launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, *grads, grad_ws, s);
+    if (launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, s)) return 1;
+    return launch_grad_scatter(*in, fw, *grads, grad_ws, s);
+}
+
+// ---- fused host prep path -------------------------------------------------------------------
+static int check_fused_inputs(const DM2FusedInputs* in) {
+    DM2_REQUIRE(in != nullptr, "inputs must not be null");
+    DM2_REQUIRE(in->B >= 0 && in->P >= 0 && in->F >= 0 && in->H >= 0 && in->W >= 0, "negative dimension");
+    DM2_REQUIRE(in->image_h >= in->H && in->image_w >= in->W, "patch larger than the frame");
+    DM2_REQUIRE(in->aa_temperature >= 0.0f && in->aa_temperature <= 1.0f, "aa_temperature must be in the range [0, 1]");
+    DM2_REQUIRE((long long)in->B * in->F < (1ll << 31), "B*F must be < 2^31");
+    DM2_REQUIRE((long long)in->B * in->H * in->W < (1ll << 31), "B*H*W must be < 2^31");
+    DM2_REQUIRE(cdiv(in->W, kTile) < 65536 && cdiv(in->H, kTile) < 65536, "patch too large");
+    return 0;
+}
+static DM2RenderInputs as_render_inputs(const DM2FusedInputs& f) {
+    DM2RenderInputs r;
+    memset(&r, 0, sizeof(r));
+    r.B = f.B; r.P = f.P; r.F = f.F; r.H = f.H; r.W = f.W;
+    r.aa_temperature = f.aa_temperature;
+    r.background = f.background; r.patch_min = f.patch_min; r.verts = f.verts; r.faces = f.faces;
+    r.verts_color = f.verts_color; r.faces_opacity = f.faces_opacity; r.faces_intense = f.faces_intense;
+    r.image_ray_o = f.ray_o; r.image_ray_d = f.ray_d; r.ray_view = f.ray_view; r.ray_h = f.image_h; r.ray_w = f.image_w;
+    return r;
+}
+
+int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream) {
+    if (check_fused_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && num_rendered_host, "dm2_fused_preprocess: null workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    *num_rendered_host = 0;
+    if (in->P == 0 || BF == 0) return 0;
+    FaceWs fw = carve_face(face_ws, BF, false);
+    if (launch_fused_preprocess(*in, fw, s)) return 1;
+    return scan_and_count(fw, BF, num_rendered_host, s);
+}
+
+int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                      int64_t num_rendered, float* out_color, float* out_depth, void* stream) {
+    if (check_fused_inputs(in)) return 2;
+    DM2_REQUIRE(in->ray_o && in->ray_d && in->ray_view, "dm2_fused_forward: null ray buffers");
+    const DM2RenderInputs r = as_render_inputs(*in);
+    return dm2_render_forward(&r, face_ws, binning_ws, image_ws, num_rendered, out_color, out_depth, stream);
+}
+
+int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void* binning_ws,
+                       const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
+                       const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws, void* stream) {
+    if (check_fused_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
+                "dm2_fused_backward: null buffer");
+    DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dfaces_intense &&
+                grads->dL_dverts_proj, "dm2_fused_backward: null gradient buffer");
+    if (in->F == 0 || num_rendered == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    const DM2RenderInputs r = as_render_inputs(*in);
+    FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
+    BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
+    ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
+    if (launch_raster_backward(r, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, s)) return 1;
+    return launch_fused_grad_scatter(*in, fw, *grads, grad_ws, s);
 }
 
 int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes) {

@@ -189,7 +189,12 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
                           const ImageWs& iw, float* out_color, float* out_depth, cudaStream_t s);
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
-                           const DM2RenderGrads& g, void* grad_ws, cudaStream_t s);
+                           void* grad_ws, cudaStream_t s);
+int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
+                        cudaStream_t s);
+int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, cudaStream_t s);
+int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
+                              cudaStream_t s);
 size_t backward_ws_bytes(long long BF);
 int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
                   void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, cudaStream_t s);

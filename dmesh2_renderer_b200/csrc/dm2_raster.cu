@@ -222,6 +222,14 @@ __device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, i
     return c;
 }
 
+// index of this pixel's ray: patch-local (B,H,W,3) buffers, or the renderer's full-resolution
+// (V,ray_h,ray_w,3) buffers addressed through ray_view + patch_min (fused path)
+__device__ __forceinline__ size_t ray_index(const DM2RenderInputs& in, const TileCtx& tc) {
+    if (in.ray_view == nullptr) return tc.pix;
+    const int pmx = in.patch_min[2 * tc.b], pmy = in.patch_min[2 * tc.b + 1];
+    return ((size_t)in.ray_view[tc.b] * in.ray_h + (tc.py + pmy)) * in.ray_w + (tc.px + pmx);
+}
+
 // =============================================================================== forward
 __global__ void __launch_bounds__(kRasterThreads, 2)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
@@ -242,8 +250,9 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     pg.pymin = (float)((uint32_t)tc.py + (uint32_t)in.patch_min[2 * tc.b + 1]);
     pg.o = f3{0, 0, 0}; pg.d = f3{0, 0, 0};
     if (tc.inside) {
-        const float* ro = in.image_ray_o + tc.pix * 3;
-        const float* rd = in.image_ray_d + tc.pix * 3;
+        const size_t rix = ray_index(in, tc);
+        const float* ro = in.image_ray_o + rix * 3;
+        const float* rd = in.image_ray_d + rix * 3;
         pg.o = f3{ro[0], ro[1], ro[2]};
         pg.d = f3{rd[0], rd[1], rd[2]};
     }
@@ -402,8 +411,9 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
     float T_final = 0.0f, prev_T_final = 0.0f;
     int my_last = 0;
     if (tc.inside) {
-        const float* ro = in.image_ray_o + tc.pix * 3;
-        const float* rd = in.image_ray_d + tc.pix * 3;
+        const size_t rix = ray_index(in, tc);
+        const float* ro = in.image_ray_o + rix * 3;
+        const float* rd = in.image_ray_d + rix * 3;
         pg.o = f3{ro[0], ro[1], ro[2]};
         pg.d = f3{rd[0], rd[1], rd[2]};
         dC[0] = dL_dcolor[tc.pix * 3 + 0]; dC[1] = dL_dcolor[tc.pix * 3 + 1]; dC[2] = dL_dcolor[tc.pix * 3 + 2];
@@ -682,11 +692,84 @@ k_grad_scatter(int B, int P, int F, const int32_t* __restrict__ faces, const uin
     for (int k = 0; k < 6; k++) gr.dL_daa_face_verts[(size_t)idx * 6 + k] = g[23 + k];
 }
 
+// Fused-path scatter: same per-face record, but the screen-space part (d/d aa verts, d/d ndc.z) is
+// chained through the CCW swap, the image transform and the perspective divide down to
+// d/d verts_proj (what torch autograd does for the reference's host prep, __init__.py:251-260 and
+// pyrenderer.py:6-30), with one 16-byte vector reduction per (view, face, vertex).
+__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touched, const float* __restrict__ records,
+                     const float* __restrict__ gface, DM2FusedGrads gr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)in.B * in.F) return;
+    if (tiles_touched[idx] == 0) return;
+    const int b = (int)(idx / in.F), f = (int)(idx % in.F);
+    const float4* g4 = reinterpret_cast<const float4*>(gface + (size_t)idx * kGradWords);
+    float g[32];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const float4 t = g4[k]; g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w; }
+    const bool flip = (__float_as_uint(records[(size_t)idx * kRecWords + R_MISC + 3]) >> 8) & 1u;
+    const float4* vp = reinterpret_cast<const float4*>(in.verts_proj) + (size_t)b * in.P;
+    const float fw = (float)in.image_w, fh = (float)in.image_h;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int v = in.faces[3 * (size_t)f + i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (g[3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts + 3 * (size_t)v + c, g[3 * i + c]);
+            if (g[9 + 3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts_color + 3 * (size_t)v + c, g[9 + 3 * i + c]);
+        }
+        // aa verts are (v0, v2, v1) when the face was flipped to CCW
+        const int k = (i == 0) ? 0 : (flip ? 3 - i : i);
+        const float dix = (k == 0) ? g[23] : ((k == 1) ? g[25] : g[27]);
+        const float diy = (k == 0) ? g[24] : ((k == 1) ? g[26] : g[28]);
+        const float dz = g[18 + i];
+        if (dix != 0.0f || diy != 0.0f || dz != 0.0f) {
+            const float4 c = vp[v];
+            float w = c.w;
+            bool clamped = false;
+            if (w >= 0.0f && w < 1e-4f) { w = 1e-4f; clamped = true; }
+            if (w < 0.0f && w > -1e-4f) { w = -1e-4f; clamped = true; }
+            const float nx = c.x / w, ny = c.y / w, nz = c.z / w;
+            const float dnx = (dix * fw) * 0.5f, dny = (diy * fh) * 0.5f;
+            const float dw = clamped ? 0.0f : -(dnx * nx + dny * ny + dz * nz) / w;
+            red_add_v4(gr.dL_dverts_proj + 4 * ((size_t)b * in.P + v), dnx / w, dny / w, dz / w, dw);
+        }
+    }
+    if (g[21] != 0.0f) atomicAdd(gr.dL_dfaces_opacity + f, g[21]);
+    gr.dL_dfaces_intense[idx] = g[22];
+}
+
 size_t backward_ws_bytes(long long BF) { return align_up((size_t)BF * kGradWords * 4, 256) + 256; }
 
+int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
+                              cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    ProfScope _ps("grad_scatter", s);
+    k_fused_grad_scatter<<<cdiv(BF, 256), 256, 0, s>>>(in, fw.tiles_touched, fw.records,
+                                                       reinterpret_cast<const float*>(grad_ws), g);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
+                        cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    ProfScope _ps("grad_scatter", s);
+    k_grad_scatter<<<cdiv(BF, 256), 256, 0, s>>>(in.B, in.P, in.F, in.faces, fw.tiles_touched,
+                                                 reinterpret_cast<const float*>(grad_ws), g);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+// zero the per-face gradient records and run the tile kernel; the caller scatters afterwards
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                           const float* dL_dcolor, const float* dL_ddepth, const DM2RenderGrads& g, void* grad_ws,
-                           cudaStream_t s) {
+                           const float* dL_dcolor, const float* dL_ddepth, void* grad_ws, cudaStream_t s) {
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     const long long BF = (long long)in.B * in.F;
@@ -707,11 +790,6 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
         k_raster_backward<<<(unsigned)nblk, kRasterThreads, sizeof(BwdSmem), s>>>(
             in, fw.records, bw.vals, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor, dL_ddepth,
             gface, gx, gy);
-        DM2_LAUNCH_CHECK();
-    }
-    {
-        ProfScope _ps("grad_scatter", s);
-        k_grad_scatter<<<cdiv(BF, 256), 256, 0, s>>>(in.B, in.P, in.F, in.faces, fw.tiles_touched, gface, g);
         DM2_LAUNCH_CHECK();
     }
     return 0;

@@ -1,0 +1,123 @@
+"""Fused host prep path of ``Renderer.forward``.
+
+The reference's ``Renderer.forward`` runs ~25 torch kernels of host-side prep before its single
+autograd Function (dmesh2_renderer/__init__.py:325-347, pyrenderer.py:6-30) and autograd replays
+them backwards.  ``FusedRenderFunction`` starts from the clip-space vertices (the two matmuls stay
+in torch so their rounding is the reference's) and lets the preprocess kernel do the w clamp, the
+perspective divide, the image transform, the per-face gather, the CCW re-ordering and the derived
+AA terms with the same IEEE operations in the same order; the backward scatter kernel applies the
+matching chain rule down to d/d verts_proj.  Colour/depth, sort order and tile ranges are
+bit-identical to the unfused ``RenderFunction`` path (tests/test_gpu_parity.py).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._C import _err, _prep, _ptr, _stream, binning_layout, face_layout, image_layout
+from ._lib import DM2FusedGrads, DM2FusedInputs
+
+
+def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
+                  verts_proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
+    f32, i32 = torch.float32, torch.int32
+    keep = dict(background=_prep(background, f32, "background"), patch_min=_prep(patch_min, i32, "patch_min"),
+                verts=_prep(verts, f32, "verts"), faces=_prep(faces, i32, "faces"),
+                verts_color=_prep(verts_color, f32, "verts_color"),
+                faces_opacity=_prep(faces_opacity, f32, "faces_opacity"),
+                verts_proj=_prep(verts_proj, f32, "verts_proj"), faces_intense=_prep(faces_intense, f32, "faces_intense"),
+                ray_o=_prep(ray_o, f32, "ray_o"), ray_d=_prep(ray_d, f32, "ray_d"),
+                ray_view=_prep(ray_view, i32, "ray_view"))
+    if keep["background"].dim() != 1 or keep["background"].size(0) != 3:
+        _err("background must have dimensions (3,)")
+    if keep["verts"].dim() != 2 or keep["verts"].size(1) != 3:
+        _err("verts must have dimensions (P, 3)")
+    if keep["faces"].dim() != 2 or keep["faces"].size(1) != 3:
+        _err("faces must have dimensions (F, 3)")
+    P, F = int(keep["verts"].size(0)), int(keep["faces"].size(0))
+    vp = keep["verts_proj"]
+    if vp.dim() != 3 or vp.size(1) != P or vp.size(2) != 4:
+        _err("verts_proj must have dimensions (B, P, 4)")
+    B = int(vp.size(0))
+    if tuple(keep["verts_color"].shape) != (P, 3):
+        _err("vert color must have dimensions (P, 3)")
+    if tuple(keep["faces_opacity"].shape) != (F,):
+        _err("face opacity must have dimensions (F,)")
+    if tuple(keep["faces_intense"].shape) != (B, F):
+        _err("faces_intense must have dimensions (B, F,)")
+    if tuple(keep["patch_min"].shape) != (B, 2) or keep["ray_view"].numel() != B:
+        _err("patch_min must have dimensions (B, 2)")
+    ro, rd = keep["ray_o"], keep["ray_d"]
+    if ro.dim() != 4 or ro.size(3) != 3 or ro.shape != rd.shape:
+        _err("image_ray_o must have dimensions (B, H, W, 3)")
+    if aa_temperature < 0 or aa_temperature > 1:
+        _err("aa_temperature must be in the range [0, 1]")
+    s = DM2FusedInputs()
+    s.B, s.P, s.F, s.H, s.W = B, P, F, int(patch_height), int(patch_width)
+    s.image_h, s.image_w = int(ro.size(1)), int(ro.size(2))
+    s.aa_temperature = float(aa_temperature)
+    for k, t in keep.items():
+        setattr(s, k, t.data_ptr() if t.numel() > 0 else 0)
+    return s, keep
+
+
+class FusedRenderFunction(torch.autograd.Function):
+    """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, verts_proj,
+    faces_intense, aa_temperature, ray_o, ray_d, ray_view) -> (color [B,H,W,3], depth_ndc [B,H,W])."""
+
+    @staticmethod
+    def forward(ctx, background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
+                verts_proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
+        lib = _lib.load_library()
+        s, keep = _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
+                                faces_opacity, verts_proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view)
+        dev = keep["verts"].device
+        B, H, W = s.B, s.H, s.W
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            color = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+            depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+            face_buffer = torch.empty((face_layout(B, s.F).total,), dtype=torch.uint8, device=dev)
+            image_buffer = torch.empty((image_layout(B, H, W).total,), dtype=torch.uint8, device=dev)
+            nr = C.c_int64(0)
+            _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), C.byref(nr), stream))
+            R = int(nr.value)
+            binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
+            _lib.check(lib.dm2_fused_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
+                                             R, _ptr(color), _ptr(depth), stream))
+        ctx.save_for_backward(*keep.values(), face_buffer, binning_buffer, image_buffer)
+        ctx.keys = list(keep.keys())
+        ctx.num_rendered = R
+        ctx.patch = (patch_width, patch_height)
+        ctx.aa_temperature = aa_temperature
+        return color, depth
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_depth):
+        lib = _lib.load_library()
+        saved = ctx.saved_tensors
+        keep = dict(zip(ctx.keys, saved[:len(ctx.keys)]))
+        face_buffer, binning_buffer, image_buffer = saved[len(ctx.keys):]
+        s, keep = _fused_struct(keep["background"], keep["patch_min"], ctx.patch[0], ctx.patch[1], keep["verts"],
+                                keep["faces"], keep["verts_color"], keep["faces_opacity"], keep["verts_proj"],
+                                keep["faces_intense"], ctx.aa_temperature, keep["ray_o"], keep["ray_d"],
+                                keep["ray_view"])
+        dev = keep["verts"].device
+        gc = _prep(grad_color, torch.float32, "dL_dout_color")
+        gd = _prep(grad_depth, torch.float32, "dL_dout_depth")
+        with torch.cuda.device(dev):
+            g_verts = torch.zeros_like(keep["verts"])
+            g_color = torch.zeros_like(keep["verts_color"])
+            g_opacity = torch.zeros_like(keep["faces_opacity"])
+            g_intense = torch.zeros_like(keep["faces_intense"])
+            g_proj = torch.zeros_like(keep["verts_proj"])
+            if s.F != 0:
+                g = DM2FusedGrads(g_verts.data_ptr(), g_color.data_ptr(), g_opacity.data_ptr(), g_intense.data_ptr(),
+                                  g_proj.data_ptr())
+                nb = C.c_size_t(0)
+                _lib.check(lib.dm2_backward_workspace_bytes(s.B, s.F, C.byref(nb)))
+                grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
+                _lib.check(lib.dm2_fused_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
+                                                  _ptr(image_buffer), ctx.num_rendered, _ptr(gc), _ptr(gd),
+                                                  C.byref(g), _ptr(grad_ws), _stream(dev)))
+        return (None, None, None, None, g_verts, None, g_color, g_opacity, g_proj, g_intense, None, None, None, None)

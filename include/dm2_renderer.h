@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 4
+#define DM2_ABI_VERSION 5
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -65,6 +65,11 @@ typedef struct DM2RenderInputs {
     const float*   aa_face_edges_normal_c;   /* (B,F,3)        */
     const float*   image_ray_o;              /* (B,H,W,3)      */
     const float*   image_ray_d;              /* (B,H,W,3)      */
+    /* Optional ray indirection (NULL/0 for the plain RenderFunction path): when ray_view != NULL the
+     * ray of patch pixel (x,y) of batch entry b is  image_ray_*[ray_view[b]][y + patch_min.y][x + patch_min.x]
+     * inside a (V, ray_h, ray_w, 3) buffer.                                                      */
+    const int32_t* ray_view;
+    int32_t ray_h, ray_w;
 } DM2RenderInputs;
 
 /* Gradient outputs of render_backward_cuda (reference render.cu:313-318, 372). */
@@ -162,6 +167,50 @@ int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes);
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
                                void* image_ws, void* geo_ws, int64_t num_rendered,
                                int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
+
+/* ---- Renderer, fused host prep ----------------------------------------
+ * Renderer.forward of the reference spends ~25 torch kernels per call on host-side prep
+ * (reference dmesh2_renderer/__init__.py:239-262, 335-347 and pyrenderer.py:6-30): the w clamp and
+ * perspective divide, the image transform, the per-face gather, the CCW re-ordering and the five
+ * derived AA tensors, plus the ray patch gather - and autograd replays all of it backwards.  The
+ * fused entry points start from the clip-space vertices  verts_proj = [verts,1] mv^T proj^T
+ * (B,P,4; the two matmuls stay in torch/cuBLAS so their rounding is the reference's) and perform
+ * every later step inside the preprocess kernel with the same IEEE operations in the same order
+ * (the packed records, tile bboxes and depth keys are bit-identical to the unfused path), and the
+ * backward scatter kernel applies the matching chain rule down to d/d verts_proj.
+ * Rays are read straight from the renderer's full-resolution ray buffers.                          */
+typedef struct DM2FusedInputs {
+    int32_t B, P, F;             /* views in this call, vertices, faces                            */
+    int32_t H, W;                /* patch_height, patch_width                                      */
+    int32_t image_h, image_w;    /* full frame size used by the NDC -> image transform             */
+    float   aa_temperature;
+    const float*   background;   /* (3)                                                            */
+    const int32_t* patch_min;    /* (B,2)                                                          */
+    const float*   verts;        /* (P,3)                                                          */
+    const int32_t* faces;        /* (F,3)                                                          */
+    const float*   verts_color;  /* (P,3)                                                          */
+    const float*   faces_opacity;/* (F)                                                            */
+    const float*   verts_proj;   /* (B,P,4) clip-space vertices                                    */
+    const float*   faces_intense;/* (B,F)                                                          */
+    const float*   ray_o;        /* (V,image_h,image_w,3) full-resolution rays of ALL views        */
+    const float*   ray_d;
+    const int32_t* ray_view;     /* (B) row of ray_o/ray_d used by batch entry b                   */
+} DM2FusedInputs;
+
+typedef struct DM2FusedGrads {   /* caller-zeroed */
+    float* dL_dverts;            /* (P,3)   through the ray/triangle hit point                     */
+    float* dL_dverts_color;      /* (P,3)                                                          */
+    float* dL_dfaces_opacity;    /* (F)                                                            */
+    float* dL_dfaces_intense;    /* (B,F)                                                          */
+    float* dL_dverts_proj;       /* (B,P,4) through depth (z/w) and AA coverage (x/w, y/w)         */
+} DM2FusedGrads;
+
+int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream);
+int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                      int64_t num_rendered, float* out_color, float* out_depth, void* stream);
+int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void* binning_ws,
+                       const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
+                       const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws, void* stream);
 
 /* ---- binning primitives exposed on their own (sort keys/s metric, parity tests) ---------- */
 /* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit).  Replaces

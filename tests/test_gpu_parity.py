@@ -346,3 +346,36 @@ def test_live_reference_mid_size(built):
     for k in g0:
         e = np.abs(g0[k] - g1[k]).max() / (np.abs(g1[k]).max() + 1e-30)
         assert e <= 5e-3, (k, e)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused host prep (Renderer.forward default) vs the reference-shaped RenderFunction path
+@pytest.mark.parametrize("tau,patch", [(1.0, None), (0.5, None), (1.0, ([[7, 20], [40, 3]], (50, 41)))])
+def test_fused_path_equals_reference_shaped_path(built, tau, patch):
+    from dmesh2_renderer_b200 import Renderer, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=700, size=96, sigma=0.15, seed=31, n_views=2)
+    st = scene_tensors(sc, dev)
+    views = [1, 0]
+    if patch is None:
+        pm, (pw, ph) = torch.zeros((2, 2), dtype=torch.int32, device=dev), (sc.width, sc.height)
+    else:
+        pm, (pw, ph) = torch.tensor(patch[0], dtype=torch.int32, device=dev), patch[1]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    wc = (torch.rand((2, ph, pw, 3), generator=g) * 2 - 1).to(dev)
+    wd = (torch.rand((2, ph, pw), generator=g) * 2 - 1).to(dev)
+    res = []
+    for fused in (True, False):
+        r = Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+        r.fused = fused
+        p = {k: st[k].detach().clone().requires_grad_(True) for k in ("verts", "verts_color", "faces_opacity")}
+        fi = st["faces_intense"][views].detach().clone().requires_grad_(True)
+        color, depth = r(views, pm, pw, ph, p["verts"], st["faces"], p["verts_color"], p["faces_opacity"], fi,
+                         st["background"], tau)
+        ((color * wc).sum() + (depth * wd).sum()).backward()
+        res.append((color.detach(), depth.detach(), {**{k: v.grad for k, v in p.items()}, "faces_intense": fi.grad}))
+    (c0, d0, g0), (c1, d1, g1) = res
+    assert torch.equal(c0, c1) and torch.equal(d0, d1), "fused forward is not bit-identical to the unfused path"
+    for k in g0:
+        e = (g0[k] - g1[k]).abs().max().item() / (g1[k].abs().max().item() + 1e-30)
+        assert e <= BWD_RTOL, (k, e)
