@@ -411,9 +411,14 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;   // 4096
 constexpr int kRadix = 256;
 
-size_t sort_temp_bytes(long long n) {
+// temp = [counts (nblk*256) | inclusive scan of counts (nblk*256) | scan partials]
+static size_t sort_counts_bytes(long long n) {
     const long long nblk = (n + kSortTile - 1) / kSortTile;
     return align_up((size_t)(nblk * kRadix + 1) * sizeof(uint32_t), 256);
+}
+size_t sort_temp_bytes(long long n) {
+    const long long nblk = (n + kSortTile - 1) / kSortTile;
+    return 2 * sort_counts_bytes(n) + align_up((size_t)scan_partials_count(nblk * kRadix) * sizeof(uint32_t), 256);
 }
 
 __device__ __forceinline__ void warp_rank_digit(uint32_t* wc /*this warp's 256 counters*/, bool valid,
@@ -500,7 +505,9 @@ k_radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ v
     __syncthreads();
     {
         const int d = threadIdx.x;
-        uint32_t run = gbase[(size_t)d * nblk + blockIdx.x];
+        // gbase holds the INCLUSIVE scan of the digit-major count matrix; exclusive = previous entry
+        const size_t gi = (size_t)d * nblk + blockIdx.x;
+        uint32_t run = (gi == 0) ? 0u : gbase[gi - 1];
 #pragma unroll
         for (int ww = 0; ww < 8; ww++) { uint32_t c = wc[ww][d]; wc[ww][d] = run; run += c; }
     }
@@ -527,6 +534,8 @@ int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, 
     const int passes = (end_bit + 7) / 8;
     ProfScope _ps("radix_sort", s);
     uint32_t* counts = reinterpret_cast<uint32_t*>(temp);
+    uint32_t* incl = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(temp) + sort_counts_bytes(n));
+    uint32_t* partials = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(temp) + 2 * sort_counts_bytes(n));
     if (passes == 0) {
         DM2_CHECK(cudaMemcpyAsync(kout, kin, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
         DM2_CHECK(cudaMemcpyAsync(vout, vin, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
@@ -548,9 +557,8 @@ int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, 
         const uint32_t mask = (1u << bits) - 1u;
         k_radix_hist<<<nblk, kSortThreads, 0, s>>>(ka, (uint32_t)n, shift, mask, counts, nblk);
         DM2_LAUNCH_CHECK();
-        k_radix_scan<<<1, 1024, 0, s>>>(counts, (uint32_t)(nblk * kRadix));
-        DM2_LAUNCH_CHECK();
-        k_radix_scatter<<<nblk, kSortThreads, 0, s>>>(ka, va, kb, vb, (uint32_t)n, shift, mask, counts, nblk);
+        if (launch_scan(counts, incl, (long long)nblk * kRadix, partials, s)) return 1;
+        k_radix_scatter<<<nblk, kSortThreads, 0, s>>>(ka, va, kb, vb, (uint32_t)n, shift, mask, incl, nblk);
         DM2_LAUNCH_CHECK();
         uint64_t* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;

@@ -34,16 +34,16 @@ static cudaEvent_t prof_event() {
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-void prof_begin(const char* name, cudaStream_t s) {
-    if (!g_prof_on) return;
+int prof_begin(const char* name, cudaStream_t s) {
+    if (!g_prof_on) return -1;
     ProfEntry p{name, prof_event(), prof_event()};
     cudaEventRecord(p.a, s);
     g_prof_pending.push_back(p);
+    return (int)g_prof_pending.size() - 1;
 }
-void prof_end(cudaStream_t s) {
-    if (!g_prof_on || g_prof_pending.empty()) return;
-    // scopes do not nest in this library: the last pending entry is the open one
-    cudaEventRecord(g_prof_pending.back().b, s);
+void prof_end(int handle, cudaStream_t s) {
+    if (handle < 0 || handle >= (int)g_prof_pending.size()) return;     // scopes may nest
+    cudaEventRecord(g_prof_pending[handle].b, s);
 }
 static void prof_collect() {
     for (auto& p : g_prof_pending) {

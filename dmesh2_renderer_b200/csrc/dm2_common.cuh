@@ -23,12 +23,13 @@ namespace dm2 {
 void set_error(const char* fmt, ...);
 void count_launch();
 // optional per-kernel timing with CUDA events on the launching stream (dm2_profile_* in the C-ABI)
-void prof_begin(const char* name, cudaStream_t s);
-void prof_end(cudaStream_t s);
+int prof_begin(const char* name, cudaStream_t s);      // returns a handle (-1 when profiling is off)
+void prof_end(int handle, cudaStream_t s);
 struct ProfScope {
     cudaStream_t s;
-    ProfScope(const char* name, cudaStream_t st) : s(st) { prof_begin(name, st); }
-    ~ProfScope() { prof_end(s); }
+    int h;
+    ProfScope(const char* name, cudaStream_t st) : s(st), h(prof_begin(name, st)) {}
+    ~ProfScope() { prof_end(h, s); }
 };
 #define DM2_CHECK(expr)                                                                   \
     do {                                                                                  \

@@ -231,7 +231,7 @@ __device__ __forceinline__ size_t ray_index(const DM2RenderInputs& in, const Til
 }
 
 // =============================================================================== forward
-__global__ void __launch_bounds__(kRasterThreads, 2)
+__global__ void __launch_bounds__(kRasterThreads, 3)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
                  const uint2* __restrict__ ranges, float* __restrict__ final_T, float* __restrict__ final_prev_T,
                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
