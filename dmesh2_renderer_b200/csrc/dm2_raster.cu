@@ -346,27 +346,41 @@ __device__ __forceinline__ f3 crossn(const f3& a, const f3& b) {
 }
 __device__ __forceinline__ float dotn(const f3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
+// a*s - t*b per component with the contraction nvcc applies to `x*y - z*w`
+__device__ __forceinline__ f3 fms3(const f3& a, float s, float t, const f3& b) {
+    return {__fmaf_rn(a.x, s, -__fmul_rn(t, b.x)), __fmaf_rn(a.y, s, -__fmul_rn(t, b.y)),
+            __fmaf_rn(a.z, s, -__fmul_rn(t, b.z))};
+}
+__device__ __forceinline__ f3 mul3(const f3& a, float s) { return {__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)}; }
+
+// The big gradients this produces are ill-conditioned (1/denom^2 with cancelling terms), so the
+// operation order is pinned to the reference's expressions with its FMA contraction pattern: results
+// then agree with the reference (and the oracle) far better than free-form re-association would.
 __device__ __forceinline__ void ray_tri_grad(const f3& o, const f3& d, const f3& p0, const f3& p1, const f3& p2,
                                              f3& du_dp0, f3& du_dp1, f3& du_dp2, f3& dv_dp0, f3& dv_dp1,
                                              f3& dv_dp2) {
-    const f3 T = subn3(o, p0), E1 = subn3(p1, p0), E2 = subn3(p2, p0);
-    const f3 PE = crossn(d, E2);
-    const float denom_sqrt = dotn(PE, E1);
-    const float denom = denom_sqrt * denom_sqrt;
-    const float denom_inv = 1.0f / denom;
-    const float v0 = dotn(PE, T);
+    const f3 T = sub3(o, p0), E1 = sub3(p1, p0), E2 = sub3(p2, p0);
+    const f3 PE = cross3(d, E2);
+    const float denom_sqrt = dot3(PE, E1);
+    const float denom = __fmul_rn(denom_sqrt, denom_sqrt);
+    const float denom_inv = __fdiv_rn(1.0f, denom);
+    const float v0 = dot3(PE, T);
     const float v1 = denom_sqrt;
-    const float v2 = dotn(crossn(T, E1), E2);
-    const f3 du_dE1 = scale3(scale3(scale3(PE, -1.0f), v0), denom_inv);
-    const f3 du_dE2 = scale3(subn3(scale3(crossn(T, d), v1), scale3(crossn(E1, d), v0)), denom_inv);
-    const f3 du_dT  = scale3(scale3(PE, v1), denom_inv);
-    const f3 dv_dE1 = scale3(subn3(scale3(crossn(E2, T), v1), scale3(PE, v2)), denom_inv);
-    const f3 dv_dE2 = scale3(subn3(scale3(crossn(T, E1), v1), scale3(crossn(E1, d), v2)), denom_inv);
-    const f3 dv_dT  = scale3(scale3(crossn(E1, E2), v1), denom_inv);
-    du_dp0 = subn3(subn3(neg3(du_dE1), du_dE2), du_dT);
-    dv_dp0 = subn3(subn3(neg3(dv_dE1), dv_dE2), dv_dT);
+    const float v2 = dot3(cross3(T, E1), E2);
+    const f3 du_dE1 = mul3(mul3(neg3(PE), v0), denom_inv);
+    const f3 du_dE2 = mul3(fms3(cross3(T, d), v1, v0, cross3(E1, d)), denom_inv);
+    const f3 du_dT  = mul3(mul3(PE, v1), denom_inv);
+    const f3 dv_dE1 = mul3(fms3(cross3(E2, T), v1, v2, PE), denom_inv);
+    const f3 dv_dE2 = mul3(fms3(cross3(T, E1), v1, v2, cross3(E1, d)), denom_inv);
+    const f3 dv_dT  = mul3(mul3(cross3(E1, E2), v1), denom_inv);
+    du_dp0 = sub3(sub3(neg3(du_dE1), du_dE2), du_dT);
+    dv_dp0 = sub3(sub3(neg3(dv_dE1), dv_dE2), dv_dT);
     du_dp1 = du_dE1; dv_dp1 = dv_dE1;
     du_dp2 = du_dE2; dv_dp2 = dv_dE2;
+}
+// dL_du * du + dL_dv * dv  ->  fma(dL_du, du, dL_dv * dv)
+__device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) {
+    return {__fmaf_rn(a, x.x, __fmul_rn(b, y.x)), __fmaf_rn(a, x.y, __fmul_rn(b, y.y)), __fmaf_rn(a, x.z, __fmul_rn(b, y.z))};
 }
 
 struct BwdSmem {
@@ -619,9 +633,9 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                             f3 du0, du1, du2, dv0, dv1, dv2;
                             ray_tri_grad(qg.o, qg.d, f3{a0.x, a0.y, a0.z}, f3{a1.x, a1.y, a1.z},
                                          f3{a2.x, a2.y, a2.z}, du0, du1, du2, dv0, dv1, dv2);
-                            const f3 g0 = add3(scale3(du0, dL_du), scale3(dv0, dL_dv));
-                            const f3 g1 = add3(scale3(du1, dL_du), scale3(dv1, dL_dv));
-                            const f3 g2 = add3(scale3(du2, dL_du), scale3(dv2, dL_dv));
+                            const f3 g0 = comb3(dL_du, du0, dL_dv, dv0);
+                            const f3 g1 = comb3(dL_du, du1, dL_dv, dv1);
+                            const f3 g2 = comb3(dL_du, du2, dL_dv, dv2);
                             v[0] = g0.x; v[1] = g0.y; v[2] = g0.z;
                             v[3] = g1.x; v[4] = g1.y; v[5] = g1.z;
                             v[6] = g2.x; v[7] = g2.y; v[8] = g2.z;

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Times the BASELINE.json configurations other than the headline one (bench.py covers cfg2) for this
+implementation and, when baseline/_ref is present, for the unmodified reference on the same GPU.
+
+    python tools/perf_configs.py [cfg1 cfg3 cfg4 cfg5] [--iters N] [--check]
+
+Prints one JSON line per (config, impl).  --check also compares integer outputs / images between the
+two implementations (layer ids exactly; colours within 1e-4 for >= 99.9 % of the pixels).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def time_it(fn, iters, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def run_soup(pkg, sc, dev, views, iters):
+    r = pkg.Renderer(t(sc.mv, dev), t(sc.proj, dev), sc.width, sc.height, dev)
+    faces, bg = t(sc.faces, dev), t(sc.background, dev)
+    p = {k: t(getattr(sc, k), dev).requires_grad_(True) for k in ("verts", "verts_color", "faces_opacity")}
+    fi = t(sc.faces_intense[views], dev).requires_grad_(True)
+    pm = torch.zeros((len(views), 2), dtype=torch.int32, device=dev)
+    wc, wd = t(sc.w_color[views], dev), t(sc.w_depth[views], dev)
+    out = {}
+
+    def step():
+        for x in list(p.values()) + [fi]:
+            x.grad = None
+        color, depth = r(views, pm, sc.width, sc.height, p["verts"], faces, p["verts_color"], p["faces_opacity"], fi, bg)
+        ((color * wc).sum() + (depth * wd).sum()).backward()
+        out["color"], out["depth"], out["g_verts"] = color.detach(), depth.detach(), p["verts"].grad.detach()
+
+    ms = time_it(step, iters)
+    return ms, out
+
+
+def run_layers(pkg, sc, dev, iters):
+    lr = pkg.LayeredRenderer(t(sc.mv, dev), t(sc.proj, dev), sc.width, sc.height, dev)
+    a = [t(getattr(sc, k), dev) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")]
+    out = {}
+
+    def step():
+        out["layers"], out["cnt"] = lr.generate([0], *a, sc.num_layers)
+
+    ms = time_it(step, iters)
+    return ms, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["cfg1", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--no-ref", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    from helpers import load_reference
+    ref = None if args.no_ref else load_reference()
+    for cfg in args.configs:
+        t0 = time.time()
+        if cfg == "cfg1":
+            sc, views, kind = scenes.cfg1(), [0], "soup"
+        elif cfg == "cfg4":
+            sc, views, kind = scenes.cfg4(n_views=8), list(range(8)), "soup"     # one 8-view micro-batch at 512^2
+        elif cfg == "cfg5":
+            sc, views, kind = scenes.cfg5(), [0], "soup"
+        elif cfg == "cfg3":
+            sc, views, kind = scenes.cfg3(), [0], "layers"
+        else:
+            raise SystemExit(f"unknown config {cfg}")
+        gen_s = time.time() - t0
+        res = {}
+        for name, pkg in (("b200", dm), ("reference", ref)):
+            if pkg is None:
+                continue
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+            try:
+                if kind == "soup":
+                    ms, out = run_soup(pkg, sc, dev, views, args.iters)
+                    unit = len(views) * 1000.0 / ms
+                else:
+                    ms, out = run_layers(pkg, sc, dev, args.iters)
+                    unit = 1000.0 / ms
+            except Exception as ex:          # e.g. the reference running out of memory at cfg5
+                print(json.dumps({"config": cfg, "impl": name, "error": str(ex)[:200]}), flush=True)
+                continue
+            res[name] = out
+            print(json.dumps({"config": sc.name, "impl": name, "ms": ms, "views_or_frames_per_s": unit,
+                              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "scene_gen_s": gen_s}),
+                  flush=True)
+        if args.check and len(res) == 2:
+            a, b = res["b200"], res["reference"]
+            if kind == "layers":
+                same = bool(torch.equal(a["layers"], b["layers"]) and torch.equal(a["cnt"], b["cnt"]))
+                nd = int((a["layers"] != b["layers"]).any(-1).sum())
+                print(json.dumps({"config": sc.name, "check": "layer ids", "bit_exact": same, "pixels_differing": nd}), flush=True)
+            else:
+                bad_c = float(((a["color"] - b["color"]).abs() > 1e-4 * (1 + b["color"].abs())).float().mean())
+                bad_d = float(((a["depth"] - b["depth"]).abs() > 1e-4 * (1 + b["depth"].abs())).float().mean())
+                ge = float((a["g_verts"] - b["g_verts"]).abs().max() / (b["g_verts"].abs().max() + 1e-30))
+                print(json.dumps({"config": sc.name, "check": "colour/depth/grad", "frac_color_outside_1e-4": bad_c,
+                                  "frac_depth_outside_1e-4": bad_d, "dverts_max_rel_err": ge}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
