@@ -153,6 +153,8 @@ __device__ __forceinline__ void classify_candidates(const float* __restrict__ sr
     classify_candidates(srec, cand, n_cand, use_aa, pxmin, pymin, lane_on, hm, [](int) { return true; });
 }
 
+__device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const PixelGeom& pg, float tau, Shade& s);
+
 // is_part: the pixel is only partially covered (aa_classify == AA_PART); ignored when tau == 0.
 template <bool GRAD>
 __device__ __forceinline__ bool shade(const float* __restrict__ rec, const PixelGeom& pg, float tau, bool is_part,
@@ -169,6 +171,12 @@ __device__ __forceinline__ bool shade(const float* __restrict__ rec, const Pixel
             if (!aa_clip<GRAD>(rec, pg.pxmin, pg.pymin, inmask, s.area, g)) return false;
         }
     }
+    return shade_tail(rec, pg, tau, s);
+}
+
+// Everything after the coverage area (s.area must be set): hit point, clamped barycentrics,
+// coverage ratio, interpolated colour and depth (forward.cu:354-395).
+__device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const PixelGeom& pg, float tau, Shade& s) {
     const float4 a0 = *reinterpret_cast<const float4*>(rec + R_P0);
     const float4 a1 = *reinterpret_cast<const float4*>(rec + R_P1);
     const float4 a2 = *reinterpret_cast<const float4*>(rec + R_P2);
@@ -196,6 +204,90 @@ __device__ __forceinline__ bool shade(const float* __restrict__ rec, const Pixel
     }
     s.iD = __fmaf_rn(s.w2, a2.w, __fmaf_rn(s.w0, a0.w, __fmul_rn(s.w1, a1.w)));
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sub-chunk processing (16 candidates at a time), shared by the forward walk and backward phase A:
+//   1. lock-step classification -> per-lane hit / partial bit masks (+ the 4-bit corner mask);
+//   2. the warp compacts all (lane, candidate) pairs that need the polygon clip into a pair list;
+//   3. the clip runs DENSE over that list - any lane clips any pixel's pair (the area does not depend
+//      on the compositing order), so all 32 lanes are busy instead of the ~12 that own a partially
+//      covered pixel at a given step; areas land in a per-warp shared-memory table;
+//   4. the sequential per-pixel walk then only looks its areas up.
+constexpr int kSub = 16;
+constexpr int kPairCap = 32 * kSub;
+struct WarpClip {
+    uint16_t plist[kPairCap];          // k | lane << 4 | inmask << 9
+    float parea[kPairCap];             // overlap area, or -1 when the reference would skip the pair
+};
+
+struct SubMasks {
+    uint32_t hit, part;                // bit k: candidate k of the sub-chunk touches / partially covers my pixel
+    int base_reg;                      // lane k holds the pair-list base of candidate k ...
+    uint32_t mask_reg;                 // ... and the ballot of lanes with a partial pixel for it
+};
+
+template <typename SlotOk>
+__device__ __forceinline__ void subchunk_prepare(const float* __restrict__ srec, const uint8_t* __restrict__ cand,
+                                                 int ncs, bool use_aa, float pxmin, float pymin, bool lane_on,
+                                                 float fx0, float fy0, WarpClip& wc, int lane, SubMasks& sm_,
+                                                 SlotOk slot_ok) {
+    uint32_t hit = 0u, part = 0u;
+    unsigned long long im = 0ull;
+    for (int k = 0; k < ncs; k++) {                            // lock-step, broadcast reads
+        const int j = cand[k];
+        int cls = AA_FULL;
+        unsigned inmask = 0xF;
+        if (use_aa) cls = aa_classify(srec + j * kRecStride, pxmin, pymin, inmask);
+        const bool on = lane_on && (cls != AA_OUT) && slot_ok(j);
+        const bool p = on && (cls == AA_PART);
+        hit |= (on ? 1u : 0u) << k;
+        part |= (p ? 1u : 0u) << k;
+        if (p) im |= (unsigned long long)inmask << (4 * k);
+    }
+    int total = 0, base_reg = 0;
+    uint32_t mask_reg = 0u;
+    if (__any_sync(0xffffffffu, part != 0u)) {
+        for (int k = 0; k < ncs; k++) {
+            const bool p = (part >> k) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (lane == k) { base_reg = total; mask_reg = m; }
+            if (p) wc.plist[total + __popc(m & ((1u << lane) - 1u))] =
+                       (uint16_t)(k | (lane << 4) | ((unsigned)((im >> (4 * k)) & 15ull) << 9));
+            total += __popc(m);
+        }
+        __syncwarp();
+        for (int pid = lane; pid < total; pid += 32) {         // dense clip
+            const unsigned e = wc.plist[pid];
+            const int k = e & 15, l = (e >> 4) & 31;
+            float area;
+            const bool ok = aa_clip<false>(srec + cand[k] * kRecStride, fx0 + (float)(l & 7), fy0 + (float)(l >> 3),
+                                           e >> 9, area, nullptr);
+            wc.parea[pid] = ok ? area : -1.0f;
+        }
+        __syncwarp();
+    }
+    sm_.hit = hit; sm_.part = part; sm_.base_reg = base_reg; sm_.mask_reg = mask_reg;
+}
+
+// Pops this lane's next hit of the sub-chunk (-1: none) and fetches its coverage area.
+// Must be called by all 32 lanes.  ok == false: the reference skips this (pixel, face) pair.
+__device__ __forceinline__ int subchunk_pop(SubMasks& sm_, bool allowed, const WarpClip& wc, int lane, bool use_aa,
+                                            float& area, bool& ok, bool& is_part) {
+    int k = -1;
+    if (allowed && sm_.hit) { k = __ffs(sm_.hit) - 1; sm_.hit &= sm_.hit - 1u; }
+    const int kk = k < 0 ? 0 : k;
+    const int b = __shfl_sync(0xffffffffu, sm_.base_reg, kk);
+    const uint32_t m = __shfl_sync(0xffffffffu, sm_.mask_reg, kk);
+    area = use_aa ? 1.0f : 0.0f;
+    ok = true;
+    is_part = false;
+    if (k >= 0 && ((sm_.part >> k) & 1u)) {
+        is_part = true;
+        area = wc.parea[b + __popc(m & ((1u << lane) - 1u))];
+        ok = !(area == -1.0f);
+    }
+    return k;
 }
 
 struct TileCtx {
@@ -244,6 +336,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
     uint8_t* cand = scand + warp * kStage;
+    WarpClip& wclip = reinterpret_cast<WarpClip*>(scand + 8 * kStage)[warp];
 
     PixelGeom pg;
     pg.pxmin = (float)((uint32_t)tc.px + (uint32_t)in.patch_min[2 * tc.b]);      // forward.cu:319-322
@@ -273,31 +366,36 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;
         const int n_cand = build_candidates(srec, cnt, use_aa, tc.fx0, tc.fy0, cand, lane);
-        // ---- classify: the warp walks its candidates in lock-step (broadcast smem reads, all lanes
-        //      busy); each lane keeps a private bit mask of the faces that touch ITS pixel
-        HitMasks hm;
-        classify_candidates(srec, cand, n_cand, use_aa, pg.pxmin, pg.pymin, !done, hm);
-        for (;;) {
-            // ---- every lane takes its own next hit (in list order); lanes work on different faces
-            bool is_part;
-            const int cpos = hm.pop(is_part);
-            if (!__any_sync(0xffffffffu, cpos >= 0)) break;
-            if (cpos >= 0) {
-                const int jj = cand[cpos];
-                const float* rec = srec + jj * kRecStride;
-                Shade s;
-                if (shade<false>(rec, pg, tau, is_part, s, nullptr)) {
-                    // forward.cu:398-415
-                    const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
-                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                    C0 = __fmaf_rn(__fmul_rn(s.iC[0], alpha), T, C0);   // C += iC*alpha*T
-                    C1 = __fmaf_rn(__fmul_rn(s.iC[1], alpha), T, C1);
-                    C2 = __fmaf_rn(__fmul_rn(s.iC[2], alpha), T, C2);
-                    D  = __fmaf_rn(__fmul_rn(s.iD, alpha), T, D);
-                    pT = T;
-                    T = test_T;
-                    last_contributor = (uint32_t)(base + jj + 1);
-                    if (T < kTEps) { done = true; hm.clear(); }
+        for (int sub = 0; sub < n_cand; sub += kSub) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const uint8_t* csub = cand + sub;
+            SubMasks sbm;
+            subchunk_prepare(srec, csub, min(kSub, n_cand - sub), use_aa, pg.pxmin, pg.pymin, !done, tc.fx0, tc.fy0,
+                             wclip, lane, sbm, [](int) { return true; });
+            for (;;) {
+                // ---- every lane takes its own next hit (in list order); lanes work on different faces
+                float area;
+                bool ok, is_part;
+                const int k = subchunk_pop(sbm, !done, wclip, lane, use_aa, area, ok, is_part);
+                if (!__any_sync(0xffffffffu, k >= 0)) break;
+                if (k >= 0 && ok) {
+                    const int jj = csub[k];
+                    const float* rec = srec + jj * kRecStride;
+                    Shade s;
+                    s.area = area;
+                    if (shade_tail(rec, pg, tau, s)) {
+                        // forward.cu:398-415
+                        const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
+                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        C0 = __fmaf_rn(__fmul_rn(s.iC[0], alpha), T, C0);   // C += iC*alpha*T
+                        C1 = __fmaf_rn(__fmul_rn(s.iC[1], alpha), T, C1);
+                        C2 = __fmaf_rn(__fmul_rn(s.iC[2], alpha), T, C2);
+                        D  = __fmaf_rn(__fmul_rn(s.iD, alpha), T, D);
+                        pT = T;
+                        T = test_T;
+                        last_contributor = (uint32_t)(base + jj + 1);
+                        if (T < kTEps) done = true;
+                    }
                 }
             }
         }
@@ -314,7 +412,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     }
 }
 
-constexpr size_t kFwdSmem = (size_t)kStage * kRecStride * 4 + 8 * kStage;
+constexpr size_t kFwdSmem = (size_t)kStage * kRecStride * 4 + 8 * kStage + 8 * sizeof(WarpClip);
 
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
                           float* out_color, float* out_depth, cudaStream_t s) {
