@@ -1,0 +1,525 @@
+// dm2_raster_bwd.cu — reverse-order backward pass of the tile compositor.
+// Behaviour of reference cuda_impl/backward.cu:17-532 (29 global atomics per (pixel, face)
+// contribution, 232 registers, a B*H*W*K*32-byte AA cache), re-designed for sm_100a.
+//
+// One CTA per 16x16 tile, one warp per 8x4 pixel block, one pixel per lane.  The tile's sorted list
+// is staged back-to-front in rounds of kStage records; everything else is WARP-LOCAL (no CTA
+// barrier besides the staging one).  Per sub-chunk of 8 candidates a warp does:
+//   1. lock-step classification (bbox + 12 half-plane tests) into per-lane hit / partial bit masks;
+//   2. a DENSE polygon clip over the warp's list of partially covered (pixel, face) pairs, which
+//      also yields the closed-form d(area)/d(aa verts); area + gradient go to a per-warp table;
+//   3. the pixel-sequential walk (each lane its own hits, back to front): recovers T (T /= 1-alpha)
+//      and computes dL/dalpha - the only order-dependent quantities - into a [candidate][lane] table;
+//   4. the face-parallel gradient phase: contributions are enumerated candidate-major straight from
+//      ballots (no queue, no sort, no atomics in shared memory); one THREAD per contribution
+//      recomputes the hit point and evaluates the 29 per-face gradient values (pixel constants are
+//      fetched from the owning lane with shuffles); the warp transposes them through shared memory,
+//      lane k sums column k over the run of one candidate and issues ONE coalesced 29-lane atomic
+//      per (warp, face) into the per-(view,face) 128-byte gradient record.
+// A second kernel scatters the records to the output tensors (or, on the fused path, chains them
+// through the perspective divide to d/d verts_proj).
+#include "dm2_raster_common.cuh"
+
+namespace dm2 {
+
+// =============================================================================== backward
+// reference cuda_impl/auxiliary.h:245-290 (note: `denom_inv` is taken BEFORE the max(), so the
+// clamp is inert; and the "v" derivative is built from dot(cross(T,E1),E2) exactly as upstream).
+__device__ __forceinline__ f3 scale3(const f3& a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 add3(const f3& a, const f3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 subn3(const f3& a, const f3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 neg3(const f3& a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ f3 crossn(const f3& a, const f3& b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float dotn(const f3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// a*s - t*b per component with the contraction nvcc applies to `x*y - z*w`
+__device__ __forceinline__ f3 fms3(const f3& a, float s, float t, const f3& b) {
+    return {__fmaf_rn(a.x, s, -__fmul_rn(t, b.x)), __fmaf_rn(a.y, s, -__fmul_rn(t, b.y)),
+            __fmaf_rn(a.z, s, -__fmul_rn(t, b.z))};
+}
+__device__ __forceinline__ f3 mul3(const f3& a, float s) { return {__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)}; }
+
+// The big gradients this produces are ill-conditioned (1/denom^2 with cancelling terms), so the
+// operation order is pinned to the reference's expressions with its FMA contraction pattern: results
+// then agree with the reference (and the oracle) far better than free-form re-association would.
+__device__ __forceinline__ void ray_tri_grad(const f3& o, const f3& d, const f3& p0, const f3& p1, const f3& p2,
+                                             f3& du_dp0, f3& du_dp1, f3& du_dp2, f3& dv_dp0, f3& dv_dp1,
+                                             f3& dv_dp2) {
+    const f3 T = sub3(o, p0), E1 = sub3(p1, p0), E2 = sub3(p2, p0);
+    const f3 PE = cross3(d, E2);
+    const float denom_sqrt = dot3(PE, E1);
+    const float denom = __fmul_rn(denom_sqrt, denom_sqrt);
+    const float denom_inv = __fdiv_rn(1.0f, denom);
+    const float v0 = dot3(PE, T);
+    const float v1 = denom_sqrt;
+    const float v2 = dot3(cross3(T, E1), E2);
+    const f3 du_dE1 = mul3(mul3(neg3(PE), v0), denom_inv);
+    const f3 du_dE2 = mul3(fms3(cross3(T, d), v1, v0, cross3(E1, d)), denom_inv);
+    const f3 du_dT  = mul3(mul3(PE, v1), denom_inv);
+    const f3 dv_dE1 = mul3(fms3(cross3(E2, T), v1, v2, PE), denom_inv);
+    const f3 dv_dE2 = mul3(fms3(cross3(T, E1), v1, v2, cross3(E1, d)), denom_inv);
+    const f3 dv_dT  = mul3(mul3(cross3(E1, E2), v1), denom_inv);
+    du_dp0 = sub3(sub3(neg3(du_dE1), du_dE2), du_dT);
+    dv_dp0 = sub3(sub3(neg3(dv_dE1), dv_dE2), dv_dT);
+    du_dp1 = du_dE1; dv_dp1 = dv_dE1;
+    du_dp2 = du_dE2; dv_dp2 = dv_dE2;
+}
+// dL_du * du + dL_dv * dv  ->  fma(dL_du, du, dL_dv * dv)
+__device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) {
+    return {__fmaf_rn(a, x.x, __fmul_rn(b, y.x)), __fmaf_rn(a, x.y, __fmul_rn(b, y.y)), __fmaf_rn(a, x.z, __fmul_rn(b, y.z))};
+}
+
+
+constexpr int kBStage = 64;                 // faces staged per round (backward)
+constexpr int kBSub = 8;                    // candidates per sub-chunk
+constexpr int kBPairCap = 32 * kBSub;       // 256 (pixel, face) pairs per warp per sub-chunk
+
+struct BwdWarpSmem {
+    float parea[kBPairCap];                 // overlap area (or -1: the reference skips the pair)
+    float pgrad[kBPairCap * 6];             // d area / d aa verts
+    float sT[kBSub * 32];                   // T before the contribution      [candidate][lane]
+    float sG[kBSub * 32];                   // dL/dalpha of the contribution   [candidate][lane]
+    float red[16 * 29];                     // half-warp transpose tile
+    uint16_t plist[kBPairCap];              // k | lane << 4 | inmask << 9
+    uint8_t cand[kBStage];
+};
+struct BwdSmem {
+    float srec[kBStage * kRecStride];
+    BwdWarpSmem w[8];
+    int max_last[8];
+};
+
+__global__ void __launch_bounds__(kRasterThreads, 2)
+k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
+                  const uint2* __restrict__ ranges, const float* __restrict__ final_T,
+                  const float* __restrict__ final_prev_T, const uint32_t* __restrict__ n_contrib,
+                  const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
+                  float* __restrict__ gface, int gx, int gy) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const TileCtx tc = tile_ctx(in, gx, gy);
+    const int warp = tc.warp, lane = tc.lane;
+    BwdWarpSmem& ws = sm.w[warp];
+    const float tau = in.aa_temperature;
+    const bool use_aa = tau > 0.0f;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    const uint2 range = ranges[blockIdx.x];
+    const size_t view_base = (size_t)tc.b * in.F;
+
+    // ---- per-pixel state (backward.cu:133-160)
+    PixelGeom pg;
+    pg.pxmin = (float)((uint32_t)tc.px + (uint32_t)in.patch_min[2 * tc.b]);
+    pg.pymin = (float)((uint32_t)tc.py + (uint32_t)in.patch_min[2 * tc.b + 1]);
+    pg.o = f3{0, 0, 0}; pg.d = f3{0, 0, 0};
+    float dC0 = 0.f, dC1 = 0.f, dC2 = 0.f, dD = 0.f;
+    float T_final = 0.0f, prev_T_final = 0.0f;
+    int my_last = 0;
+    if (tc.inside) {
+        const size_t rix = ray_index(in, tc);
+        const float* ro = in.image_ray_o + rix * 3;
+        const float* rd = in.image_ray_d + rix * 3;
+        pg.o = f3{ro[0], ro[1], ro[2]};
+        pg.d = f3{rd[0], rd[1], rd[2]};
+        dC0 = dL_dcolor[tc.pix * 3 + 0]; dC1 = dL_dcolor[tc.pix * 3 + 1]; dC2 = dL_dcolor[tc.pix * 3 + 2];
+        dD = dL_ddepth[tc.pix];
+        T_final = final_T[tc.pix];
+        prev_T_final = final_prev_T[tc.pix];
+        my_last = (int)n_contrib[tc.pix];
+    }
+    float T = prev_T_final;
+    bool first_pass = true;
+    float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f, accum_recd = 0.0f;
+    float last_alpha = 0.0f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f, last_depth = 0.0f;
+    float bg_dot = 0.0f;
+    bg_dot += in.background[0] * dC0; bg_dot += in.background[1] * dC1; bg_dot += in.background[2] * dC2;
+    const float bd_dot = dD;
+
+    // faces behind every pixel's last contributor are never touched (backward.cu:219-221)
+    const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
+    if (lane == 0) sm.max_last[warp] = warp_last;
+    __syncthreads();
+    int block_last = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) block_last = max(block_last, sm.max_last[i]);
+
+    for (int hi = block_last; hi > 0; hi -= kBStage) {
+        const int cnt = min(kBStage, hi);
+        __syncthreads();
+        // slot i holds list entry (hi-1-i): back to front
+        stage_records(sm.srec, records, list, (long long)range.x + hi - 1, -1, cnt, view_base);
+        __syncthreads();
+        if (hi - cnt >= warp_last) continue;                       // nothing for this warp in this round
+        const int n_cand = build_candidates(sm.srec, cnt, use_aa, tc.fx0, tc.fy0, ws.cand, lane);
+
+        for (int sub = 0; sub < n_cand; sub += kBSub) {
+            const uint8_t* csub = ws.cand + sub;
+            const int ncs = min(kBSub, n_cand - sub);
+
+            // ====== 1. lock-step classification
+            uint32_t hit = 0u, part = 0u, im = 0u;
+            for (int k = 0; k < ncs; k++) {
+                const int j = csub[k];
+                int cls = AA_FULL;
+                unsigned inmask = 0xF;
+                if (use_aa) cls = aa_classify(sm.srec + j * kRecStride, pg.pxmin, pg.pymin, inmask);
+                const bool on = tc.inside && (cls != AA_OUT) && (hi - 1 - j < my_last);
+                const bool p = on && (cls == AA_PART);
+                hit |= (on ? 1u : 0u) << k;
+                part |= (p ? 1u : 0u) << k;
+                if (p) im |= inmask << (4 * k);
+            }
+            if (!__any_sync(0xffffffffu, hit != 0u)) continue;
+
+            // ====== 2. pair list + dense clip with gradient
+            int pbase = 0;                    // lane k: pair-list base of candidate k
+            uint32_t pmask = 0u;              // lane k: lanes whose pixel is partially covered by candidate k
+            if (__any_sync(0xffffffffu, part != 0u)) {
+                int total = 0;
+                for (int k = 0; k < ncs; k++) {
+                    const bool p = (part >> k) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, p);
+                    if (lane == k) { pbase = total; pmask = m; }
+                    if (p) ws.plist[total + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 4) | (((im >> (4 * k)) & 15u) << 9));
+                    total += __popc(m);
+                }
+                __syncwarp();
+                for (int pid = lane; pid < total; pid += 32) {
+                    const unsigned e = ws.plist[pid];
+                    const int k = e & 15, l = (e >> 4) & 31;
+                    float area, g[6];
+                    const bool ok = aa_clip<true>(sm.srec + csub[k] * kRecStride, tc.fx0 + (float)(l & 7),
+                                                  tc.fy0 + (float)(l >> 3), e >> 9, area, g);
+                    ws.parea[pid] = ok ? area : -1.0f;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) ws.pgrad[pid * 6 + q] = g[q];
+                }
+                __syncwarp();
+            }
+
+            // ====== 3. pixel-sequential walk (back to front): T and dL/dalpha per contribution
+            uint32_t contrib = 0u;
+            for (;;) {
+                int k = -1;
+                if (hit) { k = __ffs(hit) - 1; hit &= hit - 1u; }
+                if (!__any_sync(0xffffffffu, k >= 0)) break;
+                const int kk = k < 0 ? 0 : k;
+                const int pb = __shfl_sync(0xffffffffu, pbase, kk);
+                const uint32_t pm = __shfl_sync(0xffffffffu, pmask, kk);
+                if (k < 0) continue;
+                Shade s;
+                s.area = use_aa ? 1.0f : 0.0f;
+                if ((part >> k) & 1u) {
+                    s.area = ws.parea[pb + __popc(pm & lt_mask)];
+                    if (s.area == -1.0f) continue;
+                }
+                const float* rec = sm.srec + csub[k] * kRecStride;
+                if (!shade_tail(rec, pg, tau, s)) continue;
+                const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
+                // backward.cu:340-348
+                if (!first_pass) T = T / (1.0f - alpha);
+                first_pass = false;
+                // backward.cu:357-405
+                float dL_dalpha = 0.0f;
+                accum_rec0 = last_alpha * last_c0 + (1.0f - last_alpha) * accum_rec0;
+                last_c0 = s.iC[0];
+                dL_dalpha += (s.iC[0] - accum_rec0) * dC0;
+                accum_rec1 = last_alpha * last_c1 + (1.0f - last_alpha) * accum_rec1;
+                last_c1 = s.iC[1];
+                dL_dalpha += (s.iC[1] - accum_rec1) * dC1;
+                accum_rec2 = last_alpha * last_c2 + (1.0f - last_alpha) * accum_rec2;
+                last_c2 = s.iC[2];
+                dL_dalpha += (s.iC[2] - accum_rec2) * dC2;
+                accum_recd = last_alpha * last_depth + (1.0f - last_alpha) * accum_recd;
+                last_depth = s.iD;
+                dL_dalpha += (s.iD - accum_recd) * dD;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                if (alpha == 1.0f) {
+                    dL_dalpha += (-prev_T_final) * bg_dot;
+                    dL_dalpha += (-prev_T_final) * bd_dot;
+                } else {
+                    dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                    dL_dalpha += (-T_final / (1.0f - alpha)) * bd_dot;
+                }
+                ws.sT[k * 32 + lane] = T;
+                ws.sG[k * 32 + lane] = dL_dalpha;
+                contrib |= 1u << k;
+            }
+            __syncwarp();
+
+            // ====== 4. face-parallel gradients: contributions enumerated candidate-major from ballots
+            uint32_t cmask[kBSub];
+            int cbase[kBSub + 1];
+            cbase[0] = 0;
+#pragma unroll
+            for (int k = 0; k < kBSub; k++) {
+                cmask[k] = __ballot_sync(0xffffffffu, (contrib >> k) & 1u);
+                cbase[k + 1] = cbase[k] + __popc(cmask[k]);
+            }
+            const int total_c = cbase[kBSub];
+            int cur_k = -1;
+            float carry = 0.0f;
+            for (int r0 = 0; r0 < total_c; r0 += 32) {
+                const int r = r0 + lane;
+                const bool act = r < total_c;
+                // record r -> (candidate k, owning lane src)
+                int k = 0;
+                uint32_t mk = cmask[0];
+                int bk = 0;
+#pragma unroll
+                for (int q = 1; q < kBSub; q++) {
+                    if (r >= cbase[q]) { k = q; mk = cmask[q]; bk = cbase[q]; }
+                }
+                const int src = act ? (int)__fns(mk, 0, r - bk + 1) : 0;
+                // pixel constants of the owning lane
+                const float ox = __shfl_sync(0xffffffffu, pg.o.x, src), oy = __shfl_sync(0xffffffffu, pg.o.y, src);
+                const float oz = __shfl_sync(0xffffffffu, pg.o.z, src), dx = __shfl_sync(0xffffffffu, pg.d.x, src);
+                const float dy = __shfl_sync(0xffffffffu, pg.d.y, src), dz = __shfl_sync(0xffffffffu, pg.d.z, src);
+                const float qC0 = __shfl_sync(0xffffffffu, dC0, src), qC1 = __shfl_sync(0xffffffffu, dC1, src);
+                const float qC2 = __shfl_sync(0xffffffffu, dC2, src), qD = __shfl_sync(0xffffffffu, dD, src);
+                const int pb = __shfl_sync(0xffffffffu, pbase, k);
+                const uint32_t pm = __shfl_sync(0xffffffffu, pmask, k);
+                float v[29];
+#pragma unroll
+                for (int q = 0; q < 29; q++) v[q] = 0.0f;
+                if (act) {
+                    const float* rec = sm.srec + csub[k] * kRecStride;
+                    PixelGeom qg;
+                    qg.pxmin = tc.fx0 + (float)(src & 7);
+                    qg.pymin = tc.fy0 + (float)(src >> 3);
+                    qg.o = f3{ox, oy, oz};
+                    qg.d = f3{dx, dy, dz};
+                    Shade s;
+                    s.area = use_aa ? 1.0f : 0.0f;
+                    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if ((pm >> src) & 1u) {
+                        const int pid = pb + __popc(pm & ((1u << src) - 1u));
+                        s.area = ws.parea[pid];
+#pragma unroll
+                        for (int q = 0; q < 6; q++) g[q] = ws.pgrad[pid * 6 + q];
+                    }
+                    shade_tail(rec, qg, tau, s);                   // succeeded in the walk: same function, same inputs
+                    const float Tq = ws.sT[k * 32 + src], dL_dalpha = ws.sG[k * 32 + src];
+                    const float opacity = rec[R_MISC + 1], intense = rec[R_MISC + 2];
+                    const float alpha = __fmul_rn(opacity, s.ratio);
+                    const float dL_diC[3] = {qC0 * alpha * Tq, qC1 * alpha * Tq, qC2 * alpha * Tq};
+                    const float dL_diD = qD * alpha * Tq;
+                    // backward.cu:408-415
+                    v[21] = dL_dalpha * s.ratio;
+                    const float dL_doarea = (dL_dalpha * opacity) * tau;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) v[23 + q] = dL_doarea * g[q];
+                    // backward.cu:420-455
+                    const float4 a0 = *reinterpret_cast<const float4*>(rec + R_P0);
+                    const float4 a1 = *reinterpret_cast<const float4*>(rec + R_P1);
+                    const float4 a2 = *reinterpret_cast<const float4*>(rec + R_P2);
+                    const float4 q0 = *reinterpret_cast<const float4*>(rec + R_COL);
+                    const float4 q1 = *reinterpret_cast<const float4*>(rec + R_COL + 4);
+                    const float q2b = rec[R_COL + 8];
+                    const float col0[3] = {q0.x, q0.y, q0.z}, col1[3] = {q0.w, q1.x, q1.y}, col2[3] = {q1.z, q1.w, q2b};
+                    float di0 = 0.f, di1 = 0.f, di2 = 0.f, dint = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        di0 += col0[ch] * dL_diC[ch] * intense;
+                        di1 += col1[ch] * dL_diC[ch] * intense;
+                        di2 += col2[ch] * dL_diC[ch] * intense;
+                        v[9 + ch]  = s.w0 * dL_diC[ch] * intense;
+                        v[12 + ch] = s.w1 * dL_diC[ch] * intense;
+                        v[15 + ch] = s.w2 * dL_diC[ch] * intense;
+                        dint += (s.w0 * col0[ch] + s.w1 * col1[ch] + s.w2 * col2[ch]) * dL_diC[ch];
+                    }
+                    v[22] = dint;
+                    di0 += a0.w * dL_diD; di1 += a1.w * dL_diD; di2 += a2.w * dL_diD;
+                    v[18] = s.w0 * dL_diD; v[19] = s.w1 * dL_diD; v[20] = s.w2 * dL_diD;
+                    // backward.cu:460-488, auxiliary.h:331-357
+                    float duc_du, duc_dv = 0.f, dvc_du = 0.f, dvc_dv;
+                    if (s.code == 0) { duc_du = 1.f; dvc_dv = 1.f; }
+                    else if (s.code <= 3) { duc_du = 0.f; dvc_dv = 0.f; }
+                    else if (s.code == 4) { duc_du = 0.f; dvc_dv = 1.f; }
+                    else if (s.code == 5) { duc_du = 1.f; dvc_dv = 0.f; }
+                    else { duc_du = 0.5f; dvc_du = -0.5f; duc_dv = -0.5f; dvc_dv = 0.5f; }
+                    const float di0_du = -duc_du - dvc_du, di0_dv = -duc_dv - dvc_dv;
+                    const float dL_du = di0 * di0_du + di1 * duc_du + di2 * dvc_du;
+                    const float dL_dv = di0 * di0_dv + di1 * duc_dv + di2 * dvc_dv;
+                    f3 du0, du1, du2, dv0, dv1, dv2;
+                    ray_tri_grad(qg.o, qg.d, f3{a0.x, a0.y, a0.z}, f3{a1.x, a1.y, a1.z}, f3{a2.x, a2.y, a2.z},
+                                 du0, du1, du2, dv0, dv1, dv2);
+                    const f3 g0 = comb3(dL_du, du0, dL_dv, dv0);
+                    const f3 g1 = comb3(dL_du, du1, dL_dv, dv1);
+                    const f3 g2 = comb3(dL_du, du2, dL_dv, dv2);
+                    v[0] = g0.x; v[1] = g0.y; v[2] = g0.z;
+                    v[3] = g1.x; v[4] = g1.y; v[5] = g1.z;
+                    v[6] = g2.x; v[7] = g2.y; v[8] = g2.z;
+                }
+                // ---- transpose through smem (two half-warps); lane c sums column c over one candidate's run
+                const int myk = act ? k : -1;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if ((lane >> 4) == h) {
+#pragma unroll
+                        for (int q = 0; q < 29; q++) ws.red[(lane & 15) * 29 + q] = v[q];
+                    }
+                    __syncwarp();
+#pragma unroll 4
+                    for (int rr = 0; rr < 16; rr++) {
+                        const int sk = __shfl_sync(0xffffffffu, myk, h * 16 + rr);
+                        if (lane < 29) {
+                            if (sk != cur_k) {
+                                if (cur_k >= 0 && carry != 0.0f) {
+                                    const int fid = __float_as_int(sm.srec[csub[cur_k] * kRecStride + R_FID]);
+                                    atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
+                                }
+                                cur_k = sk;
+                                carry = 0.0f;
+                            }
+                            if (sk >= 0) carry += ws.red[rr * 29 + lane];
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane < 29 && cur_k >= 0 && carry != 0.0f) {
+                const int fid = __float_as_int(sm.srec[csub[cur_k] * kRecStride + R_FID]);
+                atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Scatter the per-(view,face) gradient records to the reference's six gradient tensors
+// (render.cu:313-318).  Outputs are caller-zeroed; per-face outputs have a single writer.
+__global__ void __launch_bounds__(256)
+k_grad_scatter(int B, int P, int F, const int32_t* __restrict__ faces, const uint32_t* __restrict__ tiles_touched,
+               const float* __restrict__ gface, DM2RenderGrads gr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * F) return;
+    if (tiles_touched[idx] == 0) return;
+    const int b = (int)(idx / F), f = (int)(idx % F);
+    const float4* g4 = reinterpret_cast<const float4*>(gface + (size_t)idx * kGradWords);
+    float g[32];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const float4 t = g4[k]; g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int v = faces[3 * (size_t)f + i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (g[3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts + 3 * (size_t)v + c, g[3 * i + c]);
+            if (g[9 + 3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts_color + 3 * (size_t)v + c, g[9 + 3 * i + c]);
+        }
+        if (g[18 + i] != 0.0f) atomicAdd(gr.dL_dverts_ndc + 3 * ((size_t)b * P + v) + 2, g[18 + i]);
+    }
+    if (g[21] != 0.0f) atomicAdd(gr.dL_dfaces_opacity + f, g[21]);
+    gr.dL_dfaces_intense[idx] = g[22];
+#pragma unroll
+    for (int k = 0; k < 6; k++) gr.dL_daa_face_verts[(size_t)idx * 6 + k] = g[23 + k];
+}
+
+// Fused-path scatter: same per-face record, but the screen-space part (d/d aa verts, d/d ndc.z) is
+// chained through the CCW swap, the image transform and the perspective divide down to
+// d/d verts_proj (what torch autograd does for the reference's host prep, __init__.py:251-260 and
+// pyrenderer.py:6-30), with one 16-byte vector reduction per (view, face, vertex).
+__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touched, const float* __restrict__ records,
+                     const float* __restrict__ gface, DM2FusedGrads gr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)in.B * in.F) return;
+    if (tiles_touched[idx] == 0) return;
+    const int b = (int)(idx / in.F), f = (int)(idx % in.F);
+    const float4* g4 = reinterpret_cast<const float4*>(gface + (size_t)idx * kGradWords);
+    float g[32];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const float4 t = g4[k]; g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w; }
+    const bool flip = (__float_as_uint(records[(size_t)idx * kRecWords + R_MISC + 3]) >> 8) & 1u;
+    const float4* vp = reinterpret_cast<const float4*>(in.verts_proj) + (size_t)b * in.P;
+    const float fw = (float)in.image_w, fh = (float)in.image_h;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int v = in.faces[3 * (size_t)f + i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (g[3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts + 3 * (size_t)v + c, g[3 * i + c]);
+            if (g[9 + 3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts_color + 3 * (size_t)v + c, g[9 + 3 * i + c]);
+        }
+        // aa verts are (v0, v2, v1) when the face was flipped to CCW
+        const int k = (i == 0) ? 0 : (flip ? 3 - i : i);
+        const float dix = (k == 0) ? g[23] : ((k == 1) ? g[25] : g[27]);
+        const float diy = (k == 0) ? g[24] : ((k == 1) ? g[26] : g[28]);
+        const float dz = g[18 + i];
+        if (dix != 0.0f || diy != 0.0f || dz != 0.0f) {
+            const float4 c = vp[v];
+            float w = c.w;
+            bool clamped = false;
+            if (w >= 0.0f && w < 1e-4f) { w = 1e-4f; clamped = true; }
+            if (w < 0.0f && w > -1e-4f) { w = -1e-4f; clamped = true; }
+            const float nx = c.x / w, ny = c.y / w, nz = c.z / w;
+            const float dnx = (dix * fw) * 0.5f, dny = (diy * fh) * 0.5f;
+            const float dw = clamped ? 0.0f : -(dnx * nx + dny * ny + dz * nz) / w;
+            red_add_v4(gr.dL_dverts_proj + 4 * ((size_t)b * in.P + v), dnx / w, dny / w, dz / w, dw);
+        }
+    }
+    if (g[21] != 0.0f) atomicAdd(gr.dL_dfaces_opacity + f, g[21]);
+    gr.dL_dfaces_intense[idx] = g[22];
+}
+
+size_t backward_ws_bytes(long long BF) { return align_up((size_t)BF * kGradWords * 4, 256) + 256; }
+
+int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
+                              cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    ProfScope _ps("grad_scatter", s);
+    k_fused_grad_scatter<<<cdiv(BF, 256), 256, 0, s>>>(in, fw.tiles_touched, fw.records,
+                                                       reinterpret_cast<const float*>(grad_ws), g);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
+                        cudaStream_t s) {
+    const long long BF = (long long)in.B * in.F;
+    if (BF == 0) return 0;
+    ProfScope _ps("grad_scatter", s);
+    k_grad_scatter<<<cdiv(BF, 256), 256, 0, s>>>(in.B, in.P, in.F, in.faces, fw.tiles_touched,
+                                                 reinterpret_cast<const float*>(grad_ws), g);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+// zero the per-face gradient records and run the tile kernel; the caller scatters afterwards
+int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
+                           const float* dL_dcolor, const float* dL_ddepth, void* grad_ws, cudaStream_t s) {
+    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    const long long nblk = (long long)in.B * gx * gy;
+    const long long BF = (long long)in.B * in.F;
+    if (nblk == 0 || BF == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DM2_CHECK(cudaFuncSetAttribute(k_raster_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem)));
+        attr_set = true;
+    }
+    float* gface = reinterpret_cast<float*>(grad_ws);
+    {
+        ProfScope _ps("grad_zero", s);
+        DM2_CHECK(cudaMemsetAsync(gface, 0, (size_t)BF * kGradWords * 4, s));
+    }
+    {
+        ProfScope _ps("raster_backward", s);
+        k_raster_backward<<<(unsigned)nblk, kRasterThreads, sizeof(BwdSmem), s>>>(
+            in, fw.records, bw.vals, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor, dL_ddepth,
+            gface, gx, gy);
+        DM2_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace dm2
