@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -32,7 +32,7 @@ class DM2FusedInputs(C.Structure):
         ("B", C.c_int32), ("P", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("image_h", C.c_int32), ("image_w", C.c_int32), ("aa_temperature", C.c_float),
         ("background", C.c_void_p), ("patch_min", C.c_void_p), ("verts", C.c_void_p), ("faces", C.c_void_p),
-        ("verts_color", C.c_void_p), ("faces_opacity", C.c_void_p), ("verts_proj", C.c_void_p),
+        ("verts_color", C.c_void_p), ("faces_opacity", C.c_void_p), ("mv", C.c_void_p), ("proj", C.c_void_p),
         ("faces_intense", C.c_void_p), ("ray_o", C.c_void_p), ("ray_d", C.c_void_p), ("ray_view", C.c_void_p),
     ]
 
@@ -40,7 +40,7 @@ class DM2FusedInputs(C.Structure):
 class DM2FusedGrads(C.Structure):
     _fields_ = [
         ("dL_dverts", C.c_void_p), ("dL_dverts_color", C.c_void_p), ("dL_dfaces_opacity", C.c_void_p),
-        ("dL_dfaces_intense", C.c_void_p), ("dL_dverts_proj", C.c_void_p),
+        ("dL_dfaces_intense", C.c_void_p),
     ]
 
 

@@ -146,11 +146,12 @@ k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths
     const int b = (int)(idx / in.F), f = (int)(idx % in.F);
     const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
     const uint32_t pmx = (uint32_t)in.patch_min[2 * b], pmy = (uint32_t)in.patch_min[2 * b + 1];
-    const float4* vp = reinterpret_cast<const float4*>(in.verts_proj) + (size_t)b * in.P;
+    const float* mvb = in.mv + 16 * (size_t)b;
+    const float* prb = in.proj + 16 * (size_t)b;
     const float fw = (float)in.image_w, fh = (float)in.image_h;
-    const ProjVert a0 = project_vertex(vp[v0], fw, fh);
-    const ProjVert a1 = project_vertex(vp[v1], fw, fh);
-    const ProjVert a2 = project_vertex(vp[v2], fw, fh);
+    const ProjVert a0 = project_vertex(clip_vertex(in.verts + 3 * (size_t)v0, mvb, prb), fw, fh);
+    const ProjVert a1 = project_vertex(clip_vertex(in.verts + 3 * (size_t)v1, mvb, prb), fw, fh);
+    const ProjVert a2 = project_vertex(clip_vertex(in.verts + 3 * (size_t)v2, mvb, prb), fw, fh);
 
     // ---- preprocessFaceCUDA (reference forward.cu:41-107), same chain as preprocess_face()
     const float max_z = fmaxf(fmaxf(a0.nz, a1.nz), a2.nz);

@@ -280,6 +280,7 @@ static int check_fused_inputs(const DM2FusedInputs* in) {
     DM2_REQUIRE(in != nullptr, "inputs must not be null");
     DM2_REQUIRE(in->B >= 0 && in->P >= 0 && in->F >= 0 && in->H >= 0 && in->W >= 0, "negative dimension");
     DM2_REQUIRE(in->image_h >= in->H && in->image_w >= in->W, "patch larger than the frame");
+    DM2_REQUIRE(in->B == 0 || (in->mv && in->proj), "mv / proj must not be null");
     DM2_REQUIRE(in->aa_temperature >= 0.0f && in->aa_temperature <= 1.0f, "aa_temperature must be in the range [0, 1]");
     DM2_REQUIRE((long long)in->B * in->F < (1ll << 31), "B*F must be < 2^31");
     DM2_REQUIRE((long long)in->B * in->H * in->W < (1ll << 31), "B*H*W must be < 2^31");
@@ -323,8 +324,8 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
     if (check_fused_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
                 "dm2_fused_backward: null buffer");
-    DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dfaces_intense &&
-                grads->dL_dverts_proj, "dm2_fused_backward: null gradient buffer");
+    DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dfaces_intense,
+                "dm2_fused_backward: null gradient buffer");
     if (in->F == 0 || num_rendered == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;

@@ -152,6 +152,22 @@ __device__ __forceinline__ void patch_rect(uint32_t pmx, uint32_t pmy, float p0x
     y1 = min(gy, max(0, iy1));
 }
 
+// clip = ([v,1] mv^T) proj^T with the accumulation order cuBLAS uses for these K=4 products on
+// sm_100 (k = 0..3, first term a plain product, then fma) - bit-identical to torch.matmul
+// (tools/probe_matmul_rounding.py).  m / p: row-major 4x4.
+__device__ __forceinline__ float4 clip_vertex(const float* __restrict__ v, const float* __restrict__ m,
+                                              const float* __restrict__ p) {
+    float vw[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        vw[j] = __fmaf_rn(1.0f, m[4 * j + 3], __fmaf_rn(v[2], m[4 * j + 2], __fmaf_rn(v[1], m[4 * j + 1], __fmul_rn(v[0], m[4 * j]))));
+    float c[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        c[j] = __fmaf_rn(vw[3], p[4 * j + 3], __fmaf_rn(vw[2], p[4 * j + 2], __fmaf_rn(vw[1], p[4 * j + 1], __fmul_rn(vw[0], p[4 * j]))));
+    return make_float4(c[0], c[1], c[2], c[3]);
+}
+
 __device__ __forceinline__ float clamp01_depth(float z) {
     float d = __fmul_rn(__fadd_rn(z, 1.0f), 0.5f);
     if (d < 0.0f) d = 0.0f;

@@ -439,31 +439,40 @@ k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touch
 #pragma unroll
     for (int k = 0; k < 8; k++) { const float4 t = g4[k]; g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w; }
     const bool flip = (__float_as_uint(records[(size_t)idx * kRecWords + R_MISC + 3]) >> 8) & 1u;
-    const float4* vp = reinterpret_cast<const float4*>(in.verts_proj) + (size_t)b * in.P;
+    const float* mvb = in.mv + 16 * (size_t)b;
+    const float* prb = in.proj + 16 * (size_t)b;
     const float fw = (float)in.image_w, fh = (float)in.image_h;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int v = in.faces[3 * (size_t)f + i];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            if (g[3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts + 3 * (size_t)v + c, g[3 * i + c]);
-            if (g[9 + 3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts_color + 3 * (size_t)v + c, g[9 + 3 * i + c]);
-        }
+        float dv[3] = {g[3 * i], g[3 * i + 1], g[3 * i + 2]};        // hit-point path (d/d world-space vertex)
         // aa verts are (v0, v2, v1) when the face was flipped to CCW
         const int k = (i == 0) ? 0 : (flip ? 3 - i : i);
         const float dix = (k == 0) ? g[23] : ((k == 1) ? g[25] : g[27]);
         const float diy = (k == 0) ? g[24] : ((k == 1) ? g[26] : g[28]);
         const float dz = g[18 + i];
         if (dix != 0.0f || diy != 0.0f || dz != 0.0f) {
-            const float4 c = vp[v];
+            // image -> ndc -> clip (w clamp blocks the gradient, as torch.where does) -> view -> world
+            const float4 c = clip_vertex(in.verts + 3 * (size_t)v, mvb, prb);
             float w = c.w;
             bool clamped = false;
             if (w >= 0.0f && w < 1e-4f) { w = 1e-4f; clamped = true; }
             if (w < 0.0f && w > -1e-4f) { w = -1e-4f; clamped = true; }
             const float nx = c.x / w, ny = c.y / w, nz = c.z / w;
             const float dnx = (dix * fw) * 0.5f, dny = (diy * fh) * 0.5f;
-            const float dw = clamped ? 0.0f : -(dnx * nx + dny * ny + dz * nz) / w;
-            red_add_v4(gr.dL_dverts_proj + 4 * ((size_t)b * in.P + v), dnx / w, dny / w, dz / w, dw);
+            const float dc[4] = {dnx / w, dny / w, dz / w, clamped ? 0.0f : -(dnx * nx + dny * ny + dz * nz) / w};
+            float dview[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                dview[q] = dc[0] * prb[q] + dc[1] * prb[4 + q] + dc[2] * prb[8 + q] + dc[3] * prb[12 + q];
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                dv[q] += dview[0] * mvb[q] + dview[1] * mvb[4 + q] + dview[2] * mvb[8 + q] + dview[3] * mvb[12 + q];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (dv[c] != 0.0f) atomicAdd(gr.dL_dverts + 3 * (size_t)v + c, dv[c]);
+            if (g[9 + 3 * i + c] != 0.0f) atomicAdd(gr.dL_dverts_color + 3 * (size_t)v + c, g[9 + 3 * i + c]);
         }
     }
     if (g[21] != 0.0f) atomicAdd(gr.dL_dfaces_opacity + f, g[21]);

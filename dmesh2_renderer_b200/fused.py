@@ -2,12 +2,13 @@
 
 The reference's ``Renderer.forward`` runs ~25 torch kernels of host-side prep before its single
 autograd Function (dmesh2_renderer/__init__.py:325-347, pyrenderer.py:6-30) and autograd replays
-them backwards.  ``FusedRenderFunction`` starts from the clip-space vertices (the two matmuls stay
-in torch so their rounding is the reference's) and lets the preprocess kernel do the w clamp, the
-perspective divide, the image transform, the per-face gather, the CCW re-ordering and the derived
-AA terms with the same IEEE operations in the same order; the backward scatter kernel applies the
-matching chain rule down to d/d verts_proj.  Colour/depth, sort order and tile ranges are
-bit-identical to the unfused ``RenderFunction`` path (tests/test_gpu_parity.py).
+them backwards.  ``FusedRenderFunction`` takes the vertices and the selected mv / proj matrices and
+lets the preprocess kernel do everything: the two K=4 matmuls (as the fma chain cuBLAS runs for
+them, bit-for-bit), the w clamp, the perspective divide, the image transform, the per-face gather,
+the CCW re-ordering and the derived AA terms, with the same IEEE operations in the same order; the
+backward scatter kernel applies the matching chain rule down to d/d verts.  Colour/depth, sort
+order and tile ranges are bit-identical to the unfused ``RenderFunction`` path
+(tests/test_gpu_parity.py::test_fused_path_equals_reference_shaped_path).
 """
 import ctypes as C
 
@@ -19,13 +20,14 @@ from ._lib import DM2FusedGrads, DM2FusedInputs
 
 
 def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
-                  verts_proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
+                  mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
     f32, i32 = torch.float32, torch.int32
     keep = dict(background=_prep(background, f32, "background"), patch_min=_prep(patch_min, i32, "patch_min"),
                 verts=_prep(verts, f32, "verts"), faces=_prep(faces, i32, "faces"),
                 verts_color=_prep(verts_color, f32, "verts_color"),
                 faces_opacity=_prep(faces_opacity, f32, "faces_opacity"),
-                verts_proj=_prep(verts_proj, f32, "verts_proj"), faces_intense=_prep(faces_intense, f32, "faces_intense"),
+                mv=_prep(mv, f32, "mv"), proj=_prep(proj, f32, "proj"),
+                faces_intense=_prep(faces_intense, f32, "faces_intense"),
                 ray_o=_prep(ray_o, f32, "ray_o"), ray_d=_prep(ray_d, f32, "ray_d"),
                 ray_view=_prep(ray_view, i32, "ray_view"))
     if keep["background"].dim() != 1 or keep["background"].size(0) != 3:
@@ -35,10 +37,9 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
     if keep["faces"].dim() != 2 or keep["faces"].size(1) != 3:
         _err("faces must have dimensions (F, 3)")
     P, F = int(keep["verts"].size(0)), int(keep["faces"].size(0))
-    vp = keep["verts_proj"]
-    if vp.dim() != 3 or vp.size(1) != P or vp.size(2) != 4:
-        _err("verts_proj must have dimensions (B, P, 4)")
-    B = int(vp.size(0))
+    if keep["mv"].dim() != 3 or tuple(keep["mv"].shape[1:]) != (4, 4) or keep["mv"].shape != keep["proj"].shape:
+        _err("mv / proj must have dimensions (B, 4, 4)")
+    B = int(keep["mv"].size(0))
     if tuple(keep["verts_color"].shape) != (P, 3):
         _err("vert color must have dimensions (P, 3)")
     if tuple(keep["faces_opacity"].shape) != (F,):
@@ -62,15 +63,16 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
 
 
 class FusedRenderFunction(torch.autograd.Function):
-    """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, verts_proj,
-    faces_intense, aa_temperature, ray_o, ray_d, ray_view) -> (color [B,H,W,3], depth_ndc [B,H,W])."""
+    """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, mv [B,4,4], proj [B,4,4],
+    faces_intense, aa_temperature, ray_o, ray_d, ray_view) -> (color [B,H,W,3], depth_ndc [B,H,W]).
+    Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense."""
 
     @staticmethod
     def forward(ctx, background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
-                verts_proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
+                mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
         lib = _lib.load_library()
         s, keep = _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
-                                faces_opacity, verts_proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view)
+                                faces_opacity, mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view)
         dev = keep["verts"].device
         B, H, W = s.B, s.H, s.W
         with torch.cuda.device(dev):
@@ -99,7 +101,7 @@ class FusedRenderFunction(torch.autograd.Function):
         keep = dict(zip(ctx.keys, saved[:len(ctx.keys)]))
         face_buffer, binning_buffer, image_buffer = saved[len(ctx.keys):]
         s, keep = _fused_struct(keep["background"], keep["patch_min"], ctx.patch[0], ctx.patch[1], keep["verts"],
-                                keep["faces"], keep["verts_color"], keep["faces_opacity"], keep["verts_proj"],
+                                keep["faces"], keep["verts_color"], keep["faces_opacity"], keep["mv"], keep["proj"],
                                 keep["faces_intense"], ctx.aa_temperature, keep["ray_o"], keep["ray_d"],
                                 keep["ray_view"])
         dev = keep["verts"].device
@@ -110,14 +112,13 @@ class FusedRenderFunction(torch.autograd.Function):
             g_color = torch.zeros_like(keep["verts_color"])
             g_opacity = torch.zeros_like(keep["faces_opacity"])
             g_intense = torch.zeros_like(keep["faces_intense"])
-            g_proj = torch.zeros_like(keep["verts_proj"])
             if s.F != 0:
-                g = DM2FusedGrads(g_verts.data_ptr(), g_color.data_ptr(), g_opacity.data_ptr(), g_intense.data_ptr(),
-                                  g_proj.data_ptr())
+                g = DM2FusedGrads(g_verts.data_ptr(), g_color.data_ptr(), g_opacity.data_ptr(), g_intense.data_ptr())
                 nb = C.c_size_t(0)
                 _lib.check(lib.dm2_backward_workspace_bytes(s.B, s.F, C.byref(nb)))
                 grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
                 _lib.check(lib.dm2_fused_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
                                                   _ptr(image_buffer), ctx.num_rendered, _ptr(gc), _ptr(gd),
                                                   C.byref(g), _ptr(grad_ws), _stream(dev)))
-        return (None, None, None, None, g_verts, None, g_color, g_opacity, g_proj, g_intense, None, None, None, None)
+        return (None, None, None, None, g_verts, None, g_color, g_opacity, None, None, g_intense, None, None, None,
+                None)

@@ -125,27 +125,23 @@ class Renderer(torch.nn.Module):
     def _forward_fused(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
                        faces_opacity, faces_intense, background, aa_temperature):
         """Same result as the reference-shaped path below, with the host prep done inside the kernels
-        (fused.py).  Only the two clip-space matmuls stay in torch."""
+        (fused.py), including the two clip-space matmuls (same fma chain as cuBLAS, bit for bit)."""
         from .fused import FusedRenderFunction
         key = tuple(int(i) for i in batch_mvp_idx)
         cache = self.__dict__.setdefault("_view_cache", {})
         if key not in cache:
             cache[key] = torch.tensor(list(key), dtype=torch.int32, device=self.ray_o.device)
         ray_view = cache[key]
-        # same operand layout as compute_verts_ndc_image (transposed VIEWS of the gathered matrices), so
-        # cuBLAS runs the same kernels and the clip-space vertices are bit-identical to the unfused path
-        mv_t, proj_t = self.mv[batch_mvp_idx].transpose(1, 2), self.proj[batch_mvp_idx].transpose(1, 2)
         x0, y0 = batch_patch_min[:, 0], batch_patch_min[:, 1]
         assert (x0 + patch_width <= self.width).all(), "Some b_patch_max_x exceed self.width"
         assert (y0 + patch_height <= self.height).all(), "Some b_patch_max_y exceed self.height"
         f32 = torch.float32
-        hom = torch.cat((verts, torch.ones_like(verts[:, [0]])), dim=-1)
-        clip = torch.matmul(torch.matmul(hom, mv_t), proj_t)                       # [B, P, 4]
         dev = verts.device
         return FusedRenderFunction.apply(
             background.to(dtype=f32), batch_patch_min.to(device=dev, dtype=torch.int32), patch_width, patch_height,
             verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
-            clip.to(dtype=f32), faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view)
+            self.mv[batch_mvp_idx].to(dtype=f32), self.proj[batch_mvp_idx].to(dtype=f32),
+            faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view)
 
     def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
                        faces_opacity, faces_intense, background, aa_temperature=1.0):

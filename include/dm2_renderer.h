@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 5
+#define DM2_ABI_VERSION 6
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -173,11 +173,12 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
  * (reference dmesh2_renderer/__init__.py:239-262, 335-347 and pyrenderer.py:6-30): the w clamp and
  * perspective divide, the image transform, the per-face gather, the CCW re-ordering and the five
  * derived AA tensors, plus the ray patch gather - and autograd replays all of it backwards.  The
- * fused entry points start from the clip-space vertices  verts_proj = [verts,1] mv^T proj^T
- * (B,P,4; the two matmuls stay in torch/cuBLAS so their rounding is the reference's) and perform
- * every later step inside the preprocess kernel with the same IEEE operations in the same order
- * (the packed records, tile bboxes and depth keys are bit-identical to the unfused path), and the
- * backward scatter kernel applies the matching chain rule down to d/d verts_proj.
+ * fused entry points take verts and the selected mv / proj matrices and perform every step inside
+ * the preprocess kernel with the same IEEE operations in the same order: the two K=4 matmuls as the
+ * fma chain cuBLAS runs for them on sm_100 (k = 0..3, first term a plain product; verified
+ * bit-for-bit by tools/probe_matmul_rounding.py), then clamp / divide / image transform / CCW /
+ * AA terms.  The packed records, tile bboxes and depth keys are bit-identical to the unfused path;
+ * the backward scatter kernel applies the matching chain rule down to d/d verts.
  * Rays are read straight from the renderer's full-resolution ray buffers.                          */
 typedef struct DM2FusedInputs {
     int32_t B, P, F;             /* views in this call, vertices, faces                            */
@@ -190,7 +191,8 @@ typedef struct DM2FusedInputs {
     const int32_t* faces;        /* (F,3)                                                          */
     const float*   verts_color;  /* (P,3)                                                          */
     const float*   faces_opacity;/* (F)                                                            */
-    const float*   verts_proj;   /* (B,P,4) clip-space vertices                                    */
+    const float*   mv;           /* (B,4,4) model-view of each batch entry, row-major              */
+    const float*   proj;         /* (B,4,4) projection of each batch entry, row-major              */
     const float*   faces_intense;/* (B,F)                                                          */
     const float*   ray_o;        /* (V,image_h,image_w,3) full-resolution rays of ALL views        */
     const float*   ray_d;
@@ -198,11 +200,10 @@ typedef struct DM2FusedInputs {
 } DM2FusedInputs;
 
 typedef struct DM2FusedGrads {   /* caller-zeroed */
-    float* dL_dverts;            /* (P,3)   through the ray/triangle hit point                     */
+    float* dL_dverts;            /* (P,3)   hit point + depth (z/w) + AA coverage (x/w, y/w) paths */
     float* dL_dverts_color;      /* (P,3)                                                          */
     float* dL_dfaces_opacity;    /* (F)                                                            */
     float* dL_dfaces_intense;    /* (B,F)                                                          */
-    float* dL_dverts_proj;       /* (B,P,4) through depth (z/w) and AA coverage (x/w, y/w)         */
 } DM2FusedGrads;
 
 int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream);
