@@ -305,10 +305,18 @@ def main():
             dom_ms = stages[dom][0] / max(stages[dom][1], 1)
             ab = algorithmic_bytes(dom, 1, P, F, H, W, R)
             achieved = ab / (dom_ms * 1e-3) / 1e9 if ab else None
+            # DRAM traffic of that kernel per launch from the committed ncu --set full capture of this
+            # same workload (profiles/r01_ncu_kernels.md); only quoted for the default cfg2 workload
+            traffic = None
+            tj = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+            if os.path.exists(tj) and args.faces == 1_000_000 and args.size == 1024:
+                with open(tj) as fh:
+                    traffic = json.load(fh)["bytes_per_launch"].get("k_" + dom)
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                               "frac": (achieved / peak) if achieved else None, "traffic": None,
+                               "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                                "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": dom_ms,
-                               "note": "kernel is issue/latency bound, not HBM bound (see profiles/ and DESIGN.md)"}
+                               "note": "kernel is ALU-pipe / issue bound, not HBM bound: hundreds of fp32 compare/"
+                                       "select/fma instructions per covered (pixel, face) pair (profiles/r01_ncu_kernels.md)"}
             out["stages_ms_per_step"] = {k: v[0] / args.steps for k, v in stages.items()}
             out["num_rendered"] = R
             sort_ms = stages.get("radix_sort", (0, 0))[0] / args.steps
