@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -73,7 +73,7 @@ class DM2ImageLayout(C.Structure):
 
 
 class DM2BinningLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("keys_unsorted", "vals_unsorted", "keys", "vals", "sort_temp", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("keys_unsorted", "vals_unsorted", "keys", "vals", "sort_temp", "imask", "total")]
 
 
 # every symbol declared in include/dm2_renderer.h: (restype, argtypes)

@@ -567,10 +567,16 @@ int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, 
     return 0;
 }
 
-// ------------------------------------------------------------------ tile ranges
-// reference renderer.cu:470-492 (+ the memset at :211)
+// ------------------------------------------------------------------ tile ranges + footprint masks
+// reference renderer.cu:470-492 (+ the memset at :211).  For the render path the same pass also writes
+// one byte per sorted instance: bit w = the face's AA bounding box (aa.h:96-101) overlaps the 8x4
+// pixel footprint of warp w of its tile ((w & 1) * 8, (w >> 1) * 4) - the tile kernels build their
+// per-warp candidate lists from it with one coalesced byte load per instance.  With
+// aa_temperature == 0 the reference runs the ray test on every listed face: all bits set.
 __global__ void __launch_bounds__(256)
-k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges) {
+k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges,
+              const uint32_t* __restrict__ vals, const float* __restrict__ records, const int32_t* __restrict__ patch_min,
+              uint8_t* __restrict__ imask, int F, int gx, int gy, int use_bbox) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R) return;
     const uint32_t cur = (uint32_t)(keys[idx] >> 32);
@@ -580,13 +586,37 @@ k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__
         if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
     }
     if (idx == R - 1) ranges[cur].y = R;
+    if (imask == nullptr) return;
+    unsigned m = 0xFFu;
+    if (use_bbox) {
+        const uint32_t tiles = (uint32_t)(gx * gy);
+        const uint32_t b = cur / tiles, t_in = cur % tiles;
+        const uint32_t tx = t_in % (uint32_t)gx, ty = t_in / (uint32_t)gx;
+        const float4 bb = *reinterpret_cast<const float4*>(records + ((size_t)b * F + vals[idx]) * kRecWords + R_BBOX);
+        const uint32_t pmx = (uint32_t)patch_min[2 * b], pmy = (uint32_t)patch_min[2 * b + 1];
+        m = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const float fx0 = (float)(tx * kTile + (w & 1) * 8 + pmx);
+            const float fy0 = (float)(ty * kTile + (w >> 1) * 4 + pmy);
+            const bool hit = !((fx0 + 8.0f < bb.x) || (fx0 > bb.y) || (fy0 + 4.0f < bb.z) || (fy0 > bb.w));
+            m |= (hit ? 1u : 0u) << w;
+        }
+    }
+    imask[idx] = (uint8_t)m;
 }
 
-int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, cudaStream_t s) {
+int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, const TileMaskArgs* tm,
+                       cudaStream_t s) {
     DM2_CHECK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
     if (R > 0) {
         ProfScope _ps("tile_ranges", s);
-        k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges);
+        if (tm)
+            k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges, tm->vals, tm->records, tm->patch_min,
+                                                       tm->imask, tm->F, tm->gx, tm->gy, tm->use_bbox);
+        else
+            k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges, nullptr, nullptr, nullptr, nullptr,
+                                                       0, 1, 1, 0);
         DM2_LAUNCH_CHECK();
     }
     return 0;

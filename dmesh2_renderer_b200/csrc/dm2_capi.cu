@@ -110,6 +110,7 @@ static void binning_layout(long long R, DM2BinningLayout* L) {
     L->keys          = take((size_t)R * 8);
     L->vals          = take((size_t)R * 4);
     L->sort_temp     = take(sort_temp_bytes(R));
+    L->imask         = take((size_t)R);
     L->total         = off + 256;
 }
 
@@ -139,6 +140,7 @@ static BinWs carve_bin(void* ws, long long R) {
     b.keys_unsorted = (uint64_t*)(p + L.keys_unsorted); b.vals_unsorted = (uint32_t*)(p + L.vals_unsorted);
     b.keys = (uint64_t*)(p + L.keys); b.vals = (uint32_t*)(p + L.vals);
     b.sort_temp = p + L.sort_temp; b.sort_temp_bytes = sort_temp_bytes(R);
+    b.imask = (uint8_t*)(p + L.imask);
     return b;
 }
 
@@ -167,7 +169,7 @@ static int scan_and_count(const FaceWs& fw, long long BF, int64_t* num_rendered_
 
 // shared middle of both pipelines: keys -> sort -> ranges
 static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* key_depths, const FaceWs& fw,
-                     const BinWs& bw, const ImageWs& iw, long long R, cudaStream_t s) {
+                     const BinWs& bw, const ImageWs& iw, long long R, const TileMaskArgs* tm, cudaStream_t s) {
     const int num_tiles = B * gx * gy;
     if (R > 0) {
         if (launch_emit_keys(BF, F, gx, gy, key_depths, fw.tiles_touched, fw.face_offsets, fw.rects,
@@ -176,7 +178,7 @@ static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* ke
         if (launch_sort_pairs(bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, R, 32 + bit, bw.sort_temp,
                               bw.sort_temp_bytes, s)) return 1;
     }
-    return launch_tile_ranges(bw.keys, R, iw.ranges, num_tiles, s);
+    return launch_tile_ranges(bw.keys, R, iw.ranges, num_tiles, tm, s);
 }
 
 }  // namespace dm2
@@ -253,7 +255,8 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
         return 0;
     }
     const long long R = num_rendered;
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, s)) return 1;
+    const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, &tm, s)) return 1;
     return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, s);
 }
 
@@ -384,7 +387,7 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
     BinWs bw = carve_bin(binning_ws, num_rendered);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     // key = min depth (reference renderer.cu:603)
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, s)) return 1;
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, nullptr, s)) return 1;
     return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, s);
 }
 

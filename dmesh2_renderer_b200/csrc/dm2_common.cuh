@@ -189,6 +189,11 @@ struct ImageWs {
 struct BinWs {
     uint64_t* keys_unsorted; uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
     void* sort_temp; size_t sort_temp_bytes;
+    uint8_t* imask;               // per sorted instance: 8x4-footprint overlap bits (render path)
+};
+struct TileMaskArgs {             // optional second output of the tile-range pass (render path)
+    const uint32_t* vals; const float* records; const int32_t* patch_min; uint8_t* imask;
+    int F, gx, gy, use_bbox;
 };
 
 int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaStream_t s);
@@ -201,7 +206,8 @@ int launch_emit_keys(long long BF, int F, int gx, int gy, const float* key_depth
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
                       long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
 size_t sort_temp_bytes(long long n);
-int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, cudaStream_t s);
+int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, const TileMaskArgs* tm,
+                       cudaStream_t s);
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                           const ImageWs& iw, float* out_color, float* out_depth, cudaStream_t s);
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,

@@ -72,42 +72,35 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 }
 
 
-constexpr int kBStage = 64;                 // faces staged per round (backward)
-constexpr int kBSub = 8;                    // candidates per sub-chunk
-constexpr int kBPairCap = 32 * kBSub;       // 256 (pixel, face) pairs per warp per sub-chunk
-
 struct BwdWarpSmem {
-    float parea[kBPairCap];                 // overlap area (or -1: the reference skips the pair)
-    float pgrad[kBPairCap * 6];             // d area / d aa verts
-    float sT[kBSub * 32];                   // T before the contribution      [candidate][lane]
-    float sG[kBSub * 32];                   // dL/dalpha of the contribution   [candidate][lane]
+    float srec[kSub * kRecStride];          // staged records of the sub-chunk
+    float tA[kSlots];                       // [candidate][pixel]: alpha (or skip)  -> T before the contribution
+    float tS[kSlots];                       //                     iC.dC + iD.dD     -> dL/dalpha
+    float tArea[kSlots];                    //                     overlap area
+    float tG[6][kSlots];                    //                     d area / d aa verts (partially covered pairs)
     float red[16 * 29];                     // half-warp transpose tile
-    uint16_t plist[kBPairCap];              // k | lane << 4 | inmask << 9
-    uint8_t cand[kBStage];
-};
-struct BwdSmem {
-    float srec[kBStage * kRecStride];
-    BwdWarpSmem w[8];
-    int max_last[8];
+    WarpQueue q;
+    uint16_t plist[kSlots];                 // pair list of the dense pass, then the contribution list
 };
 
 __global__ void __launch_bounds__(kRasterThreads, 2)
 k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                  const uint2* __restrict__ ranges, const float* __restrict__ final_T,
-                  const float* __restrict__ final_prev_T, const uint32_t* __restrict__ n_contrib,
-                  const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
-                  float* __restrict__ gface, int gx, int gy) {
+                  const uint8_t* __restrict__ imask, const uint2* __restrict__ ranges,
+                  const float* __restrict__ final_T, const float* __restrict__ final_prev_T,
+                  const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
+                  const float* __restrict__ dL_ddepth, float* __restrict__ gface, int gx, int gy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const TileCtx tc = tile_ctx(in, gx, gy);
     const int warp = tc.warp, lane = tc.lane;
-    BwdWarpSmem& ws = sm.w[warp];
+    BwdWarpSmem& ws = reinterpret_cast<BwdWarpSmem*>(smem_raw)[warp];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     const uint2 range = ranges[blockIdx.x];
     const size_t view_base = (size_t)tc.b * in.F;
+    const uint32_t* tlist = list + range.x;
+    const uint8_t* tmask = imask + range.x;
 
     // ---- per-pixel state (backward.cu:133-160)
     PixelGeom pg;
@@ -131,178 +124,136 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
     }
     float T = prev_T_final;
     bool first_pass = true;
-    float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f, accum_recd = 0.0f;
-    float last_alpha = 0.0f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f, last_depth = 0.0f;
+    // backward.cu:357-405 keeps a running blend `accum_rec` per channel and sums (c - accum_rec) * dC
+    // over the channels; the blend is linear, so the same quantity is carried here as ONE scalar
+    // A = accum_rec . dC with S = c . dC per face (dense pass):  dL/dalpha = (S - A) * T + background term.
+    float accA = 0.0f, last_alpha = 0.0f, last_S = 0.0f;
     float bg_dot = 0.0f;
     bg_dot += in.background[0] * dC0; bg_dot += in.background[1] * dC1; bg_dot += in.background[2] * dC2;
     const float bd_dot = dD;
 
     // faces behind every pixel's last contributor are never touched (backward.cu:219-221)
     const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
-    if (lane == 0) sm.max_last[warp] = warp_last;
-    __syncthreads();
-    int block_last = 0;
+
+    int head = 0, count = 0, cursor = warp_last;
+    for (;;) {
+        fill_queue<true>(ws.q, head, count, cursor, warp_last, tmask, tlist, warp, lane);
+        if (count == 0) break;
+        const int ncs = min(count, kSub);
+        stage_candidates(ws.srec, records, ws.q, head, ncs, view_base, lane);
+
+        // ====== 1. lock-step classification, pair list
+        uint32_t hit, part, im;
+        classify_subchunk(ws.srec, ncs, use_aa, pg.pxmin, pg.pymin, hit, part, im, [&](int k) {
+            return tc.inside && (int)ws.q.idx[(head + k) & (kQueue - 1)] < my_last;
+        });
+        if (__any_sync(0xffffffffu, hit != 0u)) {
+            int np, npairs;
+            build_pair_list(ws.plist, ncs, hit, part, im, lane, np, npairs);
+
+            // ====== 2. dense pass over every hit pair: clip (+ area gradient), hit point, alpha, S
+            for (int p0 = 0; p0 < npairs; p0 += 32) {
+                const int pid = p0 + lane;
+                const bool act = pid < npairs;
+                const unsigned e = act ? ws.plist[pid] : 0u;
+                const int k = e & 7, l = (e >> 3) & 31;
+                PixelGeom qg;
+                qg.o.x = __shfl_sync(0xffffffffu, pg.o.x, l); qg.o.y = __shfl_sync(0xffffffffu, pg.o.y, l);
+                qg.o.z = __shfl_sync(0xffffffffu, pg.o.z, l); qg.d.x = __shfl_sync(0xffffffffu, pg.d.x, l);
+                qg.d.y = __shfl_sync(0xffffffffu, pg.d.y, l); qg.d.z = __shfl_sync(0xffffffffu, pg.d.z, l);
+                const float qC0 = __shfl_sync(0xffffffffu, dC0, l), qC1 = __shfl_sync(0xffffffffu, dC1, l);
+                const float qC2 = __shfl_sync(0xffffffffu, dC2, l), qD = __shfl_sync(0xffffffffu, dD, l);
+                if (!act) continue;
+                qg.pxmin = tc.fx0 + (float)(l & 7);
+                qg.pymin = tc.fy0 + (float)(l >> 3);
+                const float* rec = ws.srec + k * kRecStride;
+                const int slot = k * 32 + l;
+                Shade s;
+                s.area = use_aa ? 1.0f : 0.0f;
+                bool ok = true;
+                if (pid < np) {
+                    float g[6];
+                    ok = aa_clip<true>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, g);
 #pragma unroll
-    for (int i = 0; i < 8; i++) block_last = max(block_last, sm.max_last[i]);
-
-    for (int hi = block_last; hi > 0; hi -= kBStage) {
-        const int cnt = min(kBStage, hi);
-        __syncthreads();
-        // slot i holds list entry (hi-1-i): back to front
-        stage_records(sm.srec, records, list, (long long)range.x + hi - 1, -1, cnt, view_base);
-        __syncthreads();
-        if (hi - cnt >= warp_last) continue;                       // nothing for this warp in this round
-        const int n_cand = build_candidates(sm.srec, cnt, use_aa, tc.fx0, tc.fy0, ws.cand, lane);
-
-        for (int sub = 0; sub < n_cand; sub += kBSub) {
-            const uint8_t* csub = ws.cand + sub;
-            const int ncs = min(kBSub, n_cand - sub);
-
-            // ====== 1. lock-step classification
-            uint32_t hit = 0u, part = 0u, im = 0u;
-            for (int k = 0; k < ncs; k++) {
-                const int j = csub[k];
-                int cls = AA_FULL;
-                unsigned inmask = 0xF;
-                if (use_aa) cls = aa_classify(sm.srec + j * kRecStride, pg.pxmin, pg.pymin, inmask);
-                const bool on = tc.inside && (cls != AA_OUT) && (hi - 1 - j < my_last);
-                const bool p = on && (cls == AA_PART);
-                hit |= (on ? 1u : 0u) << k;
-                part |= (p ? 1u : 0u) << k;
-                if (p) im |= inmask << (4 * k);
-            }
-            if (!__any_sync(0xffffffffu, hit != 0u)) continue;
-
-            // ====== 2. pair list + dense clip with gradient
-            int pbase = 0;                    // lane k: pair-list base of candidate k
-            uint32_t pmask = 0u;              // lane k: lanes whose pixel is partially covered by candidate k
-            if (__any_sync(0xffffffffu, part != 0u)) {
-                int total = 0;
-                for (int k = 0; k < ncs; k++) {
-                    const bool p = (part >> k) & 1u;
-                    const unsigned m = __ballot_sync(0xffffffffu, p);
-                    if (lane == k) { pbase = total; pmask = m; }
-                    if (p) ws.plist[total + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 4) | (((im >> (4 * k)) & 15u) << 9));
-                    total += __popc(m);
+                    for (int q = 0; q < 6; q++) ws.tG[q][slot] = g[q];
                 }
-                __syncwarp();
-                for (int pid = lane; pid < total; pid += 32) {
-                    const unsigned e = ws.plist[pid];
-                    const int k = e & 15, l = (e >> 4) & 31;
-                    float area, g[6];
-                    const bool ok = aa_clip<true>(sm.srec + csub[k] * kRecStride, tc.fx0 + (float)(l & 7),
-                                                  tc.fy0 + (float)(l >> 3), e >> 9, area, g);
-                    ws.parea[pid] = ok ? area : -1.0f;
-#pragma unroll
-                    for (int q = 0; q < 6; q++) ws.pgrad[pid * 6 + q] = g[q];
+                ok = ok && shade_tail(rec, qg, tau, s);
+                if (ok) {
+                    ws.tA[slot] = __fmul_rn(rec[R_MISC + 1], s.ratio);
+                    ws.tS[slot] = s.iC[0] * qC0 + s.iC[1] * qC1 + s.iC[2] * qC2 + s.iD * qD;
+                    ws.tArea[slot] = s.area;
+                } else {
+                    ws.tA[slot] = __uint_as_float(kSkipBits);
                 }
-                __syncwarp();
             }
+            __syncwarp();
 
             // ====== 3. pixel-sequential walk (back to front): T and dL/dalpha per contribution
             uint32_t contrib = 0u;
-            for (;;) {
-                int k = -1;
-                if (hit) { k = __ffs(hit) - 1; hit &= hit - 1u; }
-                if (!__any_sync(0xffffffffu, k >= 0)) break;
-                const int kk = k < 0 ? 0 : k;
-                const int pb = __shfl_sync(0xffffffffu, pbase, kk);
-                const uint32_t pm = __shfl_sync(0xffffffffu, pmask, kk);
-                if (k < 0) continue;
-                Shade s;
-                s.area = use_aa ? 1.0f : 0.0f;
-                if ((part >> k) & 1u) {
-                    s.area = ws.parea[pb + __popc(pm & lt_mask)];
-                    if (s.area == -1.0f) continue;
-                }
-                const float* rec = sm.srec + csub[k] * kRecStride;
-                if (!shade_tail(rec, pg, tau, s)) continue;
-                const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
+            for (int k = 0; k < ncs; k++) {
+                if (!((hit >> k) & 1u)) continue;
+                const int slot = k * 32 + lane;
+                const float alpha = ws.tA[slot];
+                if (__float_as_uint(alpha) == kSkipBits) continue;
+                const float S = ws.tS[slot];
                 // backward.cu:340-348
                 if (!first_pass) T = T / (1.0f - alpha);
                 first_pass = false;
                 // backward.cu:357-405
-                float dL_dalpha = 0.0f;
-                accum_rec0 = last_alpha * last_c0 + (1.0f - last_alpha) * accum_rec0;
-                last_c0 = s.iC[0];
-                dL_dalpha += (s.iC[0] - accum_rec0) * dC0;
-                accum_rec1 = last_alpha * last_c1 + (1.0f - last_alpha) * accum_rec1;
-                last_c1 = s.iC[1];
-                dL_dalpha += (s.iC[1] - accum_rec1) * dC1;
-                accum_rec2 = last_alpha * last_c2 + (1.0f - last_alpha) * accum_rec2;
-                last_c2 = s.iC[2];
-                dL_dalpha += (s.iC[2] - accum_rec2) * dC2;
-                accum_recd = last_alpha * last_depth + (1.0f - last_alpha) * accum_recd;
-                last_depth = s.iD;
-                dL_dalpha += (s.iD - accum_recd) * dD;
-                dL_dalpha *= T;
+                accA = last_alpha * last_S + (1.0f - last_alpha) * accA;
+                last_S = S;
+                float dL_dalpha = (S - accA) * T;
                 last_alpha = alpha;
-                if (alpha == 1.0f) {
-                    dL_dalpha += (-prev_T_final) * bg_dot;
-                    dL_dalpha += (-prev_T_final) * bd_dot;
-                } else {
-                    dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
-                    dL_dalpha += (-T_final / (1.0f - alpha)) * bd_dot;
-                }
-                ws.sT[k * 32 + lane] = T;
-                ws.sG[k * 32 + lane] = dL_dalpha;
+                const float bgw = (alpha == 1.0f) ? -prev_T_final : -T_final / (1.0f - alpha);
+                dL_dalpha += bgw * bg_dot;
+                dL_dalpha += bgw * bd_dot;
+                ws.tA[slot] = T;
+                ws.tS[slot] = dL_dalpha;
                 contrib |= 1u << k;
             }
-            __syncwarp();
 
-            // ====== 4. face-parallel gradients: contributions enumerated candidate-major from ballots
-            uint32_t cmask[kBSub];
-            int cbase[kBSub + 1];
-            cbase[0] = 0;
-#pragma unroll
-            for (int k = 0; k < kBSub; k++) {
-                cmask[k] = __ballot_sync(0xffffffffu, (contrib >> k) & 1u);
-                cbase[k + 1] = cbase[k] + __popc(cmask[k]);
+            // ====== 4. face-parallel gradients over the candidate-major contribution list
+            int total_c = 0;
+            for (int k = 0; k < ncs; k++) {
+                const bool c = (contrib >> k) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, c);
+                if (c) ws.plist[total_c + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 3) | (((part >> k) & 1u) << 8));
+                total_c += __popc(m);
             }
-            const int total_c = cbase[kBSub];
-            int cur_k = -1;
+            __syncwarp();
             float carry = 0.0f;
             for (int r0 = 0; r0 < total_c; r0 += 32) {
                 const int r = r0 + lane;
                 const bool act = r < total_c;
-                // record r -> (candidate k, owning lane src)
-                int k = 0;
-                uint32_t mk = cmask[0];
-                int bk = 0;
-#pragma unroll
-                for (int q = 1; q < kBSub; q++) {
-                    if (r >= cbase[q]) { k = q; mk = cmask[q]; bk = cbase[q]; }
-                }
-                const int src = act ? (int)__fns(mk, 0, r - bk + 1) : 0;
+                const unsigned e = act ? ws.plist[r] : 0u;
+                const int k = e & 7, src = (e >> 3) & 31;
+                // last row of its candidate's run?
+                const bool run_end = act && ((r + 1 == total_c) || ((ws.plist[r + 1 < kSlots ? r + 1 : r] & 7) != k));
+                const unsigned flush = __ballot_sync(0xffffffffu, run_end);
                 // pixel constants of the owning lane
-                const float ox = __shfl_sync(0xffffffffu, pg.o.x, src), oy = __shfl_sync(0xffffffffu, pg.o.y, src);
-                const float oz = __shfl_sync(0xffffffffu, pg.o.z, src), dx = __shfl_sync(0xffffffffu, pg.d.x, src);
-                const float dy = __shfl_sync(0xffffffffu, pg.d.y, src), dz = __shfl_sync(0xffffffffu, pg.d.z, src);
+                PixelGeom qg;
+                qg.o.x = __shfl_sync(0xffffffffu, pg.o.x, src); qg.o.y = __shfl_sync(0xffffffffu, pg.o.y, src);
+                qg.o.z = __shfl_sync(0xffffffffu, pg.o.z, src); qg.d.x = __shfl_sync(0xffffffffu, pg.d.x, src);
+                qg.d.y = __shfl_sync(0xffffffffu, pg.d.y, src); qg.d.z = __shfl_sync(0xffffffffu, pg.d.z, src);
                 const float qC0 = __shfl_sync(0xffffffffu, dC0, src), qC1 = __shfl_sync(0xffffffffu, dC1, src);
                 const float qC2 = __shfl_sync(0xffffffffu, dC2, src), qD = __shfl_sync(0xffffffffu, dD, src);
-                const int pb = __shfl_sync(0xffffffffu, pbase, k);
-                const uint32_t pm = __shfl_sync(0xffffffffu, pmask, k);
                 float v[29];
 #pragma unroll
                 for (int q = 0; q < 29; q++) v[q] = 0.0f;
                 if (act) {
-                    const float* rec = sm.srec + csub[k] * kRecStride;
-                    PixelGeom qg;
+                    const float* rec = ws.srec + k * kRecStride;
+                    const int slot = k * 32 + src;
                     qg.pxmin = tc.fx0 + (float)(src & 7);
                     qg.pymin = tc.fy0 + (float)(src >> 3);
-                    qg.o = f3{ox, oy, oz};
-                    qg.d = f3{dx, dy, dz};
                     Shade s;
-                    s.area = use_aa ? 1.0f : 0.0f;
+                    s.area = ws.tArea[slot];
                     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if ((pm >> src) & 1u) {
-                        const int pid = pb + __popc(pm & ((1u << src) - 1u));
-                        s.area = ws.parea[pid];
+                    if ((e >> 8) & 1u) {
 #pragma unroll
-                        for (int q = 0; q < 6; q++) g[q] = ws.pgrad[pid * 6 + q];
+                        for (int q = 0; q < 6; q++) g[q] = ws.tG[q][slot];
                     }
-                    shade_tail(rec, qg, tau, s);                   // succeeded in the walk: same function, same inputs
-                    const float Tq = ws.sT[k * 32 + src], dL_dalpha = ws.sG[k * 32 + src];
+                    shade_tail(rec, qg, tau, s);                   // succeeded in the dense pass: same function, same inputs
+                    const float Tq = ws.tA[slot], dL_dalpha = ws.tS[slot];
                     const float opacity = rec[R_MISC + 1], intense = rec[R_MISC + 2];
                     const float alpha = __fmul_rn(opacity, s.ratio);
                     const float dL_diC[3] = {qC0 * alpha * Tq, qC1 * alpha * Tq, qC2 * alpha * Tq};
@@ -354,39 +305,43 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     v[3] = g1.x; v[4] = g1.y; v[5] = g1.z;
                     v[6] = g2.x; v[7] = g2.y; v[8] = g2.z;
                 }
-                // ---- transpose through smem (two half-warps); lane c sums column c over one candidate's run
-                const int myk = act ? k : -1;
+                // ---- transpose through smem (two half-warps); lane c sums column c over the rows of one
+                //      candidate's run (rows are candidate-major) and issues ONE coalesced 29-lane atomic
+                //      per (warp, face) into the per-(view,face) gradient record
+                const int nrows = min(32, total_c - r0);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
+                    if (h * 16 >= nrows) break;
                     if ((lane >> 4) == h) {
 #pragma unroll
                         for (int q = 0; q < 29; q++) ws.red[(lane & 15) * 29 + q] = v[q];
                     }
                     __syncwarp();
-#pragma unroll 4
-                    for (int rr = 0; rr < 16; rr++) {
-                        const int sk = __shfl_sync(0xffffffffu, myk, h * 16 + rr);
-                        if (lane < 29) {
-                            if (sk != cur_k) {
-                                if (cur_k >= 0 && carry != 0.0f) {
-                                    const int fid = __float_as_int(sm.srec[csub[cur_k] * kRecStride + R_FID]);
-                                    atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
-                                }
-                                cur_k = sk;
+                    const int hrows = min(16, nrows - h * 16);
+                    for (int rr0 = 0; rr0 < hrows; rr0 += 4) {
+                        float x[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) x[j] = (lane < 29 && rr0 + j < 16) ? ws.red[(rr0 + j) * 29 + lane] : 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int row = h * 16 + rr0 + j;
+                            if (row >= nrows) break;
+                            carry += x[j];
+                            if ((flush >> row) & 1u) {               // warp-uniform
+                                const int kk = __shfl_sync(0xffffffffu, k, row);
+                                const int fid = __float_as_int(ws.srec[kk * kRecStride + R_FID]);
+                                if (lane < 29 && carry != 0.0f) atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
                                 carry = 0.0f;
                             }
-                            if (sk >= 0) carry += ws.red[rr * 29 + lane];
                         }
                     }
                     __syncwarp();
                 }
             }
-            if (lane < 29 && cur_k >= 0 && carry != 0.0f) {
-                const int fid = __float_as_int(sm.srec[csub[cur_k] * kRecStride + R_FID]);
-                atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
-            }
             __syncwarp();
         }
+        head = (head + ncs) & (kQueue - 1);
+        count -= ncs;
     }
 }
 
@@ -479,6 +434,8 @@ k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touch
     gr.dL_dfaces_intense[idx] = g[22];
 }
 
+constexpr size_t kBwdSmem = sizeof(BwdWarpSmem) * (kRasterThreads / 32);
+
 size_t backward_ws_bytes(long long BF) { return align_up((size_t)BF * kGradWords * 4, 256) + 256; }
 
 int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
@@ -513,7 +470,7 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     static bool attr_set = false;
     if (!attr_set) {
         DM2_CHECK(cudaFuncSetAttribute(k_raster_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BwdSmem)));
+                                       (int)kBwdSmem));
         attr_set = true;
     }
     float* gface = reinterpret_cast<float*>(grad_ws);
@@ -523,9 +480,9 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     }
     {
         ProfScope _ps("raster_backward", s);
-        k_raster_backward<<<(unsigned)nblk, kRasterThreads, sizeof(BwdSmem), s>>>(
-            in, fw.records, bw.vals, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor, dL_ddepth,
-            gface, gx, gy);
+        k_raster_backward<<<(unsigned)nblk, kRasterThreads, kBwdSmem, s>>>(
+            in, fw.records, bw.vals, bw.imask, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor,
+            dL_ddepth, gface, gx, gy);
         DM2_LAUNCH_CHECK();
     }
     return 0;

@@ -1,6 +1,22 @@
 // dm2_raster_common.cuh — device code shared by the forward (dm2_raster_fwd.cu) and backward
-// (dm2_raster_bwd.cu) tile kernels: record staging, candidate lists, per-(pixel,face) shading,
-// sub-chunk classification + dense polygon clip.
+// (dm2_raster_bwd.cu) tile kernels.
+//
+// Both kernels are WARP-AUTONOMOUS: one CTA per 16x16 tile (the tile size is part of the reference's
+// binning contract), one warp per 8x4 pixel footprint, one pixel per lane - but after the prologue no
+// warp ever waits for another one (no CTA barrier in the main loop).  Each warp
+//   * scans the tile's sorted instance list 32 entries at a time through the 1-byte per-instance
+//     footprint mask written by k_tile_ranges (bit w: the face's AA bbox overlaps footprint w) and
+//     pushes the candidates into a private ring queue;
+//   * stages the packed 256-byte records of the next kSub candidates into its private shared
+//     memory with 16-byte cp.async (15 consecutive lanes fetch one contiguous 240-byte record);
+//   * classifies them in lock-step (bbox + 12 half-plane tests, broadcast reads) into per-lane
+//     hit / partial bit masks, compacts all hit (pixel, face) pairs into a pair list - partially
+//     covered pairs first - and runs the expensive order-independent part (polygon clip, ray/triangle
+//     intersection, barycentric clamp, attribute interpolation) DENSE over that list: any lane
+//     evaluates any pixel's pair, results land in [candidate][pixel] tables;
+//   * finally each lane walks its own hits in list order through the cheap order-dependent part.
+// The first versions of these kernels staged records per CTA behind two barriers per round: ncu
+// showed 21-27 % of all stall samples on that barrier (profiles/r01_*).
 #pragma once
 #include "dm2_common.cuh"
 #include "dm2_aa.cuh"
@@ -10,6 +26,10 @@ namespace dm2 {
 constexpr int kRecStride = 68;              // words between staged records (272 B, 16-byte aligned)
 constexpr int kRasterThreads = 256;
 constexpr int kGradWords = 32;              // per-(view,face) gradient record (29 used)
+constexpr int kSub = 8;                     // candidates per sub-chunk
+constexpr int kSlots = kSub * 32;           // (candidate, pixel) table slots per warp
+constexpr int kQueue = 64;                  // candidate ring capacity (>= kSub - 1 + 32)
+constexpr uint32_t kSkipBits = 0xFFFFFFFFu; // table marker: the reference skips this (pixel, face) pair
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -19,39 +39,51 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Stage `cnt` records.  Slot i receives the record of face list[first + i*step] (step = +1 forward,
-// -1 backward).  16 threads cooperate on one record (15 x 16-byte chunks carry data).
-__device__ __forceinline__ void stage_records(float* __restrict__ smem, const float* __restrict__ records,
-                                              const uint32_t* __restrict__ list, long long first, int step,
-                                              int cnt, size_t view_base) {
-    for (int q = threadIdx.x; q < cnt * 16; q += kRasterThreads) {
-        const int slot = q >> 4, chunk = q & 15;
-        if (chunk == 15) continue;
-        const uint32_t fid = list[first + (long long)slot * step];
-        const float* src = records + (view_base + fid) * kRecWords + chunk * 4;
-        cp_async16(smem + slot * kRecStride + chunk * 4, src);
-    }
-    cp_async_wait_all();
-}
+// ------------------------------------------------------------------------------------------------
+// per-warp candidate ring
+struct WarpQueue {
+    uint32_t fid[kQueue];                   // face id within the view
+    uint32_t idx[kQueue];                   // position in the tile's sorted list
+};
 
-// Warp-level candidate list: slots whose bbox overlaps the warp's 8x4 pixel footprint (tau > 0),
-// or every slot (tau == 0: the reference runs the ray test on every listed face).
-__device__ __forceinline__ int build_candidates(const float* __restrict__ srec, int cnt, bool use_bbox, float fx0,
-                                                float fy0, uint8_t* __restrict__ cand, int lane) {
-    int n = 0;
-    for (int c = 0; c < cnt; c += 32) {
-        const int j = c + lane;
-        bool hit = j < cnt;
-        if (hit && use_bbox) {
-            const float4 bb = *reinterpret_cast<const float4*>(srec + j * kRecStride + R_BBOX);
-            hit = !((fx0 + 8.0f < bb.x) || (fx0 > bb.y) || (fy0 + 4.0f < bb.z) || (fy0 > bb.w));
+// Scans the tile list (forward: ascending from `cursor`; REVERSE: descending, entries [0, cursor)
+// remain) until the ring holds at least kSub candidates or the list is exhausted.
+template <bool REVERSE>
+__device__ __forceinline__ void fill_queue(WarpQueue& q, int head, int& count, int& cursor, int total,
+                                           const uint8_t* __restrict__ imask, const uint32_t* __restrict__ list,
+                                           int warp, int lane) {
+    while (count < kSub && (REVERSE ? cursor > 0 : cursor < total)) {
+        const int i = REVERSE ? cursor - 1 - lane : cursor + lane;
+        const bool valid = REVERSE ? i >= 0 : i < total;
+        bool hit = false;
+        uint32_t fid = 0;
+        if (valid) {
+            hit = (imask[i] >> warp) & 1u;
+            fid = list[i];
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) cand[n + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
-        n += __popc(m);
+        if (hit) {
+            const int pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
+            q.fid[pos] = fid;
+            q.idx[pos] = (uint32_t)i;
+        }
+        count += __popc(m);
+        cursor += REVERSE ? -32 : 32;
     }
     __syncwarp();
-    return n;
+}
+
+// Stages the records of the first `ncs` queued candidates into slots 0..ncs-1.
+__device__ __forceinline__ void stage_candidates(float* __restrict__ srec, const float* __restrict__ records,
+                                                 const WarpQueue& q, int head, int ncs, size_t view_base, int lane) {
+    for (int t = lane; t < ncs * 16; t += 32) {
+        const int slot = t >> 4, chunk = t & 15;
+        if (chunk == 15) continue;
+        const uint32_t fid = q.fid[(head + slot) & (kQueue - 1)];
+        cp_async16(srec + slot * kRecStride + chunk * 4, records + (view_base + fid) * kRecWords + chunk * 4);
+    }
+    cp_async_wait_all();
+    __syncwarp();
 }
 
 struct PixelGeom {
@@ -65,27 +97,6 @@ struct Shade {
     float area, ratio, w0, w1, w2, iC[3], iD;
     int code;
 };
-
-__device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const PixelGeom& pg, float tau, Shade& s);
-
-// is_part: the pixel is only partially covered (aa_classify == AA_PART); ignored when tau == 0.
-template <bool GRAD>
-__device__ __forceinline__ bool shade(const float* __restrict__ rec, const PixelGeom& pg, float tau, bool is_part,
-                                      Shade& s, float* __restrict__ g) {
-    s.area = 0.0f;
-    if (GRAD) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) g[k] = 0.0f;
-    }
-    if (tau > 0.0f) {
-        s.area = 1.0f;
-        if (is_part) {
-            const unsigned inmask = aa_inmask(rec, pg.pxmin, pg.pymin);
-            if (!aa_clip<GRAD>(rec, pg.pxmin, pg.pymin, inmask, s.area, g)) return false;
-        }
-    }
-    return shade_tail(rec, pg, tau, s);
-}
 
 // Everything after the coverage area (s.area must be set): hit point, clamped barycentrics,
 // coverage ratio, interpolated colour and depth (forward.cu:354-395).
@@ -120,87 +131,50 @@ __device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sub-chunk processing (16 candidates at a time), shared by the forward walk and backward phase A:
-//   1. lock-step classification -> per-lane hit / partial bit masks (+ the 4-bit corner mask);
-//   2. the warp compacts all (lane, candidate) pairs that need the polygon clip into a pair list;
-//   3. the clip runs DENSE over that list - any lane clips any pixel's pair (the area does not depend
-//      on the compositing order), so all 32 lanes are busy instead of the ~12 that own a partially
-//      covered pixel at a given step; areas land in a per-warp shared-memory table;
-//   4. the sequential per-pixel walk then only looks its areas up.
-constexpr int kSub = 16;
-constexpr int kPairCap = 32 * kSub;
-struct WarpClip {
-    uint16_t plist[kPairCap];          // k | lane << 4 | inmask << 9
-    float parea[kPairCap];             // overlap area, or -1 when the reference would skip the pair
-};
-
-struct SubMasks {
-    uint32_t hit, part;                // bit k: candidate k of the sub-chunk touches / partially covers my pixel
-    int base_reg;                      // lane k holds the pair-list base of candidate k ...
-    uint32_t mask_reg;                 // ... and the ballot of lanes with a partial pixel for it
-};
-
-template <typename SlotOk>
-__device__ __forceinline__ void subchunk_prepare(const float* __restrict__ srec, const uint8_t* __restrict__ cand,
-                                                 int ncs, bool use_aa, float pxmin, float pymin, bool lane_on,
-                                                 float fx0, float fy0, WarpClip& wc, int lane, SubMasks& sm_,
-                                                 SlotOk slot_ok) {
-    uint32_t hit = 0u, part = 0u;
-    unsigned long long im = 0ull;
-    for (int k = 0; k < ncs; k++) {                            // lock-step, broadcast reads
-        const int j = cand[k];
+// Lock-step classification of the staged sub-chunk: bit k of hit / part = candidate k touches /
+// only partially covers my pixel; im holds the 4-bit inside-corner mask of every partial candidate.
+// lane_ok(k): extra per-lane admission test (forward: pixel not done; backward: inside n_contrib).
+template <typename LaneOk>
+__device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec, int ncs, bool use_aa, float pxmin,
+                                                  float pymin, uint32_t& hit, uint32_t& part, uint32_t& im,
+                                                  LaneOk lane_ok) {
+    hit = 0u; part = 0u; im = 0u;
+    for (int k = 0; k < ncs; k++) {
         int cls = AA_FULL;
         unsigned inmask = 0xF;
-        if (use_aa) cls = aa_classify(srec + j * kRecStride, pxmin, pymin, inmask);
-        const bool on = lane_on && (cls != AA_OUT) && slot_ok(j);
+        if (use_aa) cls = aa_classify(srec + k * kRecStride, pxmin, pymin, inmask);
+        const bool on = (cls != AA_OUT) && lane_ok(k);
         const bool p = on && (cls == AA_PART);
         hit |= (on ? 1u : 0u) << k;
         part |= (p ? 1u : 0u) << k;
-        if (p) im |= (unsigned long long)inmask << (4 * k);
+        if (p) im |= inmask << (4 * k);
     }
-    int total = 0, base_reg = 0;
-    uint32_t mask_reg = 0u;
-    if (__any_sync(0xffffffffu, part != 0u)) {
-        for (int k = 0; k < ncs; k++) {
-            const bool p = (part >> k) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, p);
-            if (lane == k) { base_reg = total; mask_reg = m; }
-            if (p) wc.plist[total + __popc(m & ((1u << lane) - 1u))] =
-                       (uint16_t)(k | (lane << 4) | ((unsigned)((im >> (4 * k)) & 15ull) << 9));
-            total += __popc(m);
-        }
-        __syncwarp();
-        for (int pid = lane; pid < total; pid += 32) {         // dense clip
-            const unsigned e = wc.plist[pid];
-            const int k = e & 15, l = (e >> 4) & 31;
-            float area;
-            const bool ok = aa_clip<false>(srec + cand[k] * kRecStride, fx0 + (float)(l & 7), fy0 + (float)(l >> 3),
-                                           e >> 9, area, nullptr);
-            wc.parea[pid] = ok ? area : -1.0f;
-        }
-        __syncwarp();
-    }
-    sm_.hit = hit; sm_.part = part; sm_.base_reg = base_reg; sm_.mask_reg = mask_reg;
 }
 
-// Pops this lane's next hit of the sub-chunk (-1: none) and fetches its coverage area.
-// Must be called by all 32 lanes.  ok == false: the reference skips this (pixel, face) pair.
-__device__ __forceinline__ int subchunk_pop(SubMasks& sm_, bool allowed, const WarpClip& wc, int lane, bool use_aa,
-                                            float& area, bool& ok, bool& is_part) {
-    int k = -1;
-    if (allowed && sm_.hit) { k = __ffs(sm_.hit) - 1; sm_.hit &= sm_.hit - 1u; }
-    const int kk = k < 0 ? 0 : k;
-    const int b = __shfl_sync(0xffffffffu, sm_.base_reg, kk);
-    const uint32_t m = __shfl_sync(0xffffffffu, sm_.mask_reg, kk);
-    area = use_aa ? 1.0f : 0.0f;
-    ok = true;
-    is_part = false;
-    if (k >= 0 && ((sm_.part >> k) & 1u)) {
-        is_part = true;
-        area = wc.parea[b + __popc(m & ((1u << lane) - 1u))];
-        ok = !(area == -1.0f);
+// Pair list of the sub-chunk: entries k | lane << 3 | inmask << 8, partially covered pairs in
+// [0, np), fully covered ones in [np, total) - so that at most one 32-pair batch mixes the two.
+__device__ __forceinline__ void build_pair_list(uint16_t* __restrict__ plist, int ncs, uint32_t hit, uint32_t part,
+                                                uint32_t im, int lane, int& np, int& total) {
+    const unsigned lt = (1u << lane) - 1u;
+    int n = 0;
+    for (int k = 0; k < ncs; k++) {
+        const bool p = (part >> k) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (p) plist[n + __popc(m & lt)] = (uint16_t)(k | (lane << 3) | (((im >> (4 * k)) & 15u) << 8));
+        n += __popc(m);
     }
-    return k;
+    np = n;
+    const uint32_t full = hit & ~part;
+    if (__any_sync(0xffffffffu, full != 0u)) {
+        for (int k = 0; k < ncs; k++) {
+            const bool f = (full >> k) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) plist[n + __popc(m & lt)] = (uint16_t)(k | (lane << 3));
+            n += __popc(m);
+        }
+    }
+    total = n;
+    __syncwarp();
 }
 
 struct TileCtx {

@@ -1,37 +1,30 @@
 // dm2_raster_fwd.cu — per-tile forward compositor.
 // Behaviour of reference cuda_impl/forward.cu:139-432 (renderCUDA<3>), re-designed for sm_100a.
-//
-// One CTA per 16x16 tile (the tile size is part of the reference's binning contract), one warp per
-// 8x4 pixel block, one pixel per lane.  Per round of kStage staged faces:
-//   * 16-byte cp.async staging of the packed 256-byte records (272-byte stride in shared memory so
-//     lanes reading DIFFERENT faces spread over the banks);
-//   * each warp ballots "face bbox overlaps my 8x4 footprint" into a compact candidate list;
-//   * per 16-candidate sub-chunk: lock-step classification (bbox + 12 half-plane tests), then the
-//     polygon clip runs DENSE over the warp's list of partially covered (pixel, face) pairs, then
-//     each lane walks its own hits in list order (ray/triangle, blend, early termination).
-// The reference walks every listed face in lock-step with all 256 threads and re-reads ~40 AA
-// floats per (pixel, face) from global memory.
+// Structure: see dm2_raster_common.cuh (warp-autonomous candidate queue, dense pair evaluation).
+// The reference walks every listed face in lock-step with all 256 threads of the tile behind a
+// barrier per 256-face round and re-reads ~40 AA floats per (pixel, face) from global memory.
 #include "dm2_raster_common.cuh"
 
 namespace dm2 {
 
-constexpr int kStage = 128;                 // faces staged per round
+struct FwdWarpSmem {
+    float srec[kSub * kRecStride];          // staged records of the sub-chunk
+    float tab[5][kSlots];                   // [candidate][pixel]: alpha (or skip), alpha*iC.rgb, alpha*iD
+    WarpQueue q;
+    uint16_t plist[kSlots];
+};
 
-// =============================================================================== forward
 __global__ void __launch_bounds__(kRasterThreads, 3)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                 const uint2* __restrict__ ranges, float* __restrict__ final_T, float* __restrict__ final_prev_T,
-                 uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
-                 int gx, int gy) {
-    extern __shared__ __align__(16) float smem_f[];
-    float* srec = smem_f;
-    uint8_t* scand = reinterpret_cast<uint8_t*>(srec + kStage * kRecStride);
+                 const uint8_t* __restrict__ imask, const uint2* __restrict__ ranges, float* __restrict__ final_T,
+                 float* __restrict__ final_prev_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+                 float* __restrict__ out_depth, int gx, int gy) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileCtx tc = tile_ctx(in, gx, gy);
     const int warp = tc.warp, lane = tc.lane;
+    FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[warp];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
-    uint8_t* cand = scand + warp * kStage;
-    WarpClip& wclip = reinterpret_cast<WarpClip*>(scand + 8 * kStage)[warp];
 
     PixelGeom pg;
     pg.pxmin = (float)((uint32_t)tc.px + (uint32_t)in.patch_min[2 * tc.b]);      // forward.cu:319-322
@@ -48,52 +41,80 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     const uint2 range = ranges[blockIdx.x];
     const int total = (int)(range.y - range.x);
     const size_t view_base = (size_t)tc.b * in.F;
+    const uint32_t* tlist = list + range.x;
+    const uint8_t* tmask = imask + range.x;
 
     bool done = !tc.inside;
     float T = 1.0f, pT = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last_contributor = 0;
 
-    for (int base = 0; base < total; base += kStage) {
-        // reference forward.cu:257-260: stop when the whole tile is done
-        if (__syncthreads_count(done) == kRasterThreads) break;
-        const int cnt = min(kStage, total - base);
-        stage_records(srec, records, list, (long long)range.x + base, 1, cnt, view_base);
-        __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;
-        const int n_cand = build_candidates(srec, cnt, use_aa, tc.fx0, tc.fy0, cand, lane);
-        for (int sub = 0; sub < n_cand; sub += kSub) {
-            if (__all_sync(0xffffffffu, done)) break;
-            const uint8_t* csub = cand + sub;
-            SubMasks sbm;
-            subchunk_prepare(srec, csub, min(kSub, n_cand - sub), use_aa, pg.pxmin, pg.pymin, !done, tc.fx0, tc.fy0,
-                             wclip, lane, sbm, [](int) { return true; });
-            for (;;) {
-                // ---- every lane takes its own next hit (in list order); lanes work on different faces
-                float area;
-                bool ok, is_part;
-                const int k = subchunk_pop(sbm, !done, wclip, lane, use_aa, area, ok, is_part);
-                if (!__any_sync(0xffffffffu, k >= 0)) break;
-                if (k >= 0 && ok) {
-                    const int jj = csub[k];
-                    const float* rec = srec + jj * kRecStride;
-                    Shade s;
-                    s.area = area;
-                    if (shade_tail(rec, pg, tau, s)) {
-                        // forward.cu:398-415
-                        const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
-                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                        C0 = __fmaf_rn(__fmul_rn(s.iC[0], alpha), T, C0);   // C += iC*alpha*T
-                        C1 = __fmaf_rn(__fmul_rn(s.iC[1], alpha), T, C1);
-                        C2 = __fmaf_rn(__fmul_rn(s.iC[2], alpha), T, C2);
-                        D  = __fmaf_rn(__fmul_rn(s.iD, alpha), T, D);
-                        pT = T;
-                        T = test_T;
-                        last_contributor = (uint32_t)(base + jj + 1);
-                        if (T < kTEps) done = true;
-                    }
+    int head = 0, count = 0, cursor = 0;
+    while (!__all_sync(0xffffffffu, done)) {
+        fill_queue<false>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
+        if (count == 0) break;
+        const int ncs = min(count, kSub);
+        stage_candidates(ws.srec, records, ws.q, head, ncs, view_base, lane);
+
+        // ---- lock-step classification, pair list
+        uint32_t hit, part, im;
+        classify_subchunk(ws.srec, ncs, use_aa, pg.pxmin, pg.pymin, hit, part, im, [&](int) { return !done; });
+        if (__any_sync(0xffffffffu, hit != 0u)) {
+            int np, npairs;
+            build_pair_list(ws.plist, ncs, hit, part, im, lane, np, npairs);
+
+            // ---- dense evaluation of the order-independent part of every hit pair
+            for (int p0 = 0; p0 < npairs; p0 += 32) {
+                const int pid = p0 + lane;
+                const bool act = pid < npairs;
+                const unsigned e = act ? ws.plist[pid] : 0u;
+                const int k = e & 7, l = (e >> 3) & 31;
+                PixelGeom qg;
+                qg.o.x = __shfl_sync(0xffffffffu, pg.o.x, l); qg.o.y = __shfl_sync(0xffffffffu, pg.o.y, l);
+                qg.o.z = __shfl_sync(0xffffffffu, pg.o.z, l); qg.d.x = __shfl_sync(0xffffffffu, pg.d.x, l);
+                qg.d.y = __shfl_sync(0xffffffffu, pg.d.y, l); qg.d.z = __shfl_sync(0xffffffffu, pg.d.z, l);
+                if (!act) continue;
+                qg.pxmin = tc.fx0 + (float)(l & 7);
+                qg.pymin = tc.fy0 + (float)(l >> 3);
+                const float* rec = ws.srec + k * kRecStride;
+                Shade s;
+                s.area = use_aa ? 1.0f : 0.0f;
+                bool ok = true;
+                if (pid < np) ok = aa_clip<false>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, nullptr);
+                ok = ok && shade_tail(rec, qg, tau, s);
+                const int slot = k * 32 + l;
+                if (ok) {
+                    // forward.cu:398-415: C += iC*alpha*T  ->  fma(iC*alpha, T, C)
+                    const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
+                    ws.tab[0][slot] = alpha;
+                    ws.tab[1][slot] = __fmul_rn(s.iC[0], alpha);
+                    ws.tab[2][slot] = __fmul_rn(s.iC[1], alpha);
+                    ws.tab[3][slot] = __fmul_rn(s.iC[2], alpha);
+                    ws.tab[4][slot] = __fmul_rn(s.iD, alpha);
+                } else {
+                    ws.tab[0][slot] = __uint_as_float(kSkipBits);
                 }
             }
+            __syncwarp();
+
+            // ---- order-dependent walk: every lane blends its own hits in list order
+            for (int k = 0; k < ncs; k++) {
+                if (!((hit >> k) & 1u) || done) continue;
+                const int slot = k * 32 + lane;
+                const float alpha = ws.tab[0][slot];
+                if (__float_as_uint(alpha) == kSkipBits) continue;
+                C0 = __fmaf_rn(ws.tab[1][slot], T, C0);
+                C1 = __fmaf_rn(ws.tab[2][slot], T, C1);
+                C2 = __fmaf_rn(ws.tab[3][slot], T, C2);
+                D  = __fmaf_rn(ws.tab[4][slot], T, D);
+                pT = T;
+                T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                last_contributor = ws.q.idx[(head + k) & (kQueue - 1)] + 1u;
+                if (T < kTEps) done = true;                       // forward.cu:412-415
+            }
+            __syncwarp();
         }
+        head = (head + ncs) & (kQueue - 1);
+        count -= ncs;
     }
 
     if (tc.inside) {
@@ -107,7 +128,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     }
 }
 
-constexpr size_t kFwdSmem = (size_t)kStage * kRecStride * 4 + 8 * kStage + 8 * sizeof(WarpClip);
+constexpr size_t kFwdSmem = sizeof(FwdWarpSmem) * (kRasterThreads / 32);
 
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
                           float* out_color, float* out_depth, cudaStream_t s) {
@@ -120,9 +141,9 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
         attr_set = true;
     }
     ProfScope _ps("raster_forward", s);
-    k_raster_forward<<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(in, fw.records, bw.vals, iw.ranges, iw.final_T,
-                                                                      iw.final_prev_T, iw.n_contrib, out_color,
-                                                                      out_depth, gx, gy);
+    k_raster_forward<<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(in, fw.records, bw.vals, bw.imask, iw.ranges,
+                                                                      iw.final_T, iw.final_prev_T, iw.n_contrib,
+                                                                      out_color, out_depth, gx, gy);
     DM2_LAUNCH_CHECK();
     return 0;
 }

@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 6
+#define DM2_ABI_VERSION 7
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -129,6 +129,8 @@ typedef struct DM2BinningLayout {     /* reference BinningState, state.h:41-51 *
     size_t keys;                 /* u64[R]  sorted                                              */
     size_t vals;                 /* u32[R]  sorted  (= reference face_list)                     */
     size_t sort_temp;            /* radix-sort histograms                                       */
+    size_t imask;                /* u8[R]   render path: bit w = the face's AA bbox overlaps the
+                                  *         8x4-pixel footprint w of its tile (x = (w&1)*8, y = (w>>1)*4) */
     size_t total;
 } DM2BinningLayout;
 
