@@ -73,7 +73,7 @@ class DM2ImageLayout(C.Structure):
 
 
 class DM2BinningLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("keys_unsorted", "vals_unsorted", "keys", "vals", "sort_temp", "imask", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("keys_unsorted", "vals_unsorted", "keys", "vals", "sort_temp", "imask", "meta", "total")]
 
 
 # every symbol declared in include/dm2_renderer.h: (restype, argtypes)

@@ -567,16 +567,10 @@ int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, 
     return 0;
 }
 
-// ------------------------------------------------------------------ tile ranges + footprint masks
-// reference renderer.cu:470-492 (+ the memset at :211).  For the render path the same pass also writes
-// one byte per sorted instance: bit w = the face's AA bounding box (aa.h:96-101) overlaps the 8x4
-// pixel footprint of warp w of its tile ((w & 1) * 8, (w >> 1) * 4) - the tile kernels build their
-// per-warp candidate lists from it with one coalesced byte load per instance.  With
-// aa_temperature == 0 the reference runs the ray test on every listed face: all bits set.
+// ------------------------------------------------------------------ tile ranges
+// reference renderer.cu:470-492 (+ the memset at :211)
 __global__ void __launch_bounds__(256)
-k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges,
-              const uint32_t* __restrict__ vals, const float* __restrict__ records, const int32_t* __restrict__ patch_min,
-              uint8_t* __restrict__ imask, int F, int gx, int gy, int use_bbox) {
+k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R) return;
     const uint32_t cur = (uint32_t)(keys[idx] >> 32);
@@ -586,38 +580,147 @@ k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__
         if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
     }
     if (idx == R - 1) ranges[cur].y = R;
-    if (imask == nullptr) return;
-    unsigned m = 0xFFu;
-    if (use_bbox) {
+}
+
+// ------------------------------------------------------------------ per-instance pixel classification
+// Steps 1-3 of the reference's per-(pixel, face) AA routine (aa.h:96-149, 446-496: triangle bbox
+// reject, 3 edges x 4 pixel corners half-plane tests -> outside / fully inside / partial) do not
+// depend on the compositing order, and the reference evaluates them per pixel per listed face inside
+// both raster kernels.  Here they run ONCE per sorted instance and 8x4-pixel footprint, bit-parallel:
+// the corner predicate  fma(cx, n.x, cy * n.y) - c >= 0  is monotone in cx (one rounding of an
+// affine function), so its value over the 9 corner columns of a footprint row is a run of bits whose
+// end is found with 5 exact evaluations; the 32 per-pixel outcomes then follow from shifts and ANDs.
+// Output per (footprint w, instance i), 16 bytes at meta[w * R + i]:
+//   x: bit l = pixel l of the footprint (x = l & 7, y = l >> 3) is touched (not AA_OUT)
+//   y,z: 45-bit corner grid, bit 9 * r + c = corner (c, r) lies inside all three edge half-planes
+// and imask[i] bit w = "x != 0": the tile kernels build their per-warp candidate lists from it with
+// one coalesced byte load per instance.  With aa_temperature == 0 the reference runs the ray test on
+// every listed face for every pixel: imask = 0xFF and no meta.
+struct InstGeo { float nx[3], ny[3], cc[3]; float4 bb; uint32_t ox, oy; };
+
+__device__ __forceinline__ uint32_t corner_row_mask(float nx, float ylo, float c, uint32_t X0) {
+    auto pred = [&](int cx) { return __fsub_rn(__fmaf_rn((float)(X0 + (uint32_t)cx), nx, ylo), c) >= 0.0f; };
+    const bool p0 = pred(0), p8 = pred(8);
+    int lo = 0, hi = 8;
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        const int mid = (lo + hi) >> 1;
+        const bool pm = pred(mid);
+        lo = (pm == p0) ? mid : lo;
+        hi = (pm == p0) ? hi : mid;
+    }
+    // columns 0..lo carry p0, columns hi..8 carry p8 (hi == lo + 1)
+    uint32_t m = p0 ? ((2u << lo) - 1u) : 0u;
+    m |= p8 ? (0x1FFu & ~((1u << hi) - 1u)) : 0u;
+    return m;
+}
+
+constexpr int kClsThreads = 256;
+
+__global__ void __launch_bounds__(kClsThreads)
+k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t R,
+                     const float* __restrict__ records, const int32_t* __restrict__ patch_min, int F, int gx, int gy,
+                     int use_bbox, uint8_t* __restrict__ imask, uint4* __restrict__ meta) {
+    __shared__ float s_f[13][kClsThreads];
+    __shared__ uint32_t s_o[2][kClsThreads];
+    __shared__ uint32_t s_im[kClsThreads];
+    __shared__ uint16_t s_pairs[kClsThreads * 8];
+    const int t = threadIdx.x;
+    const uint32_t i = blockIdx.x * kClsThreads + t;
+    if (!use_bbox) { if (i < R) imask[i] = 0xFF; return; }
+    unsigned bm = 0u;
+    if (i < R) {
+        const uint32_t cur = (uint32_t)(keys[i] >> 32);
         const uint32_t tiles = (uint32_t)(gx * gy);
         const uint32_t b = cur / tiles, t_in = cur % tiles;
         const uint32_t tx = t_in % (uint32_t)gx, ty = t_in / (uint32_t)gx;
-        const float4 bb = *reinterpret_cast<const float4*>(records + ((size_t)b * F + vals[idx]) * kRecWords + R_BBOX);
-        const uint32_t pmx = (uint32_t)patch_min[2 * b], pmy = (uint32_t)patch_min[2 * b + 1];
-        m = 0u;
+        const float* rec = records + ((size_t)b * F + vals[i]) * kRecWords;
+        const float4 bb = *reinterpret_cast<const float4*>(rec + R_BBOX);
+        const float4 n01 = *reinterpret_cast<const float4*>(rec + R_N01);
+        const float4 n2c = *reinterpret_cast<const float4*>(rec + R_N2C);
+        const float c2 = rec[R_MISC];
+        const uint32_t ox = tx * kTile + (uint32_t)patch_min[2 * b], oy = ty * kTile + (uint32_t)patch_min[2 * b + 1];
+        s_f[0][t] = n01.x; s_f[1][t] = n01.y; s_f[2][t] = n01.z; s_f[3][t] = n01.w; s_f[4][t] = n2c.x; s_f[5][t] = n2c.y;
+        s_f[6][t] = n2c.z; s_f[7][t] = n2c.w; s_f[8][t] = c2;
+        s_f[9][t] = bb.x; s_f[10][t] = bb.y; s_f[11][t] = bb.z; s_f[12][t] = bb.w;
+        s_o[0][t] = ox; s_o[1][t] = oy;
 #pragma unroll
         for (int w = 0; w < 8; w++) {
-            const float fx0 = (float)(tx * kTile + (w & 1) * 8 + pmx);
-            const float fy0 = (float)(ty * kTile + (w >> 1) * 4 + pmy);
+            const float fx0 = (float)(ox + (w & 1) * 8), fy0 = (float)(oy + (w >> 1) * 4);
             const bool hit = !((fx0 + 8.0f < bb.x) || (fx0 > bb.y) || (fy0 + 4.0f < bb.z) || (fy0 > bb.w));
-            m |= (hit ? 1u : 0u) << w;
+            bm |= (hit ? 1u : 0u) << w;
         }
     }
-    imask[idx] = (uint8_t)m;
+    s_im[t] = 0u;
+    uint32_t total;
+    uint32_t off = block_excl_scan(__popc(bm), total);
+    for (unsigned m = bm; m; m &= m - 1u) s_pairs[off++] = (uint16_t)((t << 3) | (__ffs(m) - 1));
+    __syncthreads();
+
+    for (uint32_t p = t; p < total; p += kClsThreads) {
+        const int e = s_pairs[p];
+        const int it = e >> 3, w = e & 7;
+        const float nxs[3] = {s_f[0][it], s_f[2][it], s_f[4][it]};
+        const float nys[3] = {s_f[1][it], s_f[3][it], s_f[5][it]};
+        const float ccs[3] = {s_f[6][it], s_f[7][it], s_f[8][it]};
+        const float bx0 = s_f[9][it], bx1 = s_f[10][it], by0 = s_f[11][it], by1 = s_f[12][it];
+        const uint32_t X0 = s_o[0][it] + (w & 1) * 8, Y0 = s_o[1][it] + (w >> 1) * 4;
+        // per-pixel triangle-bbox test (aa.h:96-101), negated so that NaN boxes reject nothing
+        uint32_t colmask = 0u, rowmask = 0u;
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const float fx = (float)(X0 + x);
+            colmask |= (!((__fadd_rn(fx, 1.0f) < bx0) || (fx > bx1)) ? 1u : 0u) << x;
+        }
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const float fy = (float)(Y0 + y);
+            rowmask |= (!((__fadd_rn(fy, 1.0f) < by0) || (fy > by1)) ? 1u : 0u) << y;
+        }
+        uint32_t anyr[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu};      // per pixel row: every edge has >= 1 corner inside
+        uint32_t allc[5] = {0x1FFu, 0x1FFu, 0x1FFu, 0x1FFu, 0x1FFu};   // per corner row: inside all edges
+#pragma unroll
+        for (int ed = 0; ed < 3; ed++) {
+            uint32_t m[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const float ylo = __fmul_rn((float)(Y0 + r), nys[ed]);
+                m[r] = corner_row_mask(nxs[ed], ylo, ccs[ed], X0);
+                allc[r] &= m[r];
+            }
+#pragma unroll
+            for (int y = 0; y < 4; y++) anyr[y] &= (m[y] | (m[y] >> 1) | m[y + 1] | (m[y + 1] >> 1)) & 0xFFu;
+        }
+        uint32_t hit = 0u;
+#pragma unroll
+        for (int y = 0; y < 4; y++) hit |= (((rowmask >> y) & 1u) ? (anyr[y] & colmask) : 0u) << (8 * y);
+        const unsigned long long corners = (unsigned long long)allc[0] | ((unsigned long long)allc[1] << 9) |
+                                           ((unsigned long long)allc[2] << 18) | ((unsigned long long)allc[3] << 27) |
+                                           ((unsigned long long)allc[4] << 36);
+        const uint32_t gi = blockIdx.x * kClsThreads + it;
+        meta[(size_t)w * R + gi] = make_uint4(hit, (uint32_t)corners, (uint32_t)(corners >> 32), 0u);
+        if (hit) atomicOr(&s_im[it], 1u << w);
+    }
+    __syncthreads();
+    if (i < R) imask[i] = (uint8_t)s_im[t];
 }
 
 int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, const TileMaskArgs* tm,
                        cudaStream_t s) {
     DM2_CHECK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
     if (R > 0) {
-        ProfScope _ps("tile_ranges", s);
-        if (tm)
-            k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges, tm->vals, tm->records, tm->patch_min,
-                                                       tm->imask, tm->F, tm->gx, tm->gy, tm->use_bbox);
-        else
-            k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges, nullptr, nullptr, nullptr, nullptr,
-                                                       0, 1, 1, 0);
-        DM2_LAUNCH_CHECK();
+        {
+            ProfScope _ps("tile_ranges", s);
+            k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges);
+            DM2_LAUNCH_CHECK();
+        }
+        if (tm) {
+            ProfScope _ps("classify", s);
+            k_classify_instances<<<cdiv(R, kClsThreads), kClsThreads, 0, s>>>(
+                keys, tm->vals, (uint32_t)R, tm->records, tm->patch_min, tm->F, tm->gx, tm->gy, tm->use_bbox, tm->imask,
+                reinterpret_cast<uint4*>(tm->meta));
+            DM2_LAUNCH_CHECK();
+        }
     }
     return 0;
 }

@@ -111,6 +111,7 @@ static void binning_layout(long long R, DM2BinningLayout* L) {
     L->vals          = take((size_t)R * 4);
     L->sort_temp     = take(sort_temp_bytes(R));
     L->imask         = take((size_t)R);
+    L->meta          = take((size_t)R * 8 * 16);
     L->total         = off + 256;
 }
 
@@ -141,6 +142,8 @@ static BinWs carve_bin(void* ws, long long R) {
     b.keys = (uint64_t*)(p + L.keys); b.vals = (uint32_t*)(p + L.vals);
     b.sort_temp = p + L.sort_temp; b.sort_temp_bytes = sort_temp_bytes(R);
     b.imask = (uint8_t*)(p + L.imask);
+    b.meta = p + L.meta;
+    b.R = R;
     return b;
 }
 
@@ -255,7 +258,7 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
         return 0;
     }
     const long long R = num_rendered;
-    const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
+    const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
     if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, &tm, s)) return 1;
     return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, s);
 }

@@ -189,10 +189,12 @@ struct ImageWs {
 struct BinWs {
     uint64_t* keys_unsorted; uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
     void* sort_temp; size_t sort_temp_bytes;
-    uint8_t* imask;               // per sorted instance: 8x4-footprint overlap bits (render path)
+    uint8_t* imask;               // per sorted instance: bit w = footprint w has a touched pixel (render path)
+    long long R;                  // num_rendered
+    void* meta;                   // uint4[8][R]: per (footprint, instance) pixel classification (k_classify_instances)
 };
 struct TileMaskArgs {             // optional second output of the tile-range pass (render path)
-    const uint32_t* vals; const float* records; const int32_t* patch_min; uint8_t* imask;
+    const uint32_t* vals; const float* records; const int32_t* patch_min; uint8_t* imask; void* meta;
     int F, gx, gy, use_bbox;
 };
 

@@ -85,7 +85,8 @@ struct BwdWarpSmem {
 
 __global__ void __launch_bounds__(kRasterThreads, 2)
 k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                  const uint8_t* __restrict__ imask, const uint2* __restrict__ ranges,
+                  const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R,
+                  const uint2* __restrict__ ranges,
                   const float* __restrict__ final_T, const float* __restrict__ final_prev_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
                   const float* __restrict__ dL_ddepth, float* __restrict__ gface, int gx, int gy) {
@@ -101,6 +102,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
     const size_t view_base = (size_t)tc.b * in.F;
     const uint32_t* tlist = list + range.x;
     const uint8_t* tmask = imask + range.x;
+    const uint4* tmeta = use_aa ? meta + (size_t)warp * R + range.x : nullptr;
 
     // ---- per-pixel state (backward.cu:133-160)
     PixelGeom pg;
@@ -140,11 +142,11 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         fill_queue<true>(ws.q, head, count, cursor, warp_last, tmask, tlist, warp, lane);
         if (count == 0) break;
         const int ncs = min(count, kSub);
-        stage_candidates(ws.srec, records, ws.q, head, ncs, view_base, lane);
+        stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
         // ====== 1. lock-step classification, pair list
         uint32_t hit, part, im;
-        classify_subchunk(ws.srec, ncs, use_aa, pg.pxmin, pg.pymin, hit, part, im, [&](int k) {
+        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im, [&](int k) {
             return tc.inside && (int)ws.q.idx[(head + k) & (kQueue - 1)] < my_last;
         });
         if (__any_sync(0xffffffffu, hit != 0u)) {
@@ -481,7 +483,7 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     {
         ProfScope _ps("raster_backward", s);
         k_raster_backward<<<(unsigned)nblk, kRasterThreads, kBwdSmem, s>>>(
-            in, fw.records, bw.vals, bw.imask, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor,
+            in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor,
             dL_ddepth, gface, gx, gy);
         DM2_LAUNCH_CHECK();
     }

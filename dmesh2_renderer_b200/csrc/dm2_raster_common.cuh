@@ -73,14 +73,21 @@ __device__ __forceinline__ void fill_queue(WarpQueue& q, int head, int& count, i
     __syncwarp();
 }
 
-// Stages the records of the first `ncs` queued candidates into slots 0..ncs-1.
+// Stages the records of the first `ncs` queued candidates into slots 0..ncs-1; the 16th 16-byte chunk
+// of a slot receives the candidate's classification words (k_classify_instances) for this warp's
+// footprint.  tmeta: meta + warp * R + range.x (nullptr when aa_temperature == 0).
+constexpr int R_META = 60;                  // staged slot only: touched-pixel mask, corner grid lo / hi
 __device__ __forceinline__ void stage_candidates(float* __restrict__ srec, const float* __restrict__ records,
-                                                 const WarpQueue& q, int head, int ncs, size_t view_base, int lane) {
+                                                 const uint4* __restrict__ tmeta, const WarpQueue& q, int head, int ncs,
+                                                 size_t view_base, int lane) {
     for (int t = lane; t < ncs * 16; t += 32) {
         const int slot = t >> 4, chunk = t & 15;
-        if (chunk == 15) continue;
-        const uint32_t fid = q.fid[(head + slot) & (kQueue - 1)];
-        cp_async16(srec + slot * kRecStride + chunk * 4, records + (view_base + fid) * kRecWords + chunk * 4);
+        const int pos = (head + slot) & (kQueue - 1);
+        if (chunk == 15) {
+            if (tmeta) cp_async16(srec + slot * kRecStride + R_META, tmeta + q.idx[pos]);
+            continue;
+        }
+        cp_async16(srec + slot * kRecStride + chunk * 4, records + (view_base + q.fid[pos]) * kRecWords + chunk * 4);
     }
     cp_async_wait_all();
     __syncwarp();
@@ -131,20 +138,25 @@ __device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Lock-step classification of the staged sub-chunk: bit k of hit / part = candidate k touches /
-// only partially covers my pixel; im holds the 4-bit inside-corner mask of every partial candidate.
-// lane_ok(k): extra per-lane admission test (forward: pixel not done; backward: inside n_contrib).
+// Per-lane view of the staged classification words: bit k of hit / part = candidate k touches / only
+// partially covers my pixel; im holds the 4-bit inside-corner mask (aa.h:103-149 corner order) of every
+// partial candidate.  lane_ok(k): extra per-lane admission test (forward: pixel not done; backward:
+// inside n_contrib).  With aa_temperature == 0 every admitted pixel is a hit and nothing is partial.
 template <typename LaneOk>
-__device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec, int ncs, bool use_aa, float pxmin,
-                                                  float pymin, uint32_t& hit, uint32_t& part, uint32_t& im,
-                                                  LaneOk lane_ok) {
+__device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec, int ncs, bool use_aa, int lane,
+                                                  uint32_t& hit, uint32_t& part, uint32_t& im, LaneOk lane_ok) {
     hit = 0u; part = 0u; im = 0u;
+    const int sh = 9 * (lane >> 3) + (lane & 7);
     for (int k = 0; k < ncs; k++) {
-        int cls = AA_FULL;
+        bool on = lane_ok(k);
         unsigned inmask = 0xF;
-        if (use_aa) cls = aa_classify(srec + k * kRecStride, pxmin, pymin, inmask);
-        const bool on = (cls != AA_OUT) && lane_ok(k);
-        const bool p = on && (cls == AA_PART);
+        if (use_aa) {
+            const uint4 m = *reinterpret_cast<const uint4*>(srec + k * kRecStride + R_META);    // broadcast
+            on = on && ((m.x >> lane) & 1u);
+            const uint32_t c = (uint32_t)((((unsigned long long)m.z << 32) | m.y) >> sh);
+            inmask = (c & 3u) | ((c >> 8) & 4u) | ((c >> 6) & 8u);      // (x,y) (x+1,y) (x+1,y+1) (x,y+1)
+        }
+        const bool p = on && (inmask != 0xF);
         hit |= (on ? 1u : 0u) << k;
         part |= (p ? 1u : 0u) << k;
         if (p) im |= inmask << (4 * k);

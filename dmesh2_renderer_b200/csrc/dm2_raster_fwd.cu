@@ -16,7 +16,8 @@ struct FwdWarpSmem {
 
 __global__ void __launch_bounds__(kRasterThreads, 3)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                 const uint8_t* __restrict__ imask, const uint2* __restrict__ ranges, float* __restrict__ final_T,
+                 const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R,
+                  const uint2* __restrict__ ranges, float* __restrict__ final_T,
                  float* __restrict__ final_prev_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                  float* __restrict__ out_depth, int gx, int gy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -43,6 +44,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     const size_t view_base = (size_t)tc.b * in.F;
     const uint32_t* tlist = list + range.x;
     const uint8_t* tmask = imask + range.x;
+    const uint4* tmeta = use_aa ? meta + (size_t)warp * R + range.x : nullptr;
 
     bool done = !tc.inside;
     float T = 1.0f, pT = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
@@ -53,11 +55,11 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         fill_queue<false>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
         if (count == 0) break;
         const int ncs = min(count, kSub);
-        stage_candidates(ws.srec, records, ws.q, head, ncs, view_base, lane);
+        stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
         // ---- lock-step classification, pair list
         uint32_t hit, part, im;
-        classify_subchunk(ws.srec, ncs, use_aa, pg.pxmin, pg.pymin, hit, part, im, [&](int) { return !done; });
+        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im, [&](int) { return !done; });
         if (__any_sync(0xffffffffu, hit != 0u)) {
             int np, npairs;
             build_pair_list(ws.plist, ncs, hit, part, im, lane, np, npairs);
@@ -141,7 +143,7 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
         attr_set = true;
     }
     ProfScope _ps("raster_forward", s);
-    k_raster_forward<<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(in, fw.records, bw.vals, bw.imask, iw.ranges,
+    k_raster_forward<<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R, iw.ranges,
                                                                       iw.final_T, iw.final_prev_T, iw.n_contrib,
                                                                       out_color, out_depth, gx, gy);
     DM2_LAUNCH_CHECK();

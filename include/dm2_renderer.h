@@ -129,8 +129,10 @@ typedef struct DM2BinningLayout {     /* reference BinningState, state.h:41-51 *
     size_t keys;                 /* u64[R]  sorted                                              */
     size_t vals;                 /* u32[R]  sorted  (= reference face_list)                     */
     size_t sort_temp;            /* radix-sort histograms                                       */
-    size_t imask;                /* u8[R]   render path: bit w = the face's AA bbox overlaps the
+    size_t imask;                /* u8[R]   render path: bit w = the face touches a pixel of the
                                   *         8x4-pixel footprint w of its tile (x = (w&1)*8, y = (w>>1)*4) */
+    size_t meta;                 /* uint4[8][R] render path: per (footprint, instance) touched-pixel mask
+                                  *         and 9x5 inside-corner grid (reference aa.h:96-149 evaluated once) */
     size_t total;
 } DM2BinningLayout;
 
