@@ -5,8 +5,10 @@ error behaviour (RuntimeError with the reference's messages) - but the work is d
 hand-written sm_100a kernels in libdm2_b200.so through the C-ABI of include/dm2_renderer.h.
 
 Differences that are private to this implementation (allowed by SURVEY.md section 8b):
-  * the four AA-cache tensors of render_forward_cuda come back EMPTY (K = 0): the backward pass
-    recomputes the overlap area instead of reading a B*H*W*K*32-byte cache;
+  * the AA cache is ONE compact pool (28 bytes per partially covered (pixel, face) pair the forward
+    pass clipped) returned in the ``oarea`` slot of the reference's 10-tuple; the other three cache
+    tensors come back empty.  ``len_oarea_buffer == 0`` disables it (the backward pass then
+    recomputes every overlap area, as it does for pairs beyond the pool capacity);
   * the three scratch buffers are laid out per DM2FaceLayout / DM2ImageLayout / DM2BinningLayout.
 """
 import ctypes as C
@@ -15,6 +17,29 @@ import torch
 
 from . import _lib
 from ._lib import DM2BinningLayout, DM2FaceLayout, DM2ImageLayout, DM2LayerInputs, DM2RenderGrads, DM2RenderInputs
+
+
+# AA-cache sizing: pairs reserved per sorted (face, tile) instance, and a hard cap on the pool size
+AA_CACHE_PAIRS_PER_INSTANCE = 32
+AA_CACHE_MAX_BYTES = 8 << 30
+
+
+def aa_cache_alloc(len_oarea_buffer, num_rendered, aa_temperature, device, want=True):
+    """Returns (pool tensor, capacity in pairs); (empty, 0) when the cache is off."""
+    cap = 0
+    if want and len_oarea_buffer > 0 and aa_temperature > 0 and num_rendered > 0:
+        cap = min(int(num_rendered) * AA_CACHE_PAIRS_PER_INSTANCE, AA_CACHE_MAX_BYTES // 28, (1 << 32) - 4096)
+    if cap == 0:
+        return torch.empty((0,), dtype=torch.float32, device=device), 0
+    nb = C.c_size_t(0)
+    _lib.check(_lib.load_library().dm2_aa_cache_bytes(cap, C.byref(nb)))
+    return torch.empty(((nb.value + 3) // 4,), dtype=torch.float32, device=device), cap
+
+
+def aa_cache_capacity(pool):
+    """Capacity (pairs) of a pool returned by aa_cache_alloc - inverse of dm2_aa_cache_bytes."""
+    n = int(pool.numel()) * 4
+    return 0 if n == 0 else ((n - 512) // 28 // 64) * 64
 
 
 def _err(msg):
@@ -160,7 +185,7 @@ def binning_layout(R):
 def render_forward_cuda(background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
                         verts_ndc, verts_image, faces_intense, aa_temperature, aa_face_verts, aa_face_edges,
                         aa_face_edges_iszero, aa_face_edges_recip, aa_face_edges_normal, aa_face_edges_normal_c,
-                        len_oarea_buffer, image_ray_o, image_ray_d):
+                        len_oarea_buffer, image_ray_o, image_ray_d, want_cache=True):
     """reference render.h:12-45 / render.cu:28-195.  Returns the reference's 10-tuple."""
     lib = _lib.load_library()
     s, keep = _render_inputs(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
@@ -180,10 +205,10 @@ def render_forward_cuda(background, patch_min, patch_width, patch_height, verts,
         _lib.check(lib.dm2_render_preprocess(C.byref(s), _ptr(face_buffer), C.byref(num_rendered), stream))
         R = int(num_rendered.value)
         binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
+        oarea, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev, want_cache)
         _lib.check(lib.dm2_render_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
-                                          R, _ptr(out_color), _ptr(out_depth), stream))
-        # AA cache placeholders (K = 0): kept so the tuple has the reference's arity
-        oarea = torch.empty((B, H, W, 0), **f_opts)
+                                          R, _ptr(out_color), _ptr(out_depth), _ptr(oarea), cap, stream))
+        # the other AA cache tensors are placeholders, kept so the tuple has the reference's arity
         tri_id = torch.empty((B, H, W, 0), dtype=torch.int32, device=dev)
         tri_cnt = torch.empty((0,), dtype=torch.int32, device=dev)
         doarea = torch.empty((B, H, W, 0, 3, 2), **f_opts)
@@ -220,9 +245,11 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
             nb = C.c_size_t(0)
             _lib.check(lib.dm2_backward_workspace_bytes(s.B, s.F, C.byref(nb)))
             grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
+            cap = aa_cache_capacity(oarea_buffer_oarea) if oarea_buffer_oarea is not None else 0
             _lib.check(lib.dm2_render_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
                                                _ptr(image_buffer), int(num_rendered), _ptr(gc), _ptr(gd),
-                                               C.byref(g), _ptr(grad_ws), _stream(dev)))
+                                               C.byref(g), _ptr(grad_ws),
+                                               _ptr(oarea_buffer_oarea) if cap else C.c_void_p(0), cap, _stream(dev)))
     return dL_dverts, dL_dverts_color, dL_dfaces_opacity, dL_dverts_ndc, dL_dfaces_intense, dL_daa_face_verts
 
 

@@ -593,6 +593,7 @@ k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__
 // Output per (footprint w, instance i), 16 bytes at meta[w * R + i]:
 //   x: bit l = pixel l of the footprint (x = l & 7, y = l >> 3) is touched (not AA_OUT)
 //   y,z: 45-bit corner grid, bit 9 * r + c = corner (c, r) lies inside all three edge half-planes
+//   w: AA-cache entry offset, written by the forward tile kernel (0xFFFFFFFF = not cached)
 // and imask[i] bit w = "x != 0": the tile kernels build their per-warp candidate lists from it with
 // one coalesced byte load per instance.  With aa_temperature == 0 the reference runs the ray test on
 // every listed face for every pixel: imask = 0xFF and no meta.
@@ -698,7 +699,7 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
                                            ((unsigned long long)allc[2] << 18) | ((unsigned long long)allc[3] << 27) |
                                            ((unsigned long long)allc[4] << 36);
         const uint32_t gi = blockIdx.x * kClsThreads + it;
-        meta[(size_t)w * R + gi] = make_uint4(hit, (uint32_t)corners, (uint32_t)(corners >> 32), 0u);
+        meta[(size_t)w * R + gi] = make_uint4(hit, (uint32_t)corners, (uint32_t)(corners >> 32), 0xFFFFFFFFu);
         if (hit) atomicOr(&s_im[it], 1u << w);
     }
     __syncthreads();

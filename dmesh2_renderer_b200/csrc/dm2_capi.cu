@@ -241,10 +241,12 @@ int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, int64_t* num
 }
 
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                       int64_t num_rendered, float* out_color, float* out_depth, void* stream) {
+                       int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
+                       int64_t aa_cache_pairs, void* stream) {
     if (check_render_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && out_color && out_depth, "dm2_render_forward: null buffer");
     DM2_REQUIRE(num_rendered >= 0 && num_rendered < (1ll << 31), "dm2_render_forward: bad num_rendered");
+    DM2_REQUIRE(aa_cache_pairs >= 0 && aa_cache_pairs < (1ll << 32) - 1, "dm2_render_forward: bad aa_cache_pairs");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
@@ -260,12 +262,13 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
     const long long R = num_rendered;
     const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
     if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, &tm, s)) return 1;
-    return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, s);
+    return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, aa_cache, aa_cache ? aa_cache_pairs : 0, s);
 }
 
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
                         const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
-                        const float* dL_dout_depth, const DM2RenderGrads* grads, void* grad_ws, void* stream) {
+                        const float* dL_dout_depth, const DM2RenderGrads* grads, void* grad_ws,
+                        const void* aa_cache, int64_t aa_cache_pairs, void* stream) {
     if (check_render_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
                 "dm2_render_backward: null buffer");
@@ -277,7 +280,8 @@ int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const vo
     FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
     BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
     ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
-    if (launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, s)) return 1;
+    if (launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, aa_cache,
+                               aa_cache ? aa_cache_pairs : 0, s)) return 1;
     return launch_grad_scatter(*in, fw, *grads, grad_ws, s);
 }
 
@@ -317,16 +321,19 @@ int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_r
 }
 
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                      int64_t num_rendered, float* out_color, float* out_depth, void* stream) {
+                      int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
+                      int64_t aa_cache_pairs, void* stream) {
     if (check_fused_inputs(in)) return 2;
     DM2_REQUIRE(in->ray_o && in->ray_d && in->ray_view, "dm2_fused_forward: null ray buffers");
     const DM2RenderInputs r = as_render_inputs(*in);
-    return dm2_render_forward(&r, face_ws, binning_ws, image_ws, num_rendered, out_color, out_depth, stream);
+    return dm2_render_forward(&r, face_ws, binning_ws, image_ws, num_rendered, out_color, out_depth, aa_cache,
+                              aa_cache_pairs, stream);
 }
 
 int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void* binning_ws,
                        const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
-                       const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws, void* stream) {
+                       const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws,
+                       const void* aa_cache, int64_t aa_cache_pairs, void* stream) {
     if (check_fused_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
                 "dm2_fused_backward: null buffer");
@@ -339,8 +346,15 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
     FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
     BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
     ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
-    if (launch_raster_backward(r, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, s)) return 1;
+    if (launch_raster_backward(r, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, aa_cache,
+                               aa_cache ? aa_cache_pairs : 0, s)) return 1;
     return launch_fused_grad_scatter(*in, fw, *grads, grad_ws, s);
+}
+
+int dm2_aa_cache_bytes(int64_t capacity_pairs, size_t* bytes) {
+    DM2_REQUIRE(bytes && capacity_pairs >= 0 && capacity_pairs < (1ll << 32) - 1, "dm2_aa_cache_bytes: bad arguments");
+    *bytes = aa_cache_bytes(capacity_pairs);
+    return 0;
 }
 
 int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes) {

@@ -211,10 +211,12 @@ size_t sort_temp_bytes(long long n);
 int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, const TileMaskArgs* tm,
                        cudaStream_t s);
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
-                          const ImageWs& iw, float* out_color, float* out_depth, cudaStream_t s);
+                          const ImageWs& iw, float* out_color, float* out_depth, void* aa_cache,
+                          long long aa_cache_pairs, cudaStream_t s);
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
-                           void* grad_ws, cudaStream_t s);
+                           void* grad_ws, const void* aa_cache, long long aa_cache_pairs, cudaStream_t s);
+size_t aa_cache_bytes(long long capacity_pairs);
 int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
                         cudaStream_t s);
 int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, cudaStream_t s);

@@ -85,7 +85,7 @@ struct BwdWarpSmem {
 
 __global__ void __launch_bounds__(kRasterThreads, 2)
 k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                  const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R,
+                  const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R, AACache cache,
                   const uint2* __restrict__ ranges,
                   const float* __restrict__ final_T, const float* __restrict__ final_prev_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
@@ -144,6 +144,11 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         const int ncs = min(count, kSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
+        if (use_aa && lane < ncs)
+            ws.srec[lane * kRecStride + R_PMASK] =
+                __uint_as_float(partial_mask(*reinterpret_cast<const uint4*>(ws.srec + lane * kRecStride + R_META)));
+        __syncwarp();
+
         // ====== 1. lock-step classification, pair list
         uint32_t hit, part, im;
         classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im, [&](int k) {
@@ -175,7 +180,17 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                 bool ok = true;
                 if (pid < np) {
                     float g[6];
-                    ok = aa_clip<true>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, g);
+                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                    if (cache.capacity != 0u && poff != kNoCache) {      // evaluated by the forward pass
+                        const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << l) - 1u));
+                        s.area = cache.area[j];
+                        ok = !(s.area == -1.0f);
+                        const float2* gj = reinterpret_cast<const float2*>(cache.grad + (size_t)j * 6);
+                        const float2 g0 = gj[0], g1 = gj[1], g2 = gj[2];
+                        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = g2.x; g[5] = g2.y;
+                    } else {
+                        ok = aa_clip<true>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, g);
+                    }
 #pragma unroll
                     for (int q = 0; q < 6; q++) ws.tG[q][slot] = g[q];
                 }
@@ -438,6 +453,12 @@ k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touch
 
 constexpr size_t kBwdSmem = sizeof(BwdWarpSmem) * (kRasterThreads / 32);
 
+size_t aa_cache_bytes(long long capacity_pairs) {
+    if (capacity_pairs <= 0) return 0;
+    const size_t c64 = (((size_t)capacity_pairs + 63) / 64) * 64;
+    return 256 + c64 * 4 + c64 * 24 + 256;
+}
+
 size_t backward_ws_bytes(long long BF) { return align_up((size_t)BF * kGradWords * 4, 256) + 256; }
 
 int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
@@ -464,7 +485,8 @@ int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2Re
 
 // zero the per-face gradient records and run the tile kernel; the caller scatters afterwards
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                           const float* dL_dcolor, const float* dL_ddepth, void* grad_ws, cudaStream_t s) {
+                           const float* dL_dcolor, const float* dL_ddepth, void* grad_ws, const void* aa_cache,
+                           long long aa_cache_pairs, cudaStream_t s) {
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     const long long BF = (long long)in.B * in.F;
@@ -483,8 +505,9 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     {
         ProfScope _ps("raster_backward", s);
         k_raster_backward<<<(unsigned)nblk, kRasterThreads, kBwdSmem, s>>>(
-            in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R, iw.ranges, iw.final_T, iw.final_prev_T, iw.n_contrib, dL_dcolor,
-            dL_ddepth, gface, gx, gy);
+            in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R,
+            aa_cache_view(const_cast<void*>(aa_cache), aa_cache_pairs), iw.ranges, iw.final_T, iw.final_prev_T,
+            iw.n_contrib, dL_dcolor, dL_ddepth, gface, gx, gy);
         DM2_LAUNCH_CHECK();
     }
     return 0;

@@ -76,7 +76,42 @@ __device__ __forceinline__ void fill_queue(WarpQueue& q, int head, int& count, i
 // Stages the records of the first `ncs` queued candidates into slots 0..ncs-1; the 16th 16-byte chunk
 // of a slot receives the candidate's classification words (k_classify_instances) for this warp's
 // footprint.  tmeta: meta + warp * R + range.x (nullptr when aa_temperature == 0).
-constexpr int R_META = 60;                  // staged slot only: touched-pixel mask, corner grid lo / hi
+constexpr int R_META = 60;                  // staged slot only: touched-pixel mask, corner grid lo / hi, AA-cache offset
+constexpr int R_PMASK = 64;                 // staged slot only: partially-covered-pixel mask of the footprint
+constexpr uint32_t kNoCache = 0xFFFFFFFFu;  // AA-cache offset: this candidate's pairs are not cached
+
+// ------------------------------------------------------------------------------------------------
+// AA cache (the role of the reference's oarea buffers, render.cu:143-146, as a compact pool): the
+// forward pass stores the overlap area and its gradient of every partially covered (pixel, face)
+// pair it evaluates, the backward pass reads them back instead of clipping again.  Entries of one
+// (instance, footprint) are contiguous, ordered by pixel; the entry offset lives in the 4th
+// classification word.  Layout: [u32 counter | pad to 256 B][area f32 x C][grad f32 x 6C].
+struct AACache {
+    uint32_t* counter;
+    float* area;
+    float* grad;
+    uint32_t capacity;
+};
+__host__ __device__ __forceinline__ AACache aa_cache_view(void* pool, long long capacity) {
+    AACache c;
+    c.counter = reinterpret_cast<uint32_t*>(pool);
+    c.area = reinterpret_cast<float*>(reinterpret_cast<char*>(pool) + 256);
+    c.grad = c.area + (((size_t)capacity + 63) / 64) * 64;
+    c.capacity = pool ? (uint32_t)capacity : 0u;
+    return c;
+}
+
+// partially covered pixels of a footprint from its classification words (touched & not all 4 corners inside)
+__device__ __forceinline__ uint32_t partial_mask(const uint4 m) {
+    const unsigned long long C = ((unsigned long long)m.z << 32) | m.y;
+    uint32_t full = 0u;
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const uint32_t r0 = (uint32_t)(C >> (9 * y)) & 0x1FFu, r1 = (uint32_t)(C >> (9 * (y + 1))) & 0x1FFu;
+        full |= (r0 & (r0 >> 1) & r1 & (r1 >> 1) & 0xFFu) << (8 * y);
+    }
+    return m.x & ~full;
+}
 __device__ __forceinline__ void stage_candidates(float* __restrict__ srec, const float* __restrict__ records,
                                                  const uint4* __restrict__ tmeta, const WarpQueue& q, int head, int ncs,
                                                  size_t view_base, int lane) {

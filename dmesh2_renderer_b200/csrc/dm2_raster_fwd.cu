@@ -14,10 +14,12 @@ struct FwdWarpSmem {
     uint16_t plist[kSlots];
 };
 
+// CACHE: also evaluate d(area)/d(aa verts) in the clip and store area + gradient in the AA cache.
+template <bool CACHE>
 __global__ void __launch_bounds__(kRasterThreads, 3)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                 const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R,
-                  const uint2* __restrict__ ranges, float* __restrict__ final_T,
+                 const uint8_t* __restrict__ imask, uint4* __restrict__ meta, uint32_t R, AACache cache,
+                 const uint2* __restrict__ ranges, float* __restrict__ final_T,
                  float* __restrict__ final_prev_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                  float* __restrict__ out_depth, int gx, int gy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -44,7 +46,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     const size_t view_base = (size_t)tc.b * in.F;
     const uint32_t* tlist = list + range.x;
     const uint8_t* tmask = imask + range.x;
-    const uint4* tmeta = use_aa ? meta + (size_t)warp * R + range.x : nullptr;
+    uint4* tmeta = use_aa ? meta + (size_t)warp * R + range.x : nullptr;
 
     bool done = !tc.inside;
     float T = 1.0f, pT = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
@@ -56,6 +58,31 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         if (count == 0) break;
         const int ncs = min(count, kSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
+
+        if (CACHE && use_aa) {
+            // reserve cache entries for every partially covered pixel of the staged candidates
+            uint32_t pm = 0u;
+            if (lane < ncs) pm = partial_mask(*reinterpret_cast<const uint4*>(ws.srec + lane * kRecStride + R_META));
+            const uint32_t cnt = __popc(pm);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < kSub; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, ncs - 1);
+            uint32_t base = 0u;
+            if (lane == 0 && tot > 0u) base = atomicAdd(cache.counter, tot);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const bool fits = (unsigned long long)base + tot <= (unsigned long long)cache.capacity;
+            if (lane < ncs) {
+                const uint32_t poff = fits ? base + incl - cnt : kNoCache;
+                ws.srec[lane * kRecStride + R_META + 3] = __uint_as_float(poff);
+                ws.srec[lane * kRecStride + R_PMASK] = __uint_as_float(pm);
+                reinterpret_cast<uint32_t*>(tmeta + ws.q.idx[(head + lane) & (kQueue - 1)])[3] = poff;
+            }
+            __syncwarp();
+        }
 
         // ---- lock-step classification, pair list
         uint32_t hit, part, im;
@@ -81,7 +108,19 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                 Shade s;
                 s.area = use_aa ? 1.0f : 0.0f;
                 bool ok = true;
-                if (pid < np) ok = aa_clip<false>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, nullptr);
+                if (pid < np) {
+                    float g[6];
+                    ok = aa_clip<CACHE>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, g);
+                    if (CACHE) {
+                        const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                        if (poff != kNoCache) {
+                            const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << l) - 1u));
+                            cache.area[j] = ok ? s.area : -1.0f;
+                            float2* gj = reinterpret_cast<float2*>(cache.grad + (size_t)j * 6);
+                            gj[0] = make_float2(g[0], g[1]); gj[1] = make_float2(g[2], g[3]); gj[2] = make_float2(g[4], g[5]);
+                        }
+                    }
+                }
                 ok = ok && shade_tail(rec, qg, tau, s);
                 const int slot = k * 32 + l;
                 if (ok) {
@@ -133,19 +172,28 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
 constexpr size_t kFwdSmem = sizeof(FwdWarpSmem) * (kRasterThreads / 32);
 
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                          float* out_color, float* out_depth, cudaStream_t s) {
+                          float* out_color, float* out_depth, void* aa_cache, long long aa_cache_pairs, cudaStream_t s) {
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     if (nblk == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        DM2_CHECK(cudaFuncSetAttribute(k_raster_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        DM2_CHECK(cudaFuncSetAttribute(k_raster_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        DM2_CHECK(cudaFuncSetAttribute(k_raster_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
         attr_set = true;
     }
+    const AACache cache = aa_cache_view(aa_cache, aa_cache_pairs);
+    const bool use_cache = cache.capacity > 0 && in.aa_temperature > 0.0f && bw.R > 0;
+    if (use_cache) DM2_CHECK(cudaMemsetAsync(cache.counter, 0, sizeof(uint32_t), s));
     ProfScope _ps("raster_forward", s);
-    k_raster_forward<<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R, iw.ranges,
-                                                                      iw.final_T, iw.final_prev_T, iw.n_contrib,
-                                                                      out_color, out_depth, gx, gy);
+    if (use_cache)
+        k_raster_forward<true><<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(
+            in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, iw.ranges,
+            iw.final_T, iw.final_prev_T, iw.n_contrib, out_color, out_depth, gx, gy);
+    else
+        k_raster_forward<false><<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(
+            in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, iw.ranges,
+            iw.final_T, iw.final_prev_T, iw.n_contrib, out_color, out_depth, gx, gy);
     DM2_LAUNCH_CHECK();
     return 0;
 }

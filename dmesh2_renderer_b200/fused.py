@@ -15,7 +15,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._C import _err, _prep, _ptr, _stream, binning_layout, face_layout, image_layout
+from ._C import (_err, _prep, _ptr, _stream, aa_cache_alloc, aa_cache_capacity, binning_layout, face_layout,
+                 image_layout)
 from ._lib import DM2FusedGrads, DM2FusedInputs
 
 
@@ -64,12 +65,13 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
 
 class FusedRenderFunction(torch.autograd.Function):
     """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, mv [B,4,4], proj [B,4,4],
-    faces_intense, aa_temperature, ray_o, ray_d, ray_view) -> (color [B,H,W,3], depth_ndc [B,H,W]).
-    Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense."""
+    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer) -> (color [B,H,W,3],
+    depth_ndc [B,H,W]).  Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense.
+    len_oarea_buffer > 0 turns the forward -> backward AA cache on (see _C.py)."""
 
     @staticmethod
     def forward(ctx, background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
-                mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
+                mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer=20):
         lib = _lib.load_library()
         s, keep = _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
                                 faces_opacity, mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view)
@@ -85,9 +87,11 @@ class FusedRenderFunction(torch.autograd.Function):
             _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), C.byref(nr), stream))
             R = int(nr.value)
             binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
+            pool, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev,
+                                       any(ctx.needs_input_grad))
             _lib.check(lib.dm2_fused_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
-                                             R, _ptr(color), _ptr(depth), stream))
-        ctx.save_for_backward(*keep.values(), face_buffer, binning_buffer, image_buffer)
+                                             R, _ptr(color), _ptr(depth), _ptr(pool), cap, stream))
+        ctx.save_for_backward(*keep.values(), face_buffer, binning_buffer, image_buffer, pool)
         ctx.keys = list(keep.keys())
         ctx.num_rendered = R
         ctx.patch = (patch_width, patch_height)
@@ -99,7 +103,7 @@ class FusedRenderFunction(torch.autograd.Function):
         lib = _lib.load_library()
         saved = ctx.saved_tensors
         keep = dict(zip(ctx.keys, saved[:len(ctx.keys)]))
-        face_buffer, binning_buffer, image_buffer = saved[len(ctx.keys):]
+        face_buffer, binning_buffer, image_buffer, pool = saved[len(ctx.keys):]
         s, keep = _fused_struct(keep["background"], keep["patch_min"], ctx.patch[0], ctx.patch[1], keep["verts"],
                                 keep["faces"], keep["verts_color"], keep["faces_opacity"], keep["mv"], keep["proj"],
                                 keep["faces_intense"], ctx.aa_temperature, keep["ray_o"], keep["ray_d"],
@@ -119,6 +123,7 @@ class FusedRenderFunction(torch.autograd.Function):
                 grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
                 _lib.check(lib.dm2_fused_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
                                                   _ptr(image_buffer), ctx.num_rendered, _ptr(gc), _ptr(gd),
-                                                  C.byref(g), _ptr(grad_ws), _stream(dev)))
+                                                  C.byref(g), _ptr(grad_ws), _ptr(pool), aa_cache_capacity(pool),
+                                                  _stream(dev)))
         return (None, None, None, None, g_verts, None, g_color, g_opacity, None, None, g_intense, None, None, None,
-                None)
+                None, None)

@@ -55,7 +55,8 @@ class Renderer(torch.nn.Module):
     def __init__(self, mv, proj, width, height, device, aa_grad_buffer_size=20):
         super().__init__()
         self._setup(mv, proj, width, height, device)
-        # kept for API parity; this implementation recomputes AA terms in the backward pass
+        # > 0: keep the forward pass's AA overlap areas + gradients for the backward pass (compact pool,
+        # _C.aa_cache_alloc); 0: recompute them in the backward pass
         self.aa_grad_buffer_size = aa_grad_buffer_size
 
     def _setup(self, mv, proj, width, height, device):
@@ -141,7 +142,7 @@ class Renderer(torch.nn.Module):
             background.to(dtype=f32), batch_patch_min.to(device=dev, dtype=torch.int32), patch_width, patch_height,
             verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
             self.mv[batch_mvp_idx].to(dtype=f32), self.proj[batch_mvp_idx].to(dtype=f32),
-            faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view)
+            faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view, self.aa_grad_buffer_size)
 
     def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
                        faces_opacity, faces_intense, background, aa_temperature=1.0):

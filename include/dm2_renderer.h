@@ -40,14 +40,14 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 7
+#define DM2_ABI_VERSION 8
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
     int32_t B, P, F;             /* views in this call, vertices, faces                     */
     int32_t H, W;                /* patch_height, patch_width                               */
     float   aa_temperature;      /* in [0,1]                                                */
-    int32_t len_oarea_buffer;    /* K; accepted for parity, unused: AA is recomputed in bwd */
+    int32_t len_oarea_buffer;    /* K; accepted for parity (the host side sizes the AA cache)  */
     const float*   background;               /* (3)            */
     const int32_t* patch_min;                /* (B,2)          */
     const float*   verts;                    /* (P,3)          */
@@ -153,14 +153,23 @@ int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws,
  * 32+bit key bits, tile ranges, then the forward tile compositor.  out_color (B,H,W,3) and
  * out_depth (B,H,W) are fully overwritten.                                                   */
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                       int64_t num_rendered, float* out_color, float* out_depth, void* stream);
+                       int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
+                       int64_t aa_cache_pairs, void* stream);
+/* Optional AA cache (the role of the reference's four oarea buffers, render.cu:143-146, as a compact
+ * pool): when aa_cache != NULL the forward pass also evaluates d(area)/d(aa verts) and stores area +
+ * gradient of every partially covered (pixel, face) pair it clips (28 bytes per pair, up to
+ * aa_cache_pairs pairs; pairs beyond the capacity are simply not cached); the backward pass reads
+ * them back instead of clipping again and falls back to recomputation for anything not cached.
+ * The same buffer and capacity must be passed to the matching backward call.  Contents are private. */
+int dm2_aa_cache_bytes(int64_t capacity_pairs, size_t* bytes);
 /* reference renderer.cu:271-392 / backward.cu:17-532.  grad_ws: scratch of
  * dm2_backward_workspace_bytes(B, F) bytes (per-(view,face) gradient records; zeroed inside).  */
 int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes);
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
                         const void* image_ws, int64_t num_rendered,
                         const float* dL_dout_color, const float* dL_dout_depth,
-                        const DM2RenderGrads* grads, void* grad_ws, void* stream);
+                        const DM2RenderGrads* grads, void* grad_ws, const void* aa_cache,
+                        int64_t aa_cache_pairs, void* stream);
 
 /* ---- LayeredRenderer: replaces generate_render_layers_cuda ------------------------------- */
 int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws,
@@ -212,10 +221,12 @@ typedef struct DM2FusedGrads {   /* caller-zeroed */
 
 int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream);
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                      int64_t num_rendered, float* out_color, float* out_depth, void* stream);
+                      int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
+                      int64_t aa_cache_pairs, void* stream);
 int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void* binning_ws,
                        const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
-                       const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws, void* stream);
+                       const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws,
+                       const void* aa_cache, int64_t aa_cache_pairs, void* stream);
 
 /* ---- binning primitives exposed on their own (sort keys/s metric, parity tests) ---------- */
 /* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit).  Replaces

@@ -126,6 +126,39 @@ def test_render_matches_reference_cache_semantics(built):
     _check_floats(cuda, ref)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_aa_cache_on_off_overflow_agree(built, fused, monkeypatch):
+    """Backward with the forward->backward AA cache (K > 0), without it (K = 0: every overlap area is
+    recomputed) and with a pool far too small (most pairs fall back to recomputation) must agree: the
+    cached values ARE the recomputed values, so only the atomic order differs."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import _C, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=1500, size=96, sigma=0.08, seed=21)
+    st = scene_tensors(sc, dev)
+
+    def run(K, pairs_per_instance):
+        monkeypatch.setattr(_C, "AA_CACHE_PAIRS_PER_INSTANCE", pairs_per_instance)
+        r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev, aa_grad_buffer_size=K)
+        r.fused = fused
+        leaves = {k: st[k].detach().clone().requires_grad_(True)
+                  for k in ("verts", "verts_color", "faces_opacity", "faces_intense")}
+        pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        color, depth = r([0], pm, sc.width, sc.height, leaves["verts"], st["faces"], leaves["verts_color"],
+                         leaves["faces_opacity"], leaves["faces_intense"], st["background"], 1.0)
+        ((color * st["w_color"][:1]).sum() + (depth * st["w_depth"][:1]).sum()).backward()
+        return color.detach(), {k: v.grad.detach().cpu().numpy() for k, v in leaves.items()}
+
+    c_on, g_on = run(20, 32)
+    c_off, g_off = run(0, 32)
+    c_ovf, g_ovf = run(20, 1)
+    assert torch.equal(c_on, c_off) and torch.equal(c_on, c_ovf), "the cache must not change the forward result"
+    for k in g_on:
+        assert np.abs(g_on[k]).max() > 0
+        for other in (g_off, g_ovf):
+            assert rel_err(other[k], g_on[k]) <= 1e-5, (k, rel_err(other[k], g_on[k]))
+
+
 def test_cfg1_vs_oracle(built):
     """BASELINE config 0: 10k triangles at 256x256 (the oracle takes a few seconds)."""
     from dmesh2_renderer_b200 import scenes
