@@ -87,24 +87,26 @@ struct FanAcc {
     int np = 0;
     float area = 0.0f;
     float fx = 0.f, fy = 0.f, qx = 0.f, qy = 0.f;       // first and previous polygon vertex
-    bool bad = false;     // polygon overflow (aa.h:45-48) or negative fan-triangle area (aa.h:410-412)
+    bool bad = false;     // negative fan-triangle area (aa.h:410-412); polygon overflow is checked at the end
     __device__ __forceinline__ void push(bool cond, float x, float y) {
-        const bool is_first = cond && (np == 0);
-        const bool is_tri = cond && (np >= 2);
-        bad = bad || (cond && (np >= 10));
+        const bool is_first = cond & (np == 0);
+        const bool is_tri = cond & (np >= 2);
         // _tri_area(first, prev, v), aa.h:88-94
         const float ax = __fsub_rn(qx, fx), by = __fsub_rn(y, fy);
         const float cx = __fsub_rn(x, fx),  dy = __fsub_rn(qy, fy);
         const float s = __fmul_rn(0.5f, __fmaf_rn(ax, by, -__fmul_rn(cx, dy)));
-        bad = bad || (is_tri && (s < 0.0f));
+        bad |= is_tri & (s < 0.0f);
         area = is_tri ? __fadd_rn(area, s) : area;
         fx = is_first ? x : fx;
         fy = is_first ? y : fy;
-        const bool set_prev = cond && (np >= 1);
+        const bool set_prev = cond & (np >= 1);
         qx = set_prev ? x : qx;
         qy = set_prev ? y : qy;
         np += cond ? 1 : 0;
     }
+    // aa.h:45-48: adding a vertex to a polygon that already holds 10 is an error; np only grows on
+    // accepted pushes, so "some push saw np >= 10" is the same as "np ended above 10"
+    __device__ __forceinline__ bool overflow() const { return np > 10; }
 };
 
 // Step 4 of aa.h:446-504 (= aa.h:151-441) for a partially covered pixel.  Returns false if the face
@@ -130,8 +132,8 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
         const float2 rc = *reinterpret_cast<const float2*>(rec + R_AAR + 2 * ti);
         const bool edge_vertical   = (zflags >> (2 * ti)) & 1u;      // edges_iszero[ti][0]
         const bool edge_horizontal = (zflags >> (2 * ti + 1)) & 1u;  // edges_iszero[ti][1]
-        const bool in0 = (p0.x >= pxmin) && (p0.x <= pxmax) && (p0.y >= pymin) && (p0.y <= pymax);
-        const bool in1 = (p1.x >= pxmin) && (p1.x <= pxmax) && (p1.y >= pymin) && (p1.y <= pymax);
+        const bool in0 = (p0.x >= pxmin) & (p0.x <= pxmax) & (p0.y >= pymin) & (p0.y <= pymax);
+        const bool in1 = (p1.x >= pxmin) & (p1.x <= pxmax) & (p1.y >= pymin) & (p1.y <= pymax);
 
         float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;     // up to two intersections, pixel-edge order
         float ta = 0.f, tb = 0.f;
@@ -149,32 +151,32 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
             const float hi1  = horiz ? pxmax : pymax;
             const float t  = __fmul_rn(__fsub_rn(cst, p0a0), ra0);   // aa.h:251
             const float i1 = __fmaf_rn(t, ea1, p0a1);                // aa.h:252
-            const bool valid = (t >= 0.0f) && (t <= 1.0f) && (i1 >= lo1) && (i1 <= hi1) && !parallel;
+            const bool valid = (t >= 0.0f) & (t <= 1.0f) & (i1 >= lo1) & (i1 <= hi1) & !parallel;
             // error 1: hits a pixel corner; error 2: more than two intersections
-            fan.bad = fan.bad || (valid && ((i1 == lo1) || (i1 == hi1) || (n >= 2)));
+            fan.bad |= valid & ((i1 == lo1) | (i1 == hi1) | (n >= 2));
             const float qx = horiz ? i1 : cst, qy = horiz ? cst : i1;
-            const bool is_a = valid && (n == 0), is_b = valid && (n == 1);
+            const bool is_a = valid & (n == 0), is_b = valid & (n == 1);
             ax = is_a ? qx : ax; ay = is_a ? qy : ay; ta = is_a ? t : ta; pa = is_a ? pi : pa;
             bx = is_b ? qx : bx; by = is_b ? qy : by; tb = is_b ? t : tb; pb = is_b ? pi : pb;
             n += valid ? 1 : 0;
         }
         // aa.h:299-400 as predicates
         const bool two = (n >= 2), one = (n == 1), none = (n == 0);
-        const bool swap = two && (ta > tb);                          // sort by t; strict '>' keeps order on ties
-        const bool enter = one && !in0 && in1;                       // intersection, then the end point
-        const bool leave = one && in0 && !in1;                       // start point inside, intersection, corners
-        const bool whole = none && in0 && in1;                       // edge entirely inside the pixel
-        fan.bad = fan.bad || (one && (in0 == in1)) || (none && (in0 != in1));      // errors 3 and 4
+        const bool swap = two & (ta > tb);                           // sort by t; strict '>' keeps order on ties
+        const bool enter = one & !in0 & in1;                         // intersection, then the end point
+        const bool leave = one & in0 & !in1;                         // start point inside, intersection, corners
+        const bool whole = none & in0 & in1;                         // edge entirely inside the pixel
+        fan.bad |= (one & (in0 == in1)) | (none & (in0 != in1));     // errors 3 and 4
         fan.push(!none, swap ? bx : ax, swap ? by : ay);
-        fan.push(two || enter || whole, two ? (swap ? ax : bx) : p1.x, two ? (swap ? ay : by) : p1.y);
+        fan.push(two | enter | whole, two ? (swap ? ax : bx) : p1.x, two ? (swap ? ay : by) : p1.y);
         // run of inside pixel corners after the last-hit pixel edge (aa.h:359-379); a partially
         // covered pixel has at most 3 inside corners
-        bool run = two || leave;
+        bool run = two | leave;
         const int final_pedge = two ? (swap ? pa : pb) : pa;
 #pragma unroll
         for (int pvi = 0; pvi < 3; pvi++) {
             const int cur = (final_pedge + 1 + pvi) & 3;
-            run = run && ((inmask >> cur) & 1u);
+            run = run & (((inmask >> cur) & 1u) != 0u);
             fan.push(run, (cur == 1 || cur == 2) ? pxmax : pxmin, (cur >= 2) ? pymax : pymin);
         }
         if (GRAD) {
@@ -192,7 +194,7 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
             }
         }
     }
-    const bool ok = !fan.bad && !(fan.area > 1.0f) && !(fan.area == 0.0f);   // error 6; caller skips oarea == 0
+    const bool ok = !fan.bad & !fan.overflow() & !(fan.area > 1.0f) & !(fan.area == 0.0f);   // error 6; caller skips oarea == 0
     area_out = fan.area;
     if (GRAD) {
 #pragma unroll

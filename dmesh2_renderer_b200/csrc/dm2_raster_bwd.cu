@@ -144,21 +144,49 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         const int ncs = min(count, kSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
-        if (use_aa && lane < ncs)
+        const bool cached = cache.capacity != 0u;
+        if (use_aa && cached && lane < ncs)
             ws.srec[lane * kRecStride + R_PMASK] =
                 __uint_as_float(partial_mask(*reinterpret_cast<const uint4*>(ws.srec + lane * kRecStride + R_META)));
         __syncwarp();
 
-        // ====== 1. lock-step classification, pair list
+        // ====== 1. per-lane hit / partial masks from the classification words
         uint32_t hit, part, im;
         classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im, [&](int k) {
             return tc.inside && (int)ws.q.idx[(head + k) & (kQueue - 1)] < my_last;
         });
         if (__any_sync(0xffffffffu, hit != 0u)) {
-            int np, npairs;
-            build_pair_list(ws.plist, ncs, hit, part, im, lane, np, npairs);
+            // every lane prefetches the AA-cache entries of ITS partially covered pixel (area + gradient,
+            // written by the forward pass) straight into the tables; the copies fly while the pair list is built
+            if (cached && part != 0u) {
+                for (int k = 0; k < ncs; k++) {
+                    if (!((part >> k) & 1u)) continue;
+                    const float* rec = ws.srec + k * kRecStride;
+                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                    if (poff == kNoCache) continue;
+                    const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & lt_mask);
+                    const int slot = k * 32 + lane;
+                    cp_async4(&ws.tArea[slot], cache.area + j);
+#pragma unroll
+                    for (int q = 0; q < 6; q++) cp_async4(&ws.tG[q][slot], cache.grad + (size_t)j * 6 + q);
+                }
+            }
+            cp_async_commit();
 
-            // ====== 2. dense pass over every hit pair: clip (+ area gradient), hit point, alpha, S
+            // candidate-major list of all hit pairs (k | lane << 3 | partial << 8 | inmask << 9); the
+            // dense pass and the gradient pass both run over it
+            int npairs = 0;
+            for (int k = 0; k < ncs; k++) {
+                const bool h = (hit >> k) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, h);
+                if (h) ws.plist[npairs + __popc(m & lt_mask)] =
+                           (uint16_t)(k | (lane << 3) | (((part >> k) & 1u) << 8) | (((im >> (4 * k)) & 15u) << 9));
+                npairs += __popc(m);
+            }
+            cp_async_wait0();
+            __syncwarp();
+
+            // ====== 2. dense pass over every hit pair: area (cached, else clip + gradient), hit point, alpha, S
             for (int p0 = 0; p0 < npairs; p0 += 32) {
                 const int pid = p0 + lane;
                 const bool act = pid < npairs;
@@ -178,27 +206,24 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                 Shade s;
                 s.area = use_aa ? 1.0f : 0.0f;
                 bool ok = true;
-                if (pid < np) {
-                    float g[6];
-                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
-                    if (cache.capacity != 0u && poff != kNoCache) {      // evaluated by the forward pass
-                        const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << l) - 1u));
-                        s.area = cache.area[j];
+                if ((e >> 8) & 1u) {
+                    if (cached && __float_as_uint(rec[R_META + 3]) != kNoCache) {      // evaluated by the forward pass
+                        s.area = ws.tArea[slot];
                         ok = !(s.area == -1.0f);
-                        const float2* gj = reinterpret_cast<const float2*>(cache.grad + (size_t)j * 6);
-                        const float2 g0 = gj[0], g1 = gj[1], g2 = gj[2];
-                        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = g2.x; g[5] = g2.y;
                     } else {
-                        ok = aa_clip<true>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, g);
-                    }
+                        float g[6];
+                        ok = aa_clip<true>(rec, qg.pxmin, qg.pymin, e >> 9, s.area, g);
+                        ws.tArea[slot] = s.area;
 #pragma unroll
-                    for (int q = 0; q < 6; q++) ws.tG[q][slot] = g[q];
+                        for (int q = 0; q < 6; q++) ws.tG[q][slot] = g[q];
+                    }
+                } else {
+                    ws.tArea[slot] = s.area;
                 }
                 ok = ok && shade_tail(rec, qg, tau, s);
                 if (ok) {
                     ws.tA[slot] = __fmul_rn(rec[R_MISC + 1], s.ratio);
                     ws.tS[slot] = s.iC[0] * qC0 + s.iC[1] * qC1 + s.iC[2] * qC2 + s.iD * qD;
-                    ws.tArea[slot] = s.area;
                 } else {
                     ws.tA[slot] = __uint_as_float(kSkipBits);
                 }
@@ -206,46 +231,40 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
             __syncwarp();
 
             // ====== 3. pixel-sequential walk (back to front): T and dL/dalpha per contribution
-            uint32_t contrib = 0u;
             for (int k = 0; k < ncs; k++) {
                 if (!((hit >> k) & 1u)) continue;
                 const int slot = k * 32 + lane;
                 const float alpha = ws.tA[slot];
                 if (__float_as_uint(alpha) == kSkipBits) continue;
                 const float S = ws.tS[slot];
-                // backward.cu:340-348
-                if (!first_pass) T = T / (1.0f - alpha);
+                // backward.cu:340-348: T = T / (1 - alpha); the same reciprocal serves the background term
+                const float r1 = __frcp_rn(1.0f - alpha);
+                if (!first_pass) T = T * r1;
                 first_pass = false;
                 // backward.cu:357-405
                 accA = last_alpha * last_S + (1.0f - last_alpha) * accA;
                 last_S = S;
                 float dL_dalpha = (S - accA) * T;
                 last_alpha = alpha;
-                const float bgw = (alpha == 1.0f) ? -prev_T_final : -T_final / (1.0f - alpha);
+                const float bgw = (alpha == 1.0f) ? -prev_T_final : -T_final * r1;
                 dL_dalpha += bgw * bg_dot;
                 dL_dalpha += bgw * bd_dot;
                 ws.tA[slot] = T;
                 ws.tS[slot] = dL_dalpha;
-                contrib |= 1u << k;
-            }
-
-            // ====== 4. face-parallel gradients over the candidate-major contribution list
-            int total_c = 0;
-            for (int k = 0; k < ncs; k++) {
-                const bool c = (contrib >> k) & 1u;
-                const unsigned m = __ballot_sync(0xffffffffu, c);
-                if (c) ws.plist[total_c + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 3) | (((part >> k) & 1u) << 8));
-                total_c += __popc(m);
             }
             __syncwarp();
+
+            // ====== 4. face-parallel gradients over the same list (skipped pairs contribute zero rows)
+            const int total_c = npairs;
             float carry = 0.0f;
             for (int r0 = 0; r0 < total_c; r0 += 32) {
                 const int r = r0 + lane;
-                const bool act = r < total_c;
-                const unsigned e = act ? ws.plist[r] : 0u;
+                const bool in_list = r < total_c;
+                const unsigned e = in_list ? ws.plist[r] : 0u;
                 const int k = e & 7, src = (e >> 3) & 31;
+                const bool act = in_list && (__float_as_uint(ws.tA[k * 32 + src]) != kSkipBits);
                 // last row of its candidate's run?
-                const bool run_end = act && ((r + 1 == total_c) || ((ws.plist[r + 1 < kSlots ? r + 1 : r] & 7) != k));
+                const bool run_end = in_list && ((r + 1 == total_c) || ((ws.plist[r + 1 < kSlots ? r + 1 : r] & 7) != k));
                 const unsigned flush = __ballot_sync(0xffffffffu, run_end);
                 // pixel constants of the owning lane
                 PixelGeom qg;
