@@ -104,11 +104,11 @@ def algorithmic_bytes(stage, B, P, F, H, W, R):
     table = {
         "raster_forward": G + 28 * B * H * W + 4 * R,
         "raster_backward": G + 28 * B * H * W + 4 * R + grads,
-        "radix_sort": 24 * R,
+        "tile_sort": 24 * R,
         "preprocess_pack": G - 24 * B * H * W + 16 * B * F,
-        "emit_keys": 12 * R + 16 * B * F,
-        "scan": 8 * B * F,
-        "tile_ranges": 8 * R,
+        "scatter_instances": 12 * R + 16 * B * F,
+        "tile_count": 12 * B * F,
+        "classify": 28 * R,
     }
     return table.get(stage)
 
@@ -319,7 +319,8 @@ def main():
                                        "select/fma instructions per covered (pixel, face) pair (profiles/r01_ncu_kernels.md)"}
             out["stages_ms_per_step"] = {k: v[0] / args.steps for k, v in stages.items()}
             out["num_rendered"] = R
-            sort_ms = stages.get("radix_sort", (0, 0))[0] / args.steps
+            # the binning sort = scatter into the tile segments + per-segment sort (dm2_tilesort.cu)
+            sort_ms = (stages.get("scatter_instances", (0, 0))[0] + stages.get("tile_sort", (0, 0))[0]) / args.steps
             if sort_ms > 0:
                 out["sort_keys_per_s"] = R / (sort_ms * 1e-3)
         if not args.no_cpu_baseline:

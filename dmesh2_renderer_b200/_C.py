@@ -202,7 +202,8 @@ def render_forward_cuda(background, patch_min, patch_width, patch_height, verts,
         face_buffer = torch.empty((face_layout(B, s.F).total,), dtype=torch.uint8, device=dev)
         image_buffer = torch.empty((image_layout(B, H, W).total,), dtype=torch.uint8, device=dev)
         num_rendered = C.c_int64(0)
-        _lib.check(lib.dm2_render_preprocess(C.byref(s), _ptr(face_buffer), C.byref(num_rendered), stream))
+        _lib.check(lib.dm2_render_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
+                                             C.byref(num_rendered), stream))
         R = int(num_rendered.value)
         binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
         oarea, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev, want_cache)
@@ -309,7 +310,8 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
         _lib.check(lib.dm2_layers_geo_bytes(F, T, C.byref(geo_bytes)))
         geo_buffer = torch.empty((geo_bytes.value,), dtype=torch.uint8, device=dev)
         num_rendered = C.c_int64(0)
-        _lib.check(lib.dm2_layers_preprocess(C.byref(s), _ptr(face_buffer), C.byref(num_rendered), stream))
+        _lib.check(lib.dm2_layers_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
+                                             C.byref(num_rendered), stream))
         R = int(num_rendered.value)
         binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
         _lib.check(lib.dm2_generate_render_layers(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
@@ -334,8 +336,7 @@ def face_taps(face_buffer, B, F, layered=False):
     return dict(depths=_view(face_buffer, L.depths, n, torch.float32),
                 min_depths=_view(face_buffer, L.min_depths, n, torch.float32),
                 max_depths=_view(face_buffer, L.max_depths, n, torch.float32),
-                tiles_touched=_view(face_buffer, L.tiles_touched, n, torch.int32),
-                face_offsets=_view(face_buffer, L.face_offsets, n, torch.int32))
+                tiles_touched=_view(face_buffer, L.tiles_touched, n, torch.int32))
 
 
 def binning_taps(binning_buffer, R):

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -63,13 +63,13 @@ class DM2LayerInputs(C.Structure):
 
 class DM2FaceLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "depths", "min_depths", "max_depths", "tiles_touched", "face_offsets", "scan_partials", "rects",
+        "depths", "min_depths", "max_depths", "tiles_touched", "rects",
         "records", "record_stride", "total")]
 
 
 class DM2ImageLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "ranges", "final_T", "final_prev_T", "n_contrib", "first_face", "first_tet", "total")]
+        "ranges", "tile_cursor", "final_T", "final_prev_T", "n_contrib", "first_face", "first_tet", "total")]
 
 
 class DM2BinningLayout(C.Structure):
@@ -84,7 +84,7 @@ SYMBOLS = {
     "dm2_face_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P(DM2FaceLayout)]),
     "dm2_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(DM2ImageLayout)]),
     "dm2_binning_layout": (C.c_int, [C.c_int64, _P(DM2BinningLayout)]),
-    "dm2_render_preprocess": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, _P(C.c_int64), C.c_void_p]),
+    "dm2_render_preprocess": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "dm2_render_forward": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dm2_aa_cache_bytes": (C.c_int, [C.c_int64, _P(C.c_size_t)]),
@@ -92,13 +92,13 @@ SYMBOLS = {
     "dm2_render_backward": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_void_p, _P(DM2RenderGrads), C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]),
-    "dm2_fused_preprocess": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, _P(C.c_int64), C.c_void_p]),
+    "dm2_fused_preprocess": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "dm2_fused_forward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dm2_fused_backward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, _P(DM2FusedGrads), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p]),
-    "dm2_layers_preprocess": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, _P(C.c_int64), C.c_void_p]),
+    "dm2_layers_preprocess": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "dm2_layers_geo_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "dm2_generate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,6 +1,7 @@
-// dm2_binning.cu — per-face preprocess + record packing, prefix scan, key emission,
-// stable LSD radix sort, tile ranges.  Replaces reference cuda_impl/forward.cu:16-137
-// (preprocessFaceCUDA), cuda_impl/renderer.cu:165-218, 415-492 and the two CUB calls.
+// dm2_binning.cu — per-face preprocess + record packing, the per-instance pixel classification
+// pre-pass, and the two stand-alone primitives (inclusive scan, stable LSD radix sort) that replace
+// the reference's CUB calls.  Replaces reference cuda_impl/forward.cu:16-137 (preprocessFaceCUDA);
+// the tile binning itself (reference renderer.cu:165-218, 415-492) lives in dm2_tilesort.cu.
 #include "dm2_common.cuh"
 
 namespace dm2 {
@@ -357,51 +358,6 @@ int launch_scan(const uint32_t* in, uint32_t* out, long long n, uint32_t* partia
 }
 
 // ------------------------------------------------------------------ key emission
-// reference renderer.cu:415-465.  key = (tile + tiles*view) << 32 | bits(depth); value = face id.
-// Faces covering more than 16 tiles are emitted cooperatively by the whole warp so that one huge
-// triangle does not serialise 2 000 stores behind a single lane.
-__global__ void __launch_bounds__(256)
-k_emit_keys(long long BF, int F, int gx, int gy, const float* __restrict__ key_depths,
-            const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
-            const uint2* __restrict__ rects, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t n = 0, off = 0, x0 = 0, y0 = 0, w = 1, dbits = 0, fid = 0, tbase = 0;
-    if (idx < BF) {
-        n = tiles_touched[idx];
-        if (n) {
-            off = (idx == 0) ? 0u : offsets[idx - 1];
-            const uint2 r = rects[idx];
-            x0 = r.x & 0xffffu; y0 = r.x >> 16;
-            w = (r.y & 0xffffu) - x0;
-            dbits = __float_as_uint(key_depths[idx]);
-            fid = (uint32_t)(idx % F);
-            tbase = (uint32_t)(idx / F) * (uint32_t)(gx * gy);
-        }
-    }
-    if (n && n <= 16) {
-        for (uint32_t i = 0; i < n; i++) {
-            uint32_t y = y0 + i / w, x = x0 + i % w;
-            keys[off + i] = ((uint64_t)(y * gx + x + tbase) << 32) | dbits;
-            vals[off + i] = fid;
-        }
-    }
-    unsigned big = __ballot_sync(0xffffffffu, n > 16);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t sn = __shfl_sync(0xffffffffu, n, src), so = __shfl_sync(0xffffffffu, off, src);
-        const uint32_t sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src);
-        const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sd = __shfl_sync(0xffffffffu, dbits, src);
-        const uint32_t sf = __shfl_sync(0xffffffffu, fid, src), st = __shfl_sync(0xffffffffu, tbase, src);
-        for (uint32_t i = lane; i < sn; i += 32) {
-            uint32_t y = sy + i / sw, x = sx + i % sw;
-            keys[so + i] = ((uint64_t)(y * gx + x + st) << 32) | sd;
-            vals[so + i] = sf;
-        }
-    }
-}
-
 // ------------------------------------------------------------------ stable LSD radix sort
 // 8-bit digits, 4096 keys per block.  Per pass: per-block digit histogram -> digit-major
 // exclusive scan -> stable scatter (warp-level match_any ranking).  Replaces
@@ -567,21 +523,6 @@ int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, 
     return 0;
 }
 
-// ------------------------------------------------------------------ tile ranges
-// reference renderer.cu:470-492 (+ the memset at :211)
-__global__ void __launch_bounds__(256)
-k_tile_ranges(const uint64_t* __restrict__ keys, uint32_t R, uint2* __restrict__ ranges) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R) return;
-    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
-    if (idx == 0) ranges[cur].x = 0;
-    else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-        if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
-    }
-    if (idx == R - 1) ranges[cur].y = R;
-}
-
 // ------------------------------------------------------------------ per-instance pixel classification
 // Steps 1-3 of the reference's per-(pixel, face) AA routine (aa.h:96-149, 446-496: triangle bbox
 // reject, 3 edges x 4 pixel corners half-plane tests -> outside / fully inside / partial) do not
@@ -706,32 +647,12 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
     if (i < R) imask[i] = (uint8_t)s_im[t];
 }
 
-int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, const TileMaskArgs* tm,
-                       cudaStream_t s) {
-    DM2_CHECK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
-    if (R > 0) {
-        {
-            ProfScope _ps("tile_ranges", s);
-            k_tile_ranges<<<cdiv(R, 256), 256, 0, s>>>(keys, (uint32_t)R, ranges);
-            DM2_LAUNCH_CHECK();
-        }
-        if (tm) {
-            ProfScope _ps("classify", s);
-            k_classify_instances<<<cdiv(R, kClsThreads), kClsThreads, 0, s>>>(
-                keys, tm->vals, (uint32_t)R, tm->records, tm->patch_min, tm->F, tm->gx, tm->gy, tm->use_bbox, tm->imask,
-                reinterpret_cast<uint4*>(tm->meta));
-            DM2_LAUNCH_CHECK();
-        }
-    }
-    return 0;
-}
-
-int launch_emit_keys(long long BF, int F, int gx, int gy, const float* key_depths,
-                           const uint32_t* tiles_touched, const uint32_t* offsets, const uint2* rects,
-                           uint64_t* keys, uint32_t* vals, cudaStream_t s) {
-    if (BF == 0) return 0;
-    ProfScope _ps("emit_keys", s);
-    k_emit_keys<<<cdiv(BF, 256), 256, 0, s>>>(BF, F, gx, gy, key_depths, tiles_touched, offsets, rects, keys, vals);
+int launch_classify(const uint64_t* keys, long long R, const TileMaskArgs& tm, cudaStream_t s) {
+    if (R <= 0) return 0;
+    ProfScope _ps("classify", s);
+    k_classify_instances<<<cdiv(R, kClsThreads), kClsThreads, 0, s>>>(
+        keys, tm.vals, (uint32_t)R, tm.records, tm.patch_min, tm.F, tm.gx, tm.gy, tm.use_bbox, tm.imask,
+        reinterpret_cast<uint4*>(tm.meta));
     DM2_LAUNCH_CHECK();
     return 0;
 }

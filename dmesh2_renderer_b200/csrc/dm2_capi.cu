@@ -75,8 +75,6 @@ static void face_layout(long long BF, bool layered, DM2FaceLayout* L) {
     L->min_depths    = take((size_t)BF * 4);
     L->max_depths    = take((size_t)BF * 4);
     L->tiles_touched = take((size_t)BF * 4);
-    L->face_offsets  = take((size_t)BF * 4);
-    L->scan_partials = take((size_t)scan_partials_count(BF) * 4);
     L->rects         = take((size_t)BF * 8);
     L->record_stride = layered ? (size_t)kLRecWords * 4 : (size_t)kRecBytes;
     L->records       = take((size_t)BF * L->record_stride);
@@ -89,6 +87,7 @@ static void image_layout(long long B, int H, int W, bool layered, DM2ImageLayout
     const long long tiles = (long long)cdiv(W, kTile) * cdiv(H, kTile);
     const size_t npix = (size_t)B * H * W;
     L->ranges = take((size_t)B * tiles * 8);
+    L->tile_cursor = take(((size_t)B * tiles + 1) * 4);
     if (layered) {
         L->final_T = L->final_prev_T = L->n_contrib = 0;
         L->first_face = take(npix * 4);
@@ -121,7 +120,6 @@ static FaceWs carve_face(void* ws, long long BF, bool layered) {
     FaceWs f;
     f.depths = (float*)(p + L.depths); f.min_depths = (float*)(p + L.min_depths);
     f.max_depths = (float*)(p + L.max_depths); f.tiles_touched = (uint32_t*)(p + L.tiles_touched);
-    f.face_offsets = (uint32_t*)(p + L.face_offsets); f.scan_partials = (uint32_t*)(p + L.scan_partials);
     f.rects = (uint2*)(p + L.rects); f.records = (float*)(p + L.records); f.record_stride = L.record_stride;
     return f;
 }
@@ -129,7 +127,7 @@ static ImageWs carve_image(void* ws, long long B, int H, int W, bool layered) {
     DM2ImageLayout L; image_layout(B, H, W, layered, &L);
     char* p = reinterpret_cast<char*>(ws);
     ImageWs i;
-    i.ranges = (uint2*)(p + L.ranges); i.final_T = (float*)(p + L.final_T);
+    i.ranges = (uint2*)(p + L.ranges); i.tile_cursor = (uint32_t*)(p + L.tile_cursor); i.final_T = (float*)(p + L.final_T);
     i.final_prev_T = (float*)(p + L.final_prev_T); i.n_contrib = (uint32_t*)(p + L.n_contrib);
     i.first_face = (int*)(p + L.first_face); i.first_tet = (int*)(p + L.first_tet);
     return i;
@@ -158,30 +156,35 @@ static int check_render_inputs(const DM2RenderInputs* in) {
     return 0;
 }
 
-// shared tail of both preprocess entry points: scan + read-back of num_rendered
-static int scan_and_count(const FaceWs& fw, long long BF, int64_t* num_rendered_host, cudaStream_t s) {
+// shared tail of the preprocess entry points: per-tile counts -> tile ranges + read-back of num_rendered
+static int count_and_scan(const FaceWs& fw, const ImageWs& iw, long long BF, int B, int F, int gx, int gy,
+                          int64_t* num_rendered_host, cudaStream_t s) {
     *num_rendered_host = 0;
-    if (BF == 0) return 0;
-    if (launch_scan(fw.tiles_touched, fw.face_offsets, BF, fw.scan_partials, s)) return 1;
+    const int num_tiles = B * gx * gy;
+    if (launch_tile_count_scan(BF, F, gx, gy, num_tiles, fw.tiles_touched, fw.rects, iw.ranges, iw.tile_cursor, s))
+        return 1;
     uint32_t r = 0;
-    DM2_CHECK(cudaMemcpyAsync(&r, fw.face_offsets + BF - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    DM2_CHECK(cudaMemcpyAsync(&r, iw.tile_cursor + num_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     DM2_CHECK(cudaStreamSynchronize(s));
     *num_rendered_host = (int64_t)r;
     return 0;
 }
 
-// shared middle of both pipelines: keys -> sort -> ranges
+// nothing to bin: every tile range is (0, 0)
+static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaStream_t s) {
+    ImageWs iw = carve_image(image_ws, B, H, W, layered);
+    const size_t nt = (size_t)B * cdiv(W, kTile) * cdiv(H, kTile);
+    DM2_CHECK(cudaMemsetAsync(iw.ranges, 0, nt * sizeof(uint2), s));
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, (nt + 1) * sizeof(uint32_t), s));
+    return 0;
+}
+
+// shared middle of both pipelines: scatter into the tile segments + per-segment sort
 static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* key_depths, const FaceWs& fw,
-                     const BinWs& bw, const ImageWs& iw, long long R, const TileMaskArgs* tm, cudaStream_t s) {
-    const int num_tiles = B * gx * gy;
-    if (R > 0) {
-        if (launch_emit_keys(BF, F, gx, gy, key_depths, fw.tiles_touched, fw.face_offsets, fw.rects,
-                             bw.keys_unsorted, bw.vals_unsorted, s)) return 1;
-        const int bit = (int)higher_msb((uint32_t)num_tiles);
-        if (launch_sort_pairs(bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, R, 32 + bit, bw.sort_temp,
-                              bw.sort_temp_bytes, s)) return 1;
-    }
-    return launch_tile_ranges(bw.keys, R, iw.ranges, num_tiles, tm, s);
+                     const BinWs& bw, const ImageWs& iw, long long R, cudaStream_t s) {
+    if (R <= 0) return 0;
+    return launch_tile_sort(BF, F, gx, gy, B * gx * gy, key_depths, fw.tiles_touched, fw.rects, iw.ranges,
+                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, s);
 }
 
 }  // namespace dm2
@@ -228,16 +231,18 @@ int dm2_binning_layout(int64_t num_rendered, DM2BinningLayout* out) {
     return 0;
 }
 
-int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream) {
+int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
+                          void* stream) {
     if (check_render_inputs(in)) return 2;
-    DM2_REQUIRE(face_ws && num_rendered_host, "dm2_render_preprocess: null workspace");
+    DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_render_preprocess: null workspace");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     *num_rendered_host = 0;
-    if (in->P == 0 || BF == 0) return 0;                       // reference render.cu:149
+    if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);    // reference render.cu:149
     FaceWs fw = carve_face(face_ws, BF, false);
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
     if (launch_render_preprocess(*in, fw, s)) return 1;
-    return scan_and_count(fw, BF, num_rendered_host, s);
+    return count_and_scan(fw, iw, BF, in->B, in->F, cdiv(in->W, kTile), cdiv(in->H, kTile), num_rendered_host, s);
 }
 
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
@@ -261,7 +266,8 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
     }
     const long long R = num_rendered;
     const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, &tm, s)) return 1;
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, s)) return 1;
+    if (launch_classify(bw.keys, R, tm, s)) return 1;
     return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, aa_cache, aa_cache ? aa_cache_pairs : 0, s);
 }
 
@@ -308,16 +314,18 @@ static DM2RenderInputs as_render_inputs(const DM2FusedInputs& f) {
     return r;
 }
 
-int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream) {
+int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
+                         void* stream) {
     if (check_fused_inputs(in)) return 2;
-    DM2_REQUIRE(face_ws && num_rendered_host, "dm2_fused_preprocess: null workspace");
+    DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_fused_preprocess: null workspace");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     *num_rendered_host = 0;
-    if (in->P == 0 || BF == 0) return 0;
+    if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);
     FaceWs fw = carve_face(face_ws, BF, false);
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
     if (launch_fused_preprocess(*in, fw, s)) return 1;
-    return scan_and_count(fw, BF, num_rendered_host, s);
+    return count_and_scan(fw, iw, BF, in->B, in->F, cdiv(in->W, kTile), cdiv(in->H, kTile), num_rendered_host, s);
 }
 
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
@@ -372,16 +380,18 @@ static int check_layer_inputs(const DM2LayerInputs* in) {
     return 0;
 }
 
-int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream) {
+int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
+                          void* stream) {
     if (check_layer_inputs(in)) return 2;
-    DM2_REQUIRE(face_ws && num_rendered_host, "dm2_layers_preprocess: null workspace");
+    DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_layers_preprocess: null workspace");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     *num_rendered_host = 0;
-    if (BF == 0) return 0;
+    if (BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, true, s);
     FaceWs fw = carve_face(face_ws, BF, true);
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     if (launch_layers_preprocess(*in, fw, s)) return 1;
-    return scan_and_count(fw, BF, num_rendered_host, s);
+    return count_and_scan(fw, iw, BF, in->B, in->F, cdiv(in->W, kTile), cdiv(in->H, kTile), num_rendered_host, s);
 }
 
 int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes) {
@@ -404,7 +414,7 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
     BinWs bw = carve_bin(binning_ws, num_rendered);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     // key = min depth (reference renderer.cu:603)
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, nullptr, s)) return 1;
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, s)) return 1;
     return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, s);
 }
 

@@ -178,12 +178,12 @@ __device__ __forceinline__ float clamp01_depth(float z) {
 // ---------------------------------------------------------------- internal launchers
 struct FaceWs {
     float* depths; float* min_depths; float* max_depths;
-    uint32_t* tiles_touched; uint32_t* face_offsets; uint32_t* scan_partials;
+    uint32_t* tiles_touched;
     uint2* rects;                 // packed tile bbox per (view,face): x = x0 | y0<<16, y = x1 | y1<<16
     float* records; size_t record_stride;
 };
 struct ImageWs {
-    uint2* ranges; float* final_T; float* final_prev_T; uint32_t* n_contrib;
+    uint2* ranges; uint32_t* tile_cursor; float* final_T; float* final_prev_T; uint32_t* n_contrib;
     int* first_face; int* first_tet;
 };
 struct BinWs {
@@ -202,14 +202,15 @@ int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaSt
 int launch_layers_preprocess(const DM2LayerInputs& in, const FaceWs& fw, cudaStream_t s);
 int launch_scan(const uint32_t* in, uint32_t* out, long long n, uint32_t* partials, cudaStream_t s);
 long long scan_partials_count(long long n);
-int launch_emit_keys(long long BF, int F, int gx, int gy, const float* key_depths,
-                     const uint32_t* tiles_touched, const uint32_t* offsets, const uint2* rects,
-                     uint64_t* keys, uint32_t* vals, cudaStream_t s);
+int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, const uint32_t* tiles_touched,
+                           const uint2* rects, uint2* ranges, uint32_t* cursor, cudaStream_t s);
+int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
+                     const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
+                     uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, cudaStream_t s);
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
                       long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
 size_t sort_temp_bytes(long long n);
-int launch_tile_ranges(const uint64_t* keys, long long R, uint2* ranges, int num_tiles, const TileMaskArgs* tm,
-                       cudaStream_t s);
+int launch_classify(const uint64_t* keys, long long R, const TileMaskArgs& tm, cudaStream_t s);
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                           const ImageWs& iw, float* out_color, float* out_depth, void* aa_cache,
                           long long aa_cache_pairs, cudaStream_t s);

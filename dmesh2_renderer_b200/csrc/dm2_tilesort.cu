@@ -1,0 +1,245 @@
+// dm2_tilesort.cu — tile binning as a two-level radix sort.
+//
+// The reference duplicates every face once per touched tile with the key (tile << 32 | depth bits),
+// sorts all R keys with cub::DeviceRadixSort::SortPairs on the low 32 + log2(tiles) bits (six 8-bit
+// passes at 1024^2) and then finds the tile ranges in the sorted keys (reference
+// cuda_impl/renderer.cu:165-218, 415-492).  Here the tile bits are ONE most-significant "digit":
+//   1. k_count_tiles        histogram of that digit: instances per tile (from the per-face tile rects);
+//   2. k_tile_scan          exclusive scan of the histogram = the reference's tile ranges, for free, and
+//                           num_rendered (the scan over per-face counts and identifyTileRanges disappear);
+//   3. k_scatter_instances  every instance goes straight into its tile's segment (the reference's
+//                           key / value pair, 12 bytes, written once);
+//   4. k_tile_sort          each segment is sorted by (depth bits, face id) in shared memory.
+// A stable sort of keys that are emitted in ascending face order (what CUB does for the reference)
+// orders equal (tile, depth) pairs by face id, so sorting each segment on the 64-bit composite
+// (depth bits << 32 | face id) yields exactly the reference's sorted key and value arrays whatever
+// order the scatter arrived in.  Four launches and ~36 bytes of traffic per instance instead of
+// thirty launches and ~170 bytes.
+#include "dm2_common.cuh"
+
+namespace dm2 {
+
+// Visits every tile of every lane's rect: small rects by their own lane, rects of more than 16 tiles
+// cooperatively by the whole warp (one huge triangle must not serialise thousands of atomics behind
+// a single lane).  f(global tile index, p0, p1) with the owning face's payload words.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t x0, uint32_t y0, uint32_t w, uint32_t tbase,
+                                              uint32_t p0, uint32_t p1, int gx, int lane, F f) {
+    if (n && n <= 16) {
+        for (uint32_t i = 0; i < n; i++) f(tbase + (y0 + i / w) * gx + (x0 + i % w), p0, p1);
+    }
+    unsigned big = __ballot_sync(0xffffffffu, n > 16);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t sn = __shfl_sync(0xffffffffu, n, src), st = __shfl_sync(0xffffffffu, tbase, src);
+        const uint32_t sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src);
+        const uint32_t sw = __shfl_sync(0xffffffffu, w, src);
+        const uint32_t s0 = __shfl_sync(0xffffffffu, p0, src), s1 = __shfl_sync(0xffffffffu, p1, src);
+        for (uint32_t i = lane; i < sn; i += 32) f(st + (sy + i / sw) * gx + (sx + i % sw), s0, s1);
+    }
+}
+
+struct FaceRect { uint32_t n, x0, y0, w, tbase; };
+__device__ __forceinline__ FaceRect load_rect(long long idx, long long BF, int F, int gx, int gy,
+                                              const uint32_t* __restrict__ tiles_touched,
+                                              const uint2* __restrict__ rects) {
+    FaceRect r{0u, 0u, 0u, 1u, 0u};
+    if (idx < BF) {
+        r.n = tiles_touched[idx];
+        if (r.n) {
+            const uint2 q = rects[idx];
+            r.x0 = q.x & 0xffffu; r.y0 = q.x >> 16;
+            r.w = (q.y & 0xffffu) - r.x0;
+            r.tbase = (uint32_t)(idx / F) * (uint32_t)(gx * gy);
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_count_tiles(long long BF, int F, int gx, int gy, const uint32_t* __restrict__ tiles_touched,
+              const uint2* __restrict__ rects, uint32_t* __restrict__ tile_count) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const FaceRect r = load_rect(idx, BF, F, gx, gy, tiles_touched, rects);
+    for_each_tile(r.n, r.x0, r.y0, r.w, r.tbase, 0u, 0u, gx, threadIdx.x & 31,
+                  [&](uint32_t t, uint32_t, uint32_t) { atomicAdd(tile_count + t, 1u); });
+}
+
+// One block: exclusive scan of the per-tile counts.  ranges[t] = [start, end) (the reference leaves
+// untouched tiles at (0,0), renderer.cu:211), cursor[t] = start (bumped by the scatter),
+// cursor[num_tiles] = num_rendered.
+__global__ void __launch_bounds__(1024)
+k_tile_scan(const uint32_t* tile_count, uint32_t num_tiles, uint2* __restrict__ ranges, uint32_t* cursor) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t per = (num_tiles + 1023u) / 1024u;
+    const uint32_t lo = min(threadIdx.x * per, num_tiles), hi = min(lo + per, num_tiles);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += tile_count[i];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t v = wsum[lane];
+        uint32_t iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = wsum[w] + inc - s;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t c = tile_count[i];
+        ranges[i] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+        cursor[i] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023) cursor[num_tiles] = run;
+}
+
+// reference renderer.cu:415-465: key = (tile + tiles*view) << 32 | bits(depth); value = face id -
+// written into the tile's segment at a position drawn from the tile's cursor.
+__global__ void __launch_bounds__(256)
+k_scatter_instances(long long BF, int F, int gx, int gy, const float* __restrict__ key_depths,
+                    const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
+                    uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const FaceRect r = load_rect(idx, BF, F, gx, gy, tiles_touched, rects);
+    uint32_t dbits = 0u, fid = 0u;
+    if (r.n) { dbits = __float_as_uint(key_depths[idx]); fid = (uint32_t)(idx % F); }
+    for_each_tile(r.n, r.x0, r.y0, r.w, r.tbase, dbits, fid, gx, threadIdx.x & 31,
+                  [&](uint32_t t, uint32_t d, uint32_t f) {
+                      const uint32_t pos = atomicAdd(cursor + t, 1u);
+                      keys[pos] = ((uint64_t)t << 32) | d;
+                      vals[pos] = f;
+                  });
+}
+
+// ------------------------------------------------------------------ per-tile segment sort
+// Bitonic network in its all-ascending form (first step of every merge mirrors the partner index),
+// so elements past the end of the segment behave as +infinity simply by being skipped.
+template <typename Load, typename Store>
+__device__ __forceinline__ void bitonic_ascending(uint32_t n, uint32_t n_pad, Load ld, Store st) {
+    for (uint32_t k = 2; k <= n_pad; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
+            const uint32_t blk = i / hk, within = i % hk;
+            const uint32_t a = blk * k + within, b = blk * k + k - 1u - within;
+            if (b < n) {
+                const uint64_t va = ld(a), vb = ld(b);
+                if (va > vb) { st(a, vb); st(b, va); }
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = hk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
+                const uint32_t a = 2u * j * (i / j) + (i % j), b = a + j;
+                if (b < n) {
+                    const uint64_t va = ld(a), vb = ld(b);
+                    if (va > vb) { st(a, vb); st(b, va); }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int kTileSortThreads = 256;
+constexpr uint32_t kSortSmallCap = 2048;      // 16 KB of shared memory
+constexpr uint32_t kSortLargeCap = 8192;      // 64 KB (dynamic); longer segments are sorted in global memory
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n) { return n <= 1u ? 1u : 1u << (32 - __clz(n - 1u)); }
+
+// LARGE = false: segments of up to kSortSmallCap instances; LARGE = true: everything longer.
+template <bool LARGE>
+__global__ void __launch_bounds__(kTileSortThreads)
+k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    extern __shared__ __align__(16) unsigned char tsort_smem[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(tsort_smem);
+    const uint2 rg = ranges[blockIdx.x];
+    const uint32_t n = rg.y - rg.x;
+    if (n == 0u || (LARGE ? n <= kSortSmallCap : n > kSortSmallCap)) return;
+    const uint64_t tile_hi = (uint64_t)blockIdx.x << 32;
+    const uint32_t n_pad = next_pow2(n);
+    if (!LARGE || n <= kSortLargeCap) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            s[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];          // depth bits << 32 | face id
+        __syncthreads();
+        bitonic_ascending(n, n_pad, [&](uint32_t i) { return s[i]; }, [&](uint32_t i, uint64_t v) { s[i] = v; });
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t v = s[i];
+            keys[rg.x + i] = tile_hi | (v >> 32);
+            vals[rg.x + i] = (uint32_t)v;
+        }
+    } else {
+        // rare: a segment longer than 8192 instances - same network on the output key buffer
+        uint64_t* g = keys + rg.x;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) g[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];
+        __syncthreads();
+        bitonic_ascending(n, n_pad, [&](uint32_t i) { return g[i]; }, [&](uint32_t i, uint64_t v) { g[i] = v; });
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t v = g[i];
+            g[i] = tile_hi | (v >> 32);
+            vals[rg.x + i] = (uint32_t)v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+// stage 1 of the binning (inside dm2_*_preprocess): per-tile counts -> ranges, cursors, num_rendered
+int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, const uint32_t* tiles_touched,
+                           const uint2* rects, uint2* ranges, uint32_t* cursor, cudaStream_t s) {
+    // the counts live in the cursor array until the scan turns them into start offsets
+    DM2_CHECK(cudaMemsetAsync(cursor, 0, ((size_t)num_tiles + 1) * sizeof(uint32_t), s));
+    if (num_tiles == 0) return 0;
+    if (BF > 0) {
+        ProfScope _ps("tile_count", s);
+        k_count_tiles<<<cdiv(BF, 256), 256, 0, s>>>(BF, F, gx, gy, tiles_touched, rects, cursor);
+        DM2_LAUNCH_CHECK();
+    }
+    {
+        ProfScope _ps("tile_scan", s);
+        k_tile_scan<<<1, 1024, 0, s>>>(cursor, (uint32_t)num_tiles, ranges, cursor);
+        DM2_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// stage 2: scatter into the tile segments and sort every segment
+int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
+                     const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
+                     uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, cudaStream_t s) {
+    if (BF == 0 || num_tiles == 0) return 0;
+    {
+        ProfScope _ps("scatter_instances", s);
+        k_scatter_instances<<<cdiv(BF, 256), 256, 0, s>>>(BF, F, gx, gy, key_depths, tiles_touched, rects, cursor,
+                                                          keys_unsorted, vals_unsorted);
+        DM2_LAUNCH_CHECK();
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortLargeCap * sizeof(uint64_t))));
+        attr_set = true;
+    }
+    ProfScope _ps("tile_sort", s);
+    k_tile_sort<false><<<num_tiles, kTileSortThreads, kSortSmallCap * sizeof(uint64_t), s>>>(ranges, keys_unsorted,
+                                                                                             vals_unsorted, keys, vals);
+    DM2_LAUNCH_CHECK();
+    k_tile_sort<true><<<num_tiles, kTileSortThreads, kSortLargeCap * sizeof(uint64_t), s>>>(ranges, keys_unsorted,
+                                                                                            vals_unsorted, keys, vals);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dm2

@@ -84,7 +84,7 @@ class FusedRenderFunction(torch.autograd.Function):
             face_buffer = torch.empty((face_layout(B, s.F).total,), dtype=torch.uint8, device=dev)
             image_buffer = torch.empty((image_layout(B, H, W).total,), dtype=torch.uint8, device=dev)
             nr = C.c_int64(0)
-            _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), C.byref(nr), stream))
+            _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer), C.byref(nr), stream))
             R = int(nr.value)
             binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
             pool, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev,

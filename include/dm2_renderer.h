@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 8
+#define DM2_ABI_VERSION 9
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -105,8 +105,6 @@ typedef struct DM2FaceLayout {        /* per (view,face) state; reference FaceSt
     size_t min_depths;           /* f32[B*F]                                                    */
     size_t max_depths;           /* f32[B*F]                                                    */
     size_t tiles_touched;        /* u32[B*F]                                                    */
-    size_t face_offsets;         /* u32[B*F]  inclusive prefix sum of tiles_touched             */
-    size_t scan_partials;        /* u32[...]  scan scratch                                      */
     size_t rects;                /* uint2[B*F] tile bbox: x = x0 | y0<<16, y = x1 | y1<<16      */
     size_t records;              /* packed per-(view,face) records staged by the tile kernels   */
     size_t record_stride;        /* bytes per record                                            */
@@ -115,6 +113,8 @@ typedef struct DM2FaceLayout {        /* per (view,face) state; reference FaceSt
 
 typedef struct DM2ImageLayout {       /* reference ImageState / ImageRenderLayerState, state.h:32-61 */
     size_t ranges;               /* uint2[B*tiles] (x = first, y = last+1; (0,0) if empty)      */
+    size_t tile_cursor;          /* u32[B*tiles+1] per-tile instance counts, then scatter cursors;
+                                  *               the last word is num_rendered                  */
     size_t final_T;              /* f32[B*H*W]   (render)                                       */
     size_t final_prev_T;         /* f32[B*H*W]   (render)                                       */
     size_t n_contrib;            /* u32[B*H*W]   (render)                                       */
@@ -124,11 +124,12 @@ typedef struct DM2ImageLayout {       /* reference ImageState / ImageRenderLayer
 } DM2ImageLayout;
 
 typedef struct DM2BinningLayout {     /* reference BinningState, state.h:41-51 */
-    size_t keys_unsorted;        /* u64[R]  (tile + tiles*view) << 32 | float bits of depth     */
-    size_t vals_unsorted;        /* u32[R]  face id within the view                             */
+    size_t keys_unsorted;        /* u64[R]  (tile + tiles*view) << 32 | float bits of depth, grouped
+                                  *         by tile, unsorted inside a tile (scatter order)      */
+    size_t vals_unsorted;        /* u32[R]  face id within the view, same order                 */
     size_t keys;                 /* u64[R]  sorted                                              */
     size_t vals;                 /* u32[R]  sorted  (= reference face_list)                     */
-    size_t sort_temp;            /* radix-sort histograms                                       */
+    size_t sort_temp;            /* unused by the pipeline (scratch of dm2_sort_pairs)          */
     size_t imask;                /* u8[R]   render path: bit w = the face touches a pixel of the
                                   *         8x4-pixel footprint w of its tile (x = (w&1)*8, y = (w>>1)*4) */
     size_t meta;                 /* uint4[8][R] render path: per (footprint, instance) touched-pixel mask
@@ -146,12 +147,14 @@ int dm2_binning_layout(int64_t num_rendered, DM2BinningLayout* out);
 
 /* ---- Renderer: replaces render_forward_cuda / render_backward_cuda ---------------------- */
 /* Stage 1 (reference renderer.cu:150-179): per-face depth / tile bbox / tiles_touched, the
- * packed face records, the inclusive scan, and the num_rendered read-back (waits on stream). */
-int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws,
+ * packed face records, the per-tile instance counts and their scan (= the tile ranges), and
+ * the num_rendered read-back (waits on stream).                                              */
+int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_ws,
                           int64_t* num_rendered_host, void* stream);
-/* Stage 2 (reference renderer.cu:181-266): key emission, stable radix sort on the low
- * 32+bit key bits, tile ranges, then the forward tile compositor.  out_color (B,H,W,3) and
- * out_depth (B,H,W) are fully overwritten.                                                   */
+/* Stage 2 (reference renderer.cu:181-266): key emission straight into the tile segments, per-
+ * segment sort by (depth bits, face id) - together the reference's stable radix sort on the low
+ * 32+bit key bits -, the per-instance pixel classification, then the forward tile compositor.
+ * out_color (B,H,W,3) and out_depth (B,H,W) are fully overwritten.                           */
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
                        int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
                        int64_t aa_cache_pairs, void* stream);
@@ -172,7 +175,7 @@ int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const vo
                         int64_t aa_cache_pairs, void* stream);
 
 /* ---- LayeredRenderer: replaces generate_render_layers_cuda ------------------------------- */
-int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws,
+int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws,
                           int64_t* num_rendered_host, void* stream);
 /* render_layers (B,H,W,L) must be pre-filled with -1 and render_layers_cnt (B,H,W) with 0 by
  * the caller (reference render.cu:437-438); geo_ws needs dm2_layers_geo_bytes(F,T) bytes.    */
@@ -219,7 +222,8 @@ typedef struct DM2FusedGrads {   /* caller-zeroed */
     float* dL_dfaces_intense;    /* (B,F)                                                          */
 } DM2FusedGrads;
 
-int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, int64_t* num_rendered_host, void* stream);
+int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
+                         void* stream);
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
                       int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
                       int64_t aa_cache_pairs, void* stream);
@@ -229,8 +233,9 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
                        const void* aa_cache, int64_t aa_cache_pairs, void* stream);
 
 /* ---- binning primitives exposed on their own (sort keys/s metric, parity tests) ---------- */
-/* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit).  Replaces
- * cub::DeviceRadixSort::SortPairs (reference renderer.cu:202-207).  temp: sort_temp area.   */
+/* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit): a stand-alone
+ * equivalent of cub::DeviceRadixSort::SortPairs (reference renderer.cu:202-207), kept as a
+ * primitive and as the cross-check of the pipeline's tile-segmented sort.  temp: sort_temp area. */
 int dm2_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out,
                    uint32_t* vals_out, int64_t n, int32_t end_bit, void* temp, size_t temp_bytes,
                    void* stream);

@@ -33,7 +33,7 @@ def test_workspace_layouts_are_aligned_and_disjoint(built):
     from dmesh2_renderer_b200 import _C
     for layered in (False, True):
         L = _C.face_layout(3, 1000, layered)
-        offs = [L.depths, L.min_depths, L.max_depths, L.tiles_touched, L.face_offsets, L.scan_partials, L.rects, L.records]
+        offs = [L.depths, L.min_depths, L.max_depths, L.tiles_touched, L.rects, L.records]
         assert all(o % 256 == 0 for o in offs) and offs == sorted(offs) and len(set(offs)) == len(offs)
         assert L.total >= L.records + 3 * 1000 * L.record_stride
     L = _C.binning_layout(12345)
