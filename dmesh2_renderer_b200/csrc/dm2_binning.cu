@@ -140,9 +140,15 @@ __device__ __forceinline__ ProjVert project_vertex(const float4 c, float img_w, 
 __global__ void __launch_bounds__(256)
 k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths, float* __restrict__ min_depths,
                    float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
-                   float* __restrict__ records) {
+                   float* __restrict__ records, uint32_t* __restrict__ patch_flags) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long BF = (long long)in.B * in.F;
+    if (idx < in.B) {
+        // the reference asserts these on the host with a device sync (__init__.py:283-284); here the
+        // verdict travels back with num_rendered
+        if (in.patch_min[2 * idx] + in.W > in.image_w) atomicOr(patch_flags, 1u);
+        if (in.patch_min[2 * idx + 1] + in.H > in.image_h) atomicOr(patch_flags, 2u);
+    }
     if (idx >= BF) return;
     const int b = (int)(idx / in.F), f = (int)(idx % in.F);
     const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
@@ -220,13 +226,13 @@ k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths
     rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
 }
 
-int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, cudaStream_t s) {
+int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, uint32_t* patch_flags, cudaStream_t s) {
     const long long BF = (long long)in.B * in.F;
     if (BF == 0) return 0;
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     ProfScope _ps("preprocess_pack", s);
     k_fused_preprocess<<<cdiv(BF, 256), 256, 0, s>>>(in, gx, gy, fw.depths, fw.min_depths, fw.max_depths,
-                                                     fw.tiles_touched, fw.rects, fw.records);
+                                                     fw.tiles_touched, fw.rects, fw.records, patch_flags);
     DM2_LAUNCH_CHECK();
     return 0;
 }

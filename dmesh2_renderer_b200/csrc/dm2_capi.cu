@@ -87,7 +87,7 @@ static void image_layout(long long B, int H, int W, bool layered, DM2ImageLayout
     const long long tiles = (long long)cdiv(W, kTile) * cdiv(H, kTile);
     const size_t npix = (size_t)B * H * W;
     L->ranges = take((size_t)B * tiles * 8);
-    L->tile_cursor = take(((size_t)B * tiles + 1) * 4);
+    L->tile_cursor = take(((size_t)B * tiles + 2) * 4);
     if (layered) {
         L->final_T = L->final_prev_T = L->n_contrib = 0;
         L->first_face = take(npix * 4);
@@ -157,16 +157,23 @@ static int check_render_inputs(const DM2RenderInputs* in) {
 }
 
 // shared tail of the preprocess entry points: per-tile counts -> tile ranges + read-back of num_rendered
+// The caller zeroes iw.tile_cursor[0 .. num_tiles + 1] BEFORE its preprocess kernel (which may raise
+// patch flags in the last word).
 static int count_and_scan(const FaceWs& fw, const ImageWs& iw, long long BF, int B, int F, int gx, int gy,
-                          int64_t* num_rendered_host, cudaStream_t s) {
+                          int64_t* num_rendered_host, uint32_t* flags_host, cudaStream_t s) {
     *num_rendered_host = 0;
     const int num_tiles = B * gx * gy;
     if (launch_tile_count_scan(BF, F, gx, gy, num_tiles, fw.tiles_touched, fw.rects, iw.ranges, iw.tile_cursor, s))
         return 1;
-    uint32_t r = 0;
-    DM2_CHECK(cudaMemcpyAsync(&r, iw.tile_cursor + num_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t r[2] = {0u, 0u};
+    DM2_CHECK(cudaMemcpyAsync(r, iw.tile_cursor + num_tiles, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     DM2_CHECK(cudaStreamSynchronize(s));
-    *num_rendered_host = (int64_t)r;
+    *num_rendered_host = (int64_t)r[0];
+    if (flags_host) *flags_host = r[1];
+    return 0;
+}
+static int zero_cursor(const ImageWs& iw, int B, int gx, int gy, cudaStream_t s) {
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, ((size_t)B * gx * gy + 2) * sizeof(uint32_t), s));
     return 0;
 }
 
@@ -175,7 +182,7 @@ static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaSt
     ImageWs iw = carve_image(image_ws, B, H, W, layered);
     const size_t nt = (size_t)B * cdiv(W, kTile) * cdiv(H, kTile);
     DM2_CHECK(cudaMemsetAsync(iw.ranges, 0, nt * sizeof(uint2), s));
-    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, (nt + 1) * sizeof(uint32_t), s));
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, (nt + 2) * sizeof(uint32_t), s));
     return 0;
 }
 
@@ -241,8 +248,10 @@ int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_
     if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);    // reference render.cu:149
     FaceWs fw = carve_face(face_ws, BF, false);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
+    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+    if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
     if (launch_render_preprocess(*in, fw, s)) return 1;
-    return count_and_scan(fw, iw, BF, in->B, in->F, cdiv(in->W, kTile), cdiv(in->H, kTile), num_rendered_host, s);
+    return count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, num_rendered_host, nullptr, s);
 }
 
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
@@ -324,8 +333,15 @@ int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, void* image_ws
     if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);
     FaceWs fw = carve_face(face_ws, BF, false);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
-    if (launch_fused_preprocess(*in, fw, s)) return 1;
-    return count_and_scan(fw, iw, BF, in->B, in->F, cdiv(in->W, kTile), cdiv(in->H, kTile), num_rendered_host, s);
+    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+    if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
+    if (launch_fused_preprocess(*in, fw, iw.tile_cursor + (size_t)in->B * gx * gy + 1, s)) return 1;
+    uint32_t flags = 0;
+    if (count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, num_rendered_host, &flags, s)) return 1;
+    // same messages as the reference's host-side asserts (__init__.py:283-284)
+    DM2_REQUIRE(!(flags & 1u), "Some b_patch_max_x exceed self.width");
+    DM2_REQUIRE(!(flags & 2u), "Some b_patch_max_y exceed self.height");
+    return 0;
 }
 
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
@@ -390,8 +406,10 @@ int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_w
     if (BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, true, s);
     FaceWs fw = carve_face(face_ws, BF, true);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
+    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+    if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
     if (launch_layers_preprocess(*in, fw, s)) return 1;
-    return count_and_scan(fw, iw, BF, in->B, in->F, cdiv(in->W, kTile), cdiv(in->H, kTile), num_rendered_host, s);
+    return count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, num_rendered_host, nullptr, s);
 }
 
 int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes) {

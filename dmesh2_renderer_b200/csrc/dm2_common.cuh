@@ -220,7 +220,7 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
 size_t aa_cache_bytes(long long capacity_pairs);
 int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
                         cudaStream_t s);
-int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, cudaStream_t s);
+int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, uint32_t* patch_flags, cudaStream_t s);
 int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
                               cudaStream_t s);
 size_t backward_ws_bytes(long long BF);

@@ -199,8 +199,7 @@ k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_
 // stage 1 of the binning (inside dm2_*_preprocess): per-tile counts -> ranges, cursors, num_rendered
 int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, const uint32_t* tiles_touched,
                            const uint2* rects, uint2* ranges, uint32_t* cursor, cudaStream_t s) {
-    // the counts live in the cursor array until the scan turns them into start offsets
-    DM2_CHECK(cudaMemsetAsync(cursor, 0, ((size_t)num_tiles + 1) * sizeof(uint32_t), s));
+    // the counts live in the cursor array (zeroed by the caller) until the scan turns them into start offsets
     if (num_tiles == 0) return 0;
     if (BF > 0) {
         ProfScope _ps("tile_count", s);

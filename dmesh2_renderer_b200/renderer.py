@@ -131,17 +131,21 @@ class Renderer(torch.nn.Module):
         key = tuple(int(i) for i in batch_mvp_idx)
         cache = self.__dict__.setdefault("_view_cache", {})
         if key not in cache:
-            cache[key] = torch.tensor(list(key), dtype=torch.int32, device=self.ray_o.device)
-        ray_view = cache[key]
-        x0, y0 = batch_patch_min[:, 0], batch_patch_min[:, 1]
-        assert (x0 + patch_width <= self.width).all(), "Some b_patch_max_x exceed self.width"
-        assert (y0 + patch_height <= self.height).all(), "Some b_patch_max_y exceed self.height"
+            idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
+            cache[key] = (idx.to(torch.int32), idx)
+        ray_view, view_idx = cache[key]
+        if not batch_patch_min.is_cuda:
+            # the reference's asserts (__init__.py:283-284); for a CUDA tensor they would force a device sync
+            # per call - there the preprocess kernel checks the bounds and the verdict comes back with
+            # num_rendered (same messages, raised as RuntimeError)
+            assert (batch_patch_min[:, 0] + patch_width <= self.width).all(), "Some b_patch_max_x exceed self.width"
+            assert (batch_patch_min[:, 1] + patch_height <= self.height).all(), "Some b_patch_max_y exceed self.height"
         f32 = torch.float32
         dev = verts.device
         return FusedRenderFunction.apply(
             background.to(dtype=f32), batch_patch_min.to(device=dev, dtype=torch.int32), patch_width, patch_height,
             verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
-            self.mv[batch_mvp_idx].to(dtype=f32), self.proj[batch_mvp_idx].to(dtype=f32),
+            self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
             faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view, self.aa_grad_buffer_size)
 
     def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,

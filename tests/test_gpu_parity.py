@@ -222,6 +222,26 @@ def test_error_behaviour(built):
         _C.render_forward_cuda(*bad)
 
 
+def test_patch_bounds_are_checked_without_a_host_sync(built):
+    """The reference asserts patch_min + patch size <= frame on the host (a device sync per call for CUDA
+    tensors); the fused path checks inside the preprocess kernel and raises with the same message."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=50, size=64)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    args = (st["verts"], st["faces"], st["verts_color"], st["faces_opacity"], st["faces_intense"][:1], st["background"])
+    ok = torch.tensor([[24, 16]], dtype=torch.int32, device=dev)
+    r([0], ok, 40, 48, *args)
+    with pytest.raises(RuntimeError, match="b_patch_max_x"):
+        r([0], torch.tensor([[25, 16]], dtype=torch.int32, device=dev), 40, 48, *args)
+    with pytest.raises(RuntimeError, match="b_patch_max_y"):
+        r([0], torch.tensor([[24, 17]], dtype=torch.int32, device=dev), 40, 48, *args)
+    with pytest.raises(AssertionError, match="b_patch_max_x"):
+        r([0], torch.tensor([[25, 16]], dtype=torch.int32), 40, 48, *args)
+
+
 def test_sort_pairs_stable_and_bit_range(built):
     from dmesh2_renderer_b200 import _C
     dev = _dev()
