@@ -72,13 +72,22 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 }
 
 
+// Transpose tile of 16 rows (contributions) x 29 columns (gradient values).  Columns are stored in
+// groups of four so that a row is written with 7 STS.128 + 1 STS.32; the group stride of 68 words makes
+// both the 16-byte row stores and the per-column 4-byte reads bank-conflict free.
+constexpr int kRedGroup = 68;
+constexpr int kRedWords = 7 * kRedGroup + 16;
+__device__ __forceinline__ int red_index(int q, int row) {
+    return q < 28 ? (q >> 2) * kRedGroup + row * 4 + (q & 3) : 7 * kRedGroup + row;
+}
+
 struct BwdWarpSmem {
     float srec[kSub * kRecStride];          // staged records of the sub-chunk
     float tA[kSlots];                       // [candidate][pixel]: alpha (or skip)  -> T before the contribution
     float tS[kSlots];                       //                     iC.dC + iD.dD     -> dL/dalpha
     float tArea[kSlots];                    //                     overlap area
     float tG[6][kSlots];                    //                     d area / d aa verts (partially covered pairs)
-    float red[16 * 29];                     // half-warp transpose tile
+    float red[kRedWords];                   // half-warp transpose tile (layout: red_index)
     WarpQueue q;
     uint16_t plist[kSlots];                 // pair list of the dense pass, then the contribution list
 };
@@ -231,8 +240,8 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
             __syncwarp();
 
             // ====== 3. pixel-sequential walk (back to front): T and dL/dalpha per contribution
-            for (int k = 0; k < ncs; k++) {
-                if (!((hit >> k) & 1u)) continue;
+            for (uint32_t hh = hit; hh != 0u; hh &= hh - 1u) {
+                const int k = __ffs(hh) - 1;
                 const int slot = k * 32 + lane;
                 const float alpha = ws.tA[slot];
                 if (__float_as_uint(alpha) == kSkipBits) continue;
@@ -349,15 +358,21 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                 for (int h = 0; h < 2; h++) {
                     if (h * 16 >= nrows) break;
                     if ((lane >> 4) == h) {
+                        const int rw = lane & 15;
 #pragma unroll
-                        for (int q = 0; q < 29; q++) ws.red[(lane & 15) * 29 + q] = v[q];
+                        for (int g4 = 0; g4 < 7; g4++)
+                            *reinterpret_cast<float4*>(&ws.red[g4 * kRedGroup + rw * 4]) =
+                                make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                        ws.red[7 * kRedGroup + rw] = v[28];
                     }
                     __syncwarp();
                     const int hrows = min(16, nrows - h * 16);
+                    const int col0 = red_index(min(lane, 28), 0);
+                    const int cstep = lane < 28 ? 4 : 1;
                     for (int rr0 = 0; rr0 < hrows; rr0 += 4) {
                         float x[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) x[j] = (lane < 29 && rr0 + j < 16) ? ws.red[(rr0 + j) * 29 + lane] : 0.0f;
+                        for (int j = 0; j < 4; j++) x[j] = ws.red[col0 + (rr0 + j) * cstep];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const int row = h * 16 + rr0 + j;
