@@ -40,26 +40,69 @@ __device__ __forceinline__ PreOut preprocess_face(int b, int P, int v0, int v1, 
     return o;
 }
 
+// ------------------------------------------------------------------ coalesced record write-out
+// Every thread builds its 240-byte record in shared memory (272-byte stride: conflict-free 16-byte
+// accesses); the warp then writes its 32 records as contiguous 16-byte chunks - 512 bytes per store
+// instruction instead of 32 chunks scattered at a 256-byte stride.
+constexpr int kPreThreads = 256;
+constexpr int kPreSlot = 17;                                    // float4 per staged record (15 used)
+constexpr size_t kPreSmem = (size_t)kPreThreads * kPreSlot * sizeof(float4);
+
+__device__ __forceinline__ void write_records_coalesced(const float4* __restrict__ s_warp, bool live, long long idx,
+                                                        long long BF, float* __restrict__ records, int lane) {
+    __syncwarp();
+    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+    const long long base = idx - lane;
+    float4* out = reinterpret_cast<float4*>(records);
+#pragma unroll 4
+    for (int c = lane; c < 32 * 16; c += 32) {
+        const int slot = c >> 4, chunk = c & 15;
+        if (chunk < 15 && ((live_mask >> slot) & 1u) && base + slot < BF)
+            out[(size_t)(base + slot) * (kRecWords / 4) + chunk] = s_warp[slot * kPreSlot + chunk];
+    }
+}
+
+__device__ __forceinline__ bool render_preprocess_one(const DM2RenderInputs& in, int gx, int gy, long long idx,
+                                                      float* __restrict__ depths, float* __restrict__ min_depths,
+                                                      float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched,
+                                                      uint2* __restrict__ rects, float4* __restrict__ rec);
+__device__ __forceinline__ bool fused_preprocess_one(const DM2FusedInputs& in, int gx, int gy, long long idx,
+                                                     float* __restrict__ depths, float* __restrict__ min_depths,
+                                                     float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched,
+                                                     uint2* __restrict__ rects, float4* __restrict__ rec,
+                                                     uint32_t* __restrict__ patch_flags);
+
 // ------------------------------------------------------------------ render preprocess + pack
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPreThreads)
 k_render_preprocess(DM2RenderInputs in, int gx, int gy, float* __restrict__ depths,
                     float* __restrict__ min_depths, float* __restrict__ max_depths,
                     uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
                     float* __restrict__ records) {
+    extern __shared__ __align__(16) float4 s_pre[];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long BF = (long long)in.B * in.F;
-    if (idx >= BF) return;
+    const int lane = threadIdx.x & 31;
+    float4* const s_warp = s_pre + (threadIdx.x - lane) * kPreSlot;
+    bool live = false;
+    if (idx < BF) live = render_preprocess_one(in, gx, gy, idx, depths, min_depths, max_depths, tiles_touched, rects,
+                                               s_warp + lane * kPreSlot);
+    write_records_coalesced(s_warp, live, idx, BF, records, lane);
+}
+
+__device__ __forceinline__ bool render_preprocess_one(const DM2RenderInputs& in, int gx, int gy, long long idx,
+                                                      float* __restrict__ depths, float* __restrict__ min_depths,
+                                                      float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched,
+                                                      uint2* __restrict__ rects, float4* __restrict__ rec) {
     const int b = (int)(idx / in.F), f = (int)(idx % in.F);
     const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
     const uint32_t pmx = (uint32_t)in.patch_min[2 * b], pmy = (uint32_t)in.patch_min[2 * b + 1];
     const PreOut o = preprocess_face(b, in.P, v0, v1, v2, in.verts_ndc, in.verts_image, pmx, pmy, gx, gy);
-    if (!o.live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return; }
+    if (!o.live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return false; }
     tiles_touched[idx] = (uint32_t)(o.y1 - o.y0) * (uint32_t)(o.x1 - o.x0);
     rects[idx] = make_uint2((uint32_t)o.x0 | ((uint32_t)o.y0 << 16), (uint32_t)o.x1 | ((uint32_t)o.y1 << 16));
     depths[idx] = o.depth; min_depths[idx] = o.dmin; max_depths[idx] = o.dmax;
 
     // ---- packed record (layout: dm2_common.cuh) ----
-    float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * kRecWords);
     const float* av = in.aa_face_verts + (size_t)idx * 6;
     const float* ae = in.aa_face_edges + (size_t)idx * 6;
     const float* ar = in.aa_face_edges_recip + (size_t)idx * 6;
@@ -106,15 +149,22 @@ k_render_preprocess(DM2RenderInputs in, int gx, int gy, float* __restrict__ dept
     rec[12] = make_float4(e[2], e[3], e[4], e[5]);
     rec[13] = make_float4(r[0], r[1], r[2], r[3]);
     rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
+    return true;
 }
 
 int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaStream_t s) {
     const long long BF = (long long)in.B * in.F;
     if (BF == 0) return 0;
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DM2_CHECK(cudaFuncSetAttribute(k_render_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPreSmem));
+        attr_set = true;
+    }
     ProfScope _ps("preprocess_pack", s);
-    k_render_preprocess<<<cdiv(BF, 256), 256, 0, s>>>(in, gx, gy, fw.depths, fw.min_depths, fw.max_depths,
-                                                      fw.tiles_touched, fw.rects, fw.records);
+    k_render_preprocess<<<cdiv(BF, kPreThreads), kPreThreads, kPreSmem, s>>>(in, gx, gy, fw.depths, fw.min_depths,
+                                                                             fw.max_depths, fw.tiles_touched, fw.rects,
+                                                                             fw.records);
     DM2_LAUNCH_CHECK();
     return 0;
 }
@@ -137,19 +187,32 @@ __device__ __forceinline__ ProjVert project_vertex(const float4 c, float img_w, 
     return o;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPreThreads)
 k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths, float* __restrict__ min_depths,
                    float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
                    float* __restrict__ records, uint32_t* __restrict__ patch_flags) {
+    extern __shared__ __align__(16) float4 s_pre[];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long BF = (long long)in.B * in.F;
+    const int lane = threadIdx.x & 31;
+    float4* const s_warp = s_pre + (threadIdx.x - lane) * kPreSlot;
+    bool live = false;
+    if (idx < BF) live = fused_preprocess_one(in, gx, gy, idx, depths, min_depths, max_depths, tiles_touched, rects,
+                                              s_warp + lane * kPreSlot, patch_flags);
+    write_records_coalesced(s_warp, live, idx, BF, records, lane);
+}
+
+__device__ __forceinline__ bool fused_preprocess_one(const DM2FusedInputs& in, int gx, int gy, long long idx,
+                                                     float* __restrict__ depths, float* __restrict__ min_depths,
+                                                     float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched,
+                                                     uint2* __restrict__ rects, float4* __restrict__ rec,
+                                                     uint32_t* __restrict__ patch_flags) {
     if (idx < in.B) {
         // the reference asserts these on the host with a device sync (__init__.py:283-284); here the
         // verdict travels back with num_rendered
         if (in.patch_min[2 * idx] + in.W > in.image_w) atomicOr(patch_flags, 1u);
         if (in.patch_min[2 * idx + 1] + in.H > in.image_h) atomicOr(patch_flags, 2u);
     }
-    if (idx >= BF) return;
     const int b = (int)(idx / in.F), f = (int)(idx % in.F);
     const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
     const uint32_t pmx = (uint32_t)in.patch_min[2 * b], pmy = (uint32_t)in.patch_min[2 * b + 1];
@@ -171,7 +234,7 @@ k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths
         patch_rect(pmx, pmy, a0.ix, a0.iy, a1.ix, a1.iy, a2.ix, a2.iy, gx, gy, x0, y0, x1, y1);
         live = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) != 0u;
     }
-    if (!live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return; }
+    if (!live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return false; }
     tiles_touched[idx] = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
     rects[idx] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
     depths[idx] = clamp01_depth(depth);
@@ -208,7 +271,6 @@ k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths
     const float* q0 = in.verts_color + 3 * (size_t)v0;
     const float* q1 = in.verts_color + 3 * (size_t)v1;
     const float* q2 = in.verts_color + 3 * (size_t)v2;
-    float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * kRecWords);
     rec[0]  = make_float4(txmin, txmax, tymin, tymax);
     rec[1]  = make_float4(n[0], n[1], n[2], n[3]);
     rec[2]  = make_float4(n[4], n[5], c0, c1);
@@ -224,15 +286,22 @@ k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths
     rec[12] = make_float4(e[2], e[3], e[4], e[5]);
     rec[13] = make_float4(r[0], r[1], r[2], r[3]);
     rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
+    return true;
 }
 
 int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, uint32_t* patch_flags, cudaStream_t s) {
     const long long BF = (long long)in.B * in.F;
     if (BF == 0) return 0;
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DM2_CHECK(cudaFuncSetAttribute(k_fused_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPreSmem));
+        attr_set = true;
+    }
     ProfScope _ps("preprocess_pack", s);
-    k_fused_preprocess<<<cdiv(BF, 256), 256, 0, s>>>(in, gx, gy, fw.depths, fw.min_depths, fw.max_depths,
-                                                     fw.tiles_touched, fw.rects, fw.records, patch_flags);
+    k_fused_preprocess<<<cdiv(BF, kPreThreads), kPreThreads, kPreSmem, s>>>(in, gx, gy, fw.depths, fw.min_depths,
+                                                                            fw.max_depths, fw.tiles_touched, fw.rects,
+                                                                            fw.records, patch_flags);
     DM2_LAUNCH_CHECK();
     return 0;
 }
@@ -546,21 +615,23 @@ int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, 
 // every listed face for every pixel: imask = 0xFF and no meta.
 struct InstGeo { float nx[3], ny[3], cc[3]; float4 bb; uint32_t ox, oy; };
 
-__device__ __forceinline__ uint32_t corner_row_mask(float nx, float ylo, float c, uint32_t X0) {
-    auto pred = [&](int cx) { return __fsub_rn(__fmaf_rn((float)(X0 + (uint32_t)cx), nx, ylo), c) >= 0.0f; };
-    const bool p0 = pred(0), p8 = pred(8);
-    int lo = 0, hi = 8;
+// X0f = (float)X0 (exact); corner columns are X0f + 0 .. X0f + 8, exact in fp32 for coordinates < 2^24.
+// The bisection runs on float column offsets (midpoints of small integers are exact) so that no
+// int -> float conversion sits inside the loop.
+__device__ __forceinline__ uint32_t corner_row_mask(float nx, float ylo, float c, float X0f) {
+    auto pred = [&](float cx) { return __fsub_rn(__fmaf_rn(__fadd_rn(X0f, cx), nx, ylo), c) >= 0.0f; };
+    const bool p0 = pred(0.0f), p8 = pred(8.0f);
+    float lo = 0.0f, hi = 8.0f;
 #pragma unroll
     for (int it = 0; it < 3; it++) {
-        const int mid = (lo + hi) >> 1;
-        const bool pm = pred(mid);
-        lo = (pm == p0) ? mid : lo;
-        hi = (pm == p0) ? hi : mid;
+        const float mid = 0.5f * (lo + hi);
+        const bool same = pred(mid) == p0;
+        lo = same ? mid : lo;
+        hi = same ? hi : mid;
     }
     // columns 0..lo carry p0, columns hi..8 carry p8 (hi == lo + 1)
-    uint32_t m = p0 ? ((2u << lo) - 1u) : 0u;
-    m |= p8 ? (0x1FFu & ~((1u << hi) - 1u)) : 0u;
-    return m;
+    const uint32_t below = (1u << (int)hi) - 1u;                 // bits 0 .. lo
+    return (p0 ? below : 0u) | (p8 ? (0x1FFu & ~below) : 0u);
 }
 
 constexpr int kClsThreads = 256;
@@ -613,6 +684,7 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
         const float ccs[3] = {s_f[6][it], s_f[7][it], s_f[8][it]};
         const float bx0 = s_f[9][it], bx1 = s_f[10][it], by0 = s_f[11][it], by1 = s_f[12][it];
         const uint32_t X0 = s_o[0][it] + (w & 1) * 8, Y0 = s_o[1][it] + (w >> 1) * 4;
+        const float X0f = (float)X0;
         // per-pixel triangle-bbox test (aa.h:96-101), negated so that NaN boxes reject nothing
         uint32_t colmask = 0u, rowmask = 0u;
 #pragma unroll
@@ -633,7 +705,7 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
 #pragma unroll
             for (int r = 0; r < 5; r++) {
                 const float ylo = __fmul_rn((float)(Y0 + r), nys[ed]);
-                m[r] = corner_row_mask(nxs[ed], ylo, ccs[ed], X0);
+                m[r] = corner_row_mask(nxs[ed], ylo, ccs[ed], X0f);
                 allc[r] &= m[r];
             }
 #pragma unroll

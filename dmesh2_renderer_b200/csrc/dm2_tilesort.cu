@@ -21,12 +21,24 @@ namespace dm2 {
 
 // Visits every tile of every lane's rect: small rects by their own lane, rects of more than 16 tiles
 // cooperatively by the whole warp (one huge triangle must not serialise thousands of atomics behind
-// a single lane).  f(global tile index, p0, p1) with the owning face's payload words.
-template <typename F>
+// a single lane).  Two-phase callbacks so that the atomics of up to four tiles are in flight together:
+// a(global tile index) -> ticket, then b(global tile index, ticket, p0, p1) with the owning face's payload.
+template <typename A, typename B>
 __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t x0, uint32_t y0, uint32_t w, uint32_t tbase,
-                                              uint32_t p0, uint32_t p1, int gx, int lane, F f) {
+                                              uint32_t p0, uint32_t p1, int gx, int lane, A a, B b) {
     if (n && n <= 16) {
-        for (uint32_t i = 0; i < n; i++) f(tbase + (y0 + i / w) * gx + (x0 + i % w), p0, p1);
+        for (uint32_t i0 = 0; i0 < n; i0 += 4) {
+            uint32_t t[4], k[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = i0 + j;
+                t[j] = tbase + (y0 + i / w) * gx + (x0 + i % w);
+                if (i < n) k[j] = a(t[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (i0 + j < n) b(t[j], k[j], p0, p1);
+        }
     }
     unsigned big = __ballot_sync(0xffffffffu, n > 16);
     while (big) {
@@ -36,7 +48,10 @@ __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t x0, uint32_t 
         const uint32_t sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src);
         const uint32_t sw = __shfl_sync(0xffffffffu, w, src);
         const uint32_t s0 = __shfl_sync(0xffffffffu, p0, src), s1 = __shfl_sync(0xffffffffu, p1, src);
-        for (uint32_t i = lane; i < sn; i += 32) f(st + (sy + i / sw) * gx + (sx + i % sw), s0, s1);
+        for (uint32_t i = lane; i < sn; i += 32) {
+            const uint32_t t = st + (sy + i / sw) * gx + (sx + i % sw);
+            b(t, a(t), s0, s1);
+        }
     }
 }
 
@@ -63,7 +78,8 @@ k_count_tiles(long long BF, int F, int gx, int gy, const uint32_t* __restrict__ 
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const FaceRect r = load_rect(idx, BF, F, gx, gy, tiles_touched, rects);
     for_each_tile(r.n, r.x0, r.y0, r.w, r.tbase, 0u, 0u, gx, threadIdx.x & 31,
-                  [&](uint32_t t, uint32_t, uint32_t) { atomicAdd(tile_count + t, 1u); });
+                  [&](uint32_t t) { atomicAdd(tile_count + t, 1u); return 0u; },
+                  [&](uint32_t, uint32_t, uint32_t, uint32_t) {});
 }
 
 // One block: exclusive scan of the per-tile counts.  ranges[t] = [start, end) (the reference leaves
@@ -117,8 +133,8 @@ k_scatter_instances(long long BF, int F, int gx, int gy, const float* __restrict
     uint32_t dbits = 0u, fid = 0u;
     if (r.n) { dbits = __float_as_uint(key_depths[idx]); fid = (uint32_t)(idx % F); }
     for_each_tile(r.n, r.x0, r.y0, r.w, r.tbase, dbits, fid, gx, threadIdx.x & 31,
-                  [&](uint32_t t, uint32_t d, uint32_t f) {
-                      const uint32_t pos = atomicAdd(cursor + t, 1u);
+                  [&](uint32_t t) { return atomicAdd(cursor + t, 1u); },
+                  [&](uint32_t t, uint32_t pos, uint32_t d, uint32_t f) {
                       keys[pos] = ((uint64_t)t << 32) | d;
                       vals[pos] = f;
                   });
