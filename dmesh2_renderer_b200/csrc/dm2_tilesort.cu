@@ -56,30 +56,57 @@ __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t x0, uint32_t 
 }
 
 struct FaceRect { uint32_t n, x0, y0, w, tbase; };
-__device__ __forceinline__ FaceRect load_rect(long long idx, long long BF, int F, int gx, int gy,
-                                              const uint32_t* __restrict__ tiles_touched,
-                                              const uint2* __restrict__ rects) {
+// Count / scatter run with one grid row per view (blockIdx.y) so that a block only sees the gx*gy tiles
+// of ONE view: when they fit, the per-tile counters are privatised in shared memory (shared-memory
+// atomics per instance, one global atomic per touched tile and block - 2.3 M same-address-heavy global
+// atomics per view otherwise).  kFacesPerThread faces per thread, strided.
+constexpr int kBinThreads = 256;
+constexpr int kFacesPerThread = 16;
+constexpr int kBinFaces = kBinThreads * kFacesPerThread;
+constexpr int kMaxSmemTiles = 16384;            // 64 KB of counters (2048^2 frame)
+
+__device__ __forceinline__ FaceRect load_rect_view(int f, int F, int view, int gx, int gy,
+                                                   const uint32_t* __restrict__ tiles_touched,
+                                                   const uint2* __restrict__ rects) {
     FaceRect r{0u, 0u, 0u, 1u, 0u};
-    if (idx < BF) {
+    if (f < F) {
+        const size_t idx = (size_t)view * F + f;
         r.n = tiles_touched[idx];
         if (r.n) {
             const uint2 q = rects[idx];
             r.x0 = q.x & 0xffffu; r.y0 = q.x >> 16;
             r.w = (q.y & 0xffffu) - r.x0;
-            r.tbase = (uint32_t)(idx / F) * (uint32_t)(gx * gy);
         }
     }
     return r;
 }
 
-__global__ void __launch_bounds__(256)
-k_count_tiles(long long BF, int F, int gx, int gy, const uint32_t* __restrict__ tiles_touched,
-              const uint2* __restrict__ rects, uint32_t* __restrict__ tile_count) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const FaceRect r = load_rect(idx, BF, F, gx, gy, tiles_touched, rects);
-    for_each_tile(r.n, r.x0, r.y0, r.w, r.tbase, 0u, 0u, gx, threadIdx.x & 31,
-                  [&](uint32_t t) { atomicAdd(tile_count + t, 1u); return 0u; },
-                  [&](uint32_t, uint32_t, uint32_t, uint32_t) {});
+template <bool SMEM>
+__global__ void __launch_bounds__(kBinThreads)
+k_count_tiles(int F, int gx, int gy, const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
+              uint32_t* __restrict__ tile_count) {
+    extern __shared__ uint32_t s_cnt[];
+    const int view = blockIdx.y, tiles = gx * gy, lane = threadIdx.x & 31;
+    uint32_t* gcnt = tile_count + (size_t)view * tiles;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < tiles; i += kBinThreads) s_cnt[i] = 0u;
+        __syncthreads();
+    }
+    uint32_t* cnt = SMEM ? s_cnt : gcnt;
+    for (int it = 0; it < kFacesPerThread; it++) {
+        const int f = blockIdx.x * kBinFaces + it * kBinThreads + threadIdx.x;
+        const FaceRect r = load_rect_view(f, F, view, gx, gy, tiles_touched, rects);
+        for_each_tile(r.n, r.x0, r.y0, r.w, 0u, 0u, 0u, gx, lane,
+                      [&](uint32_t t) { atomicAdd(cnt + t, 1u); return 0u; },
+                      [&](uint32_t, uint32_t, uint32_t, uint32_t) {});
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < tiles; i += kBinThreads) {
+            const uint32_t c = s_cnt[i];
+            if (c) atomicAdd(gcnt + i, c);
+        }
+    }
 }
 
 // One block: exclusive scan of the per-tile counts.  ranges[t] = [start, end) (the reference leaves
@@ -123,21 +150,49 @@ k_tile_scan(const uint32_t* tile_count, uint32_t num_tiles, uint2* __restrict__ 
 }
 
 // reference renderer.cu:415-465: key = (tile + tiles*view) << 32 | bits(depth); value = face id -
-// written into the tile's segment at a position drawn from the tile's cursor.
-__global__ void __launch_bounds__(256)
-k_scatter_instances(long long BF, int F, int gx, int gy, const float* __restrict__ key_depths,
+// written into the tile's segment at a position drawn from the tile's cursor.  SMEM: the block first
+// counts its own instances per tile in shared memory, reserves one range per touched tile with a single
+// global atomic, then hands out positions inside its ranges with shared-memory atomics.
+template <bool SMEM>
+__global__ void __launch_bounds__(kBinThreads)
+k_scatter_instances(int F, int gx, int gy, const float* __restrict__ key_depths,
                     const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
                     uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const FaceRect r = load_rect(idx, BF, F, gx, gy, tiles_touched, rects);
-    uint32_t dbits = 0u, fid = 0u;
-    if (r.n) { dbits = __float_as_uint(key_depths[idx]); fid = (uint32_t)(idx % F); }
-    for_each_tile(r.n, r.x0, r.y0, r.w, r.tbase, dbits, fid, gx, threadIdx.x & 31,
-                  [&](uint32_t t) { return atomicAdd(cursor + t, 1u); },
-                  [&](uint32_t t, uint32_t pos, uint32_t d, uint32_t f) {
-                      keys[pos] = ((uint64_t)t << 32) | d;
-                      vals[pos] = f;
-                  });
+    extern __shared__ uint32_t s_cnt[];
+    const int view = blockIdx.y, tiles = gx * gy, lane = threadIdx.x & 31;
+    const uint32_t tbase = (uint32_t)view * (uint32_t)tiles;
+    uint32_t* gcur = cursor + (size_t)tbase;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < tiles; i += kBinThreads) s_cnt[i] = 0u;
+        __syncthreads();
+        for (int it = 0; it < kFacesPerThread; it++) {
+            const int f = blockIdx.x * kBinFaces + it * kBinThreads + threadIdx.x;
+            const FaceRect r = load_rect_view(f, F, view, gx, gy, tiles_touched, rects);
+            for_each_tile(r.n, r.x0, r.y0, r.w, 0u, 0u, 0u, gx, lane,
+                          [&](uint32_t t) { atomicAdd(s_cnt + t, 1u); return 0u; },
+                          [&](uint32_t, uint32_t, uint32_t, uint32_t) {});
+        }
+        __syncthreads();
+        // s_cnt[t] := first position of this block's range in tile t's segment
+        for (int i = threadIdx.x; i < tiles; i += kBinThreads) {
+            const uint32_t c = s_cnt[i];
+            if (c) s_cnt[i] = atomicAdd(gcur + i, c);
+        }
+        __syncthreads();
+    }
+    uint32_t* cur = SMEM ? s_cnt : gcur;
+    for (int it = 0; it < kFacesPerThread; it++) {
+        const int f = blockIdx.x * kBinFaces + it * kBinThreads + threadIdx.x;
+        const FaceRect r = load_rect_view(f, F, view, gx, gy, tiles_touched, rects);
+        uint32_t dbits = 0u;
+        if (r.n) dbits = __float_as_uint(key_depths[(size_t)view * F + f]);
+        for_each_tile(r.n, r.x0, r.y0, r.w, 0u, dbits, (uint32_t)f, gx, lane,
+                      [&](uint32_t t) { return atomicAdd(cur + t, 1u); },
+                      [&](uint32_t t, uint32_t pos, uint32_t d, uint32_t fid) {
+                          keys[pos] = ((uint64_t)(tbase + t) << 32) | d;
+                          vals[pos] = fid;
+                      });
+    }
 }
 
 // ------------------------------------------------------------------ per-tile segment sort
@@ -169,7 +224,8 @@ __device__ __forceinline__ void bitonic_ascending(uint32_t n, uint32_t n_pad, Lo
     }
 }
 
-constexpr int kTileSortThreads = 256;
+constexpr int kTileSortThreads = 256;          // segments of up to kSortSmallCap instances
+constexpr int kTileSortThreadsLarge = 1024;    // longer segments: 8 elements per thread at 8192
 constexpr uint32_t kSortSmallCap = 2048;      // 16 KB of shared memory
 constexpr uint32_t kSortLargeCap = 8192;      // 64 KB (dynamic); longer segments are sorted in global memory
 
@@ -177,7 +233,7 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) { return n <= 1u ? 1u 
 
 // LARGE = false: segments of up to kSortSmallCap instances; LARGE = true: everything longer.
 template <bool LARGE>
-__global__ void __launch_bounds__(kTileSortThreads)
+__global__ void __launch_bounds__(LARGE ? kTileSortThreadsLarge : kTileSortThreads)
 k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
@@ -218,8 +274,20 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
     // the counts live in the cursor array (zeroed by the caller) until the scan turns them into start offsets
     if (num_tiles == 0) return 0;
     if (BF > 0) {
+        static bool cattr = false;
+        if (!cattr) {
+            DM2_CHECK(cudaFuncSetAttribute(k_count_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTiles * 4));
+            DM2_CHECK(cudaFuncSetAttribute(k_scatter_instances<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kMaxSmemTiles * 4));
+            cattr = true;
+        }
         ProfScope _ps("tile_count", s);
-        k_count_tiles<<<cdiv(BF, 256), 256, 0, s>>>(BF, F, gx, gy, tiles_touched, rects, cursor);
+        const int tiles = gx * gy;
+        const dim3 grid(cdiv(F, kBinFaces), (unsigned)(BF / F));
+        if (tiles <= kMaxSmemTiles)
+            k_count_tiles<true><<<grid, kBinThreads, (size_t)tiles * 4, s>>>(F, gx, gy, tiles_touched, rects, cursor);
+        else
+            k_count_tiles<false><<<grid, kBinThreads, 0, s>>>(F, gx, gy, tiles_touched, rects, cursor);
         DM2_LAUNCH_CHECK();
     }
     {
@@ -237,8 +305,14 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
     if (BF == 0 || num_tiles == 0) return 0;
     {
         ProfScope _ps("scatter_instances", s);
-        k_scatter_instances<<<cdiv(BF, 256), 256, 0, s>>>(BF, F, gx, gy, key_depths, tiles_touched, rects, cursor,
-                                                          keys_unsorted, vals_unsorted);
+        const int tiles = gx * gy;
+        const dim3 grid(cdiv(F, kBinFaces), (unsigned)(BF / F));
+        if (tiles <= kMaxSmemTiles)
+            k_scatter_instances<true><<<grid, kBinThreads, (size_t)tiles * 4, s>>>(
+                F, gx, gy, key_depths, tiles_touched, rects, cursor, keys_unsorted, vals_unsorted);
+        else
+            k_scatter_instances<false><<<grid, kBinThreads, 0, s>>>(F, gx, gy, key_depths, tiles_touched, rects, cursor,
+                                                                  keys_unsorted, vals_unsorted);
         DM2_LAUNCH_CHECK();
     }
     static bool attr_set = false;
@@ -251,8 +325,8 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
     k_tile_sort<false><<<num_tiles, kTileSortThreads, kSortSmallCap * sizeof(uint64_t), s>>>(ranges, keys_unsorted,
                                                                                              vals_unsorted, keys, vals);
     DM2_LAUNCH_CHECK();
-    k_tile_sort<true><<<num_tiles, kTileSortThreads, kSortLargeCap * sizeof(uint64_t), s>>>(ranges, keys_unsorted,
-                                                                                            vals_unsorted, keys, vals);
+    k_tile_sort<true><<<num_tiles, kTileSortThreadsLarge, kSortLargeCap * sizeof(uint64_t), s>>>(
+        ranges, keys_unsorted, vals_unsorted, keys, vals);
     DM2_LAUNCH_CHECK();
     return 0;
 }

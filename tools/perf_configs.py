@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also print this library's per-stage CUDA-event times")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     import dmesh2_renderer_b200 as dm
@@ -114,6 +115,14 @@ def main():
                 print(json.dumps({"config": cfg, "impl": name, "error": str(ex)[:200]}), flush=True)
                 continue
             res[name] = out
+            if args.stages and name == "b200":
+                from dmesh2_renderer_b200 import _lib
+                _lib.profile_reset(); _lib.profile_enable(True)
+                n = 3
+                for _ in range(n):
+                    (run_soup if kind == "soup" else run_layers)(*((pkg, sc, dev, views, 1) if kind == "soup" else (pkg, sc, dev, 1)))
+                st = _lib.profile_report(); _lib.profile_enable(False)
+                print(json.dumps({"config": sc.name, "stages_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in st.items()}}), flush=True)
             print(json.dumps({"config": sc.name, "impl": name, "ms": ms, "views_or_frames_per_s": unit,
                               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "scene_gen_s": gen_s}),
                   flush=True)
