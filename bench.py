@@ -10,8 +10,9 @@ plus the fraction of the measured HBM roofline of the dominant kernel.
 
 A "step" is one optimisation step of one view per GPU: Renderer.forward + loss + backward through
 the public API (and, for N > 1, ONE NCCL allreduce of [dverts | dverts_color | dfaces_opacity]).
-`value` is measured with the scene parameters resident in HBM; `e2e` additionally copies the step's
-inputs (verts, colours, opacity, intensity) from pinned host memory and reads the loss back.
+`value` is measured with the scene parameters resident in HBM; `e2e` additionally copies every step's
+inputs (verts, colours, opacity, intensity) from pinned host memory inside the timed region (copy stream,
+double buffered: the copy for step i+1 overlaps the compute of step i) and reads the loss back each step.
 Prints exactly one JSON line on rank 0.
 """
 import argparse
@@ -157,6 +158,16 @@ def cpu_baseline(args, sc):
 
 def main():
     args = parse()
+    # exactly ONE line on stdout: libraries (NCCL's version banner, ...) write to fd 1 too, so everything
+    # but the final JSON line is routed to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,11 +179,11 @@ def main():
         if rank == 0:
             sc = make_scene(args, 0)
             cb = cpu_baseline(args, sc)
-            print(json.dumps({"impl": "reference", "metric": "fwd+bwd frames/s", "value": cb["value"],
-                              "unit": "frames/s", "n_gpus": 0, "steps": 1, "warmup": 0, "higher_is_better": True,
-                              "cpu_baseline": cb, "config": {"workload": sc.name},
-                              "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
-                                      "d2h_bytes_per_step": 0}}))
+            emit({"impl": "reference", "metric": "fwd+bwd frames/s", "value": cb["value"],
+                  "unit": "frames/s", "n_gpus": 0, "steps": 1, "warmup": 0, "higher_is_better": True,
+                  "cpu_baseline": cb, "config": {"workload": sc.name},
+                  "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                          "d2h_bytes_per_step": 0}})
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
@@ -189,7 +200,7 @@ def main():
         ref_dir = os.path.join(ROOT, "baseline", "_ref")
         if not os.path.isdir(os.path.join(ref_dir, "dmesh2_renderer")):
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not built (baseline/build_ref.sh)"}))
+                emit({"impl": "reference", "unavailable": "baseline/_ref not built (baseline/build_ref.sh)"})
             return
         sys.path.insert(0, ref_dir)
         import dmesh2_renderer as pkg          # the UNMODIFIED reference package
@@ -209,24 +220,54 @@ def main():
     P, F = sc.verts.shape[0], sc.faces.shape[0]
     bucket = torch.zeros(3 * P + 3 * P + F, dtype=torch.float32, device=dev) if world > 1 else None
 
-    def step(e2e):
-        if e2e:
-            with torch.no_grad():
-                for k in params:
-                    params[k].copy_(host[k], non_blocking=True)
-        for p in params.values():
+    def compute(prm):
+        for p in prm.values():
             p.grad = None
-        color, depth = renderer([0], patch_min, W, H, params["verts"], faces, params["verts_color"],
-                                params["faces_opacity"], params["faces_intense"], background)
+        color, depth = renderer([0], patch_min, W, H, prm["verts"], faces, prm["verts_color"],
+                                prm["faces_opacity"], prm["faces_intense"], background)
         loss = (color * wc).sum() + (depth * wd).sum()
         loss.backward()
         if world > 1:
             # one allreduce per optimisation step over the flat [dverts | dverts_color | dfaces_opacity] bucket
-            torch.cat((params["verts"].grad.reshape(-1), params["verts_color"].grad.reshape(-1),
-                       params["faces_opacity"].grad.reshape(-1)), out=bucket)
+            torch.cat((prm["verts"].grad.reshape(-1), prm["verts_color"].grad.reshape(-1),
+                       prm["faces_opacity"].grad.reshape(-1)), out=bucket)
             dist.all_reduce(bucket)
+        return loss
+
+    # e2e input feed (both arms): every step's parameters are copied from pinned host memory inside the
+    # timed region, on a copy stream and double buffered - a prefetching loader: the copy for step i+1
+    # runs while step i computes; the compute stream waits on the copy's event, the copy waits on the
+    # event of the step that last used its buffers.  The loss is read back to the host every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    sets = [params, {k: torch.empty_like(v).requires_grad_(True) for k, v in params.items()}]
+    ready, free = [None, None], [None, None]
+
+    def prefetch(j):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            if free[j] is not None:
+                copy_stream.wait_event(free[j])
+            for k in sets[j]:
+                sets[j][k].copy_(host[k], non_blocking=True)
+            ready[j] = torch.cuda.Event()
+            ready[j].record(copy_stream)
+
+    def step_e2e(i, last):
+        j = i & 1
+        if ready[j] is None:
+            prefetch(j)
+        torch.cuda.current_stream(dev).wait_event(ready[j])
+        ready[j] = None
+        if not last:
+            prefetch(j ^ 1)
+        loss = compute(sets[j])
+        free[j] = torch.cuda.Event()
+        free[j].record(torch.cuda.current_stream(dev))
+        return float(loss.item())
+
+    def step(e2e):
         if e2e:
-            return float(loss.item())
+            return step_e2e(0, True)
+        compute(params)
         return None
 
     def timed(n, e2e):
@@ -235,8 +276,11 @@ def main():
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(n):
-            step(e2e)
+        for i in range(n):
+            if e2e:
+                step_e2e(i, i == n - 1)
+            else:
+                compute(params)
         b.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -315,8 +359,9 @@ def main():
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                                "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": dom_ms,
-                               "note": "kernel is ALU-pipe / issue bound, not HBM bound: hundreds of fp32 compare/"
-                                       "select/fma instructions per covered (pixel, face) pair (profiles/r01_ncu_kernels.md)"}
+                               "note": "instruction/latency bound, not HBM bound: hundreds of fp32 instructions per "
+                                       "covered (pixel, face) pair; ncu: issue slots 57 % busy at 16 warps/SM, DRAM 6 % "
+                                       "(profiles/r01_ncu_kernels.md, DESIGN.md section 3)"}
             out["stages_ms_per_step"] = {k: v[0] / args.steps for k, v in stages.items()}
             out["num_rendered"] = R
             # the binning sort = scatter into the tile segments + per-segment sort (dm2_tilesort.cu)
@@ -329,7 +374,7 @@ def main():
             except Exception as ex:
                 out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port",
                                        "sample": f"failed: {ex}"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
