@@ -255,9 +255,17 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
 
 
 def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, tet_faces, face_existence, verts_ndc,
-                                verts_image, image_ray_o, image_ray_d, num_layers, return_taps=False):
-    """reference render.h:101-119 / render.cu:378-476.  Returns (render_layers, render_layers_cnt)."""
+                                verts_image, image_ray_o, image_ray_d, num_layers, return_taps=False, fused=None):
+    """reference render.h:101-119 / render.cu:378-476.  Returns (render_layers, render_layers_cnt).
+
+    fused = (mv [B,4,4], proj [B,4,4], ray_view [B] int32): the fused host prep - the preprocess kernel
+    projects the vertices itself (verts_ndc / verts_image are then ignored and may be None) and
+    image_ray_o / image_ray_d are the renderer's full (V,H,W,3) buffers indexed through ray_view."""
     lib = _lib.load_library()
+    if fused is not None:       # shape-only placeholders (never dereferenced: the kernel projects the vertices itself)
+        nb = int(fused[0].size(0))
+        verts_ndc = verts.new_empty((nb, 0, 3))
+        verts_image = verts.new_empty((nb, 0, 2))
     if verts.dim() != 2 or verts.size(1) != 3:
         _err("verts must have dimensions (P, 3)")
     if faces.dim() != 2 or faces.size(1) != 3:
@@ -290,15 +298,22 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
     H, W, L = int(height), int(width), int(num_layers)
     if face_tets.size(0) != F or tet_faces.size(0) != T:
         _err("face_tets / tet_faces must have dimensions (F, 2) / (T, 4)")
-    if verts_ndc.size(1) != P or tuple(verts_image.shape[:2]) != (B, P):
+    if fused is None and (verts_ndc.size(1) != P or tuple(verts_image.shape[:2]) != (B, P)):
         _err("verts_ndc / verts_image must have dimensions (B, P, .)")
     for t in (keep["image_ray_o"], keep["image_ray_d"]):
-        if tuple(t.shape[:3]) != (B, H, W):
+        if tuple(t.shape[1:3]) != (H, W) or (fused is None and t.size(0) != B):
             _err("image rays must have dimensions (B, height, width, 3)")
     s = DM2LayerInputs()
     s.B, s.P, s.F, s.T, s.H, s.W, s.num_layers = B, P, F, T, H, W, L
     for k, t in keep.items():
         setattr(s, k, t.data_ptr() if t.numel() > 0 else 0)
+    if fused is not None:
+        keep["mv"], keep["proj"] = _prep(fused[0], f32, "mv"), _prep(fused[1], f32, "proj")
+        keep["ray_view"] = _prep(fused[2], i32, "ray_view")
+        if tuple(keep["mv"].shape) != (B, 4, 4) or tuple(keep["proj"].shape) != (B, 4, 4) or keep["ray_view"].numel() != B:
+            _err("mv / proj must have dimensions (B, 4, 4)")
+        s.mv, s.proj, s.ray_view = keep["mv"].data_ptr(), keep["proj"].data_ptr(), keep["ray_view"].data_ptr()
+        s.verts_ndc = s.verts_image = 0
     dev = keep["verts"].device
     with torch.cuda.device(dev):
         stream = _stream(dev)

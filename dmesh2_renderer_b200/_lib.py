@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -58,6 +58,7 @@ class DM2LayerInputs(C.Structure):
         ("verts", C.c_void_p), ("faces", C.c_void_p), ("tets", C.c_void_p), ("face_tets", C.c_void_p),
         ("tet_faces", C.c_void_p), ("face_existence", C.c_void_p), ("verts_ndc", C.c_void_p),
         ("verts_image", C.c_void_p), ("image_ray_o", C.c_void_p), ("image_ray_d", C.c_void_p),
+        ("mv", C.c_void_p), ("proj", C.c_void_p), ("ray_view", C.c_void_p),
     ]
 
 

@@ -317,7 +317,32 @@ k_layers_preprocess(DM2LayerInputs in, int gx, int gy, float* __restrict__ depth
     if (idx >= BF) return;
     const int b = (int)(idx / in.F), f = (int)(idx % in.F);
     const int v0 = in.faces[3 * (size_t)f], v1 = in.faces[3 * (size_t)f + 1], v2 = in.faces[3 * (size_t)f + 2];
-    const PreOut o = preprocess_face(b, in.P, v0, v1, v2, in.verts_ndc, in.verts_image, 0u, 0u, gx, gy);
+    PreOut o;
+    if (in.mv != nullptr) {
+        // fused host prep: same projection chain as k_fused_preprocess, then preprocess_face()'s arithmetic
+        const float* mvb = in.mv + 16 * (size_t)b;
+        const float* prb = in.proj + 16 * (size_t)b;
+        const float fw = (float)in.W, fh = (float)in.H;
+        const ProjVert a0 = project_vertex(clip_vertex(in.verts + 3 * (size_t)v0, mvb, prb), fw, fh);
+        const ProjVert a1 = project_vertex(clip_vertex(in.verts + 3 * (size_t)v1, mvb, prb), fw, fh);
+        const ProjVert a2 = project_vertex(clip_vertex(in.verts + 3 * (size_t)v2, mvb, prb), fw, fh);
+        o.live = false; o.x0 = o.y0 = o.x1 = o.y1 = 0; o.depth = o.dmin = o.dmax = 0.f;
+        const float max_z = fmaxf(fmaxf(a0.nz, a1.nz), a2.nz);
+        const float min_z = fminf(fminf(a0.nz, a1.nz), a2.nz);
+        float depth = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, a0.nz), a1.nz), a2.nz);
+        depth = __fdiv_rn(depth, 3.0f);
+        if (!(max_z < -1.0f || min_z > 1.0f)) {
+            patch_rect(0u, 0u, a0.ix, a0.iy, a1.ix, a1.iy, a2.ix, a2.iy, gx, gy, o.x0, o.y0, o.x1, o.y1);
+            if ((uint32_t)(o.x1 - o.x0) * (uint32_t)(o.y1 - o.y0) != 0u) {
+                o.live = true;
+                o.depth = clamp01_depth(depth);
+                o.dmin = clamp01_depth(min_z);
+                o.dmax = clamp01_depth(max_z);
+            }
+        }
+    } else {
+        o = preprocess_face(b, in.P, v0, v1, v2, in.verts_ndc, in.verts_image, 0u, 0u, gx, gy);
+    }
     if (!o.live) { tiles_touched[idx] = 0; rects[idx] = make_uint2(0, 0); return; }
     tiles_touched[idx] = (uint32_t)(o.y1 - o.y0) * (uint32_t)(o.x1 - o.x0);
     rects[idx] = make_uint2((uint32_t)o.x0 | ((uint32_t)o.y0 << 16), (uint32_t)o.x1 | ((uint32_t)o.y1 << 16));

@@ -3,8 +3,10 @@
 // first L existing faces.  Behaviour of reference cuda_impl/forward.cu:538-709
 // (firstIntersectCUDA), :744-1000 (generateRenderLayersCUDA) and auxiliary.h:382-431
 // (tet_face_outward_normal); re-designed:
-//   * unit face normals and tet centroids are computed once per call into 48-byte / 32-byte
-//     records instead of being rebuilt from 21 scattered vertex loads at every walk step;
+//   * unit face normals, the two adjacent tets and the existence flag of every face go into ONE
+//     64-byte record per face, tet centroid sums + the four face ids into a 32-byte record per tet,
+//     once per call: a walk step is two dependent loads (the tet, then its three other faces in
+//     parallel) instead of ~30 scattered vertex / index loads in four dependent rounds;
 //   * first hit and walk run in ONE kernel (first_face/first_tet stay in registers; they are still
 //     written out as debug taps);
 //   * out-of-image threads are bounds-checked (the reference writes first_face[-1..] for them when
@@ -16,7 +18,7 @@
 namespace dm2 {
 
 constexpr int kLStage = 256;
-constexpr int kFGeoWords = 12;     // p0.xyz p1.xyz p2.xyz n.xyz   (n: unit normal, not yet oriented)
+constexpr int kFGeoWords = 16;     // p0.xyz p1.xyz p2.xyz n.xyz (unit normal, not yet oriented) face_tets[2] existence pad
 constexpr int kTGeoWords = 8;      // centroid.xyz, pad, tet_faces[4]
 
 size_t layers_geo_bytes(int F, int T) {
@@ -24,7 +26,8 @@ size_t layers_geo_bytes(int F, int T) {
 }
 
 __global__ void __launch_bounds__(256)
-k_face_geo(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces, float* __restrict__ fgeo) {
+k_face_geo(int F, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+           const int32_t* __restrict__ face_tets, const int32_t* __restrict__ face_existence, float* __restrict__ fgeo) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const int v0 = faces[3 * (size_t)f], v1 = faces[3 * (size_t)f + 1], v2 = faces[3 * (size_t)f + 2];
@@ -40,6 +43,8 @@ k_face_geo(int F, const float* __restrict__ verts, const int32_t* __restrict__ f
     o[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
     o[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
     o[2] = make_float4(p2.z, n.x, n.y, n.z);
+    o[3] = make_float4(__int_as_float(face_tets[2 * (size_t)f]), __int_as_float(face_tets[2 * (size_t)f + 1]),
+                       __int_as_float(face_existence[f]), 0.0f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -62,11 +67,12 @@ k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ te
     o[1] = make_float4(__int_as_float(tf.x), __int_as_float(tf.y), __int_as_float(tf.z), __int_as_float(tf.w));
 }
 
-struct FGeo { f3 p0, p1, p2, n; };
+struct FGeo { f3 p0, p1, p2, n; int ft0, ft1, exist; };
 __device__ __forceinline__ FGeo load_fgeo(const float* __restrict__ fgeo, int f) {
     const float4* p = reinterpret_cast<const float4*>(fgeo + (size_t)f * kFGeoWords);
-    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    return FGeo{f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, f3{c.y, c.z, c.w}};
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    return FGeo{f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, f3{c.y, c.z, c.w},
+                __float_as_int(d.x), __float_as_int(d.y), __float_as_int(d.z)};
 }
 
 // dot(outward normal of `face` w.r.t. tet `tet`, ray_d)   (auxiliary.h:382-431 + the caller's dot)
@@ -100,8 +106,9 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
     const size_t pix = inside ? ((size_t)b * in.H + py) * in.W + px : 0;
     f3 ro{0, 0, 0}, rd{0, 0, 0};
     if (inside) {
-        const float* o = in.image_ray_o + pix * 3;
-        const float* d = in.image_ray_d + pix * 3;
+        const size_t rix = in.ray_view ? ((size_t)in.ray_view[b] * in.H + py) * in.W + px : pix;
+        const float* o = in.image_ray_o + rix * 3;
+        const float* d = in.image_ray_d + rix * 3;
         ro = f3{o[0], o[1], o[2]};
         rd = f3{d[0], d[1], d[2]};
     }
@@ -143,26 +150,27 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
 
     // ---------------- entry tet (forward.cu:683-708)
     int first_tet = -1;
+    FGeo cur{};
     if (first_face >= 0) {
-        const FGeo g = load_fgeo(fgeo, first_face);
+        cur = load_fgeo(fgeo, first_face);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-            const int tet = in.face_tets[2 * (size_t)first_face + i];
+            const int tet = i == 0 ? cur.ft0 : cur.ft1;
             if (tet < 0) continue;
             const float4 ts = __ldg(reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords));
-            if (outward_dot(g, ts, rd) < 0.0f) first_tet = tet;
+            if (outward_dot(cur, ts, rd) < 0.0f) first_tet = tet;
         }
     }
     first_face_out[pix] = first_face;
     first_tet_out[pix] = first_tet;
 
-    // ---------------- walk (forward.cu:842-999)
+    // ---------------- walk (forward.cu:842-999); `cur` is the record of curr_face
     const int L = in.num_layers;
     int curr_face = first_face, curr_tet = first_tet, n_done = 0;
     bool wdone = (curr_face == -1 || curr_tet == -1);
     long long guard = (long long)in.T + in.F + 16;          // safety net against cyclic walks
     while (!wdone && guard-- > 0) {
-        if (in.face_existence[curr_face]) {
+        if (cur.exist) {
             if (n_done < L) layers[pix * L + n_done] = curr_face;
             n_done++;
             if (n_done >= L) break;
@@ -177,25 +185,20 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
 #pragma unroll
         for (int i = 0; i < 4; i++) if (tf[i] != curr_face) { others[k < 3 ? k : 3] = tf[i]; k++; }
         if (k != 3) break;
-        {
-            const FGeo g = load_fgeo(fgeo, curr_face);
-            if (outward_dot(g, ts, rd) >= 0.0f) break;
-        }
-        int next_face = -1, next_cnt = 0;
+        if (outward_dot(cur, ts, rd) >= 0.0f) break;
+        const FGeo g0 = load_fgeo(fgeo, others[0]), g1 = load_fgeo(fgeo, others[1]), g2 = load_fgeo(fgeo, others[2]);
+        int next_cnt = 0, next_i = 0;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            const FGeo g = load_fgeo(fgeo, others[i]);
-            float t, u, v;
-            if (!ray_tri(ro, rd, g.p0, g.p1, g.p2, t, u, v)) continue;
-            const bool hit = t >= 0.0f && u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f;
-            if (hit && outward_dot(g, ts, rd) > 0.0f) { next_face = others[i]; next_cnt++; }
+            const FGeo& g = i == 0 ? g0 : (i == 1 ? g1 : g2);
+            if (hit_test(ro, rd, g) && outward_dot(g, ts, rd) > 0.0f) { next_i = i; next_cnt++; }
         }
         if (next_cnt != 1) break;
+        cur = next_i == 0 ? g0 : (next_i == 1 ? g1 : g2);
         int next_tet = -1;
-        const int ft0 = in.face_tets[2 * (size_t)next_face], ft1 = in.face_tets[2 * (size_t)next_face + 1];
-        if (ft0 != curr_tet) next_tet = ft0;
-        else if (ft1 != curr_tet) next_tet = ft1;
-        curr_face = next_face;
+        if (cur.ft0 != curr_tet) next_tet = cur.ft0;
+        else if (cur.ft1 != curr_tet) next_tet = cur.ft1;
+        curr_face = others[next_i];
         curr_tet = next_tet;
     }
     layers_cnt[pix] = n_done;
@@ -210,7 +213,7 @@ int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, c
     float* tgeo = reinterpret_cast<float*>(reinterpret_cast<char*>(geo_ws) + align_up((size_t)in.F * kFGeoWords * 4, 256));
     ProfScope _ps("layers_geo+first_hit+walk", s);
     if (in.F > 0) {
-        k_face_geo<<<cdiv(in.F, 256), 256, 0, s>>>(in.F, in.verts, in.faces, fgeo);
+        k_face_geo<<<cdiv(in.F, 256), 256, 0, s>>>(in.F, in.verts, in.faces, in.face_tets, in.face_existence, fgeo);
         DM2_LAUNCH_CHECK();
     }
     if (in.T > 0) {

@@ -71,8 +71,10 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                 if (lane >= o) incl += t;
             }
             const uint32_t tot = __shfl_sync(0xffffffffu, incl, ncs - 1);
-            uint32_t base = 0u;
-            if (lane == 0 && tot > 0u) base = atomicAdd(cache.counter, tot);
+            // (a pool that is already full is not bumped any further: the 32-bit counter must never wrap)
+            uint32_t base = cache.capacity;
+            if (lane == 0 && tot > 0u && *reinterpret_cast<volatile uint32_t*>(cache.counter) < cache.capacity)
+                base = atomicAdd(cache.counter, tot);
             base = __shfl_sync(0xffffffffu, base, 0);
             const bool fits = (unsigned long long)base + tot <= (unsigned long long)cache.capacity;
             if (lane < ncs) {

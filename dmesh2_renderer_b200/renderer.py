@@ -197,9 +197,24 @@ class LayeredRenderer(Renderer):
                  tet_faces: torch.Tensor,           # [T, 4]
                  faces_existence: torch.Tensor,     # [F,]
                  num_layers: int):
+        f32, i32 = torch.float32, torch.int32
+        if getattr(self, "fused", True) and verts.is_cuda:
+            # fused host prep (as Renderer._forward_fused): projection inside the preprocess kernel, rays read
+            # in place from the full-resolution buffers - bit-identical layer ids, no torch prep kernels
+            key = tuple(int(i) for i in batch_mvp_idx)
+            cache = self.__dict__.setdefault("_view_cache", {})
+            if key not in cache:
+                idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
+                cache[key] = (idx.to(torch.int32), idx)
+            ray_view, view_idx = cache[key]
+            return _C.generate_render_layers_cuda(
+                self.width, self.height,
+                verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),
+                tet_faces.to(dtype=i32), faces_existence.to(dtype=i32), None, None, self.ray_o, self.ray_d, num_layers,
+                fused=(self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
+                       ray_view))
         verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])
         ray_o, ray_d = self.ray_o[batch_mvp_idx], self.ray_d[batch_mvp_idx]
-        f32, i32 = torch.float32, torch.int32
         return _C.generate_render_layers_cuda(
             self.width, self.height,
             verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),

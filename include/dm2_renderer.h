@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 9
+#define DM2_ABI_VERSION 10
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -97,6 +97,14 @@ typedef struct DM2LayerInputs {
     const float*   verts_image;              /* (B,P,2) */
     const float*   image_ray_o;              /* (B,H,W,3) */
     const float*   image_ray_d;              /* (B,H,W,3) */
+    /* Optional fused host prep (NULL for the plain generate_render_layers_cuda path), as for the
+     * Renderer: with mv / proj != NULL the preprocess kernel projects the vertices itself (same
+     * fma chain and IEEE operations as compute_verts_ndc_image, reference __init__.py:239-262;
+     * verts_ndc / verts_image may then be NULL), and with ray_view != NULL image_ray_* are the
+     * renderer's full (V,H,W,3) buffers and batch entry b uses row ray_view[b].               */
+    const float*   mv;                       /* (B,4,4) */
+    const float*   proj;                     /* (B,4,4) */
+    const int32_t* ray_view;                 /* (B)     */
 } DM2LayerInputs;
 
 /* Byte offsets inside the three workspaces (all 256-byte aligned).                         */
