@@ -186,19 +186,18 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
         for (int i = 0; i < 4; i++) if (tf[i] != curr_face) { others[k < 3 ? k : 3] = tf[i]; k++; }
         if (k != 3) break;
         if (outward_dot(cur, ts, rd) >= 0.0f) break;
-        const FGeo g0 = load_fgeo(fgeo, others[0]), g1 = load_fgeo(fgeo, others[1]), g2 = load_fgeo(fgeo, others[2]);
-        int next_cnt = 0, next_i = 0;
+        int next_cnt = 0, next_face = -1;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            const FGeo& g = i == 0 ? g0 : (i == 1 ? g1 : g2);
-            if (hit_test(ro, rd, g) && outward_dot(g, ts, rd) > 0.0f) { next_i = i; next_cnt++; }
+            const FGeo g = load_fgeo(fgeo, others[i]);
+            if (hit_test(ro, rd, g) && outward_dot(g, ts, rd) > 0.0f) { next_face = others[i]; next_cnt++; }
         }
         if (next_cnt != 1) break;
-        cur = next_i == 0 ? g0 : (next_i == 1 ? g1 : g2);
+        cur = load_fgeo(fgeo, next_face);                   // just read: an L1 hit, cheaper than 15 selects x 2
         int next_tet = -1;
         if (cur.ft0 != curr_tet) next_tet = cur.ft0;
         else if (cur.ft1 != curr_tet) next_tet = cur.ft1;
-        curr_face = others[next_i];
+        curr_face = next_face;
         curr_tet = next_tet;
     }
     layers_cnt[pix] = n_done;
