@@ -28,7 +28,7 @@ def aa_cache_alloc(len_oarea_buffer, num_rendered, aa_temperature, device, want=
     """Returns (pool tensor, capacity in pairs); (empty, 0) when the cache is off."""
     cap = 0
     if want and len_oarea_buffer > 0 and aa_temperature > 0 and num_rendered > 0:
-        cap = min(int(num_rendered) * AA_CACHE_PAIRS_PER_INSTANCE, AA_CACHE_MAX_BYTES // 28, (1 << 32) - 4096)
+        cap = min(int(num_rendered) * AA_CACHE_PAIRS_PER_INSTANCE, AA_CACHE_MAX_BYTES // 28, (1 << 32) - (1 << 28))
     if cap == 0:
         return torch.empty((0,), dtype=torch.float32, device=device), 0
     nb = C.c_size_t(0)

@@ -260,7 +260,7 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
     if (check_render_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && out_color && out_depth, "dm2_render_forward: null buffer");
     DM2_REQUIRE(num_rendered >= 0 && num_rendered < (1ll << 31), "dm2_render_forward: bad num_rendered");
-    DM2_REQUIRE(aa_cache_pairs >= 0 && aa_cache_pairs < (1ll << 32) - 1, "dm2_render_forward: bad aa_cache_pairs");
+    DM2_REQUIRE(aa_cache_pairs >= 0 && aa_cache_pairs <= (1ll << 32) - (1ll << 28), "dm2_render_forward: bad aa_cache_pairs");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);

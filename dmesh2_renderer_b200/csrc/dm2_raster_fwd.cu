@@ -53,6 +53,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     uint32_t last_contributor = 0;
 
     int head = 0, count = 0, cursor = 0;
+    bool pool_full = false;
     while (!__all_sync(0xffffffffu, done)) {
         fill_queue<false>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
         if (count == 0) break;
@@ -71,12 +72,13 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                 if (lane >= o) incl += t;
             }
             const uint32_t tot = __shfl_sync(0xffffffffu, incl, ncs - 1);
-            // (a pool that is already full is not bumped any further: the 32-bit counter must never wrap)
+            // (a warp that once found the pool full stops bumping it: every warp overshoots by at most one
+            // sub-chunk, so the 32-bit counter cannot wrap - the host keeps the capacity below 2^32 - 2^28)
             uint32_t base = cache.capacity;
-            if (lane == 0 && tot > 0u && *reinterpret_cast<volatile uint32_t*>(cache.counter) < cache.capacity)
-                base = atomicAdd(cache.counter, tot);
+            if (lane == 0 && tot > 0u && !pool_full) base = atomicAdd(cache.counter, tot);
             base = __shfl_sync(0xffffffffu, base, 0);
             const bool fits = (unsigned long long)base + tot <= (unsigned long long)cache.capacity;
+            pool_full = pool_full || !fits;
             if (lane < ncs) {
                 const uint32_t poff = fits ? base + incl - cnt : kNoCache;
                 ws.srec[lane * kRecStride + R_META + 3] = __uint_as_float(poff);

@@ -15,6 +15,7 @@
 // (depth bits << 32 | face id) yields exactly the reference's sorted key and value arrays whatever
 // order the scatter arrived in.  Four launches and ~36 bytes of traffic per instance instead of
 // thirty launches and ~170 bytes.
+#include <algorithm>
 #include "dm2_common.cuh"
 
 namespace dm2 {
@@ -61,8 +62,7 @@ struct FaceRect { uint32_t n, x0, y0, w, tbase; };
 // atomics per instance, one global atomic per touched tile and block - 2.3 M same-address-heavy global
 // atomics per view otherwise).  kFacesPerThread faces per thread, strided.
 constexpr int kBinThreads = 256;
-constexpr int kFacesPerThread = 16;
-constexpr int kBinFaces = kBinThreads * kFacesPerThread;
+constexpr int kMaxFacesPerThread = 16;          // fewer for small scenes, so that the grid still fills the GPU
 constexpr int kMaxSmemTiles = 16384;            // 64 KB of counters (2048^2 frame)
 
 __device__ __forceinline__ FaceRect load_rect_view(int f, int F, int view, int gx, int gy,
@@ -83,8 +83,8 @@ __device__ __forceinline__ FaceRect load_rect_view(int f, int F, int view, int g
 
 template <bool SMEM>
 __global__ void __launch_bounds__(kBinThreads)
-k_count_tiles(int F, int gx, int gy, const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
-              uint32_t* __restrict__ tile_count) {
+k_count_tiles(int F, int fpt, int gx, int gy, const uint32_t* __restrict__ tiles_touched,
+              const uint2* __restrict__ rects, uint32_t* __restrict__ tile_count) {
     extern __shared__ uint32_t s_cnt[];
     const int view = blockIdx.y, tiles = gx * gy, lane = threadIdx.x & 31;
     uint32_t* gcnt = tile_count + (size_t)view * tiles;
@@ -93,8 +93,8 @@ k_count_tiles(int F, int gx, int gy, const uint32_t* __restrict__ tiles_touched,
         __syncthreads();
     }
     uint32_t* cnt = SMEM ? s_cnt : gcnt;
-    for (int it = 0; it < kFacesPerThread; it++) {
-        const int f = blockIdx.x * kBinFaces + it * kBinThreads + threadIdx.x;
+    for (int it = 0; it < fpt; it++) {
+        const int f = (blockIdx.x * fpt + it) * kBinThreads + threadIdx.x;
         const FaceRect r = load_rect_view(f, F, view, gx, gy, tiles_touched, rects);
         for_each_tile(r.n, r.x0, r.y0, r.w, 0u, 0u, 0u, gx, lane,
                       [&](uint32_t t) { atomicAdd(cnt + t, 1u); return 0u; },
@@ -155,7 +155,7 @@ k_tile_scan(const uint32_t* tile_count, uint32_t num_tiles, uint2* __restrict__ 
 // global atomic, then hands out positions inside its ranges with shared-memory atomics.
 template <bool SMEM>
 __global__ void __launch_bounds__(kBinThreads)
-k_scatter_instances(int F, int gx, int gy, const float* __restrict__ key_depths,
+k_scatter_instances(int F, int fpt, int gx, int gy, const float* __restrict__ key_depths,
                     const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
                     uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     extern __shared__ uint32_t s_cnt[];
@@ -165,8 +165,8 @@ k_scatter_instances(int F, int gx, int gy, const float* __restrict__ key_depths,
     if (SMEM) {
         for (int i = threadIdx.x; i < tiles; i += kBinThreads) s_cnt[i] = 0u;
         __syncthreads();
-        for (int it = 0; it < kFacesPerThread; it++) {
-            const int f = blockIdx.x * kBinFaces + it * kBinThreads + threadIdx.x;
+        for (int it = 0; it < fpt; it++) {
+            const int f = (blockIdx.x * fpt + it) * kBinThreads + threadIdx.x;
             const FaceRect r = load_rect_view(f, F, view, gx, gy, tiles_touched, rects);
             for_each_tile(r.n, r.x0, r.y0, r.w, 0u, 0u, 0u, gx, lane,
                           [&](uint32_t t) { atomicAdd(s_cnt + t, 1u); return 0u; },
@@ -181,8 +181,8 @@ k_scatter_instances(int F, int gx, int gy, const float* __restrict__ key_depths,
         __syncthreads();
     }
     uint32_t* cur = SMEM ? s_cnt : gcur;
-    for (int it = 0; it < kFacesPerThread; it++) {
-        const int f = blockIdx.x * kBinFaces + it * kBinThreads + threadIdx.x;
+    for (int it = 0; it < fpt; it++) {
+        const int f = (blockIdx.x * fpt + it) * kBinThreads + threadIdx.x;
         const FaceRect r = load_rect_view(f, F, view, gx, gy, tiles_touched, rects);
         uint32_t dbits = 0u;
         if (r.n) dbits = __float_as_uint(key_depths[(size_t)view * F + f]);
@@ -198,11 +198,14 @@ k_scatter_instances(int F, int gx, int gy, const float* __restrict__ key_depths,
 // ------------------------------------------------------------------ per-tile segment sort
 // Bitonic network in its all-ascending form (first step of every merge mirrors the partner index),
 // so elements past the end of the segment behave as +infinity simply by being skipped.
-template <typename Load, typename Store>
-__device__ __forceinline__ void bitonic_ascending(uint32_t n, uint32_t n_pad, Load ld, Store st) {
+// Generic over the cooperating group: (tid, nthr, sync) = a whole CTA with __syncthreads or one warp
+// with __syncwarp.
+template <typename Load, typename Store, typename Sync>
+__device__ __forceinline__ void bitonic_ascending(uint32_t n, uint32_t n_pad, uint32_t tid, uint32_t nthr, Load ld,
+                                                  Store st, Sync sync) {
     for (uint32_t k = 2; k <= n_pad; k <<= 1) {
         const uint32_t hk = k >> 1;
-        for (uint32_t i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
+        for (uint32_t i = tid; i < (n_pad >> 1); i += nthr) {
             const uint32_t blk = i / hk, within = i % hk;
             const uint32_t a = blk * k + within, b = blk * k + k - 1u - within;
             if (b < n) {
@@ -210,56 +213,134 @@ __device__ __forceinline__ void bitonic_ascending(uint32_t n, uint32_t n_pad, Lo
                 if (va > vb) { st(a, vb); st(b, va); }
             }
         }
-        __syncthreads();
+        sync();
         for (uint32_t j = hk >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < (n_pad >> 1); i += blockDim.x) {
+            for (uint32_t i = tid; i < (n_pad >> 1); i += nthr) {
                 const uint32_t a = 2u * j * (i / j) + (i % j), b = a + j;
                 if (b < n) {
                     const uint64_t va = ld(a), vb = ld(b);
                     if (va > vb) { st(a, vb); st(b, va); }
                 }
             }
-            __syncthreads();
+            sync();
         }
     }
 }
 
-constexpr int kTileSortThreads = 256;          // segments of up to kSortSmallCap instances
-constexpr int kTileSortThreadsLarge = 1024;    // longer segments: 8 elements per thread at 8192
-constexpr uint32_t kSortSmallCap = 2048;      // 16 KB of shared memory
-constexpr uint32_t kSortLargeCap = 8192;      // 64 KB (dynamic); longer segments are sorted in global memory
+// Three tiers by segment length (one launch each, CTAs of the other tiers exit at once):
+constexpr uint32_t kSortCap0 = 2048;          // tier 0:  256 threads,  16 KB of shared memory
+constexpr uint32_t kSortCap1 = 8192;          // tier 1: 1024 threads,  64 KB
+constexpr uint32_t kSortCap2 = 24576;         // tier 2: 1024 threads, 192 KB; longer segments: global memory
+constexpr uint32_t kSortDirectMax = 256;      // up to here one block-wide network; above: depth bins first
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t n) { return n <= 1u ? 1u : 1u << (32 - __clz(n - 1u)); }
 
-// LARGE = false: segments of up to kSortSmallCap instances; LARGE = true: everything longer.
-template <bool LARGE>
-__global__ void __launch_bounds__(LARGE ? kTileSortThreadsLarge : kTileSortThreads)
+// Sorts one tile segment (composite keys: depth bits << 32 | face id) into s[0..n) with the whole CTA.
+// Segments of more than kSortDirectMax elements are first split into 2 * (number of warps) bins by a
+// MONOTONE function of the depth bits (one more most-significant radix digit, linear between the
+// segment's min and max depth): histogram and scatter straight from the global input, then every warp
+// sorts its bins with the bitonic network on its own, without block barriers - O(n) + small sorts
+// instead of log^2(n) block-wide stages.  A segment whose keys crowd into one bin (> n / 4) falls back
+// to the block-wide network.
+template <int THREADS>
+__device__ __forceinline__ void sort_segment_smem(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                  uint64_t* __restrict__ s, uint32_t n) {
+    constexpr int NW = THREADS / 32, NB = 2 * NW;
+    __shared__ uint32_t s_bin[NB + 1];
+    __shared__ uint32_t s_red[2 * NW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    bool binned = n > kSortDirectMax;
+    if (binned) {
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        for (uint32_t i = tid; i < n; i += THREADS) {
+            const uint32_t d = (uint32_t)kin[i];
+            lo = min(lo, d); hi = max(hi, d);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_red[warp] = lo; s_red[NW + warp] = hi; }
+        if (tid <= NB) s_bin[tid] = 0u;
+        __syncthreads();
+        lo = 0xFFFFFFFFu; hi = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { lo = min(lo, s_red[w]); hi = max(hi, s_red[NW + w]); }
+        const uint32_t dmin = lo;
+        const uint64_t span = (uint64_t)(hi - lo) + 1ull;
+        auto bin_of = [&](uint32_t d) { return (uint32_t)(((uint64_t)(d - dmin) * NB) / span); };
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += THREADS) atomicAdd(&s_bin[bin_of((uint32_t)kin[i])], 1u);
+        __syncthreads();
+        // exclusive scan of the NB counters (warp 0), largest bin
+        if (warp == 0) {
+            const uint32_t c0 = lane < NB ? s_bin[lane] : 0u, c1 = (NB > 32 && lane + 32 < NB) ? s_bin[lane + 32] : 0u;
+            uint32_t i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += t0; i1 += t1; }
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+            const uint32_t big = __reduce_max_sync(0xffffffffu, max(c0, c1));
+            if (lane < NB) s_bin[lane] = i0 - c0;
+            if (NB > 32 && lane + 32 < NB) s_bin[lane + 32] = tot0 + i1 - c1;
+            if (lane == 0) s_red[0] = big;
+        }
+        __syncthreads();
+        binned = s_red[0] <= n / 4u;
+        if (binned) {
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const uint64_t k = kin[i];
+                const uint32_t pos = atomicAdd(&s_bin[bin_of((uint32_t)k)], 1u);
+                s[pos] = (k << 32) | vin[i];
+            }
+            __syncthreads();
+            // s_bin[b] now holds the END of bin b; every warp sorts bins warp, warp + NW
+            for (uint32_t b = warp; b < (uint32_t)NB; b += NW) {
+                const uint32_t e = s_bin[b], st0 = b == 0 ? 0u : s_bin[b - 1];
+                const uint32_t m = e - st0;
+                if (m > 1u) {
+                    uint64_t* sb = s + st0;
+                    bitonic_ascending(m, next_pow2(m), lane, 32u, [&](uint32_t i) { return sb[i]; },
+                                      [&](uint32_t i, uint64_t x) { sb[i] = x; }, [] { __syncwarp(); });
+                }
+            }
+            __syncthreads();
+            return;
+        }
+    }
+    for (uint32_t i = tid; i < n; i += THREADS) s[i] = (kin[i] << 32) | vin[i];          // depth bits << 32 | face id
+    __syncthreads();
+    bitonic_ascending(n, next_pow2(n), tid, (uint32_t)THREADS, [&](uint32_t i) { return s[i]; },
+                      [&](uint32_t i, uint64_t x) { s[i] = x; }, [] { __syncthreads(); });
+}
+
+template <int TIER>
+__global__ void __launch_bounds__(TIER == 0 ? 256 : 1024)
 k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
+    constexpr int THREADS = TIER == 0 ? 256 : 1024;
+    constexpr uint32_t LO = TIER == 0 ? 0u : (TIER == 1 ? kSortCap0 : kSortCap1);
+    constexpr uint32_t HI = TIER == 0 ? kSortCap0 : (TIER == 1 ? kSortCap1 : 0xFFFFFFFFu);
     uint64_t* s = reinterpret_cast<uint64_t*>(tsort_smem);
     const uint2 rg = ranges[blockIdx.x];
     const uint32_t n = rg.y - rg.x;
-    if (n == 0u || (LARGE ? n <= kSortSmallCap : n > kSortSmallCap)) return;
+    if (n == 0u || n <= LO || n > HI) return;
     const uint64_t tile_hi = (uint64_t)blockIdx.x << 32;
-    const uint32_t n_pad = next_pow2(n);
-    if (!LARGE || n <= kSortLargeCap) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-            s[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];          // depth bits << 32 | face id
-        __syncthreads();
-        bitonic_ascending(n, n_pad, [&](uint32_t i) { return s[i]; }, [&](uint32_t i, uint64_t v) { s[i] = v; });
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    if (TIER < 2 || n <= kSortCap2) {
+        sort_segment_smem<THREADS>(keys_in + rg.x, vals_in + rg.x, s, n);
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
             const uint64_t v = s[i];
             keys[rg.x + i] = tile_hi | (v >> 32);
             vals[rg.x + i] = (uint32_t)v;
         }
     } else {
-        // rare: a segment longer than 8192 instances - same network on the output key buffer
+        // rare: a segment longer than kSortCap2 instances - block-wide network on the output key buffer
         uint64_t* g = keys + rg.x;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) g[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) g[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];
         __syncthreads();
-        bitonic_ascending(n, n_pad, [&](uint32_t i) { return g[i]; }, [&](uint32_t i, uint64_t v) { g[i] = v; });
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        bitonic_ascending(n, next_pow2(n), threadIdx.x, (uint32_t)THREADS, [&](uint32_t i) { return g[i]; },
+                          [&](uint32_t i, uint64_t v) { g[i] = v; }, [] { __syncthreads(); });
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
             const uint64_t v = g[i];
             g[i] = tile_hi | (v >> 32);
             vals[rg.x + i] = (uint32_t)v;
@@ -268,6 +349,13 @@ k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_
 }
 
 // ------------------------------------------------------------------ launchers
+// faces per thread of the count / scatter kernels: as many as keep ~4 blocks per SM busy
+static int faces_per_thread(long long BF) {
+    const long long want_blocks = 148 * 4;
+    long long fpt = BF / (want_blocks * kBinThreads);
+    return (int)std::max(1ll, std::min((long long)kMaxFacesPerThread, fpt));
+}
+
 // stage 1 of the binning (inside dm2_*_preprocess): per-tile counts -> ranges, cursors, num_rendered
 int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, const uint32_t* tiles_touched,
                            const uint2* rects, uint2* ranges, uint32_t* cursor, cudaStream_t s) {
@@ -283,11 +371,12 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
         }
         ProfScope _ps("tile_count", s);
         const int tiles = gx * gy;
-        const dim3 grid(cdiv(F, kBinFaces), (unsigned)(BF / F));
+        const int fpt = faces_per_thread(BF);
+        const dim3 grid(cdiv(F, kBinThreads * fpt), (unsigned)(BF / F));
         if (tiles <= kMaxSmemTiles)
-            k_count_tiles<true><<<grid, kBinThreads, (size_t)tiles * 4, s>>>(F, gx, gy, tiles_touched, rects, cursor);
+            k_count_tiles<true><<<grid, kBinThreads, (size_t)tiles * 4, s>>>(F, fpt, gx, gy, tiles_touched, rects, cursor);
         else
-            k_count_tiles<false><<<grid, kBinThreads, 0, s>>>(F, gx, gy, tiles_touched, rects, cursor);
+            k_count_tiles<false><<<grid, kBinThreads, 0, s>>>(F, fpt, gx, gy, tiles_touched, rects, cursor);
         DM2_LAUNCH_CHECK();
     }
     {
@@ -306,27 +395,30 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
     {
         ProfScope _ps("scatter_instances", s);
         const int tiles = gx * gy;
-        const dim3 grid(cdiv(F, kBinFaces), (unsigned)(BF / F));
+        const int fpt = faces_per_thread(BF);
+        const dim3 grid(cdiv(F, kBinThreads * fpt), (unsigned)(BF / F));
         if (tiles <= kMaxSmemTiles)
             k_scatter_instances<true><<<grid, kBinThreads, (size_t)tiles * 4, s>>>(
-                F, gx, gy, key_depths, tiles_touched, rects, cursor, keys_unsorted, vals_unsorted);
+                F, fpt, gx, gy, key_depths, tiles_touched, rects, cursor, keys_unsorted, vals_unsorted);
         else
-            k_scatter_instances<false><<<grid, kBinThreads, 0, s>>>(F, gx, gy, key_depths, tiles_touched, rects, cursor,
-                                                                  keys_unsorted, vals_unsorted);
+            k_scatter_instances<false><<<grid, kBinThreads, 0, s>>>(F, fpt, gx, gy, key_depths, tiles_touched, rects,
+                                                                  cursor, keys_unsorted, vals_unsorted);
         DM2_LAUNCH_CHECK();
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kSortLargeCap * sizeof(uint64_t))));
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortCap1 * sizeof(uint64_t))));
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortCap2 * sizeof(uint64_t))));
         attr_set = true;
     }
     ProfScope _ps("tile_sort", s);
-    k_tile_sort<false><<<num_tiles, kTileSortThreads, kSortSmallCap * sizeof(uint64_t), s>>>(ranges, keys_unsorted,
-                                                                                             vals_unsorted, keys, vals);
+    k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
     DM2_LAUNCH_CHECK();
-    k_tile_sort<true><<<num_tiles, kTileSortThreadsLarge, kSortLargeCap * sizeof(uint64_t), s>>>(
-        ranges, keys_unsorted, vals_unsorted, keys, vals);
+    k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
+    DM2_LAUNCH_CHECK();
+    k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
     DM2_LAUNCH_CHECK();
     return 0;
 }

@@ -158,15 +158,16 @@ def test_aa_cache_on_off_overflow_agree(built, fused, monkeypatch):
             assert rel_err(other[k], g_on[k]) <= 1e-5, (k, rel_err(other[k], g_on[k]))
 
 
-@pytest.mark.parametrize("n_faces", [12_000, 45_000])
-def test_long_tile_lists_sort_paths(built, n_faces):
-    """4 tiles with ~3 000 (shared-memory path for long segments) and > 8 192 (global-memory path)
-    instances each: the tile-segmented sort must still equal the stable sort of the oracle."""
+@pytest.mark.parametrize("n_faces,longest", [(12_000, 2048), (45_000, 8192), (130_000, 24576)])
+def test_long_tile_lists_sort_paths(built, n_faces, longest):
+    """4 tiles with > 2 048, > 8 192 and > 24 576 instances each (the three longer tiers of the tile-segmented
+    sort: depth-binned in 64 KB / 192 KB of shared memory, block-wide network in global memory): sorted keys,
+    values and ranges must still equal the stable sort of the oracle."""
     from dmesh2_renderer_b200 import scenes
     sc = scenes.triangle_soup("long_lists", n_faces, 32, 0.01, seed=31)
     cuda, ref = _oracle_and_cuda(sc)
     lens = ref["ranges"][:, 1].astype(np.int64) - ref["ranges"][:, 0]
-    assert lens.max() > (8192 if n_faces > 20_000 else 2048)
+    assert lens.max() > longest
     _check_ints(cuda, ref)
     _check_floats(cuda, ref)
 
