@@ -87,7 +87,7 @@ static void image_layout(long long B, int H, int W, bool layered, DM2ImageLayout
     const long long tiles = (long long)cdiv(W, kTile) * cdiv(H, kTile);
     const size_t npix = (size_t)B * H * W;
     L->ranges = take((size_t)B * tiles * 8);
-    L->tile_cursor = take(((size_t)B * tiles + 2) * 4);
+    L->tile_cursor = take(((size_t)B * tiles + 3) * 4);
     if (layered) {
         L->final_T = L->final_prev_T = L->n_contrib = 0;
         L->first_face = take(npix * 4);
@@ -156,6 +156,10 @@ static int check_render_inputs(const DM2RenderInputs* in) {
     return 0;
 }
 
+// longest tile segment seen by the last preprocess call on a given image workspace (host-side hint that
+// lets the forward call skip the sort tiers nothing falls into; -1 / absent = unknown)
+static thread_local std::map<const void*, long long> g_longest;
+
 // shared tail of the preprocess entry points: per-tile counts -> tile ranges + read-back of num_rendered
 // The caller zeroes iw.tile_cursor[0 .. num_tiles + 1] BEFORE its preprocess kernel (which may raise
 // patch flags in the last word).
@@ -165,15 +169,16 @@ static int count_and_scan(const FaceWs& fw, const ImageWs& iw, long long BF, int
     const int num_tiles = B * gx * gy;
     if (launch_tile_count_scan(BF, F, gx, gy, num_tiles, fw.tiles_touched, fw.rects, iw.ranges, iw.tile_cursor, s))
         return 1;
-    uint32_t r[2] = {0u, 0u};
-    DM2_CHECK(cudaMemcpyAsync(r, iw.tile_cursor + num_tiles, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t r[3] = {0u, 0u, 0u};
+    DM2_CHECK(cudaMemcpyAsync(r, iw.tile_cursor + num_tiles, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     DM2_CHECK(cudaStreamSynchronize(s));
     *num_rendered_host = (int64_t)r[0];
     if (flags_host) *flags_host = r[1];
+    g_longest[iw.tile_cursor] = r[2];          // consumed by the matching forward call (bin_faces)
     return 0;
 }
 static int zero_cursor(const ImageWs& iw, int B, int gx, int gy, cudaStream_t s) {
-    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, ((size_t)B * gx * gy + 2) * sizeof(uint32_t), s));
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, ((size_t)B * gx * gy + 3) * sizeof(uint32_t), s));
     return 0;
 }
 
@@ -182,7 +187,7 @@ static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaSt
     ImageWs iw = carve_image(image_ws, B, H, W, layered);
     const size_t nt = (size_t)B * cdiv(W, kTile) * cdiv(H, kTile);
     DM2_CHECK(cudaMemsetAsync(iw.ranges, 0, nt * sizeof(uint2), s));
-    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, (nt + 2) * sizeof(uint32_t), s));
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, (nt + 3) * sizeof(uint32_t), s));
     return 0;
 }
 
@@ -190,8 +195,11 @@ static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaSt
 static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* key_depths, const FaceWs& fw,
                      const BinWs& bw, const ImageWs& iw, long long R, cudaStream_t s) {
     if (R <= 0) return 0;
+    long long longest = -1;
+    auto it = g_longest.find(iw.tile_cursor);
+    if (it != g_longest.end()) { longest = it->second; g_longest.erase(it); }
     return launch_tile_sort(BF, F, gx, gy, B * gx * gy, key_depths, fw.tiles_touched, fw.rects, iw.ranges,
-                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, s);
+                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, longest, s);
 }
 
 }  // namespace dm2

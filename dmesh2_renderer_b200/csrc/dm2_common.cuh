@@ -206,7 +206,8 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
                            const uint2* rects, uint2* ranges, uint32_t* cursor, cudaStream_t s);
 int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
                      const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
-                     uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, cudaStream_t s);
+                     uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
+                     long long longest, cudaStream_t s);
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
                       long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
 size_t sort_temp_bytes(long long n);

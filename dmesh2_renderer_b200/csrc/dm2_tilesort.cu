@@ -111,14 +111,17 @@ k_count_tiles(int F, int fpt, int gx, int gy, const uint32_t* __restrict__ tiles
 
 // One block: exclusive scan of the per-tile counts.  ranges[t] = [start, end) (the reference leaves
 // untouched tiles at (0,0), renderer.cu:211), cursor[t] = start (bumped by the scatter),
-// cursor[num_tiles] = num_rendered.
+// cursor[num_tiles] = num_rendered, cursor[num_tiles + 2] = the longest segment (zeroed by the caller;
+// the host skips the sort tiers no segment falls into).
 __global__ void __launch_bounds__(1024)
 k_tile_scan(const uint32_t* tile_count, uint32_t num_tiles, uint2* __restrict__ ranges, uint32_t* cursor) {
     __shared__ uint32_t wsum[32];
     const uint32_t per = (num_tiles + 1023u) / 1024u;
     const uint32_t lo = min(threadIdx.x * per, num_tiles), hi = min(lo + per, num_tiles);
-    uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += tile_count[i];
+    uint32_t s = 0, longest = 0;
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t c = tile_count[i]; s += c; longest = max(longest, c); }
+    longest = __reduce_max_sync(0xffffffffu, longest);
+    if ((threadIdx.x & 31) == 0 && longest) atomicMax(cursor + num_tiles + 2, longest);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t inc = s;
 #pragma unroll
@@ -390,8 +393,10 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
 // stage 2: scatter into the tile segments and sort every segment
 int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
                      const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
-                     uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, cudaStream_t s) {
+                     uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
+                     long long longest, cudaStream_t s) {
     if (BF == 0 || num_tiles == 0) return 0;
+    if (longest < 0) longest = 1ll << 40;            // unknown: launch every tier
     {
         ProfScope _ps("scatter_instances", s);
         const int tiles = gx * gy;
@@ -416,10 +421,14 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
     ProfScope _ps("tile_sort", s);
     k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
     DM2_LAUNCH_CHECK();
-    k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
-    DM2_LAUNCH_CHECK();
-    k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
-    DM2_LAUNCH_CHECK();
+    if (longest > kSortCap0) {
+        k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
+        DM2_LAUNCH_CHECK();
+    }
+    if (longest > kSortCap1) {
+        k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
+        DM2_LAUNCH_CHECK();
+    }
     return 0;
 }
 

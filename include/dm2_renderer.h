@@ -121,8 +121,9 @@ typedef struct DM2FaceLayout {        /* per (view,face) state; reference FaceSt
 
 typedef struct DM2ImageLayout {       /* reference ImageState / ImageRenderLayerState, state.h:32-61 */
     size_t ranges;               /* uint2[B*tiles] (x = first, y = last+1; (0,0) if empty)      */
-    size_t tile_cursor;          /* u32[B*tiles+2] per-tile instance counts, then scatter cursors;
-                                  *               then num_rendered and the patch-bound flags    */
+    size_t tile_cursor;          /* u32[B*tiles+3] per-tile instance counts, then scatter cursors;
+                                  *               then num_rendered, the patch-bound flags and the
+                                  *               longest tile segment                           */
     size_t final_T;              /* f32[B*H*W]   (render)                                       */
     size_t final_prev_T;         /* f32[B*H*W]   (render)                                       */
     size_t n_contrib;            /* u32[B*H*W]   (render)                                       */
