@@ -255,12 +255,17 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
 
 
 def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, tet_faces, face_existence, verts_ndc,
-                                verts_image, image_ray_o, image_ray_d, num_layers, return_taps=False, fused=None):
+                                verts_image, image_ray_o, image_ray_d, num_layers, return_taps=False, fused=None,
+                                reuse=None):
     """reference render.h:101-119 / render.cu:378-476.  Returns (render_layers, render_layers_cnt).
 
     fused = (mv [B,4,4], proj [B,4,4], ray_view [B] int32): the fused host prep - the preprocess kernel
     projects the vertices itself (verts_ndc / verts_image are then ignored and may be None) and
-    image_ray_o / image_ray_d are the renderer's full (V,H,W,3) buffers indexed through ray_view."""
+    image_ray_o / image_ray_d are the renderer's full (V,H,W,3) buffers indexed through ray_view.
+
+    reuse = the `taps` dict of an earlier call with IDENTICAL geometry, views and rays (return_taps=True):
+    only face_existence may differ - binning and first hits are reused, the tet walk alone is redone
+    (dm2_regenerate_render_layers).  The caller vouches for the condition."""
     lib = _lib.load_library()
     if fused is not None:       # shape-only placeholders (never dereferenced: the kernel projects the vertices itself)
         nb = int(fused[0].size(0))
@@ -319,6 +324,10 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
         stream = _stream(dev)
         render_layers_cnt = torch.zeros((B, H, W), dtype=i32, device=dev)
         render_layers = torch.full((B, H, W, L), -1, dtype=i32, device=dev)
+        if reuse is not None:
+            _lib.check(lib.dm2_regenerate_render_layers(C.byref(s), _ptr(reuse["image_buffer"]), _ptr(reuse["geo_buffer"]),
+                                                        _ptr(render_layers), _ptr(render_layers_cnt), stream))
+            return (render_layers, render_layers_cnt, reuse) if return_taps else (render_layers, render_layers_cnt)
         face_buffer = torch.empty((face_layout(B, F, True).total,), dtype=torch.uint8, device=dev)
         image_buffer = torch.empty((image_layout(B, H, W, True).total,), dtype=torch.uint8, device=dev)
         geo_bytes = C.c_size_t(0)
@@ -334,7 +343,8 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
                                                   _ptr(render_layers_cnt), stream))
     if return_taps:
         return render_layers, render_layers_cnt, dict(num_rendered=R, face_buffer=face_buffer,
-                                                      binning_buffer=binning_buffer, image_buffer=image_buffer)
+                                                      binning_buffer=binning_buffer, image_buffer=image_buffer,
+                                                      geo_buffer=geo_buffer)
     return render_layers, render_layers_cnt
 
 

@@ -441,7 +441,18 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     // key = min depth (reference renderer.cu:603)
     if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, s)) return 1;
-    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, s);
+    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, false, s);
+}
+
+int dm2_regenerate_render_layers(const DM2LayerInputs* in, void* image_ws, void* geo_ws, int32_t* render_layers,
+                                 int32_t* render_layers_cnt, void* stream) {
+    if (check_layer_inputs(in)) return 2;
+    DM2_REQUIRE(image_ws && geo_ws && render_layers_cnt, "dm2_regenerate_render_layers: null buffer");
+    DM2_REQUIRE(render_layers || in->num_layers == 0, "dm2_regenerate_render_layers: null render_layers");
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
+    FaceWs fw{};
+    BinWs bw{};
+    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, true, (cudaStream_t)stream);
 }
 
 int dm2_sort_temp_bytes(int64_t n, size_t* bytes) {

@@ -226,7 +226,7 @@ int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const 
                               cudaStream_t s);
 size_t backward_ws_bytes(long long BF);
 int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                  void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, cudaStream_t s);
+                  void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, cudaStream_t s);
 size_t layers_geo_bytes(int F, int T);
 
 }  // namespace dm2

@@ -90,6 +90,10 @@ __device__ __forceinline__ bool hit_test(const f3& o, const f3& d, const FGeo& g
     return t >= 0.0f && u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f;
 }
 
+// WALK_ONLY: the geometry (and hence the binning and every pixel's first hit / entry tet) is unchanged
+// since an earlier full call on the same workspaces - only face_existence moved: start from the stored
+// first_face / first_tet.
+template <bool WALK_ONLY>
 __global__ void __launch_bounds__(256)
 k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __restrict__ list,
          const uint2* __restrict__ ranges, const float* __restrict__ fgeo, const float* __restrict__ tgeo,
@@ -120,7 +124,7 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
     bool done = !inside;
     float min_T = -1.0f, min_T_max_depth = -1.0f;
     int first_face = -1;
-    for (int base = 0; base < total; base += kLStage) {
+    for (int base = 0; !WALK_ONLY && base < total; base += kLStage) {
         if (__syncthreads_count(done) == 256) break;
         const int cnt = min(kLStage, total - base);
         for (int q = threadIdx.x; q < cnt * 3; q += 256) {
@@ -151,18 +155,24 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
     // ---------------- entry tet (forward.cu:683-708)
     int first_tet = -1;
     FGeo cur{};
-    if (first_face >= 0) {
-        cur = load_fgeo(fgeo, first_face);
+    if (WALK_ONLY) {
+        first_face = first_face_out[pix];
+        first_tet = first_tet_out[pix];
+        if (first_face >= 0) cur = load_fgeo(fgeo, first_face);
+    } else {
+        if (first_face >= 0) {
+            cur = load_fgeo(fgeo, first_face);
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int tet = i == 0 ? cur.ft0 : cur.ft1;
-            if (tet < 0) continue;
-            const float4 ts = __ldg(reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords));
-            if (outward_dot(cur, ts, rd) < 0.0f) first_tet = tet;
+            for (int i = 0; i < 2; i++) {
+                const int tet = i == 0 ? cur.ft0 : cur.ft1;
+                if (tet < 0) continue;
+                const float4 ts = __ldg(reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords));
+                if (outward_dot(cur, ts, rd) < 0.0f) first_tet = tet;
+            }
         }
+        first_face_out[pix] = first_face;
+        first_tet_out[pix] = first_tet;
     }
-    first_face_out[pix] = first_face;
-    first_tet_out[pix] = first_tet;
 
     // ---------------- walk (forward.cu:842-999); `cur` is the record of curr_face
     const int L = in.num_layers;
@@ -204,23 +214,27 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
 }
 
 int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, void* geo_ws,
-                  int32_t* render_layers, int32_t* render_layers_cnt, cudaStream_t s) {
+                  int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, cudaStream_t s) {
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     if (nblk == 0) return 0;
     float* fgeo = reinterpret_cast<float*>(geo_ws);
     float* tgeo = reinterpret_cast<float*>(reinterpret_cast<char*>(geo_ws) + align_up((size_t)in.F * kFGeoWords * 4, 256));
-    ProfScope _ps("layers_geo+first_hit+walk", s);
+    ProfScope _ps(walk_only ? "layers_geo+walk" : "layers_geo+first_hit+walk", s);
     if (in.F > 0) {
         k_face_geo<<<cdiv(in.F, 256), 256, 0, s>>>(in.F, in.verts, in.faces, in.face_tets, in.face_existence, fgeo);
         DM2_LAUNCH_CHECK();
     }
-    if (in.T > 0) {
+    if (in.T > 0 && !walk_only) {
         k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.tet_faces, tgeo);
         DM2_LAUNCH_CHECK();
     }
-    k_layers<<<(unsigned)nblk, 256, 0, s>>>(in, fw.records, bw.vals, iw.ranges, fgeo, tgeo, iw.first_face,
-                                            iw.first_tet, render_layers, render_layers_cnt, gx, gy);
+    if (walk_only)
+        k_layers<true><<<(unsigned)nblk, 256, 0, s>>>(in, nullptr, nullptr, iw.ranges, fgeo, tgeo, iw.first_face,
+                                                      iw.first_tet, render_layers, render_layers_cnt, gx, gy);
+    else
+        k_layers<false><<<(unsigned)nblk, 256, 0, s>>>(in, fw.records, bw.vals, iw.ranges, fgeo, tgeo, iw.first_face,
+                                                       iw.first_tet, render_layers, render_layers_cnt, gx, gy);
     DM2_LAUNCH_CHECK();
     return 0;
 }

@@ -207,12 +207,22 @@ class LayeredRenderer(Renderer):
                 idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
                 cache[key] = (idx.to(torch.int32), idx)
             ray_view, view_idx = cache[key]
-            return _C.generate_render_layers_cuda(
+            # Incremental re-generation ("fixed point positions" in DMesh++'s layered stage): when
+            # the geometry tensors, cameras and views are the SAME OBJECTS at the SAME VERSION as in the previous
+            # call, only face_existence can have changed - binning and first hits are reused and the tet walk
+            # alone is redone.  In-place updates bump torch's version counter and invalidate the entry.
+            geo = (verts, faces, tets, face_tets, tet_faces, self.mv, self.proj, self.ray_o, self.ray_d)
+            sig = (key, self.width, self.height) + tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in geo)
+            prev = self.__dict__.get("_layer_cache") if getattr(self, "incremental", True) else None
+            reuse = prev[1] if prev is not None and prev[0] == sig else None
+            layers, cnt, taps = _C.generate_render_layers_cuda(
                 self.width, self.height,
                 verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),
                 tet_faces.to(dtype=i32), faces_existence.to(dtype=i32), None, None, self.ray_o, self.ray_d, num_layers,
                 fused=(self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
-                       ray_view))
+                       ray_view), return_taps=True, reuse=reuse)
+            self.__dict__["_layer_cache"] = (sig, taps)
+            return layers, cnt
         verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])
         ray_o, ray_d = self.ray_o[batch_mvp_idx], self.ray_d[batch_mvp_idx]
         return _C.generate_render_layers_cuda(

@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 10
+#define DM2_ABI_VERSION 11
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -192,6 +192,14 @@ int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes);
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
                                void* image_ws, void* geo_ws, int64_t num_rendered,
                                int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
+
+/* Incremental re-generation: when ONLY face_existence changed since a
+ * dm2_generate_render_layers call on the same image_ws / geo_ws (same geometry, views and rays),
+ * the binning, every pixel's first hit and entry tet are still valid: this entry point refreshes the
+ * per-face existence flags and redoes the tet walk alone.  render_layers / render_layers_cnt must be
+ * pre-filled as above.  The caller is responsible for the "only face_existence changed" condition. */
+int dm2_regenerate_render_layers(const DM2LayerInputs* in, void* image_ws, void* geo_ws,
+                                 int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
 
 /* ---- Renderer, fused host prep ----------------------------------------
  * Renderer.forward of the reference spends ~25 torch kernels per call on host-side prep

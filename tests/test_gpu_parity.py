@@ -313,6 +313,32 @@ def test_layers_ragged_multiview(built):
     _layers_both(sc, views=[1, 0])
 
 
+def test_layers_incremental_regenerate(built):
+    """Same geometry, new face_existence: the walk-only path must give what a full generate gives, and
+    an in-place geometry update must invalidate the cache."""
+    from dmesh2_renderer_b200 import LayeredRenderer, scenes
+    dev = _dev()
+    sc = scenes.small_tets(n_points=400, size=80, seed=5, num_layers=5)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    full = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    full.incremental = False
+    geo = [t(getattr(sc, k)) for k in ("verts", "faces", "tets", "face_tets", "tet_faces")]
+    rng = np.random.default_rng(0)
+    for step in range(4):
+        ex = t((rng.random(sc.faces.shape[0]) < 0.1 + 0.2 * step).astype(np.int32))
+        a = lr.generate([0], *geo, ex, sc.num_layers)
+        b = full.generate([0], *geo, ex, sc.num_layers)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), step
+        if step == 0:
+            assert "_layer_cache" in lr.__dict__
+        if step == 2:                      # move the points in place: version bump -> full path again
+            geo[0].mul_(0.97)
+    sig_before = lr.__dict__["_layer_cache"][0]
+    lr.generate([0], *geo, ex, 3)          # a different layer count reuses the same cache entry
+    assert lr.__dict__["_layer_cache"][0] == sig_before
+
+
 def test_layers_properties(built):
     """Size-independent properties: every recorded id exists, no id repeats along a ray, entries beyond cnt are -1."""
     from dmesh2_renderer_b200 import scenes
