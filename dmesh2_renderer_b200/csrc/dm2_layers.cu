@@ -18,8 +18,8 @@
 namespace dm2 {
 
 constexpr int kLStage = 256;
-constexpr int kFGeoWords = 16;     // p0.xyz p1.xyz p2.xyz n.xyz (unit normal, not yet oriented) face_tets[2] existence pad
-constexpr int kTGeoWords = 8;      // centroid.xyz, pad, tet_faces[4]
+constexpr int kFGeoWords = 16;     // p0.xyz E1.xyz E2.xyz n.xyz (unit normal, not yet oriented) face_tets[2] existence pad
+constexpr int kTGeoWords = 8;      // centroid sum.xyz, flip bits (slot i: the face normal points INTO the tet), tet_faces[4]
 
 size_t layers_geo_bytes(int F, int T) {
     return align_up((size_t)F * kFGeoWords * 4, 256) + align_up((size_t)T * kTGeoWords * 4, 256) + 256;
@@ -40,16 +40,20 @@ k_face_geo(int F, const float* __restrict__ verts, const int32_t* __restrict__ f
     nn = fmaxf(nn, 0.0001f);
     n = f3{__fdiv_rn(n.x, nn), __fdiv_rn(n.y, nn), __fdiv_rn(n.z, nn)};
     float4* o = reinterpret_cast<float4*>(fgeo + (size_t)f * kFGeoWords);
-    o[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
-    o[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
-    o[2] = make_float4(p2.z, n.x, n.y, n.z);
+    // the two edge vectors of Moeller-Trumbore (auxiliary.h:218-219) are ray independent: stored, not p1 / p2
+    const f3 e1 = sub3(p1, p0), e2 = sub3(p2, p0);
+    o[0] = make_float4(p0.x, p0.y, p0.z, e1.x);
+    o[1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    o[2] = make_float4(e2.z, n.x, n.y, n.z);
     o[3] = make_float4(__int_as_float(face_tets[2 * (size_t)f]), __int_as_float(face_tets[2 * (size_t)f + 1]),
                        __int_as_float(face_existence[f]), 0.0f);
 }
 
+// (runs after k_face_geo: the orientation test of auxiliary.h:421-427 - is the face normal on the
+// centroid's side? - does not depend on the ray either and is evaluated here once per (tet, face slot))
 __global__ void __launch_bounds__(256)
 k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ tets,
-          const int32_t* __restrict__ tet_faces, float* __restrict__ tgeo) {
+          const int32_t* __restrict__ tet_faces, const float* __restrict__ fgeo, int F, float* __restrict__ tgeo) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int4 q = *reinterpret_cast<const int4*>(tets + 4 * (size_t)t);
@@ -62,12 +66,23 @@ k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ te
     const float sy = __fadd_rn(__fadd_rn(__fadd_rn(a[1], b[1]), c[1]), d[1]);
     const float sz = __fadd_rn(__fadd_rn(__fadd_rn(a[2], b[2]), c[2]), d[2]);
     const int4 tf = *reinterpret_cast<const int4*>(tet_faces + 4 * (size_t)t);
+    const int tfi[4] = {tf.x, tf.y, tf.z, tf.w};
+    unsigned flip = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (tfi[i] < 0 || tfi[i] >= F) continue;
+        const float4* fp = reinterpret_cast<const float4*>(fgeo + (size_t)tfi[i] * kFGeoWords);
+        const float4 fa = fp[0], fc = fp[2];
+        // d = centroid - p0 with centroid = sum * 0.25  ->  fma(sum, 0.25, -p0);  side = dot(n, d)
+        const f3 dd{__fmaf_rn(sx, 0.25f, -fa.x), __fmaf_rn(sy, 0.25f, -fa.y), __fmaf_rn(sz, 0.25f, -fa.z)};
+        if (dot3(f3{fc.y, fc.z, fc.w}, dd) > 0.0f) flip |= 1u << i;
+    }
     float4* o = reinterpret_cast<float4*>(tgeo + (size_t)t * kTGeoWords);
-    o[0] = make_float4(sx, sy, sz, 0.0f);       // the *sum*; the 0.25 scale is fused below
+    o[0] = make_float4(sx, sy, sz, __uint_as_float(flip));
     o[1] = make_float4(__int_as_float(tf.x), __int_as_float(tf.y), __int_as_float(tf.z), __int_as_float(tf.w));
 }
 
-struct FGeo { f3 p0, p1, p2, n; int ft0, ft1, exist; };
+struct FGeo { f3 p0, e1, e2, n; int ft0, ft1, exist; };
 __device__ __forceinline__ FGeo load_fgeo(const float* __restrict__ fgeo, int f) {
     const float4* p = reinterpret_cast<const float4*>(fgeo + (size_t)f * kFGeoWords);
     const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
@@ -75,26 +90,42 @@ __device__ __forceinline__ FGeo load_fgeo(const float* __restrict__ fgeo, int f)
                 __float_as_int(d.x), __float_as_int(d.y), __float_as_int(d.z)};
 }
 
-// dot(outward normal of `face` w.r.t. tet `tet`, ray_d)   (auxiliary.h:382-431 + the caller's dot)
-__device__ __forceinline__ float outward_dot(const FGeo& g, const float4 tsum, const f3& rd) {
-    // d = centroid - p0 with centroid = sum * 0.25  ->  fma(sum, 0.25, -p0)
-    const f3 d{__fmaf_rn(tsum.x, 0.25f, -g.p0.x), __fmaf_rn(tsum.y, 0.25f, -g.p0.y), __fmaf_rn(tsum.z, 0.25f, -g.p0.z)};
-    const float side = dot3(g.n, d);
+// dot(outward normal of the face in slot `slot` of a tet, ray_d)   (auxiliary.h:382-431 + the caller's dot)
+__device__ __forceinline__ float outward_dot(const FGeo& g, unsigned flip, int slot, const f3& rd) {
     const float nd = dot3(g.n, rd);
-    return (side > 0.0f) ? -nd : nd;     // dot(-n, rd) == -dot(n, rd) exactly
+    return ((flip >> slot) & 1u) ? -nd : nd;     // dot(-n, rd) == -dot(n, rd) exactly
 }
 
+// Moeller-Trumbore (auxiliary.h:212-243) with the stored edge vectors: same operations as ray_tri()
 __device__ __forceinline__ bool hit_test(const f3& o, const f3& d, const FGeo& g) {
-    float t, u, v;
-    if (!ray_tri(o, d, g.p0, g.p1, g.p2, t, u, v)) return false;
+    const f3 T = sub3(o, g.p0);
+    const f3 Pv = cross3(d, g.e2);
+    const f3 Q = cross3(T, g.e1);
+    const float denom = dot3(Pv, g.e1);
+    if (denom == 0.0f) return false;
+    const float inv = __fdiv_rn(1.0f, denom);
+    const float t = __fmul_rn(dot3(Q, g.e2), inv);
+    const float u = __fmul_rn(dot3(Pv, T), inv);
+    const float v = __fmul_rn(dot3(Q, d), inv);
     return t >= 0.0f && u >= 0.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f;
+}
+
+__device__ __forceinline__ int slot_of(const float4 tfw, int face) {
+    return __float_as_int(tfw.x) == face ? 0 : __float_as_int(tfw.y) == face ? 1 : __float_as_int(tfw.z) == face ? 2
+         : __float_as_int(tfw.w) == face ? 3 : -1;
+}
+// the same quantity from the geometry (face not listed by the tet: inconsistent adjacency input)
+__device__ __forceinline__ float outward_dot_geo(const FGeo& g, const float4 tsum, const f3& rd) {
+    const f3 d{__fmaf_rn(tsum.x, 0.25f, -g.p0.x), __fmaf_rn(tsum.y, 0.25f, -g.p0.y), __fmaf_rn(tsum.z, 0.25f, -g.p0.z)};
+    const float nd = dot3(g.n, rd);
+    return (dot3(g.n, d) > 0.0f) ? -nd : nd;
 }
 
 // WALK_ONLY: the geometry (and hence the binning and every pixel's first hit / entry tet) is unchanged
 // since an earlier full call on the same workspaces - only face_existence moved: start from the stored
 // first_face / first_tet.
 template <bool WALK_ONLY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __restrict__ list,
          const uint2* __restrict__ ranges, const float* __restrict__ fgeo, const float* __restrict__ tgeo,
          int* __restrict__ first_face_out, int* __restrict__ first_tet_out, int32_t* __restrict__ layers,
@@ -166,8 +197,11 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
             for (int i = 0; i < 2; i++) {
                 const int tet = i == 0 ? cur.ft0 : cur.ft1;
                 if (tet < 0) continue;
-                const float4 ts = __ldg(reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords));
-                if (outward_dot(cur, ts, rd) < 0.0f) first_tet = tet;
+                const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords);
+                const float4 ts = __ldg(tp), tfw = __ldg(tp + 1);
+                const int sl = slot_of(tfw, first_face);
+                const float od = sl >= 0 ? outward_dot(cur, __float_as_uint(ts.w), sl, rd) : outward_dot_geo(cur, ts, rd);
+                if (od < 0.0f) first_tet = tet;
             }
         }
         first_face_out[pix] = first_face;
@@ -190,17 +224,20 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
         const float4 ts = __ldg(tp);
         const float4 tfw = __ldg(tp + 1);
         const int tf[4] = {__float_as_int(tfw.x), __float_as_int(tfw.y), __float_as_int(tfw.z), __float_as_int(tfw.w)};
-        int others[4];
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (tf[i] != curr_face) { others[k < 3 ? k : 3] = tf[i]; k++; }
-        if (k != 3) break;
-        if (outward_dot(cur, ts, rd) >= 0.0f) break;
+        const unsigned flip = __float_as_uint(ts.w);
+        // the 3 other faces of the tet, in slot order (forward.cu:880-893: stop unless curr_face appears
+        // exactly once); written with selects - indexed local arrays cost a quarter of this kernel
+        const int m0 = tf[0] == curr_face, m1 = tf[1] == curr_face, m2 = tf[2] == curr_face, m3 = tf[3] == curr_face;
+        if (m0 + m1 + m2 + m3 != 1) break;
+        const int cslot = m0 ? 0 : m1 ? 1 : m2 ? 2 : 3;
+        const int oslot[3] = {cslot == 0 ? 1 : 0, cslot <= 1 ? 2 : 1, cslot <= 2 ? 3 : 2};
+        const int others[3] = {cslot == 0 ? tf[1] : tf[0], cslot <= 1 ? tf[2] : tf[1], cslot <= 2 ? tf[3] : tf[2]};
+        if (outward_dot(cur, flip, cslot, rd) >= 0.0f) break;
         int next_cnt = 0, next_face = -1;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const FGeo g = load_fgeo(fgeo, others[i]);
-            if (hit_test(ro, rd, g) && outward_dot(g, ts, rd) > 0.0f) { next_face = others[i]; next_cnt++; }
+            if (hit_test(ro, rd, g) && outward_dot(g, flip, oslot[i], rd) > 0.0f) { next_face = others[i]; next_cnt++; }
         }
         if (next_cnt != 1) break;
         cur = load_fgeo(fgeo, next_face);                   // just read: an L1 hit, cheaper than 15 selects x 2
@@ -226,7 +263,7 @@ int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, c
         DM2_LAUNCH_CHECK();
     }
     if (in.T > 0 && !walk_only) {
-        k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.tet_faces, tgeo);
+        k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.tet_faces, fgeo, in.F, tgeo);
         DM2_LAUNCH_CHECK();
     }
     if (walk_only)
