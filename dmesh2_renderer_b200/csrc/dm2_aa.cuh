@@ -4,9 +4,10 @@
 // Design differences from the reference (same results, different machine code):
 //   * all per-face operands come from the packed record in shared memory instead of ~70 scalar
 //     global loads through 64-bit accessor arithmetic;
-//   * two stages: aa_classify() (bbox + 12 half-plane tests: outside / fully inside / partial) is the
-//     cheap filter every (pixel, face) pair runs; aa_clip() (the polygon clip) only runs for
-//     partially covered pixels;
+//   * two stages: the classification (bbox + 12 half-plane tests: outside / fully inside / partial,
+//     aa.h:96-149) runs once per sorted instance and 8x4-pixel footprint, bit-parallel, in
+//     k_classify_instances (dm2_binning.cu); aa_clip() (the polygon clip) only runs for partially
+//     covered pixels and receives the 4-bit inside-corner mask from that pre-pass;
 //   * the clipped polygon is never materialised: vertices are streamed into a fan accumulator
 //     (first / previous / current vertex), so there are no local-memory arrays (the reference keeps
 //     polygon[10][2] + two [10][4] Jacobian arrays on the stack);
@@ -22,64 +23,6 @@
 #include "dm2_common.cuh"
 
 namespace dm2 {
-
-enum AAClass : int { AA_OUT = 0, AA_FULL = 1, AA_PART = 2 };
-
-// Steps 1-3 of aa.h:446-496.  inmask bit k: pixel corner k lies inside all three edge half-planes.
-__device__ __forceinline__ int aa_classify(const float* __restrict__ rec, float pxmin, float pymin,
-                                           unsigned& inmask) {
-    const float pxmax = __fadd_rn(pxmin, 1.0f);
-    const float pymax = __fadd_rn(pymin, 1.0f);
-    {   // triangle bounding box (aa.h:96-101)
-        const float4 bb = *reinterpret_cast<const float4*>(rec + R_BBOX);
-        if ((pxmax < bb.x) || (pxmin > bb.y) || (pymax < bb.z) || (pymin > bb.w)) return AA_OUT;
-    }
-    const float4 n01 = *reinterpret_cast<const float4*>(rec + R_N01);
-    const float4 n2c = *reinterpret_cast<const float4*>(rec + R_N2C);
-    const float c2 = rec[R_MISC];
-    const float nx[3] = {n01.x, n01.z, n2c.x};
-    const float ny[3] = {n01.y, n01.w, n2c.y};
-    const float cc[3] = {n2c.z, n2c.w, c2};
-    unsigned m = 0xF;
-#pragma unroll
-    for (int ti = 0; ti < 3; ti++) {
-        // (vert[0]*n[0]) + (vert[1]*n[1]) - c >= 0, aa.h:20, for the 4 pixel corners (aa.h:103-149)
-        const float ylo = __fmul_rn(pymin, ny[ti]);
-        const float yhi = __fmul_rn(pymax, ny[ti]);
-        const bool i0 = __fsub_rn(__fmaf_rn(pxmin, nx[ti], ylo), cc[ti]) >= 0.0f;
-        const bool i1 = __fsub_rn(__fmaf_rn(pxmax, nx[ti], ylo), cc[ti]) >= 0.0f;
-        const bool i2 = __fsub_rn(__fmaf_rn(pxmax, nx[ti], yhi), cc[ti]) >= 0.0f;
-        const bool i3 = __fsub_rn(__fmaf_rn(pxmin, nx[ti], yhi), cc[ti]) >= 0.0f;
-        if (!(i0 || i1 || i2 || i3)) return AA_OUT;          // all four corners outside one edge
-        m &= (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
-    }
-    inmask = m;
-    return (m == 0xF) ? AA_FULL : AA_PART;
-}
-
-// inmask of a pixel already known to be AA_PART (same arithmetic as aa_classify, no early outs)
-__device__ __forceinline__ unsigned aa_inmask(const float* __restrict__ rec, float pxmin, float pymin) {
-    const float pxmax = __fadd_rn(pxmin, 1.0f);
-    const float pymax = __fadd_rn(pymin, 1.0f);
-    const float4 n01 = *reinterpret_cast<const float4*>(rec + R_N01);
-    const float4 n2c = *reinterpret_cast<const float4*>(rec + R_N2C);
-    const float c2 = rec[R_MISC];
-    const float nx[3] = {n01.x, n01.z, n2c.x};
-    const float ny[3] = {n01.y, n01.w, n2c.y};
-    const float cc[3] = {n2c.z, n2c.w, c2};
-    unsigned m = 0xF;
-#pragma unroll
-    for (int ti = 0; ti < 3; ti++) {
-        const float ylo = __fmul_rn(pymin, ny[ti]);
-        const float yhi = __fmul_rn(pymax, ny[ti]);
-        const bool i0 = __fsub_rn(__fmaf_rn(pxmin, nx[ti], ylo), cc[ti]) >= 0.0f;
-        const bool i1 = __fsub_rn(__fmaf_rn(pxmax, nx[ti], ylo), cc[ti]) >= 0.0f;
-        const bool i2 = __fsub_rn(__fmaf_rn(pxmax, nx[ti], yhi), cc[ti]) >= 0.0f;
-        const bool i3 = __fsub_rn(__fmaf_rn(pxmin, nx[ti], yhi), cc[ti]) >= 0.0f;
-        m &= (i0 ? 1u : 0u) | (i1 ? 2u : 0u) | (i2 ? 4u : 0u) | (i3 ? 8u : 0u);
-    }
-    return m;
-}
 
 // Fan accumulator with PREDICATED pushes: every lane executes the same instruction stream whatever
 // its polygon looks like (the branchy formulation ran at 2-3 active lanes per instruction).

@@ -108,7 +108,7 @@ static void binning_layout(long long R, DM2BinningLayout* L) {
     L->vals_unsorted = take((size_t)R * 4);
     L->keys          = take((size_t)R * 8);
     L->vals          = take((size_t)R * 4);
-    L->sort_temp     = take(sort_temp_bytes(R));
+    L->sort_temp     = take(0);                         // the pipeline's tile-segmented sort needs no scratch
     L->imask         = take((size_t)R);
     L->meta          = take((size_t)R * 8 * 16);
     L->total         = off + 256;
@@ -138,7 +138,7 @@ static BinWs carve_bin(void* ws, long long R) {
     BinWs b;
     b.keys_unsorted = (uint64_t*)(p + L.keys_unsorted); b.vals_unsorted = (uint32_t*)(p + L.vals_unsorted);
     b.keys = (uint64_t*)(p + L.keys); b.vals = (uint32_t*)(p + L.vals);
-    b.sort_temp = p + L.sort_temp; b.sort_temp_bytes = sort_temp_bytes(R);
+    b.sort_temp = p + L.sort_temp; b.sort_temp_bytes = 0;
     b.imask = (uint8_t*)(p + L.imask);
     b.meta = p + L.meta;
     b.R = R;
