@@ -81,15 +81,17 @@ __device__ __forceinline__ int red_index(int q, int row) {
     return q < 28 ? (q >> 2) * kRedGroup + row * 4 + (q & 3) : 7 * kRedGroup + row;
 }
 
+constexpr int kBSub = 16;                   // candidates per sub-chunk (backward): twice the forward's, so that the
+constexpr int kBSlots = kBSub * 32;         // two dense passes run over ~150 pairs (5 batches) instead of ~75 (3)
+
 struct BwdWarpSmem {
-    float srec[kSub * kRecStride];          // staged records of the sub-chunk
-    float tA[kSlots];                       // [candidate][pixel]: alpha (or skip)  -> T before the contribution
-    float tS[kSlots];                       //                     iC.dC + iD.dD     -> dL/dalpha
-    float tArea[kSlots];                    //                     overlap area
-    float tG[6][kSlots];                    //                     d area / d aa verts (partially covered pairs)
+    float srec[kBSub * kRecStride];         // staged records of the sub-chunk
+    float tA[kBSlots];                      // [candidate][pixel]: alpha (or skip)  -> T before the contribution
+    float tS[kBSlots];                      //                     iC.dC + iD.dD     -> dL/dalpha
+    float tArea[kBSlots];                   //                     overlap area
     float red[kRedWords];                   // half-warp transpose tile (layout: red_index)
     WarpQueue q;
-    uint16_t plist[kSlots];                 // pair list of the dense pass, then the contribution list
+    uint16_t plist[kBSlots];                // candidate-major list of all hit pairs: k | lane << 4 | partial << 9
 };
 
 __global__ void __launch_bounds__(kRasterThreads, 2)
@@ -145,62 +147,58 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
 
     // faces behind every pixel's last contributor are never touched (backward.cu:219-221)
     const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
+    const bool cached = cache.capacity != 0u;
 
     int head = 0, count = 0, cursor = warp_last;
     for (;;) {
-        fill_queue<true>(ws.q, head, count, cursor, warp_last, tmask, tlist, warp, lane);
+        fill_queue<true, kBSub>(ws.q, head, count, cursor, warp_last, tmask, tlist, warp, lane);
         if (count == 0) break;
-        const int ncs = min(count, kSub);
+        const int ncs = min(count, kBSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
-        const bool cached = cache.capacity != 0u;
         if (use_aa && cached && lane < ncs)
             ws.srec[lane * kRecStride + R_PMASK] =
                 __uint_as_float(partial_mask(*reinterpret_cast<const uint4*>(ws.srec + lane * kRecStride + R_META)));
         __syncwarp();
 
         // ====== 1. per-lane hit / partial masks from the classification words
-        uint32_t hit, part, im;
-        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im, [&](int k) {
+        uint32_t hit, part, im_unused;
+        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im_unused, [&](int k) {
             return tc.inside && (int)ws.q.idx[(head + k) & (kQueue - 1)] < my_last;
         });
         if (__any_sync(0xffffffffu, hit != 0u)) {
-            // every lane prefetches the AA-cache entries of ITS partially covered pixel (area + gradient,
-            // written by the forward pass) straight into the tables; the copies fly while the pair list is built
-            if (cached && part != 0u) {
-                for (int k = 0; k < ncs; k++) {
-                    if (!((part >> k) & 1u)) continue;
+            // every lane prefetches the cached overlap area of ITS partially covered pixel (written by the
+            // forward pass) straight into the table; the copies fly while the pair list is built
+            if (cached) {
+                for (uint32_t pp = part; pp != 0u; pp &= pp - 1u) {
+                    const int k = __ffs(pp) - 1;
                     const float* rec = ws.srec + k * kRecStride;
                     const uint32_t poff = __float_as_uint(rec[R_META + 3]);
                     if (poff == kNoCache) continue;
                     const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & lt_mask);
-                    const int slot = k * 32 + lane;
-                    cp_async4(&ws.tArea[slot], cache.area + j);
-#pragma unroll
-                    for (int q = 0; q < 6; q++) cp_async4(&ws.tG[q][slot], cache.grad + (size_t)j * 6 + q);
+                    cp_async4(&ws.tArea[k * 32 + lane], cache.area + j);
                 }
             }
             cp_async_commit();
 
-            // candidate-major list of all hit pairs (k | lane << 3 | partial << 8 | inmask << 9); the
-            // dense pass and the gradient pass both run over it
+            // candidate-major list of all hit pairs (k | lane << 4 | partial << 9); the dense pass and the
+            // gradient pass both run over it
             int npairs = 0;
             for (int k = 0; k < ncs; k++) {
                 const bool h = (hit >> k) & 1u;
                 const unsigned m = __ballot_sync(0xffffffffu, h);
-                if (h) ws.plist[npairs + __popc(m & lt_mask)] =
-                           (uint16_t)(k | (lane << 3) | (((part >> k) & 1u) << 8) | (((im >> (4 * k)) & 15u) << 9));
+                if (h) ws.plist[npairs + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 4) | (((part >> k) & 1u) << 9));
                 npairs += __popc(m);
             }
             cp_async_wait0();
             __syncwarp();
 
-            // ====== 2. dense pass over every hit pair: area (cached, else clip + gradient), hit point, alpha, S
+            // ====== 2. dense pass over every hit pair: area (cached, else clipped), hit point, alpha, S
             for (int p0 = 0; p0 < npairs; p0 += 32) {
                 const int pid = p0 + lane;
                 const bool act = pid < npairs;
                 const unsigned e = act ? ws.plist[pid] : 0u;
-                const int k = e & 7, l = (e >> 3) & 31;
+                const int k = e & 15, l = (e >> 4) & 31;
                 PixelGeom qg;
                 qg.o.x = __shfl_sync(0xffffffffu, pg.o.x, l); qg.o.y = __shfl_sync(0xffffffffu, pg.o.y, l);
                 qg.o.z = __shfl_sync(0xffffffffu, pg.o.z, l); qg.d.x = __shfl_sync(0xffffffffu, pg.d.x, l);
@@ -215,16 +213,14 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                 Shade s;
                 s.area = use_aa ? 1.0f : 0.0f;
                 bool ok = true;
-                if ((e >> 8) & 1u) {
+                if ((e >> 9) & 1u) {
                     if (cached && __float_as_uint(rec[R_META + 3]) != kNoCache) {      // evaluated by the forward pass
                         s.area = ws.tArea[slot];
                         ok = !(s.area == -1.0f);
                     } else {
-                        float g[6];
-                        ok = aa_clip<true>(rec, qg.pxmin, qg.pymin, e >> 9, s.area, g);
+                        const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
+                        ok = aa_clip<false>(rec, qg.pxmin, qg.pymin, inm, s.area, nullptr);
                         ws.tArea[slot] = s.area;
-#pragma unroll
-                        for (int q = 0; q < 6; q++) ws.tG[q][slot] = g[q];
                     }
                 } else {
                     ws.tArea[slot] = s.area;
@@ -270,10 +266,10 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                 const int r = r0 + lane;
                 const bool in_list = r < total_c;
                 const unsigned e = in_list ? ws.plist[r] : 0u;
-                const int k = e & 7, src = (e >> 3) & 31;
+                const int k = e & 15, src = (e >> 4) & 31;
                 const bool act = in_list && (__float_as_uint(ws.tA[k * 32 + src]) != kSkipBits);
                 // last row of its candidate's run?
-                const bool run_end = in_list && ((r + 1 == total_c) || ((ws.plist[r + 1 < kSlots ? r + 1 : r] & 7) != k));
+                const bool run_end = in_list && ((r + 1 == total_c) || ((ws.plist[r + 1 < kBSlots ? r + 1 : r] & 15) != k));
                 const unsigned flush = __ballot_sync(0xffffffffu, run_end);
                 // pixel constants of the owning lane
                 PixelGeom qg;
@@ -290,13 +286,24 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     const int slot = k * 32 + src;
                     qg.pxmin = tc.fx0 + (float)(src & 7);
                     qg.pymin = tc.fy0 + (float)(src >> 3);
+                    // d(area)/d(aa verts) of a partially covered pixel: straight from the AA cache (global; the
+                    // loads are issued first and consumed last), else clipped again
+                    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if ((e >> 9) & 1u) {
+                        const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                        if (cached && poff != kNoCache) {
+                            const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << src) - 1u));
+                            const float2* gj = reinterpret_cast<const float2*>(cache.grad + (size_t)j * 6);
+                            const float2 g0 = __ldg(gj), g1 = __ldg(gj + 1), g2 = __ldg(gj + 2);
+                            g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = g2.x; g[5] = g2.y;
+                        } else {
+                            float area_again;
+                            const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), src);
+                            aa_clip<true>(rec, qg.pxmin, qg.pymin, inm, area_again, g);
+                        }
+                    }
                     Shade s;
                     s.area = ws.tArea[slot];
-                    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if ((e >> 8) & 1u) {
-#pragma unroll
-                        for (int q = 0; q < 6; q++) g[q] = ws.tG[q][slot];
-                    }
                     shade_tail(rec, qg, tau, s);                   // succeeded in the dense pass: same function, same inputs
                     const float Tq = ws.tA[slot], dL_dalpha = ws.tS[slot];
                     const float opacity = rec[R_MISC + 1], intense = rec[R_MISC + 2];
@@ -305,9 +312,6 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     const float dL_diD = qD * alpha * Tq;
                     // backward.cu:408-415
                     v[21] = dL_dalpha * s.ratio;
-                    const float dL_doarea = (dL_dalpha * opacity) * tau;
-#pragma unroll
-                    for (int q = 0; q < 6; q++) v[23 + q] = dL_doarea * g[q];
                     // backward.cu:420-455
                     const float4 a0 = *reinterpret_cast<const float4*>(rec + R_P0);
                     const float4 a1 = *reinterpret_cast<const float4*>(rec + R_P1);
@@ -349,6 +353,9 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     v[0] = g0.x; v[1] = g0.y; v[2] = g0.z;
                     v[3] = g1.x; v[4] = g1.y; v[5] = g1.z;
                     v[6] = g2.x; v[7] = g2.y; v[8] = g2.z;
+                    const float dL_doarea = (dL_dalpha * opacity) * tau;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) v[23 + q] = dL_doarea * g[q];
                 }
                 // ---- transpose through smem (two half-warps); lane c sums column c over the rows of one
                 //      candidate's run (rows are candidate-major) and issues ONE coalesced 29-lane atomic

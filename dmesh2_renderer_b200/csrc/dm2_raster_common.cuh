@@ -26,9 +26,9 @@ namespace dm2 {
 constexpr int kRecStride = 68;              // words between staged records (272 B, 16-byte aligned)
 constexpr int kRasterThreads = 256;
 constexpr int kGradWords = 32;              // per-(view,face) gradient record (29 used)
-constexpr int kSub = 8;                     // candidates per sub-chunk
-constexpr int kSlots = kSub * 32;           // (candidate, pixel) table slots per warp
-constexpr int kQueue = 64;                  // candidate ring capacity (>= kSub - 1 + 32)
+constexpr int kSub = 8;                     // candidates per sub-chunk (forward)
+constexpr int kSlots = kSub * 32;           // (candidate, pixel) table slots per warp (forward)
+constexpr int kQueue = 64;                  // candidate ring capacity (>= sub-chunk - 1 + 32)
 constexpr uint32_t kSkipBits = 0xFFFFFFFFu; // table marker: the reference skips this (pixel, face) pair
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -53,12 +53,13 @@ struct WarpQueue {
 };
 
 // Scans the tile list (forward: ascending from `cursor`; REVERSE: descending, entries [0, cursor)
-// remain) until the ring holds at least kSub candidates or the list is exhausted.
-template <bool REVERSE>
+// remain) until the ring holds at least SUB candidates or the list is exhausted.
+template <bool REVERSE, int SUB>
 __device__ __forceinline__ void fill_queue(WarpQueue& q, int head, int& count, int& cursor, int total,
                                            const uint8_t* __restrict__ imask, const uint32_t* __restrict__ list,
                                            int warp, int lane) {
-    while (count < kSub && (REVERSE ? cursor > 0 : cursor < total)) {
+    static_assert(SUB - 1 + 32 <= kQueue, "candidate ring too small");
+    while (count < SUB && (REVERSE ? cursor > 0 : cursor < total)) {
         const int i = REVERSE ? cursor - 1 - lane : cursor + lane;
         const bool valid = REVERSE ? i >= 0 : i < total;
         bool hit = false;
@@ -183,24 +184,29 @@ __device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const 
 // partially covers my pixel; im holds the 4-bit inside-corner mask (aa.h:103-149 corner order) of every
 // partial candidate.  lane_ok(k): extra per-lane admission test (forward: pixel not done; backward:
 // inside n_contrib).  With aa_temperature == 0 every admitted pixel is a hit and nothing is partial.
+// 4-bit inside-corner mask of pixel `l` of the footprint from the staged classification words
+__device__ __forceinline__ unsigned corner_mask_of(const uint4 m, int l) {
+    const int sh = 9 * (l >> 3) + (l & 7);
+    const uint32_t c = (uint32_t)((((unsigned long long)m.z << 32) | m.y) >> sh);
+    return (c & 3u) | ((c >> 8) & 4u) | ((c >> 6) & 8u);      // (x,y) (x+1,y) (x+1,y+1) (x,y+1)
+}
+
 template <typename LaneOk>
 __device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec, int ncs, bool use_aa, int lane,
                                                   uint32_t& hit, uint32_t& part, uint32_t& im, LaneOk lane_ok) {
     hit = 0u; part = 0u; im = 0u;
-    const int sh = 9 * (lane >> 3) + (lane & 7);
     for (int k = 0; k < ncs; k++) {
         bool on = lane_ok(k);
         unsigned inmask = 0xF;
         if (use_aa) {
             const uint4 m = *reinterpret_cast<const uint4*>(srec + k * kRecStride + R_META);    // broadcast
             on = on && ((m.x >> lane) & 1u);
-            const uint32_t c = (uint32_t)((((unsigned long long)m.z << 32) | m.y) >> sh);
-            inmask = (c & 3u) | ((c >> 8) & 4u) | ((c >> 6) & 8u);      // (x,y) (x+1,y) (x+1,y+1) (x,y+1)
+            inmask = corner_mask_of(m, lane);
         }
         const bool p = on && (inmask != 0xF);
         hit |= (on ? 1u : 0u) << k;
         part |= (p ? 1u : 0u) << k;
-        if (p) im |= inmask << (4 * k);
+        if (p && k < 8) im |= inmask << (4 * k);               // (only kept for sub-chunks of up to 8)
     }
 }
 

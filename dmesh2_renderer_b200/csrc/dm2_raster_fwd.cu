@@ -55,7 +55,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     int head = 0, count = 0, cursor = 0;
     bool pool_full = false;
     while (!__all_sync(0xffffffffu, done)) {
-        fill_queue<false>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
+        fill_queue<false, kSub>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
         if (count == 0) break;
         const int ncs = min(count, kSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
