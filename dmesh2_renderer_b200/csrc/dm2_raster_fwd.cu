@@ -7,11 +7,14 @@
 
 namespace dm2 {
 
+constexpr int kFSub = 16;                   // candidates per sub-chunk
+constexpr int kFSlots = kFSub * 32;
+
 struct FwdWarpSmem {
-    float srec[kSub * kRecStride];          // staged records of the sub-chunk
-    float tab[5][kSlots];                   // [candidate][pixel]: alpha (or skip), alpha*iC.rgb, alpha*iD
+    float srec[kFSub * kRecStride];         // staged records of the sub-chunk
+    float parea[kFSlots];                   // [candidate][pixel]: overlap area of a partially covered pixel (-1: skip)
     WarpQueue q;
-    uint16_t plist[kSlots];
+    uint16_t plist[kFSlots];                // partially covered (pixel, face) pairs: k | lane << 4
 };
 
 // CACHE: also evaluate d(area)/d(aa verts) in the clip and store area + gradient in the AA cache.
@@ -28,6 +31,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[warp];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     PixelGeom pg;
     pg.pxmin = (float)((uint32_t)tc.px + (uint32_t)in.patch_min[2 * tc.b]);      // forward.cu:319-322
@@ -55,9 +59,9 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     int head = 0, count = 0, cursor = 0;
     bool pool_full = false;
     while (!__all_sync(0xffffffffu, done)) {
-        fill_queue<false, kSub>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
+        fill_queue<false, kFSub>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
         if (count == 0) break;
-        const int ncs = min(count, kSub);
+        const int ncs = min(count, kFSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
         if (CACHE && use_aa) {
@@ -67,7 +71,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
             const uint32_t cnt = __popc(pm);
             uint32_t incl = cnt;
 #pragma unroll
-            for (int o = 1; o < kSub; o <<= 1) {
+            for (int o = 1; o < kFSub; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
@@ -88,69 +92,59 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
             __syncwarp();
         }
 
-        // ---- lock-step classification, pair list
-        uint32_t hit, part, im;
-        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im, [&](int) { return !done; });
+        // ---- per-lane hit / partial masks from the classification words
+        uint32_t hit, part, im_unused;
+        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im_unused, [&](int) { return !done; });
         if (__any_sync(0xffffffffu, hit != 0u)) {
-            int np, npairs;
-            build_pair_list(ws.plist, ncs, hit, part, im, lane, np, npairs);
-
-            // ---- dense evaluation of the order-independent part of every hit pair
-            for (int p0 = 0; p0 < npairs; p0 += 32) {
-                const int pid = p0 + lane;
-                const bool act = pid < npairs;
-                const unsigned e = act ? ws.plist[pid] : 0u;
-                const int k = e & 7, l = (e >> 3) & 31;
-                PixelGeom qg;
-                qg.o.x = __shfl_sync(0xffffffffu, pg.o.x, l); qg.o.y = __shfl_sync(0xffffffffu, pg.o.y, l);
-                qg.o.z = __shfl_sync(0xffffffffu, pg.o.z, l); qg.d.x = __shfl_sync(0xffffffffu, pg.d.x, l);
-                qg.d.y = __shfl_sync(0xffffffffu, pg.d.y, l); qg.d.z = __shfl_sync(0xffffffffu, pg.d.z, l);
-                if (!act) continue;
-                qg.pxmin = tc.fx0 + (float)(l & 7);
-                qg.pymin = tc.fy0 + (float)(l >> 3);
-                const float* rec = ws.srec + k * kRecStride;
-                Shade s;
-                s.area = use_aa ? 1.0f : 0.0f;
-                bool ok = true;
-                if (pid < np) {
-                    float g[6];
-                    ok = aa_clip<CACHE>(rec, qg.pxmin, qg.pymin, e >> 8, s.area, g);
+            // ---- the polygon clip - by far the most expensive step - runs DENSE over the list of all
+            //      partially covered (pixel, face) pairs of the sub-chunk: any lane clips any pixel's pair
+            int np = 0;
+            if (__any_sync(0xffffffffu, part != 0u)) {
+                for (int k = 0; k < ncs; k++) {
+                    const bool p = (part >> k) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, p);
+                    if (p) ws.plist[np + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 4));
+                    np += __popc(m);
+                }
+                __syncwarp();
+                for (int pid = lane; pid < np; pid += 32) {
+                    const unsigned e = ws.plist[pid];
+                    const int k = e & 15, l = (e >> 4) & 31;
+                    const float* rec = ws.srec + k * kRecStride;
+                    const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
+                    float area, g[6];
+                    const bool ok = aa_clip<CACHE>(rec, tc.fx0 + (float)(l & 7), tc.fy0 + (float)(l >> 3), inm, area, g);
+                    ws.parea[k * 32 + l] = ok ? area : -1.0f;
                     if (CACHE) {
                         const uint32_t poff = __float_as_uint(rec[R_META + 3]);
                         if (poff != kNoCache) {
                             const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << l) - 1u));
-                            cache.area[j] = ok ? s.area : -1.0f;
+                            cache.area[j] = ok ? area : -1.0f;
                             float2* gj = reinterpret_cast<float2*>(cache.grad + (size_t)j * 6);
                             gj[0] = make_float2(g[0], g[1]); gj[1] = make_float2(g[2], g[3]); gj[2] = make_float2(g[4], g[5]);
                         }
                     }
                 }
-                ok = ok && shade_tail(rec, qg, tau, s);
-                const int slot = k * 32 + l;
-                if (ok) {
-                    // forward.cu:398-415: C += iC*alpha*T  ->  fma(iC*alpha, T, C)
-                    const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
-                    ws.tab[0][slot] = alpha;
-                    ws.tab[1][slot] = __fmul_rn(s.iC[0], alpha);
-                    ws.tab[2][slot] = __fmul_rn(s.iC[1], alpha);
-                    ws.tab[3][slot] = __fmul_rn(s.iC[2], alpha);
-                    ws.tab[4][slot] = __fmul_rn(s.iD, alpha);
-                } else {
-                    ws.tab[0][slot] = __uint_as_float(kSkipBits);
-                }
+                __syncwarp();
             }
-            __syncwarp();
 
-            // ---- order-dependent walk: every lane blends its own hits in list order
-            for (int k = 0; k < ncs; k++) {
-                if (!((hit >> k) & 1u) || done) continue;
-                const int slot = k * 32 + lane;
-                const float alpha = ws.tab[0][slot];
-                if (__float_as_uint(alpha) == kSkipBits) continue;
-                C0 = __fmaf_rn(ws.tab[1][slot], T, C0);
-                C1 = __fmaf_rn(ws.tab[2][slot], T, C1);
-                C2 = __fmaf_rn(ws.tab[3][slot], T, C2);
-                D  = __fmaf_rn(ws.tab[4][slot], T, D);
+            // ---- every lane walks its own hits in list order: hit point, barycentrics, blend, termination
+            for (uint32_t hh = hit; hh != 0u && !done; hh &= hh - 1u) {
+                const int k = __ffs(hh) - 1;
+                const float* rec = ws.srec + k * kRecStride;
+                Shade s;
+                s.area = use_aa ? 1.0f : 0.0f;
+                if ((part >> k) & 1u) {
+                    s.area = ws.parea[k * 32 + lane];
+                    if (s.area == -1.0f) continue;
+                }
+                if (!shade_tail(rec, pg, tau, s)) continue;
+                // forward.cu:398-415
+                const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
+                C0 = __fmaf_rn(__fmul_rn(s.iC[0], alpha), T, C0);   // C += iC*alpha*T
+                C1 = __fmaf_rn(__fmul_rn(s.iC[1], alpha), T, C1);
+                C2 = __fmaf_rn(__fmul_rn(s.iC[2], alpha), T, C2);
+                D  = __fmaf_rn(__fmul_rn(s.iD, alpha), T, D);
                 pT = T;
                 T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
                 last_contributor = ws.q.idx[(head + k) & (kQueue - 1)] + 1u;
