@@ -72,14 +72,12 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 }
 
 
-// Transpose tile of 16 rows (contributions) x 29 columns (gradient values).  Columns are stored in
-// groups of four so that a row is written with 7 STS.128 + 1 STS.32; the group stride of 68 words makes
-// both the 16-byte row stores and the per-column 4-byte reads bank-conflict free.
+// Transpose tile of 16 rows (contributions) x 32 columns (29 gradient values + padding).  Columns are
+// stored in groups of four - element (q, row) at (q >> 2) * 68 + row * 4 + (q & 3) - so that a row is
+// written with 8 STS.128 and a column is read at a fixed stride of 4 words; the group stride of 68 words
+// makes both bank-conflict free.
 constexpr int kRedGroup = 68;
-constexpr int kRedWords = 7 * kRedGroup + 16;
-__device__ __forceinline__ int red_index(int q, int row) {
-    return q < 28 ? (q >> 2) * kRedGroup + row * 4 + (q & 3) : 7 * kRedGroup + row;
-}
+constexpr int kRedWords = 8 * kRedGroup;
 
 constexpr int kBSub = 16;                   // candidates per sub-chunk (backward): twice the forward's, so that the
 constexpr int kBSlots = kBSub * 32;         // two dense passes run over ~150 pairs (5 batches) instead of ~75 (3)
@@ -370,27 +368,24 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                         for (int g4 = 0; g4 < 7; g4++)
                             *reinterpret_cast<float4*>(&ws.red[g4 * kRedGroup + rw * 4]) =
                                 make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
-                        ws.red[7 * kRedGroup + rw] = v[28];
+                        *reinterpret_cast<float4*>(&ws.red[7 * kRedGroup + rw * 4]) = make_float4(v[28], 0.f, 0.f, 0.f);
                     }
                     __syncwarp();
-                    const int hrows = min(16, nrows - h * 16);
-                    const int col0 = red_index(min(lane, 28), 0);
-                    const int cstep = lane < 28 ? 4 : 1;
-                    for (int rr0 = 0; rr0 < hrows; rr0 += 4) {
-                        float x[4];
+                    // rows past the end of the list were stored as zeros (v = 0 for inactive lanes): all 16
+                    // rows of the half are summed, run boundaries come from the warp-uniform flush mask
+                    const float* colp = ws.red + (lane >> 2) * kRedGroup + (lane & 3);
+                    const unsigned fl = (flush >> (h * 16)) & 0xFFFFu;
+                    float x[16];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) x[j] = ws.red[col0 + (rr0 + j) * cstep];
+                    for (int j = 0; j < 16; j++) x[j] = colp[j * 4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int row = h * 16 + rr0 + j;
-                            if (row >= nrows) break;
-                            carry += x[j];
-                            if ((flush >> row) & 1u) {               // warp-uniform
-                                const int kk = __shfl_sync(0xffffffffu, k, row);
-                                const int fid = __float_as_int(ws.srec[kk * kRecStride + R_FID]);
-                                if (lane < 29 && carry != 0.0f) atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
-                                carry = 0.0f;
-                            }
+                    for (int j = 0; j < 16; j++) {
+                        carry += x[j];
+                        if ((fl >> j) & 1u) {                        // warp-uniform
+                            const int kk = __shfl_sync(0xffffffffu, k, h * 16 + j);
+                            const int fid = __float_as_int(ws.srec[kk * kRecStride + R_FID]);
+                            if (lane < 29 && carry != 0.0f) atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
+                            carry = 0.0f;
                         }
                     }
                     __syncwarp();
