@@ -43,6 +43,27 @@ def test_workspace_layouts_are_aligned_and_disjoint(built):
     assert I.final_T >= I.ranges + 2 * 4 * 5 * 8 and I.total > I.n_contrib
 
 
+def test_aa_cache_sizing_roundtrip(built, monkeypatch):
+    """Host-side AA-cache policy: off for K = 0 / tau = 0 / no instances / no grad; capacity recovered from the
+    pool size (the backward call gets only the pool tensor back from autograd)."""
+    import torch
+    from dmesh2_renderer_b200 import _C
+    cpu = torch.device("cpu")
+    for args in ((0, 1000, 1.0), (20, 1000, 0.0), (20, 0, 1.0)):
+        pool, cap = _C.aa_cache_alloc(*args, cpu)
+        assert cap == 0 and pool.numel() == 0 and _C.aa_cache_capacity(pool) == 0
+    pool, cap = _C.aa_cache_alloc(20, 1000, 1.0, cpu, want=False)
+    assert cap == 0
+    for R in (1, 7, 1000, 12345):
+        pool, cap = _C.aa_cache_alloc(20, R, 0.5, cpu)
+        assert cap == R * _C.AA_CACHE_PAIRS_PER_INSTANCE
+        assert _C.aa_cache_capacity(pool) >= cap and _C.aa_cache_capacity(pool) - cap < 64
+        assert pool.numel() * 4 >= 256 + 28 * cap
+    monkeypatch.setattr(_C, "AA_CACHE_MAX_BYTES", 28 * 500)
+    _pool, cap = _C.aa_cache_alloc(20, 1000, 1.0, cpu)
+    assert cap == 500
+
+
 def test_higher_msb_matches_reference_formula(built):
     from dmesh2_renderer_b200 import _lib
     from oracle import oracle as orc
