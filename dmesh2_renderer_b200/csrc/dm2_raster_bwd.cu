@@ -92,7 +92,7 @@ struct BwdWarpSmem {
     uint16_t plist[kBSlots];                // candidate-major list of all hit pairs: k | lane << 4 | partial << 9
 };
 
-__global__ void __launch_bounds__(kRasterThreads, 2)
+__global__ void __launch_bounds__(kRasterThreads, 2 * kCtasPerTile)
 k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
                   const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R, AACache cache,
                   const uint2* __restrict__ ranges,
@@ -102,12 +102,12 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileCtx tc = tile_ctx(in, gx, gy);
     const int warp = tc.warp, lane = tc.lane;
-    BwdWarpSmem& ws = reinterpret_cast<BwdWarpSmem*>(smem_raw)[warp];
+    BwdWarpSmem& ws = reinterpret_cast<BwdWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    const uint2 range = ranges[blockIdx.x];
+    const uint2 range = ranges[tc.tile];
     const size_t view_base = (size_t)tc.b * in.F;
     const uint32_t* tlist = list + range.x;
     const uint8_t* tmask = imask + range.x;
@@ -540,7 +540,7 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     }
     {
         ProfScope _ps("raster_backward", s);
-        k_raster_backward<<<(unsigned)nblk, kRasterThreads, kBwdSmem, s>>>(
+        k_raster_backward<<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kBwdSmem, s>>>(
             in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R,
             aa_cache_view(const_cast<void*>(aa_cache), aa_cache_pairs), iw.ranges, iw.final_T, iw.final_prev_T,
             iw.n_contrib, dL_dcolor, dL_ddepth, gface, gx, gy);

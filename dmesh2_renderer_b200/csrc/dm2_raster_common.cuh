@@ -24,7 +24,9 @@
 namespace dm2 {
 
 constexpr int kRecStride = 68;              // words between staged records (272 B, 16-byte aligned)
-constexpr int kRasterThreads = 256;
+constexpr int kWarpsPerCta = 4;              // a CTA renders half a tile (4 of its 8 footprints): the warps never
+constexpr int kRasterThreads = 32 * kWarpsPerCta;   // talk to each other, smaller CTAs free their SM slots sooner
+constexpr int kCtasPerTile = 8 / kWarpsPerCta;
 constexpr int kGradWords = 32;              // per-(view,face) gradient record (29 used)
 constexpr int kSub = 8;                     // candidates per sub-chunk (forward)
 constexpr int kSlots = kSub * 32;           // (candidate, pixel) table slots per warp (forward)
@@ -237,7 +239,7 @@ __device__ __forceinline__ void build_pair_list(uint16_t* __restrict__ plist, in
 }
 
 struct TileCtx {
-    int b, tile_x, tile_y, warp, lane, px, py;
+    int tile, b, tile_x, tile_y, warp, lane, px, py;
     bool inside;
     float fx0, fy0;
     size_t pix;
@@ -246,10 +248,12 @@ struct TileCtx {
 __device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, int gy) {
     TileCtx c;
     const int tiles = gx * gy;
-    c.b = blockIdx.x / tiles;
-    const int t_in = blockIdx.x % tiles;
+    c.tile = blockIdx.x / kCtasPerTile;                 // global tile index (view * tiles + tile in view)
+    c.b = c.tile / tiles;
+    const int t_in = c.tile % tiles;
     c.tile_x = t_in % gx; c.tile_y = t_in / gx;
-    c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+    c.warp = (blockIdx.x % kCtasPerTile) * kWarpsPerCta + (threadIdx.x >> 5);      // footprint 0..7 of the tile
+    c.lane = threadIdx.x & 31;
     c.px = c.tile_x * kTile + (c.warp & 1) * 8 + (c.lane & 7);
     c.py = c.tile_y * kTile + (c.warp >> 1) * 4 + (c.lane >> 3);
     c.inside = (c.px < in.W) && (c.py < in.H);

@@ -19,7 +19,7 @@ struct FwdWarpSmem {
 
 // CACHE: also evaluate d(area)/d(aa verts) in the clip and store area + gradient in the AA cache.
 template <bool CACHE>
-__global__ void __launch_bounds__(kRasterThreads, 3)
+__global__ void __launch_bounds__(kRasterThreads, 3 * kCtasPerTile)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
                  const uint8_t* __restrict__ imask, uint4* __restrict__ meta, uint32_t R, AACache cache,
                  const uint2* __restrict__ ranges, float* __restrict__ final_T,
@@ -28,7 +28,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileCtx tc = tile_ctx(in, gx, gy);
     const int warp = tc.warp, lane = tc.lane;
-    FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[warp];
+    FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -45,7 +45,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         pg.d = f3{rd[0], rd[1], rd[2]};
     }
 
-    const uint2 range = ranges[blockIdx.x];
+    const uint2 range = ranges[tc.tile];
     const int total = (int)(range.y - range.x);
     const size_t view_base = (size_t)tc.b * in.F;
     const uint32_t* tlist = list + range.x;
@@ -185,11 +185,11 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
     if (use_cache) DM2_CHECK(cudaMemsetAsync(cache.counter, 0, sizeof(uint32_t), s));
     ProfScope _ps("raster_forward", s);
     if (use_cache)
-        k_raster_forward<true><<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(
+        k_raster_forward<true><<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kFwdSmem, s>>>(
             in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, iw.ranges,
             iw.final_T, iw.final_prev_T, iw.n_contrib, out_color, out_depth, gx, gy);
     else
-        k_raster_forward<false><<<(unsigned)nblk, kRasterThreads, kFwdSmem, s>>>(
+        k_raster_forward<false><<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kFwdSmem, s>>>(
             in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, iw.ranges,
             iw.final_T, iw.final_prev_T, iw.n_contrib, out_color, out_depth, gx, gy);
     DM2_LAUNCH_CHECK();
