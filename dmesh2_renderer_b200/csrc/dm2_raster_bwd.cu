@@ -79,8 +79,11 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 constexpr int kRedGroup = 68;
 constexpr int kRedWords = 8 * kRedGroup;
 
-constexpr int kBSub = 16;                   // candidates per sub-chunk (backward): twice the forward's, so that the
-constexpr int kBSlots = kBSub * 32;         // two dense passes run over ~150 pairs (5 batches) instead of ~75 (3)
+// Candidates per sub-chunk.  Measured at cfg2 (ms): 8 candidates / 6 CTAs of 4 warps per SM 1.86;
+// 16 / 4 CTAs 1.69; 12 / 5 CTAs 1.66 - the dense passes want many pairs per sub-chunk (~110 here, 4
+// batches), the latency-bound walk wants warps; 45 KB of shared memory per CTA lets 5 CTAs share an SM.
+constexpr int kBSub = 12;
+constexpr int kBSlots = kBSub * 32;
 
 struct BwdWarpSmem {
     float srec[kBSub * kRecStride];         // staged records of the sub-chunk
@@ -92,7 +95,7 @@ struct BwdWarpSmem {
     uint16_t plist[kBSlots];                // candidate-major list of all hit pairs: k | lane << 4 | partial << 9
 };
 
-__global__ void __launch_bounds__(kRasterThreads, 2 * kCtasPerTile)
+__global__ void __launch_bounds__(kRasterThreads, 5)
 k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
                   const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R, AACache cache,
                   const uint2* __restrict__ ranges,
