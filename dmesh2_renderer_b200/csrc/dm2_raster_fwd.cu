@@ -7,7 +7,9 @@
 
 namespace dm2 {
 
-constexpr int kFSub = 16;                   // candidates per sub-chunk
+// Candidates per sub-chunk.  Measured at cfg2 (ms, CTAs of 4 warps): 12 candidates / 7 CTAs per SM 1.23;
+// 16 / 6 CTAs 1.155; 20 / 5 CTAs 1.17; 24 / 4 CTAs 1.21.
+constexpr int kFSub = 16;
 constexpr int kFSlots = kFSub * 32;
 
 struct FwdWarpSmem {
