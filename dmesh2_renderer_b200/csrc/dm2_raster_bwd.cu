@@ -72,6 +72,22 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 }
 
 
+// Recomputation of the clip for pairs the forward pass did not cache (K = 0 or pool overflow): kept out of
+// line so that the rarely taken path does not sit in the instruction stream of the hot loops (the kernel
+// showed "no instruction" fetch stalls with the clip inlined twice).
+__device__ __noinline__ bool clip_area_only(const float* rec, float pxmin, float pymin, unsigned inmask, float* area) {
+    float a;
+    const bool ok = aa_clip<false>(rec, pxmin, pymin, inmask, a, nullptr);
+    *area = a;
+    return ok;
+}
+__device__ __noinline__ void clip_gradient(const float* rec, float pxmin, float pymin, unsigned inmask, float* g) {
+    float a, gg[6];
+    aa_clip<true>(rec, pxmin, pymin, inmask, a, gg);
+#pragma unroll
+    for (int q = 0; q < 6; q++) g[q] = gg[q];
+}
+
 // Transpose tile of 16 rows (contributions) x 32 columns (29 gradient values + padding).  Columns are
 // stored in groups of four - element (q, row) at (q >> 2) * 68 + row * 4 + (q & 3) - so that a row is
 // written with 8 STS.128 and a column is read at a fixed stride of 4 words; the group stride of 68 words
@@ -220,8 +236,10 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                         ok = !(s.area == -1.0f);
                     } else {
                         const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
-                        ok = aa_clip<false>(rec, qg.pxmin, qg.pymin, inm, s.area, nullptr);
-                        ws.tArea[slot] = s.area;
+                        float at;
+                        ok = clip_area_only(rec, qg.pxmin, qg.pymin, inm, &at);
+                        s.area = at;
+                        ws.tArea[slot] = at;
                     }
                 } else {
                     ws.tArea[slot] = s.area;
@@ -298,9 +316,11 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                             const float2 g0 = __ldg(gj), g1 = __ldg(gj + 1), g2 = __ldg(gj + 2);
                             g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = g2.x; g[5] = g2.y;
                         } else {
-                            float area_again;
                             const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), src);
-                            aa_clip<true>(rec, qg.pxmin, qg.pymin, inm, area_again, g);
+                            float gt[6];
+                            clip_gradient(rec, qg.pxmin, qg.pymin, inm, gt);
+#pragma unroll
+                            for (int q = 0; q < 6; q++) g[q] = gt[q];
                         }
                     }
                     Shade s;
