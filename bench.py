@@ -369,7 +369,7 @@ def main():
                                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                                "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": dom_ms,
                                "note": "instruction/latency bound, not HBM bound: hundreds of fp32 instructions per "
-                                       "covered (pixel, face) pair; ncu: issue slots 57 % busy at 16 warps/SM, DRAM 6 % "
+                                       "covered (pixel, face) pair; ncu: issue slots 64 % busy at 20 warps/SM, DRAM 9 % "
                                        "(profiles/r01_ncu_kernels.md, DESIGN.md section 3)"}
             out["stages_ms_per_step"] = {k: v[0] / args.steps for k, v in stages.items()}
             out["num_rendered"] = R
