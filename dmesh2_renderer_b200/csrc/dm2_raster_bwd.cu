@@ -402,13 +402,20 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
 #pragma unroll
                     for (int j = 0; j < 16; j++) x[j] = colp[j * 4];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        carry += x[j];
-                        if ((fl >> j) & 1u) {                        // warp-uniform
-                            const int kk = __shfl_sync(0xffffffffu, k, h * 16 + j);
-                            const int fid = __float_as_int(ws.srec[kk * kRecStride + R_FID]);
-                            if (lane < 29 && carry != 0.0f) atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
-                            carry = 0.0f;
+                    for (int j0 = 0; j0 < 16; j0 += 4) {
+                        if (((fl >> j0) & 0xFu) == 0u) {             // no run ends in these 4 rows: tree sum
+                            carry += (x[j0] + x[j0 + 1]) + (x[j0 + 2] + x[j0 + 3]);
+                            continue;
+                        }
+#pragma unroll
+                        for (int j = j0; j < j0 + 4; j++) {
+                            carry += x[j];
+                            if ((fl >> j) & 1u) {                    // warp-uniform
+                                const int kk = __shfl_sync(0xffffffffu, k, h * 16 + j);
+                                const int fid = __float_as_int(ws.srec[kk * kRecStride + R_FID]);
+                                if (lane < 29 && carry != 0.0f) atomicAdd(gface + (view_base + fid) * kGradWords + lane, carry);
+                                carry = 0.0f;
+                            }
                         }
                     }
                     __syncwarp();
