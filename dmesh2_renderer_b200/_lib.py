@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -24,6 +24,7 @@ class DM2RenderInputs(C.Structure):
         ("aa_face_edges_normal", C.c_void_p), ("aa_face_edges_normal_c", C.c_void_p),
         ("image_ray_o", C.c_void_p), ("image_ray_d", C.c_void_p),
         ("ray_view", C.c_void_p), ("ray_h", C.c_int32), ("ray_w", C.c_int32),
+        ("depth_unit", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -34,6 +35,7 @@ class DM2FusedInputs(C.Structure):
         ("background", C.c_void_p), ("patch_min", C.c_void_p), ("verts", C.c_void_p), ("faces", C.c_void_p),
         ("verts_color", C.c_void_p), ("faces_opacity", C.c_void_p), ("mv", C.c_void_p), ("proj", C.c_void_p),
         ("faces_intense", C.c_void_p), ("ray_o", C.c_void_p), ("ray_d", C.c_void_p), ("ray_view", C.c_void_p),
+        ("depth_unit", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

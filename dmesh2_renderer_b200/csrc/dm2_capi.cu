@@ -328,6 +328,7 @@ static DM2RenderInputs as_render_inputs(const DM2FusedInputs& f) {
     r.background = f.background; r.patch_min = f.patch_min; r.verts = f.verts; r.faces = f.faces;
     r.verts_color = f.verts_color; r.faces_opacity = f.faces_opacity; r.faces_intense = f.faces_intense;
     r.image_ray_o = f.ray_o; r.image_ray_d = f.ray_d; r.ray_view = f.ray_view; r.ray_h = f.image_h; r.ray_w = f.image_w;
+    r.depth_unit = f.depth_unit;
     return r;
 }
 

@@ -148,6 +148,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         pg.d = f3{rd[0], rd[1], rd[2]};
         dC0 = dL_dcolor[tc.pix * 3 + 0]; dC1 = dL_dcolor[tc.pix * 3 + 1]; dC2 = dL_dcolor[tc.pix * 3 + 2];
         dD = dL_ddepth[tc.pix];
+        if (in.depth_unit) dD = -0.5f * dD;      // d(1 - (z + 1) / 2)/dz, exact
         T_final = final_T[tc.pix];
         prev_T_final = final_prev_T[tc.pix];
         my_last = (int)n_contrib[tc.pix];

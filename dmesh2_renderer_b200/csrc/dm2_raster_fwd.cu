@@ -165,7 +165,9 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         out_color[tc.pix * 3 + 0] = __fmaf_rn(T, in.background[0], C0);
         out_color[tc.pix * 3 + 1] = __fmaf_rn(T, in.background[1], C1);
         out_color[tc.pix * 3 + 2] = __fmaf_rn(T, in.background[2], C2);
-        out_depth[tc.pix] = __fadd_rn(D, T);
+        const float dn = __fadd_rn(D, T);
+        // depth_unit: the three torch ops of reference __init__.py:377-378, 1 - (depth + 1) / 2
+        out_depth[tc.pix] = in.depth_unit ? __fsub_rn(1.0f, __fmul_rn(__fadd_rn(dn, 1.0f), 0.5f)) : dn;
     }
 }
 

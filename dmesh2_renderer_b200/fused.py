@@ -21,7 +21,7 @@ from ._lib import DM2FusedGrads, DM2FusedInputs
 
 
 def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
-                  mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view):
+                  mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, depth_unit=False):
     f32, i32 = torch.float32, torch.int32
     keep = dict(background=_prep(background, f32, "background"), patch_min=_prep(patch_min, i32, "patch_min"),
                 verts=_prep(verts, f32, "verts"), faces=_prep(faces, i32, "faces"),
@@ -58,6 +58,7 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
     s.B, s.P, s.F, s.H, s.W = B, P, F, int(patch_height), int(patch_width)
     s.image_h, s.image_w = int(ro.size(1)), int(ro.size(2))
     s.aa_temperature = float(aa_temperature)
+    s.depth_unit = 1 if depth_unit else 0
     for k, t in keep.items():
         setattr(s, k, t.data_ptr() if t.numel() > 0 else 0)
     return s, keep
@@ -65,16 +66,25 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
 
 class FusedRenderFunction(torch.autograd.Function):
     """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, mv [B,4,4], proj [B,4,4],
-    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer) -> (color [B,H,W,3],
-    depth_ndc [B,H,W]).  Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense.
-    len_oarea_buffer > 0 turns the forward -> backward AA cache on (see _C.py)."""
+    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer, depth_unit) -> (color [B,H,W,3],
+    depth [B,H,W]).  Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense.
+    len_oarea_buffer > 0 turns the forward -> backward AA cache on (see _C.py).  depth_unit = False: depth is
+    the NDC depth render_forward_cuda returns; True: the kernels apply Renderer.forward's remap
+    1 - (depth_ndc + 1) / 2 (reference __init__.py:377-378) themselves, bit-identically, forward and backward."""
+
+    # num_rendered of the last call per problem shape: the binning workspace and the AA cache are allocated
+    # from it BEFORE the preprocess call, so that nothing but the comparison sits between the num_rendered
+    # read-back (the one host wait of the pipeline) and the launch of the remaining kernels
+    _size_hint = {}
 
     @staticmethod
     def forward(ctx, background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
-                mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer=20):
+                mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer=20,
+                depth_unit=False):
         lib = _lib.load_library()
         s, keep = _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
-                                faces_opacity, mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view)
+                                faces_opacity, mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view,
+                                depth_unit)
         dev = keep["verts"].device
         B, H, W = s.B, s.H, s.W
         with torch.cuda.device(dev):
@@ -83,19 +93,32 @@ class FusedRenderFunction(torch.autograd.Function):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
             face_buffer = torch.empty((face_layout(B, s.F).total,), dtype=torch.uint8, device=dev)
             image_buffer = torch.empty((image_layout(B, H, W).total,), dtype=torch.uint8, device=dev)
+            want_cache = any(ctx.needs_input_grad)
+            hint_key = (B, s.P, s.F, H, W, dev.index)
+            hint = FusedRenderFunction._size_hint.get(hint_key, 0)
+            binning_buffer = pool = None
+            if hint > 0:
+                R_cap = hint + hint // 16 + 1024
+                binning_buffer = torch.empty((binning_layout(R_cap).total,), dtype=torch.uint8, device=dev)
+                pool, cap = aa_cache_alloc(int(len_oarea_buffer), R_cap, float(aa_temperature), dev, want_cache)
             nr = C.c_int64(0)
             _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer), C.byref(nr), stream))
             R = int(nr.value)
-            binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
-            pool, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev,
-                                       any(ctx.needs_input_grad))
+            if hint <= 0 or R > R_cap:
+                # (the layout of R instances is a prefix-compatible carving of any larger workspace)
+                binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
+                pool, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev, want_cache)
             _lib.check(lib.dm2_fused_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
                                              R, _ptr(color), _ptr(depth), _ptr(pool), cap, stream))
+            FusedRenderFunction._size_hint[hint_key] = R
+            if depth_unit and s.P == 0:
+                depth.fill_(0.5)          # the library's P == 0 shortcut writes depth_ndc = 0
         ctx.save_for_backward(*keep.values(), face_buffer, binning_buffer, image_buffer, pool)
         ctx.keys = list(keep.keys())
         ctx.num_rendered = R
         ctx.patch = (patch_width, patch_height)
         ctx.aa_temperature = aa_temperature
+        ctx.depth_unit = bool(depth_unit)
         return color, depth
 
     @staticmethod
@@ -107,7 +130,7 @@ class FusedRenderFunction(torch.autograd.Function):
         s, keep = _fused_struct(keep["background"], keep["patch_min"], ctx.patch[0], ctx.patch[1], keep["verts"],
                                 keep["faces"], keep["verts_color"], keep["faces_opacity"], keep["mv"], keep["proj"],
                                 keep["faces_intense"], ctx.aa_temperature, keep["ray_o"], keep["ray_d"],
-                                keep["ray_view"])
+                                keep["ray_view"], ctx.depth_unit)
         dev = keep["verts"].device
         gc = _prep(grad_color, torch.float32, "dL_dout_color")
         gd = _prep(grad_depth, torch.float32, "dL_dout_depth")
@@ -126,4 +149,4 @@ class FusedRenderFunction(torch.autograd.Function):
                                                   C.byref(g), _ptr(grad_ws), _ptr(pool), aa_cache_capacity(pool),
                                                   _stream(dev)))
         return (None, None, None, None, g_verts, None, g_color, g_opacity, None, None, g_intense, None, None, None,
-                None, None)
+                None, None, None)

@@ -113,9 +113,10 @@ class Renderer(torch.nn.Module):
                 background: torch.Tensor,           # [3]
                 aa_temperature: float = 1.0):
         if getattr(self, "fused", True) and verts.is_cuda:
-            color, depth = self._forward_fused(batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts,
-                                               faces, verts_color, faces_opacity, faces_intense, background,
-                                               aa_temperature)
+            # (the NDC z -> [0, 1] remap below happens inside the kernels, bit-identically: depth_unit)
+            return self._forward_fused(batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts,
+                                       faces, verts_color, faces_opacity, faces_intense, background,
+                                       aa_temperature)
         else:
             args = self.prepare_inputs(batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces,
                                        verts_color, faces_opacity, faces_intense, background, aa_temperature)
@@ -146,7 +147,8 @@ class Renderer(torch.nn.Module):
             background.to(dtype=f32), batch_patch_min.to(device=dev, dtype=torch.int32), patch_width, patch_height,
             verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
             self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
-            faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view, self.aa_grad_buffer_size)
+            faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view, self.aa_grad_buffer_size,
+            True)
 
     def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
                        faces_opacity, faces_intense, background, aa_temperature=1.0):

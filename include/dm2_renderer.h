@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 11
+#define DM2_ABI_VERSION 12
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -70,6 +70,12 @@ typedef struct DM2RenderInputs {
      * inside a (V, ray_h, ray_w, 3) buffer.                                                      */
     const int32_t* ray_view;
     int32_t ray_h, ray_w;
+    /* != 0: out_depth receives the depth the reference's Renderer.forward returns,
+     * 1 - (depth_ndc + 1) / 2 (reference __init__.py:377-378; same IEEE operations as the three torch
+     * ops, so bit-identical), and dL_dout_depth is the gradient w.r.t. THAT value (the backward pass
+     * applies the exact factor -1/2).  0: out_depth = depth_ndc, as render_forward_cuda returns it.   */
+    int32_t depth_unit;
+    int32_t reserved_;
 } DM2RenderInputs;
 
 /* Gradient outputs of render_backward_cuda (reference render.cu:313-318, 372). */
@@ -230,6 +236,8 @@ typedef struct DM2FusedInputs {
     const float*   ray_o;        /* (V,image_h,image_w,3) full-resolution rays of ALL views        */
     const float*   ray_d;
     const int32_t* ray_view;     /* (B) row of ray_o/ray_d used by batch entry b                   */
+    int32_t depth_unit;          /* as DM2RenderInputs.depth_unit                                  */
+    int32_t reserved_;
 } DM2FusedInputs;
 
 typedef struct DM2FusedGrads {   /* caller-zeroed */
