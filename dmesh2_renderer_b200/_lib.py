@@ -127,7 +127,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("DM2_LIB") or LIB_PATH      # DM2_LIB: A/B builds of tools/build_variant.py
     if not os.path.exists(p):
         raise RuntimeError(
             f"dmesh2_renderer_b200: CUDA library {p} not found; run `python __graft_entry__.py` "

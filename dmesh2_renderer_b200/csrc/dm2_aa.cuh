@@ -66,7 +66,11 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
     const unsigned zflags = __float_as_uint(rec[R_MISC + 3]);
     float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
-#pragma unroll 1
+#ifndef DM2_CLIP_UNROLL
+#define DM2_CLIP_UNROLL 1
+#endif
+    constexpr int kClipUnroll = DM2_CLIP_UNROLL;
+#pragma unroll kClipUnroll
     for (int ti = 0; ti < 3; ti++) {
         const int tj = (ti == 2) ? 0 : ti + 1;
         const float2 p0 = *reinterpret_cast<const float2*>(rec + R_AAV + 2 * ti);

@@ -174,14 +174,11 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         const int ncs = min(count, kBSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
-        if (use_aa && cached && lane < ncs)
-            ws.srec[lane * kRecStride + R_PMASK] =
-                __uint_as_float(partial_mask(*reinterpret_cast<const uint4*>(ws.srec + lane * kRecStride + R_META)));
-        __syncwarp();
+        if (use_aa) store_partial_masks(ws.srec, ncs, lane);
 
         // ====== 1. per-lane hit / partial masks from the classification words
-        uint32_t hit, part, im_unused;
-        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im_unused, [&](int k) {
+        uint32_t hit, part;
+        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, [&](int k) {
             return tc.inside && (int)ws.q.idx[(head + k) & (kQueue - 1)] < my_last;
         });
         if (__any_sync(0xffffffffu, hit != 0u)) {

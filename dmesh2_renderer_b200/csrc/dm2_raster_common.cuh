@@ -193,10 +193,19 @@ __device__ __forceinline__ unsigned corner_mask_of(const uint4 m, int l) {
     return (c & 3u) | ((c >> 8) & 4u) | ((c >> 6) & 8u);      // (x,y) (x+1,y) (x+1,y+1) (x,y+1)
 }
 
+// The staged slots must carry the partial masks (store_partial_masks) when use_aa.
+__device__ __forceinline__ void store_partial_masks(float* __restrict__ srec, int ncs, int lane) {
+    if (lane < ncs)
+        srec[lane * kRecStride + R_PMASK] =
+            __uint_as_float(partial_mask(*reinterpret_cast<const uint4*>(srec + lane * kRecStride + R_META)));
+    __syncwarp();
+}
+
 template <typename LaneOk>
 __device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec, int ncs, bool use_aa, int lane,
-                                                  uint32_t& hit, uint32_t& part, uint32_t& im, LaneOk lane_ok) {
-    hit = 0u; part = 0u; im = 0u;
+                                                  uint32_t& hit, uint32_t& part, LaneOk lane_ok) {
+    hit = 0u; part = 0u;
+#ifdef DM2_CLASSIFY_OLD
     for (int k = 0; k < ncs; k++) {
         bool on = lane_ok(k);
         unsigned inmask = 0xF;
@@ -208,34 +217,20 @@ __device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec
         const bool p = on && (inmask != 0xF);
         hit |= (on ? 1u : 0u) << k;
         part |= (p ? 1u : 0u) << k;
-        if (p && k < 8) im |= inmask << (4 * k);               // (only kept for sub-chunks of up to 8)
     }
-}
-
-// Pair list of the sub-chunk: entries k | lane << 3 | inmask << 8, partially covered pairs in
-// [0, np), fully covered ones in [np, total) - so that at most one 32-pair batch mixes the two.
-__device__ __forceinline__ void build_pair_list(uint16_t* __restrict__ plist, int ncs, uint32_t hit, uint32_t part,
-                                                uint32_t im, int lane, int& np, int& total) {
-    const unsigned lt = (1u << lane) - 1u;
-    int n = 0;
+#else
+    // bit `lane` of every candidate's touched-pixel and partially-covered-pixel masks (two broadcast reads)
     for (int k = 0; k < ncs; k++) {
-        const bool p = (part >> k) & 1u;
-        const unsigned m = __ballot_sync(0xffffffffu, p);
-        if (p) plist[n + __popc(m & lt)] = (uint16_t)(k | (lane << 3) | (((im >> (4 * k)) & 15u) << 8));
-        n += __popc(m);
-    }
-    np = n;
-    const uint32_t full = hit & ~part;
-    if (__any_sync(0xffffffffu, full != 0u)) {
-        for (int k = 0; k < ncs; k++) {
-            const bool f = (full >> k) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, f);
-            if (f) plist[n + __popc(m & lt)] = (uint16_t)(k | (lane << 3));
-            n += __popc(m);
+        uint32_t touched = 0xFFFFFFFFu, pm = 0u;
+        if (use_aa) {
+            touched = __float_as_uint(srec[k * kRecStride + R_META]);
+            pm = __float_as_uint(srec[k * kRecStride + R_PMASK]);
         }
+        const uint32_t on = lane_ok(k) ? ((touched >> lane) & 1u) : 0u;
+        hit |= on << k;
+        part |= (on & (pm >> lane)) << k;
     }
-    total = n;
-    __syncwarp();
+#endif
 }
 
 struct TileCtx {
@@ -245,14 +240,15 @@ struct TileCtx {
     size_t pix;
 };
 
-__device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, int gy) {
+// context of footprint `footprint` (0..7) of global tile `tile` (view * tiles + tile in view) for this lane
+__device__ __forceinline__ TileCtx tile_ctx_of(const DM2RenderInputs& in, int gx, int gy, int tile, int footprint) {
     TileCtx c;
     const int tiles = gx * gy;
-    c.tile = blockIdx.x / kCtasPerTile;                 // global tile index (view * tiles + tile in view)
+    c.tile = tile;
     c.b = c.tile / tiles;
     const int t_in = c.tile % tiles;
     c.tile_x = t_in % gx; c.tile_y = t_in / gx;
-    c.warp = (blockIdx.x % kCtasPerTile) * kWarpsPerCta + (threadIdx.x >> 5);      // footprint 0..7 of the tile
+    c.warp = footprint;
     c.lane = threadIdx.x & 31;
     c.px = c.tile_x * kTile + (c.warp & 1) * 8 + (c.lane & 7);
     c.py = c.tile_y * kTile + (c.warp >> 1) * 4 + (c.lane >> 3);
@@ -262,6 +258,11 @@ __device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, i
     c.fy0 = (float)((uint32_t)(c.tile_y * kTile + (c.warp >> 1) * 4) + pmy);
     c.pix = c.inside ? ((size_t)c.b * in.H + c.py) * in.W + c.px : 0;
     return c;
+}
+// static assignment: CTA blockIdx.x renders kWarpsPerCta footprints of tile blockIdx.x / kCtasPerTile
+__device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, int gy) {
+    return tile_ctx_of(in, gx, gy, blockIdx.x / kCtasPerTile,
+                       (blockIdx.x % kCtasPerTile) * kWarpsPerCta + (threadIdx.x >> 5));
 }
 
 // index of this pixel's ray: patch-local (B,H,W,3) buffers, or the renderer's full-resolution

@@ -66,10 +66,11 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         const int ncs = min(count, kFSub);
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
+        if (use_aa) store_partial_masks(ws.srec, ncs, lane);
         if (CACHE && use_aa) {
             // reserve cache entries for every partially covered pixel of the staged candidates
             uint32_t pm = 0u;
-            if (lane < ncs) pm = partial_mask(*reinterpret_cast<const uint4*>(ws.srec + lane * kRecStride + R_META));
+            if (lane < ncs) pm = __float_as_uint(ws.srec[lane * kRecStride + R_PMASK]);
             const uint32_t cnt = __popc(pm);
             uint32_t incl = cnt;
 #pragma unroll
@@ -88,25 +89,34 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
             if (lane < ncs) {
                 const uint32_t poff = fits ? base + incl - cnt : kNoCache;
                 ws.srec[lane * kRecStride + R_META + 3] = __uint_as_float(poff);
-                ws.srec[lane * kRecStride + R_PMASK] = __uint_as_float(pm);
                 reinterpret_cast<uint32_t*>(tmeta + ws.q.idx[(head + lane) & (kQueue - 1)])[3] = poff;
             }
             __syncwarp();
         }
 
         // ---- per-lane hit / partial masks from the classification words
-        uint32_t hit, part, im_unused;
-        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, im_unused, [&](int) { return !done; });
+        uint32_t hit, part;
+        classify_subchunk(ws.srec, ncs, use_aa, lane, hit, part, [&](int) { return !done; });
         if (__any_sync(0xffffffffu, hit != 0u)) {
             // ---- the polygon clip - by far the most expensive step - runs DENSE over the list of all
             //      partially covered (pixel, face) pairs of the sub-chunk: any lane clips any pixel's pair
             int np = 0;
             if (__any_sync(0xffffffffu, part != 0u)) {
-                for (int k = 0; k < ncs; k++) {
-                    const bool p = (part >> k) & 1u;
-                    const unsigned m = __ballot_sync(0xffffffffu, p);
-                    if (p) ws.plist[np + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 4));
-                    np += __popc(m);
+                // lane-major compaction: an exclusive scan of the per-lane pair counts, then every lane writes
+                // its own pairs (the clip results are addressed by (candidate, pixel): the list order is free;
+                // 16 ballot rounds, one per candidate, cost 0.03 ms more)
+                {
+                    const int mine = __popc(part);
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    np = __shfl_sync(0xffffffffu, incl, 31);
+                    int w = incl - mine;
+                    for (uint32_t pp = part; pp != 0u; pp &= pp - 1u)
+                        ws.plist[w++] = (uint16_t)((__ffs(pp) - 1) | (lane << 4));
                 }
                 __syncwarp();
                 for (int pid = lane; pid < np; pid += 32) {
