@@ -219,7 +219,21 @@ def main():
     host = {k: t(getattr(sc, k)).pin_memory() for k in ("verts", "verts_color", "faces_opacity", "faces_intense")}
     params = {k: v.to(dev).requires_grad_(True) for k, v in host.items()}
     P, F = sc.verts.shape[0], sc.faces.shape[0]
-    bucket = torch.zeros(3 * P + 3 * P + F, dtype=torch.float32, device=dev) if world > 1 else None
+    # N > 1: the flat gradient bucket lives in NVLink peer-mapped memory and is summed by the library's own
+    # allreduce kernel (multiview.PeerGradBucket, csrc/dm2_peer.cu); the reference arm uses NCCL
+    bucket = None
+    if world > 1:
+        if args.impl == "reference":
+            class _NcclBucket:                      # plain torch + NCCL: nothing of this repo on the reference arm
+                def __init__(self):
+                    self.flat = torch.zeros(3 * P + 3 * P + F, dtype=torch.float32, device=dev)
+
+                def allreduce(self):
+                    dist.all_reduce(self.flat)
+            bucket = _NcclBucket()
+        else:
+            from dmesh2_renderer_b200.multiview import make_grad_bucket
+            bucket = make_grad_bucket(P, F, dev)
 
     def compute(prm):
         for p in prm.values():
@@ -231,8 +245,8 @@ def main():
         if world > 1:
             # one allreduce per optimisation step over the flat [dverts | dverts_color | dfaces_opacity] bucket
             torch.cat((prm["verts"].grad.reshape(-1), prm["verts_color"].grad.reshape(-1),
-                       prm["faces_opacity"].grad.reshape(-1)), out=bucket)
-            dist.all_reduce(bucket)
+                       prm["faces_opacity"].grad.reshape(-1)), out=bucket.flat)
+            bucket.allreduce()
         return loss
 
     # e2e input feed (both arms): every step's parameters are copied from pinned host memory inside the
@@ -325,6 +339,10 @@ def main():
 
     ms_step = ms_total / args.steps
     value = world * 1000.0 / ms_step
+    exchange = "NCCL allreduce"
+    if bucket is not None and hasattr(bucket, "uses_multicast"):
+        exchange = "peer-memory allreduce kernel (" + ("NVLS multimem" if bucket.uses_multicast else "P2P ld/st") + ")"
+
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     out = {
         "metric": "fwd+bwd frames/s, 1M tris @1024^2", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -332,7 +350,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{sc.name}: Renderer fwd+bwd, {F} random semi-transparent triangles, {W}x{H}, "
                                f"1 view per GPU (SURVEY 8d cfg2, seed 2, sigma 0.0115, aa_temperature 1.0)",
-                   "views_per_step": world, "parallelism": f"view-sharded dp{world}, 1 NCCL allreduce/step" if world > 1 else "single GPU",
+                   "views_per_step": world, "parallelism": f"view-sharded dp{world}, 1 {exchange}/step" if world > 1 else "single GPU",
                    "l2": "working set (packed face records 256 MB + inputs ~190 MB) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": world * 1000.0 * args.steps / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},

@@ -384,6 +384,11 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
     return launch_fused_grad_scatter(*in, fw, *grads, grad_ws, s);
 }
 
+int dm2_peer_allreduce_sum(const void* const* peer_ptrs, void* multicast_ptr, int32_t world, int32_t rank,
+                           int64_t n_floats, void* stream) {
+    return launch_peer_allreduce(peer_ptrs, multicast_ptr, world, rank, n_floats, (cudaStream_t)stream);
+}
+
 int dm2_aa_cache_bytes(int64_t capacity_pairs, size_t* bytes) {
     DM2_REQUIRE(bytes && capacity_pairs >= 0 && capacity_pairs < (1ll << 32) - 1, "dm2_aa_cache_bytes: bad arguments");
     *bytes = aa_cache_bytes(capacity_pairs);

@@ -12,6 +12,7 @@
 //      x + a*b            ->  fma(a, b, x)
 // The CPU oracle (oracle/dm2_oracle.cpp) restates the same sequences with fmaf().
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -219,6 +220,8 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
                            void* grad_ws, const void* aa_cache, long long aa_cache_pairs, cudaStream_t s);
 size_t aa_cache_bytes(long long capacity_pairs);
+int launch_peer_allreduce(const void* const* peer_ptrs, void* multicast_ptr, int world, int rank, long long n_floats,
+                          cudaStream_t s);
 int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
                         cudaStream_t s);
 int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, uint32_t* patch_flags, cudaStream_t s);

@@ -60,6 +60,76 @@ class GradBucket:
         return self
 
 
+class PeerGradBucket(GradBucket):
+    """GradBucket whose allreduce is this library's own kernel over NVLink peer memory
+    (csrc/dm2_peer.cu) instead of a library collective.
+
+    The flat buffer is a symmetric allocation (torch.distributed._symmetric_memory: every rank's
+    buffer is mapped into every process, plus one NVSwitch multicast mapping when the fabric
+    supports it - plumbing only).  allreduce() = cross-GPU barrier, ONE kernel in which rank r sums
+    slice r of all buckets (multimem.ld_reduce: the add happens inside the switch; peer loads in
+    rank order without multicast) and writes the sum into every rank's bucket, cross-GPU barrier.
+    Requires CUDA tensors and an initialised NCCL process group on ONE node; use GradBucket
+    (torch.distributed.all_reduce) anywhere else.  `use_multicast`: None = the switch reduction from 4
+    ranks up when the fabric offers a multicast mapping (measured on 8 x B200, 76 MB bucket: 0.236 ms,
+    peer load/store kernel 0.252 ms, NCCL all_reduce 0.311 ms; on 2 GPUs the peer load/store kernel wins:
+    0.134 ms vs 0.22 ms, NCCL 0.170 ms); True / False force one kernel.
+    """
+
+    def __init__(self, num_verts: int, num_faces: int, device, group=None, use_multicast=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self.P, self.F = int(num_verts), int(num_faces)
+        n = 6 * self.P + self.F
+        self._n_padded = (n + 3) // 4 * 4                      # the kernel moves 16-byte vectors
+        self._group = group if group is not None else dist.group.WORLD
+        self._storage = symm_mem.empty(self._n_padded, dtype=torch.float32, device=device)
+        self._storage.zero_()
+        self._hdl = symm_mem.rendezvous(self._storage, self._group)
+        self.world, self.rank = int(self._hdl.world_size), int(self._hdl.rank)
+        self.flat = self._storage[:n]
+        self.dverts = self.flat[:3 * self.P].view(self.P, 3)
+        self.dverts_color = self.flat[3 * self.P:6 * self.P].view(self.P, 3)
+        self.dfaces_opacity = self.flat[6 * self.P:]
+        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        self._peer_ptrs = (C.c_void_p * self.world)(*ptrs)
+        if use_multicast is None:
+            use_multicast = self.world >= 4
+        mc = int(self._hdl.multicast_ptr) if (use_multicast and self._hdl.has_multicast_support) else 0
+        self._multicast_ptr = C.c_void_p(mc)
+        self.uses_multicast = mc != 0
+        self._lib = _lib
+        self._device = torch.device(device)
+
+    def allreduce(self, group=None):
+        if self.world == 1:
+            return self
+        lib = self._lib.load_library()
+        stream = torch.cuda.current_stream(self._device)
+        self._hdl.barrier(channel=0)                    # every rank's bucket is complete
+        self._lib.check(lib.dm2_peer_allreduce_sum(self._peer_ptrs, self._multicast_ptr, self.world, self.rank,
+                                                   self._n_padded, stream.cuda_stream))
+        self._hdl.barrier(channel=1)                    # every rank's stores have landed
+        return self
+
+
+def make_grad_bucket(num_verts: int, num_faces: int, device, peer: bool = True, group=None):
+    """PeerGradBucket on a multi-GPU NCCL job (falls back to GradBucket + NCCL allreduce if the symmetric
+    allocation cannot be set up, with the reason on stderr), GradBucket otherwise."""
+    dev = torch.device(device)
+    if (peer and dev.type == "cuda" and dist.is_available() and dist.is_initialized()
+            and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl"):
+        try:
+            return PeerGradBucket(num_verts, num_faces, dev, group)
+        except Exception as ex:      # noqa: BLE001 - any set-up failure means "no peer mapping on this box"
+            import sys
+            print(f"dmesh2_renderer_b200: peer-memory bucket unavailable ({ex}); using NCCL all_reduce", file=sys.stderr)
+    return GradBucket(num_verts, num_faces, dev)
+
+
 def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts: torch.Tensor,
                    verts_color: torch.Tensor, faces_opacity: torch.Tensor, bucket: Optional[GradBucket] = None,
                    micro_batch: int = 8, world_size: Optional[int] = None, rank: Optional[int] = None, group=None):

@@ -257,6 +257,20 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
                        const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws,
                        const void* aa_cache, int64_t aa_cache_pairs, void* stream);
 
+/* ---- multi-view optimisation step: the gradient exchange ----------------
+ * The reference is single-GPU; DMesh++'s multi-view step shards views over the GPUs of one box and
+ * sums the replicated-parameter gradients [dverts | dverts_color | dfaces_opacity] once per step.
+ * In-place sum over `world` ranks of an n_floats-long fp32 bucket (n_floats % 4 == 0) that every rank
+ * holds at the same offset of a symmetric peer-mapped allocation: peer_ptrs[q] = rank q's bucket as
+ * mapped into THIS process (host array of `world` device pointers), multicast_ptr = the bucket through
+ * the NVSwitch multicast mapping, or NULL.  Rank r reduces slice r and writes the sum into every rank's
+ * bucket: with a multicast mapping through multimem.ld_reduce / multimem.st (the add happens inside the
+ * switch), else with peer loads in rank order + peer stores.  The CALLER provides the two cross-GPU
+ * barriers around the call (all buckets complete before; all stores landed after) - see
+ * dmesh2_renderer_b200/multiview.py:PeerGradBucket.                                                   */
+int dm2_peer_allreduce_sum(const void* const* peer_ptrs, void* multicast_ptr, int32_t world, int32_t rank,
+                           int64_t n_floats, void* stream);
+
 /* ---- binning primitives exposed on their own (sort keys/s metric, parity tests) ---------- */
 /* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit): a stand-alone
  * equivalent of cub::DeviceRadixSort::SortPairs (reference renderer.cu:202-207), kept as a

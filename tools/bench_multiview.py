@@ -8,8 +8,8 @@ triangle scene - sharded over the GPUs of one box.
 
 A step = every rank renders its views (view i belongs to rank i mod N) forward + backward in
 micro-batches of 8 views through the public Renderer API, accumulates the replicated-parameter
-gradients in a flat bucket and the ranks sum the bucket with ONE NCCL allreduce
-(dmesh2_renderer_b200.multiview).  STRONG scaling: the 64 views are fixed, N grows.  Timed with CUDA
+gradients in a flat bucket and the ranks sum the bucket ONCE per step with the library's peer-memory
+allreduce kernel over NVLink (dmesh2_renderer_b200.multiview.PeerGradBucket, csrc/dm2_peer.cu).  STRONG scaling: the 64 views are fixed, N grows.  Timed with CUDA
 events between barriers, max over ranks; rank 0 prints one JSON line (views/s over the whole job).
 """
 import argparse
@@ -58,7 +58,7 @@ def main():
     intense = {v: t(sc.faces_intense[v]).to(dev) for v in mine}
     wc = {v: t(sc.w_color[v]).to(dev) for v in mine}
     wd = {v: t(sc.w_depth[v]).to(dev) for v in mine}
-    bucket = multiview.GradBucket(verts.shape[0], faces.shape[0], dev)
+    bucket = multiview.make_grad_bucket(verts.shape[0], faces.shape[0], dev)
     pm = {}
 
     def render_view_batch(views, v, c, o):
@@ -105,6 +105,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ar_ms = e0.elapsed_time(e1) / 10
+    exchange = ("NCCL allreduce" if not isinstance(bucket, multiview.PeerGradBucket) else
+                "peer-memory allreduce kernel (" + ("NVLS multimem" if bucket.uses_multicast else "P2P ld/st") + ")")
     loss, _ = step()
     grad_norm = float(bucket.dverts.norm().item())
     if rank == 0:
@@ -114,7 +116,7 @@ def main():
             "warmup": max(a.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{sc.name}: {a.views} views at {a.size}x{a.size}, {a.faces} triangles, view i on "
-                                   f"rank i mod {world}, micro-batches of {a.micro_batch} views, one NCCL allreduce "
+                                   f"rank i mod {world}, micro-batches of {a.micro_batch} views, one {exchange} "
                                    f"of [dverts|dverts_color|dfaces_opacity] ({bucket.nbytes / 1e6:.0f} MB) per step"},
             "allreduce_ms": ar_ms, "views_per_rank": len(mine), "dverts_norm_after_allreduce": grad_norm}) + "\n")
         real_stdout.flush()
