@@ -537,3 +537,34 @@ def test_fused_path_equals_reference_shaped_path(built, tau, patch):
     for k in g0:
         e = (g0[k] - g1[k]).abs().max().item() / (g1[k].abs().max().item() + 1e-30)
         assert e <= BWD_RTOL, (k, e)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU gradient exchange (csrc/dm2_peer.cu): needs >= 2 GPUs on the box, skipped otherwise
+def test_peer_allreduce_degenerate_arguments(built):
+    import ctypes as C
+    from dmesh2_renderer_b200 import _lib
+    _dev()
+    lib = _lib.load_library()
+    ptrs = (C.c_void_p * 1)(0)
+    # world 1 / empty bucket: nothing to do; bad arguments are rejected before any launch
+    assert lib.dm2_peer_allreduce_sum(ptrs, None, 1, 0, 1024, None) == 0
+    assert lib.dm2_peer_allreduce_sum(ptrs, None, 2, 0, 0, None) == 0
+    assert lib.dm2_peer_allreduce_sum(ptrs, None, 2, 2, 1024, None) != 0
+    assert lib.dm2_peer_allreduce_sum(ptrs, None, 2, 0, 1023, None) != 0
+    assert lib.dm2_peer_allreduce_sum(None, None, 2, 0, 1024, None) != 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_allreduce_matches_nccl_two_gpus(built):
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533",
+           os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_peer_allreduce.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("small_p2p", "cfg2_p2p"):
+        assert res[k]["max_rel_err_vs_nccl"] < 1e-6 and res[k]["same_on_all_ranks"]
