@@ -9,7 +9,8 @@ plus the fraction of the measured HBM roofline of the dominant kernel.
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # one rank per GPU (weak scaling)
 
 A "step" is one optimisation step of one view per GPU: Renderer.forward + loss + backward through
-the public API (and, for N > 1, ONE NCCL allreduce of [dverts | dverts_color | dfaces_opacity]).
+the public API (and, for N > 1, ONE sum of [dverts | dverts_color | dfaces_opacity] over the ranks with the
+library's peer-memory allreduce kernel over NVLink, csrc/dm2_peer.cu; the reference arm uses NCCL).
 `value` is measured with the scene parameters resident in HBM; `e2e` additionally copies every step's
 inputs (verts, colours, opacity, intensity) from pinned host memory inside the timed region (copy stream,
 double buffered: the copy for step i+1 overlaps the compute of step i) and copies the loss back to pinned
@@ -387,7 +388,7 @@ def main():
                                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                                "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": dom_ms,
                                "note": "instruction/latency bound, not HBM bound: hundreds of fp32 instructions per "
-                                       "covered (pixel, face) pair; ncu: issue slots 64 % busy at 20 warps/SM, DRAM 9 % "
+                                       "covered (pixel, face) pair; ncu: issue slots 65 % busy at 20 warps/SM, DRAM 9 % "
                                        "(profiles/r01_ncu_kernels.md, DESIGN.md section 3)"}
             out["stages_ms_per_step"] = {k: v[0] / args.steps for k, v in stages.items()}
             out["num_rendered"] = R
