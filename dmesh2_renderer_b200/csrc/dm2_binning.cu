@@ -156,10 +156,9 @@ int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaSt
     const long long BF = (long long)in.B * in.F;
     if (BF == 0) return 0;
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_render_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPreSmem));
-        attr_set = true;
     }
     ProfScope _ps("preprocess_pack", s);
     k_render_preprocess<<<cdiv(BF, kPreThreads), kPreThreads, kPreSmem, s>>>(in, gx, gy, fw.depths, fw.min_depths,
@@ -293,10 +292,9 @@ int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, uint32_t
     const long long BF = (long long)in.B * in.F;
     if (BF == 0) return 0;
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_fused_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPreSmem));
-        attr_set = true;
     }
     ProfScope _ps("preprocess_pack", s);
     k_fused_preprocess<<<cdiv(BF, kPreThreads), kPreThreads, kPreSmem, s>>>(in, gx, gy, fw.depths, fw.min_depths,

@@ -56,6 +56,20 @@ struct ProfScope {
         if (!(cond)) { dm2::set_error("%s", msg); return 2; }                             \
     } while (0)
 
+// cudaFuncSetAttribute applies to the CURRENT device: one-time kernel set-up is tracked per device, so that
+// renderers on several GPUs of one process all get their shared-memory opt-in.
+struct PerDeviceOnce {
+    unsigned long long done = 0ull;
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return true;
+        const unsigned long long bit = 1ull << (d & 63);
+        if (done & bit) return false;
+        done |= bit;
+        return true;
+    }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -90,12 +90,9 @@ int launch_peer_allreduce(const void* const* peer_ptrs, void* multicast_ptr, int
     const long long per = (n4 + world - 1) / world;
     const long long b4 = std::min(n4, per * rank), e4 = std::min(n4, per * (rank + 1));
     if (e4 <= b4) return 0;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        DM2_CHECK(cudaGetDevice(&dev));
-        DM2_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int dev = 0, num_sms = 0;
+    DM2_CHECK(cudaGetDevice(&dev));
+    DM2_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     static int mc_unroll = 0, grid_mult = 0;
     if (mc_unroll == 0) {                 // tuning knobs (defaults measured on 8 x B200)
         const char* u = getenv("DM2_PEER_MC_UNROLL");

@@ -555,11 +555,10 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     const long long nblk = (long long)in.B * gx * gy;
     const long long BF = (long long)in.B * in.F;
     if (nblk == 0 || BF == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_raster_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kBwdSmem));
-        attr_set = true;
     }
     float* gface = reinterpret_cast<float*>(grad_ws);
     {

@@ -188,11 +188,10 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     if (nblk == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_raster_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
         DM2_CHECK(cudaFuncSetAttribute(k_raster_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
-        attr_set = true;
     }
     const AACache cache = aa_cache_view(aa_cache, aa_cache_pairs);
     const bool use_cache = cache.capacity > 0 && in.aa_temperature > 0.0f && bw.R > 0;

@@ -365,12 +365,11 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
     // the counts live in the cursor array (zeroed by the caller) until the scan turns them into start offsets
     if (num_tiles == 0) return 0;
     if (BF > 0) {
-        static bool cattr = false;
-        if (!cattr) {
+        static PerDeviceOnce cattr;
+        if (cattr.first()) {
             DM2_CHECK(cudaFuncSetAttribute(k_count_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTiles * 4));
             DM2_CHECK(cudaFuncSetAttribute(k_scatter_instances<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kMaxSmemTiles * 4));
-            cattr = true;
         }
         ProfScope _ps("tile_count", s);
         const int tiles = gx * gy;
@@ -410,13 +409,12 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
                                                                   cursor, keys_unsorted, vals_unsorted);
         DM2_LAUNCH_CHECK();
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap1 * sizeof(uint64_t))));
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap2 * sizeof(uint64_t))));
-        attr_set = true;
     }
     ProfScope _ps("tile_sort", s);
     k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);

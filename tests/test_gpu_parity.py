@@ -568,3 +568,28 @@ def test_peer_allreduce_matches_nccl_two_gpus(built):
     res = json.loads(out.stdout.strip().splitlines()[-1])
     for k in ("small_p2p", "cfg2_p2p"):
         assert res[k]["max_rel_err_vs_nccl"] < 1e-6 and res[k]["same_on_all_ranks"]
+
+
+def test_fused_workspace_hint_survives_a_much_larger_frame(built):
+    """The fused route sizes its binning workspace / AA cache from the previous call's num_rendered of the same
+    problem shape; a following call with the same shapes but far more instances must re-allocate, not overflow."""
+    from dmesh2_renderer_b200 import Renderer, scenes
+    dev = _dev()
+    res = {}
+    for fused in (True, False):
+        out = []
+        for sigma in (0.01, 0.25, 0.01):            # same (B, P, F, H, W); num_rendered differs by > 10x
+            sc = scenes.small(n_faces=500, size=96, sigma=sigma, seed=5)
+            st = scene_tensors(sc, dev)
+            r = Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+            r.fused = fused
+            v = st["verts"].detach().clone().requires_grad_(True)
+            pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+            color, depth = r([0], pm, sc.width, sc.height, v, st["faces"], st["verts_color"], st["faces_opacity"],
+                             st["faces_intense"][:1], st["background"])
+            (color.sum() + depth.sum()).backward()
+            out.append((color.detach(), depth.detach(), v.grad.detach()))
+        res[fused] = out
+    for (c0, d0, g0), (c1, d1, g1) in zip(res[True], res[False]):
+        assert torch.equal(c0, c1) and torch.equal(d0, d1)
+        assert (g0 - g1).abs().max().item() <= BWD_RTOL * (g1.abs().max().item() + 1e-30)

@@ -123,3 +123,10 @@ def test_two_rank_allreduce_equals_single_rank(built):
     for rank, flat, total in res:
         assert np.allclose(flat, single, rtol=1e-5, atol=1e-6), f"rank {rank}: allreduced bucket != single-rank gradient"
         assert abs(total - float(loss1)) <= 1e-4 * abs(float(loss1)) + 1e-4
+
+
+def test_make_grad_bucket_is_the_portable_bucket_without_a_multi_gpu_nccl_job():
+    from dmesh2_renderer_b200.multiview import GradBucket, PeerGradBucket, make_grad_bucket
+    b = make_grad_bucket(4, 2, "cpu")
+    assert type(b) is GradBucket and not isinstance(b, PeerGradBucket) and b.flat.numel() == 26
+    b.allreduce()          # no process group: a no-op
