@@ -33,7 +33,6 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
-    const unsigned lt_mask = (1u << lane) - 1u;
 
     PixelGeom pg;
     pg.pxmin = (float)((uint32_t)tc.px + (uint32_t)in.patch_min[2 * tc.b]);      // forward.cu:319-322
