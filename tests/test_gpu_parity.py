@@ -593,3 +593,108 @@ def test_fused_workspace_hint_survives_a_much_larger_frame(built):
     for (c0, d0, g0), (c1, d1, g1) in zip(res[True], res[False]):
         assert torch.equal(c0, c1) and torch.equal(d0, d1)
         assert (g0 - g1).abs().max().item() <= BWD_RTOL * (g1.abs().max().item() + 1e-30)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json's headline size (cfg2: 1 M triangles at 1024^2), where the oracle is too slow to be the
+# checker: size-independent properties of the path
+@pytest.fixture(scope="module")
+def cfg2_state(built):
+    from dmesh2_renderer_b200 import scenes
+    dev = _dev()
+    sc = scenes.cfg2()
+    r, st, args = render_args(sc, dev)
+    return sc, r, st, args
+
+
+def test_full_size_binning_properties(cfg2_state):
+    """sortedness, the range table as a partition of the sorted list, instance counts per face = tiles_touched,
+    a checksum of the emitted pairs - on all 2.26 M instances of the headline frame."""
+    from dmesh2_renderer_b200 import _C
+    sc, r, st, args = cfg2_state
+    with torch.no_grad():
+        R, color, depth, _, _, _, _, fb, bb, ib = _C.render_forward_cuda(*args)
+    F, W, H = args[5].shape[0], sc.width, sc.height
+    ft, bt, it = _C.face_taps(fb, 1, F), _C.binning_taps(bb, R), _C.image_taps(ib, 1, H, W)
+    tt = ft["tiles_touched"].to(torch.int64)
+    assert int(tt.sum()) == R and R > 2_000_000
+    keys, vals = bt["keys"].to(torch.int64), bt["vals"].to(torch.int64)        # 45 significant bits: no sign issue
+    assert bool((keys[1:] >= keys[:-1]).all()), "sorted keys are not non-decreasing"
+    same = keys[1:] == keys[:-1]
+    assert bool((vals[1:][same] > vals[:-1][same]).all()), "equal (tile, depth) keys must be in ascending face order"
+    # every face appears exactly tiles_touched times; its key carries its own depth bits
+    assert torch.equal(torch.bincount(vals, minlength=F), tt)
+    dbits = ft["depths"].view(torch.int32).to(torch.int64)
+    assert torch.equal(keys & 0xFFFFFFFF, dbits[vals])
+    # the unsorted buffer holds the same multiset of pairs (checksums of keys and of key * (face + 1))
+    ku, vu = bt["keys_unsorted"].to(torch.int64), bt["vals_unsorted"].to(torch.int64)
+    assert int(ku.sum()) == int(keys.sum()) and int((ku % 1000003 * (vu + 1)).sum()) == int((keys % 1000003 * (vals + 1)).sum())
+    # ranges: a partition of [0, R) in tile order, entries of range t carry tile id t
+    rg = it["ranges"].to(torch.int64).view(-1, 2)
+    tiles = (W // 16) * (H // 16)
+    assert rg.shape[0] == tiles
+    lens = rg[:, 1] - rg[:, 0]
+    nz = lens > 0
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    starts = torch.cumsum(lens, 0) - lens
+    assert torch.equal(rg[nz, 0], starts[nz])
+    tile_of = keys >> 32
+    assert torch.equal(torch.bincount(tile_of, minlength=tiles), lens)
+    # n_contrib never points past the tile's list
+    nc = it["n_contrib"].to(torch.int64).view(H // 16, 16, W // 16, 16).permute(0, 2, 1, 3).reshape(tiles, 256)
+    assert bool((nc.max(dim=1).values <= lens).all())
+
+
+def test_full_size_forward_properties(cfg2_state):
+    """run-to-run determinism, background linearity (colour = C + T * background), value ranges, fused route =
+    reference-shaped route bit for bit - at the headline size."""
+    from dmesh2_renderer_b200 import _C
+    sc, r, st, args = cfg2_state
+    with torch.no_grad():
+        a1 = list(args)
+        res1 = _C.render_forward_cuda(*a1)
+        res2 = _C.render_forward_cuda(*a1)
+        assert torch.equal(res1[1], res2[1]) and torch.equal(res1[2], res2[2]), "forward is not deterministic"
+        a0 = list(args)
+        a0[0] = torch.zeros_like(args[0])                       # black background
+        res0 = _C.render_forward_cuda(*a0)
+        T = _C.image_taps(res1[9], 1, sc.height, sc.width)["final_T"].view(1, sc.height, sc.width)
+        diff = res1[1] - res0[1]                                 # = T * (1, 1, 1)
+        assert bool((T >= 0).all()) and bool((T <= 1).all())
+        assert float((diff - T.unsqueeze(-1)).abs().max()) <= 1e-6
+        assert torch.equal(res1[2], res0[2]), "depth must not depend on the background"
+        assert bool(torch.isfinite(res1[1]).all()) and bool(torch.isfinite(res1[2]).all())
+        # public fused route (depth already mapped to [0, 1]) against the reference-shaped route
+        pm = torch.zeros((1, 2), dtype=torch.int32, device=args[4].device)
+        color_f, depth_f = r([0], pm, sc.width, sc.height, st["verts"], st["faces"], st["verts_color"],
+                             st["faces_opacity"], st["faces_intense"][:1], st["background"])
+        assert torch.equal(color_f, res1[1])
+        assert torch.equal(depth_f, 1.0 - (res1[2] + 1.0) / 2.0)
+
+
+def test_full_size_backward_is_linear_in_the_output_gradient(cfg2_state):
+    """gradients(2 * dL/dout) = 2 * gradients(dL/dout) and gradients(dL1 + dL2) = gradients(dL1) + gradients(dL2)
+    within the backward tolerance (atomic-order nondeterminism) - all six outputs, headline size."""
+    from dmesh2_renderer_b200 import RenderFunction
+    sc, r, st, args = cfg2_state
+    dev = args[4].device
+    leaf_idx = [4, 6, 7, 8, 10, 12]
+    g = torch.Generator(device="cpu").manual_seed(11)
+    w = [((torch.rand((1, sc.height, sc.width, 3), generator=g) * 2 - 1).to(dev),
+          (torch.rand((1, sc.height, sc.width), generator=g) * 2 - 1).to(dev)) for _ in range(2)]
+
+    def grads(wc, wd):
+        a = list(args)
+        for i in leaf_idx:
+            a[i] = args[i].detach().clone().requires_grad_(True)
+        color, depth = RenderFunction.apply(*a)
+        ((color * wc).sum() + (depth * wd).sum()).backward()
+        return [a[i].grad for i in leaf_idx]
+
+    g1, g2 = grads(*w[0]), grads(*w[1])
+    g12 = grads(w[0][0] + w[1][0], w[0][1] + w[1][1])
+    g1x2 = grads(2 * w[0][0], 2 * w[0][1])
+    for a_, b_, ab, a2, name in zip(g1, g2, g12, g1x2, GRAD_NAMES):
+        scale = float(torch.maximum(a_.abs().max(), b_.abs().max())) + 1e-30
+        assert float((a2 - 2 * a_).abs().max()) <= BWD_RTOL * 2 * scale, name
+        assert float((ab - (a_ + b_)).abs().max()) <= BWD_RTOL * 2 * scale, name
