@@ -698,3 +698,59 @@ def test_full_size_backward_is_linear_in_the_output_gradient(cfg2_state):
         scale = float(torch.maximum(a_.abs().max(), b_.abs().max())) + 1e-30
         assert float((a2 - 2 * a_).abs().max()) <= BWD_RTOL * 2 * scale, name
         assert float((ab - (a_ + b_)).abs().max()) <= BWD_RTOL * 2 * scale, name
+
+
+def test_full_size_layers_properties(built):
+    """cfg3 of BASELINE.json (Delaunay mesh of 37 300 points, ~500 k faces, 1024^2, 8 layers): every recorded id
+    exists, no id repeats along a ray, entries beyond cnt are -1, hit distances increase along each ray,
+    two runs agree, the incremental walk-only path equals a full generate, and - with every face existing - the
+    first layer is the first hit of the ray."""
+    from dmesh2_renderer_b200 import LayeredRenderer, scenes
+    dev = _dev()
+    sc = scenes.cfg3()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    geo = [t(getattr(sc, k)) for k in ("verts", "faces", "tets", "face_tets", "tet_faces")]
+    ex = t(sc.face_existence)
+    layers, cnt = lr.generate([0], *geo, ex, sc.num_layers)
+    again = lr.generate([0], *geo, ex, sc.num_layers)                  # walk-only (incremental) path
+    full = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    full.incremental = False
+    ref = full.generate([0], *geo, ex, sc.num_layers)
+    assert torch.equal(layers, again[0]) and torch.equal(cnt, again[1])
+    assert torch.equal(layers, ref[0]) and torch.equal(cnt, ref[1])
+    L = sc.num_layers
+    k = torch.arange(L, device=dev).view(1, 1, 1, L)
+    valid = k < cnt.clamp(max=L).unsqueeze(-1)
+    assert bool((layers[~valid] == -1).all()) and bool((layers[valid] >= 0).all())
+    assert int(cnt.max()) == L and float((cnt > 0).float().mean()) > 0.5
+    assert bool((ex[layers[valid].long()] != 0).all())
+    srt = torch.sort(torch.where(valid, layers, -k - 1), dim=-1).values
+    assert bool((srt[..., 1:] != srt[..., :-1]).all()), "a face id repeats along a ray"
+    # hit distance of every recorded face along its ray (plain fp32 Moller-Trumbore in torch): non-decreasing
+    ids = layers.clamp(min=0).long()
+    tri = geo[0][geo[1].long()[ids]]                                    # [1, H, W, L, 3, 3]
+    o, d = lr.ray_o[[0]].unsqueeze(-2), lr.ray_d[[0]].unsqueeze(-2)     # [1, H, W, 1, 3]
+    e1, e2 = tri[..., 1, :] - tri[..., 0, :], tri[..., 2, :] - tri[..., 0, :]
+    pv = torch.cross(d.expand_as(e2), e2, dim=-1)
+    den = (pv * e1).sum(-1)
+    tt = (torch.cross((o - tri[..., 0, :]), e1, dim=-1) * e2).sum(-1) / den
+    ok = valid[..., 1:] & valid[..., :-1]
+    assert bool((tt[..., 1:][ok] >= tt[..., :-1][ok] - 1e-4).all()), "layers are not in depth order along the ray"
+    assert bool((tt[valid] >= -1e-4).all())
+    # all faces exist: layer 0 is the ray's first hit and the walk fills all 8 layers wherever it enters the mesh
+    all_layers, all_cnt = full.generate([0], *geo, torch.ones_like(ex), sc.num_layers)
+    hit = all_cnt > 0
+    assert bool((all_cnt[hit] >= 1).all()) and float(hit.float().mean()) > 0.5
+    first = all_layers[..., 0]
+    sub = layers[..., 0]
+    both = hit & (cnt > 0)
+    # the first EXISTING face along a ray can only be at or behind the first face of the full walk
+    t_first = tt[..., 0]
+    tri0 = geo[0][geo[1].long()[first.clamp(min=0).long()]]
+    e1f, e2f = tri0[..., 1, :] - tri0[..., 0, :], tri0[..., 2, :] - tri0[..., 0, :]
+    of, df = lr.ray_o[[0]], lr.ray_d[[0]]
+    pvf = torch.cross(df, e2f, dim=-1)
+    t0 = (torch.cross(of - tri0[..., 0, :], e1f, dim=-1) * e2f).sum(-1) / (pvf * e1f).sum(-1)
+    assert bool((t_first[both] >= t0[both] - 1e-4).all())
+    assert bool((sub[both & (ex[first.clamp(min=0).long()] != 0)] == first[both & (ex[first.clamp(min=0).long()] != 0)]).all())
