@@ -56,6 +56,9 @@ METRICS = [
     ("DRAM write MB", "dram__bytes_write.sum", "MB"),
     ("DRAM throughput %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", None),
     ("L2 hit %", "lts__t_sector_hit_rate.pct", None),
+    ("global RED requests (warp level)", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", None),
+    ("global ATOM requests (warp level)", "l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum", None),
+    ("RED sectors to L2 (32 B)", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum", None),
 ]
 
 
