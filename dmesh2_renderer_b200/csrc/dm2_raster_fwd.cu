@@ -21,7 +21,10 @@ struct FwdWarpSmem {
 
 // CACHE: also evaluate d(area)/d(aa verts) in the clip and store area + gradient in the AA cache.
 template <bool CACHE>
-__global__ void __launch_bounds__(kRasterThreads, 3 * kCtasPerTile)
+#ifndef DM2_FWD_MINBLOCKS
+#define DM2_FWD_MINBLOCKS (3 * kCtasPerTile)
+#endif
+__global__ void __launch_bounds__(kRasterThreads, DM2_FWD_MINBLOCKS)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
                  const uint8_t* __restrict__ imask, uint4* __restrict__ meta, uint32_t R, AACache cache,
                  const uint2* __restrict__ ranges, float* __restrict__ final_T,
