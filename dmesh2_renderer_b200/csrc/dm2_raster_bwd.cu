@@ -2,22 +2,21 @@
 // Behaviour of reference cuda_impl/backward.cu:17-532 (29 global atomics per (pixel, face)
 // contribution, 232 registers, a B*H*W*K*32-byte AA cache), re-designed for sm_100a.
 //
-// One CTA per 16x16 tile, one warp per 8x4 pixel block, one pixel per lane.  The tile's sorted list
-// is staged back-to-front in rounds of kStage records; everything else is WARP-LOCAL (no CTA
-// barrier besides the staging one).  Per sub-chunk of 8 candidates a warp does:
-//   1. lock-step classification (bbox + 12 half-plane tests) into per-lane hit / partial bit masks;
-//   2. a DENSE polygon clip over the warp's list of partially covered (pixel, face) pairs, which
-//      also yields the closed-form d(area)/d(aa verts); area + gradient go to a per-warp table;
-//   3. the pixel-sequential walk (each lane its own hits, back to front): recovers T (T /= 1-alpha)
-//      and computes dL/dalpha - the only order-dependent quantities - into a [candidate][lane] table;
-//   4. the face-parallel gradient phase: contributions are enumerated candidate-major straight from
-//      ballots (no queue, no sort, no atomics in shared memory); one THREAD per contribution
-//      recomputes the hit point and evaluates the 29 per-face gradient values (pixel constants are
-//      fetched from the owning lane with shuffles); the warp transposes them through shared memory,
-//      lane k sums column k over the run of one candidate and issues ONE coalesced 29-lane atomic
-//      per (warp, face) into the per-(view,face) 128-byte gradient record.
+// Warp-autonomous like the forward kernel (dm2_raster_common.cuh): one warp per 8x4-pixel footprint, one
+// pixel per lane, the tile's sorted list scanned back to front.  Per sub-chunk of kBSub candidates a warp does:
+//   1. per-lane hit / partial bit masks from the staged classification words;
+//   2. a DENSE pass over the candidate-major list of all hit pairs: overlap area (read back from the AA cache
+//      the forward pass filled; clipped again only for pairs it did not cache), hit point, alpha and
+//      S = iC . dL/dC + iD . dL/dD into [candidate][pixel] tables;
+//   3. the pixel-sequential walk (each lane its own hits, back to front): recovers T (T /= 1 - alpha)
+//      and computes dL/dalpha - the only order-dependent quantities - into the same tables;
+//   4. the face-parallel gradient phase over the same list: one THREAD per contribution recomputes the hit
+//      point and evaluates the 29 per-face gradient values (pixel constants are fetched from the owning
+//      lane with shuffles, d(area)/d(aa verts) from the AA cache); the warp transposes them through shared
+//      memory, lane q sums column q over the run of one candidate and issues ONE coalesced 29-lane atomic
+//      per (warp, face) into the per-(view, face) 128-byte gradient record.
 // A second kernel scatters the records to the output tensors (or, on the fused path, chains them
-// through the perspective divide to d/d verts_proj).
+// through the perspective divide to d/d verts).
 #include "dm2_raster_common.cuh"
 
 namespace dm2 {

@@ -1,22 +1,23 @@
 // dm2_raster_common.cuh — device code shared by the forward (dm2_raster_fwd.cu) and backward
 // (dm2_raster_bwd.cu) tile kernels.
 //
-// Both kernels are WARP-AUTONOMOUS: one CTA per 16x16 tile (the tile size is part of the reference's
-// binning contract), one warp per 8x4 pixel footprint, one pixel per lane - but after the prologue no
-// warp ever waits for another one (no CTA barrier in the main loop).  Each warp
-//   * scans the tile's sorted instance list 32 entries at a time through the 1-byte per-instance
-//     footprint mask written by k_tile_ranges (bit w: the face's AA bbox overlaps footprint w) and
-//     pushes the candidates into a private ring queue;
-//   * stages the packed 256-byte records of the next kSub candidates into its private shared
-//     memory with 16-byte cp.async (15 consecutive lanes fetch one contiguous 240-byte record);
-//   * classifies them in lock-step (bbox + 12 half-plane tests, broadcast reads) into per-lane
-//     hit / partial bit masks, compacts all hit (pixel, face) pairs into a pair list - partially
-//     covered pairs first - and runs the expensive order-independent part (polygon clip, ray/triangle
-//     intersection, barycentric clamp, attribute interpolation) DENSE over that list: any lane
-//     evaluates any pixel's pair, results land in [candidate][pixel] tables;
-//   * finally each lane walks its own hits in list order through the cheap order-dependent part.
-// The first versions of these kernels staged records per CTA behind two barriers per round: ncu
-// showed 21-27 % of all stall samples on that barrier (profiles/r01_*).
+// Both kernels are WARP-AUTONOMOUS: a CTA of four warps renders half of a 16x16 tile (the tile size is part
+// of the reference's binning contract), one warp per 8x4-pixel footprint, one pixel per lane - and after the
+// prologue no warp ever waits for another one (no CTA barrier in the main loop).  Each warp
+//   * scans the tile's sorted instance list 32 entries at a time through the 1-byte per-instance footprint
+//     mask written by k_classify_instances (bit w: the face touches a pixel of footprint w) and pushes the
+//     candidates into a private ring queue;
+//   * stages the packed 256-byte records of the next sub-chunk of candidates into its private shared memory
+//     with 16-byte cp.async (15 consecutive lanes fetch one contiguous 240-byte record), together with the
+//     candidate's 16-byte classification word for this footprint;
+//   * turns the classification words into per-lane hit / partial bit masks (lane k first reduces candidate
+//     k's corner grid to a "partially covered pixels" mask, then every lane extracts its own bit from two
+//     broadcast words per candidate), compacts the partially covered (pixel, face) pairs into a pair list and
+//     runs the expensive polygon clip DENSE over that list: any lane clips any pixel's pair;
+//   * finally each lane walks its own hits in list order through the order-dependent part (forward: hit
+//     point, barycentrics, blend, termination; backward: transmittance recovery and dL/dalpha).
+// The first versions of these kernels staged records per CTA behind two barriers per round: ncu showed
+// 21-27 % of all stall samples on that barrier.
 #pragma once
 #include "dm2_common.cuh"
 #include "dm2_aa.cuh"
