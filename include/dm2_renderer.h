@@ -17,8 +17,8 @@
  *     name ends in `_host`;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing in the
  *     library calls cudaDeviceSynchronize — the only host wait is the one in
- *     dm2_*_preprocess, which waits on `stream` for the 4-byte num_rendered read-back that
- *     the reference also performs (reference cuda_impl/renderer.cu:174-179);
+ *     dm2_*_preprocess, which waits on `stream` for the 12-byte read-back (num_rendered, patch-bound
+ *     flags, longest tile segment) - the reference performs the num_rendered one too (reference cuda_impl/renderer.cu:174-179);
  *   - workspaces are caller-allocated byte buffers (torch caching allocator on the host
  *     side); their sizes come from the dm2_*_bytes functions and their internal layout from
  *     DM2FaceLayout / DM2ImageLayout / DM2BinningLayout (used by the parity tests as the
@@ -291,7 +291,7 @@ uint32_t dm2_higher_msb(uint32_t n);
 int64_t dm2_launch_count(int32_t reset);
 
 /* Optional per-stage device timing: CUDA events recorded on the launching stream around each
- * stage (preprocess_pack, scan, emit_keys, radix_sort, tile_ranges, raster_forward,
+ * stage (preprocess_pack, tile_count, tile_scan, scatter_instances, tile_sort, classify, raster_forward,
  * raster_backward, ...).  dm2_profile_report fills buf with "name total_ms count" lines
  * (it waits for the recorded events) and returns the buffer size needed.                      */
 void dm2_profile_enable(int32_t on);
