@@ -135,9 +135,17 @@ def main():
             else:
                 bad_c = float(((a["color"] - b["color"]).abs() > 1e-4 * (1 + b["color"].abs())).float().mean())
                 bad_d = float(((a["depth"] - b["depth"]).abs() > 1e-4 * (1 + b["depth"].abs())).float().mean())
-                ge = float((a["g_verts"] - b["g_verts"]).abs().max() / (b["g_verts"].abs().max() + 1e-30))
+                gmax = float(b["g_verts"].abs().max()) + 1e-30
+                gd = (a["g_verts"] - b["g_verts"]).abs()
+                ge = float(gd.max()) / gmax
+                # the reference accumulates dL/dverts with fp32 atomics in a nondeterministic order and its own
+                # formula is ill-conditioned for grazing rays (1/denom^2): the maximum is set
+                # by a handful of such entries, the element-wise count shows how many there are
+                n_out = int((gd > 1e-3 * gmax).sum())
                 print(json.dumps({"config": sc.name, "check": "colour/depth/grad", "frac_color_outside_1e-4": bad_c,
-                                  "frac_depth_outside_1e-4": bad_d, "dverts_max_rel_err": ge}), flush=True)
+                                  "frac_depth_outside_1e-4": bad_d, "dverts_max_rel_err": ge,
+                                  "dverts_elements_outside_1e-3_of_max": n_out, "dverts_elements": int(gd.numel())}),
+                      flush=True)
 
 
 if __name__ == "__main__":
