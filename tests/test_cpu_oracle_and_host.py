@@ -318,3 +318,40 @@ def test_oracle_layers_match_reference_cuda_goldens(built, name, n_points, size)
     # differ in the last bit), so a handful of rays may legitimately differ.
     same = np.all(out["render_layers"] == g["render_layers"], axis=-1) & (out["render_layers_cnt"] == g["render_layers_cnt"])
     assert same.mean() >= 0.995, same.mean()
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py contract (no GPU in this container: the reference arm falls back to the CPU oracle port)
+def test_bench_reference_arm_prints_one_json_line_without_a_gpu(built):
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU box: the reference arm runs the reference's CUDA extension there")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--faces", "3000",
+                          "--size", "128", "--cpu-sample-patch", "64"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_bench_algorithmic_bytes_follow_survey_8d():
+    """A_fwd = G + 28 BHW + 28 R split over the stages, A_bwd = G + 28 BHW + 4 R + grads."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    B, F, H, W, R = 1, 1_000_000, 1024, 1024, 2_258_496
+    P = 3 * F
+    G = 12 * F + 24 * P + 4 * F + B * (20 * P + 4 * F + 24 * F) + 24 * B * H * W
+    grads = 24 * P + 4 * F + B * (12 * P + 4 * F + 24 * F)
+    assert bench.algorithmic_bytes("raster_forward", B, P, F, H, W, R) == G + 28 * B * H * W + 4 * R
+    assert bench.algorithmic_bytes("raster_backward", B, P, F, H, W, R) == G + 28 * B * H * W + 4 * R + grads
+    assert bench.algorithmic_bytes("tile_sort", B, P, F, H, W, R) == 24 * R
+    # the forward stages together move the 28 R instance-list bytes of A_fwd (12 w + 12 r in the sort, 4 r in the raster)
+    assert bench.algorithmic_bytes("tile_sort", B, P, F, H, W, R) + 4 * R == 28 * R
