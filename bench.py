@@ -379,14 +379,24 @@ def main():
             achieved = ab / (dom_ms * 1e-3) / 1e9 if ab else None
             # DRAM traffic of that kernel per launch from the committed ncu --set full capture of this
             # same workload (profiles/r01_ncu_kernels.md); only quoted for the default cfg2 workload
-            traffic = None
+            traffic = issue_frac = None
             tj = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
             if os.path.exists(tj) and args.faces == 1_000_000 and args.size == 1024:
                 with open(tj) as fh:
-                    traffic = json.load(fh)["bytes_per_launch"].get("k_" + dom)
+                    prof_json = json.load(fh)
+                traffic = prof_json["bytes_per_launch"].get("k_" + dom)
+                # the limiter that actually binds (not a roofline the contract names, reported beside it): warp
+                # instructions of that kernel (same ncu capture) / live kernel time, against the SMs' issue rate
+                # (4 schedulers per SM, one warp instruction per clock each, at the sampled SM clock)
+                wi = prof_json.get("warp_instructions_per_launch", {}).get("k_" + dom)
+                props = torch.cuda.get_device_properties(dev)
+                mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+                if wi and mhz:
+                    issue_frac = wi / (dom_ms * 1e-3) / (props.multi_processor_count * 4 * mhz * 1e6)
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                                "peak_source": peak_src, "algorithmic_bytes": ab, "kernel_ms": dom_ms,
+                               "issue_slot_frac": issue_frac,
                                "note": "instruction/latency bound, not HBM bound: hundreds of fp32 instructions per "
                                        "covered (pixel, face) pair; ncu: issue slots 65 % busy at 20 warps/SM, DRAM 9 % "
                                        "(profiles/r01_ncu_kernels.md, DESIGN.md section 3)"}

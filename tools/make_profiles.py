@@ -67,7 +67,7 @@ def kernels(rep, out_md, out_json, cmd):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     stalls = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")]
-    cols, traffic = [], {}
+    cols, traffic, winst = [], {}, {}
     for r in rows[2:]:
         name = short(r[hdr.index("Kernel Name")])
         full = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
@@ -89,6 +89,7 @@ def kernels(rep, out_md, out_json, cmd):
         col["top stalls (warps per issue)"] = ", ".join(f"{n} {v:.2f}" for v, n in st[:4])
         cols.append(col)
         traffic[name] = (col.get("DRAM read MB", 0.0) + col.get("DRAM write MB", 0.0)) * 1e6
+        winst[name] = col.get("warp instructions", 0.0)
     with open(out_md, "w") as f:
         f.write("# ncu --set full --clock-control none (one launch of each kernel of one bench step; cfg2: 1M tris @1024^2)\n")
         f.write(f"# command: {cmd} ; numbers under the profiler are NOT bench values\n\n")
@@ -102,7 +103,8 @@ def kernels(rep, out_md, out_json, cmd):
             f.write(f"| {label} | " + " | ".join(cells) + " |\n")
     with open(out_json, "w") as f:
         json.dump({"source": os.path.basename(out_md) + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, cfg2)",
-                   "bytes_per_launch": traffic}, f, indent=1)
+                   "bytes_per_launch": traffic,
+                   "warp_instructions_per_launch": winst}, f, indent=1)
 
 
 def main():
