@@ -754,3 +754,51 @@ def test_full_size_layers_properties(built):
     t0 = (torch.cross(of - tri0[..., 0, :], e1f, dim=-1) * e2f).sum(-1) / (pvf * e1f).sum(-1)
     assert bool((t_first[both] >= t0[both] - 1e-4).all())
     assert bool((sub[both & (ex[first.clamp(min=0).long()] != 0)] == first[both & (ex[first.clamp(min=0).long()] != 0)]).all())
+
+
+def test_runs_on_the_callers_stream(built):
+    """Everything is enqueued on torch's CURRENT stream (the reference uses the legacy default stream with device
+    syncs): a frame rendered on a side stream while the default stream is kept busy must equal the
+    frame rendered on the default stream, forward bit for bit."""
+    from dmesh2_renderer_b200 import LayeredRenderer, Renderer, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=3000, size=128, sigma=0.1, seed=17)
+    st = scene_tensors(sc, dev)
+    pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+
+    def frame():
+        r = Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+        v = st["verts"].detach().clone().requires_grad_(True)
+        color, depth = r([0], pm, sc.width, sc.height, v, st["faces"], st["verts_color"], st["faces_opacity"],
+                         st["faces_intense"][:1], st["background"])
+        ((color * st["w_color"][:1]).sum() + (depth * st["w_depth"][:1]).sum()).backward()
+        return color.detach(), depth.detach(), v.grad.detach()
+
+    base = frame()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)
+    busy = torch.randn(4096, 4096, device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    for _ in range(20):                                   # ~tens of ms of work queued on the default stream
+        busy = busy @ busy * 1e-4
+    with torch.cuda.stream(side):
+        other = frame()
+    side.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(base[0], other[0]) and torch.equal(base[1], other[1])
+    assert float((base[2] - other[2]).abs().max()) <= BWD_RTOL * float(base[2].abs().max())
+
+    tets = scenes.small_tets(n_points=300, size=64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    geo = [t(getattr(tets, k)) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")]
+    lr = LayeredRenderer(t(tets.mv), t(tets.proj), tets.width, tets.height, dev)
+    a = lr.generate([0], *geo, tets.num_layers)
+    torch.cuda.synchronize()
+    for _ in range(10):
+        busy = busy @ busy * 1e-4
+    with torch.cuda.stream(side):
+        lr2 = LayeredRenderer(t(tets.mv), t(tets.proj), tets.width, tets.height, dev)
+        b = lr2.generate([0], *geo, tets.num_layers)
+    side.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
