@@ -802,3 +802,33 @@ def test_runs_on_the_callers_stream(built):
     side.synchronize()
     torch.cuda.synchronize()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_non_contiguous_and_int64_inputs(built):
+    """The reference reads its inputs through stride-aware accessors and converts dtypes in Renderer.forward;
+    strided views (a column slice of a wider tensor) and int64 faces must give the same frame and gradients."""
+    from dmesh2_renderer_b200 import Renderer, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=800, size=96, sigma=0.12, seed=23)
+    st = scene_tensors(sc, dev)
+    pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    r = Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+
+    def run(verts, colours, faces):
+        color, depth = r([0], pm, sc.width, sc.height, verts, faces, colours, st["faces_opacity"],
+                         st["faces_intense"][:1], st["background"])
+        ((color * st["w_color"][:1]).sum() + (depth * st["w_depth"][:1]).sum()).backward()
+        return color.detach(), depth.detach()
+
+    v0 = st["verts"].detach().clone().requires_grad_(True)
+    c0 = st["verts_color"].detach().clone().requires_grad_(True)
+    base = run(v0, c0, st["faces"])
+    wide_v = torch.cat((st["verts"], torch.zeros_like(st["verts"][:, :1])), dim=1).detach().clone().requires_grad_(True)
+    wide_c = torch.cat((torch.ones_like(st["verts_color"][:, :2]), st["verts_color"]), dim=1).detach().clone().requires_grad_(True)
+    v1, c1 = wide_v[:, :3], wide_c[:, 2:]
+    assert not v1.is_contiguous() and not c1.is_contiguous()
+    other = run(v1, c1, st["faces"].to(torch.int64))
+    assert torch.equal(base[0], other[0]) and torch.equal(base[1], other[1])
+    assert float((wide_v.grad[:, :3] - v0.grad).abs().max()) <= BWD_RTOL * float(v0.grad.abs().max())
+    assert float((wide_c.grad[:, 2:] - c0.grad).abs().max()) <= BWD_RTOL * float(c0.grad.abs().max())
+    assert float(wide_v.grad[:, 3].abs().max()) == 0.0 and float(wide_c.grad[:, :2].abs().max()) == 0.0
