@@ -832,3 +832,33 @@ def test_non_contiguous_and_int64_inputs(built):
     assert float((wide_v.grad[:, :3] - v0.grad).abs().max()) <= BWD_RTOL * float(v0.grad.abs().max())
     assert float((wide_c.grad[:, 2:] - c0.grad).abs().max()) <= BWD_RTOL * float(c0.grad.abs().max())
     assert float(wide_v.grad[:, 3].abs().max()) == 0.0 and float(wide_c.grad[:, :2].abs().max()) == 0.0
+
+
+def test_double_backward_call_and_no_grad_forward(built):
+    """backward through the same graph twice (retain_graph) accumulates exactly twice the gradient - the per-face
+    gradient records are re-zeroed per call and the AA cache is read-only in the backward pass; a forward under
+    no_grad (no AA cache is allocated) returns the same frame."""
+    from dmesh2_renderer_b200 import Renderer, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=1500, size=96, sigma=0.1, seed=29)
+    st = scene_tensors(sc, dev)
+    pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    r = Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    p = {k: st[k].detach().clone().requires_grad_(True) for k in ("verts", "verts_color", "faces_opacity")}
+    fi = st["faces_intense"][:1].detach().clone().requires_grad_(True)
+    color, depth = r([0], pm, sc.width, sc.height, p["verts"], st["faces"], p["verts_color"], p["faces_opacity"], fi,
+                     st["background"])
+    loss = (color * st["w_color"][:1]).sum() + (depth * st["w_depth"][:1]).sum()
+    loss.backward(retain_graph=True)
+    once = {k: v.grad.detach().clone() for k, v in p.items()}
+    once["fi"] = fi.grad.detach().clone()
+    loss.backward()
+    twice = {k: v.grad.detach() for k, v in p.items()}
+    twice["fi"] = fi.grad.detach()
+    for k in once:
+        scale = float(once[k].abs().max()) + 1e-30
+        assert float((twice[k] - 2 * once[k]).abs().max()) <= BWD_RTOL * 2 * scale, k
+    with torch.no_grad():
+        c2, d2 = r([0], pm, sc.width, sc.height, p["verts"], st["faces"], p["verts_color"], p["faces_opacity"], fi,
+                   st["background"])
+    assert torch.equal(color.detach(), c2) and torch.equal(depth.detach(), d2)
