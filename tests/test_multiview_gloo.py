@@ -85,9 +85,12 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from dmesh2_renderer_b200.multiview import multiview_step
+        from dmesh2_renderer_b200.multiview import GradBucket, make_grad_bucket, multiview_step
         sc, fn, (v, c, o) = _make_render_fn()
-        loss, bucket = multiview_step(fn, list(range(4)), v, c, o, micro_batch=1)
+        # under gloo / on the CPU the factory must hand out the portable bucket (torch.distributed.all_reduce)
+        bucket = make_grad_bucket(v.shape[0], o.shape[0], "cpu")
+        assert type(bucket) is GradBucket
+        loss, bucket = multiview_step(fn, list(range(4)), v, c, o, bucket, micro_batch=1)
         total = loss.clone()
         dist.all_reduce(total)
         q.put((rank, bucket.flat.numpy().copy(), float(total)))
