@@ -73,6 +73,27 @@ class Renderer(torch.nn.Module):
     def _init_rays(self):
         self.ray_o, self.ray_d = _unproject_pixel_rays(self.mv, self.proj, self.width, self.height, self.device)
 
+    def _view_ids(self, batch_mvp_idx):
+        """(key, ray_view int32 [B], view_idx int64 [B]) for the fused routes.  Python-style negative view ids
+        are normalised (the reference's `self.mv[idx]` accepts them); out-of-range ids raise IndexError as
+        torch indexing does."""
+        n = self.num_batch
+        key = []
+        for i in batch_mvp_idx:
+            i = int(i)
+            if not -n <= i < n:
+                raise IndexError(f"index {i} is out of bounds for dimension 0 with size {n}")
+            key.append(i + n if i < 0 else i)
+        key = tuple(key)
+        cache = self.__dict__.setdefault("_view_cache", {})
+        if key not in cache:
+            idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
+            cache[key] = (idx.to(torch.int32), idx)
+        return (key,) + cache[key]
+
+    def _cameras_need_grad(self):
+        return torch.is_grad_enabled() and (self.mv.requires_grad or self.proj.requires_grad)
+
     def compute_verts_ndc_image(self, verts, mv, proj):
         """verts [P,3], mv/proj [B,4,4] -> (verts_ndc [B,P,3], verts_image [B,P,2]) (reference :239-262)."""
         hom = torch.cat((verts, torch.ones_like(verts[:, [0]])), dim=-1)           # [P, 4]
@@ -112,7 +133,10 @@ class Renderer(torch.nn.Module):
                 faces_intense: torch.Tensor,        # [B, F]
                 background: torch.Tensor,           # [3]
                 aa_temperature: float = 1.0):
-        if getattr(self, "fused", True) and verts.is_cuda:
+        # The fused route does not differentiate w.r.t. the cameras: when mv / proj require grad the
+        # reference-shaped route below is used (autograd then reaches them through the torch matmuls of
+        # compute_verts_ndc_image, exactly as in the reference).
+        if getattr(self, "fused", True) and verts.is_cuda and not self._cameras_need_grad():
             # (the NDC z -> [0, 1] remap below happens inside the kernels, bit-identically: depth_unit)
             return self._forward_fused(batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts,
                                        faces, verts_color, faces_opacity, faces_intense, background,
@@ -129,12 +153,7 @@ class Renderer(torch.nn.Module):
         """Same result as the reference-shaped path below, with the host prep done inside the kernels
         (fused.py), including the two clip-space matmuls (same fma chain as cuBLAS, bit for bit)."""
         from .fused import FusedRenderFunction
-        key = tuple(int(i) for i in batch_mvp_idx)
-        cache = self.__dict__.setdefault("_view_cache", {})
-        if key not in cache:
-            idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
-            cache[key] = (idx.to(torch.int32), idx)
-        ray_view, view_idx = cache[key]
+        _key, ray_view, view_idx = self._view_ids(batch_mvp_idx)
         if not batch_patch_min.is_cuda:
             # the reference's asserts (__init__.py:283-284); for a CUDA tensor they would force a device sync
             # per call - there the preprocess kernel checks the bounds and the verdict comes back with
@@ -201,29 +220,32 @@ class LayeredRenderer(Renderer):
                  num_layers: int):
         f32, i32 = torch.float32, torch.int32
         if getattr(self, "fused", True) and verts.is_cuda:
-            # fused host prep (as Renderer._forward_fused): projection inside the preprocess kernel, rays read
+            # fused host prep (as Renderer._forward_fused; generate() is not differentiable, so cameras that
+            # require grad change nothing here): projection inside the preprocess kernel, rays read
             # in place from the full-resolution buffers - bit-identical layer ids, no torch prep kernels
-            key = tuple(int(i) for i in batch_mvp_idx)
-            cache = self.__dict__.setdefault("_view_cache", {})
-            if key not in cache:
-                idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
-                cache[key] = (idx.to(torch.int32), idx)
-            ray_view, view_idx = cache[key]
+            key, ray_view, view_idx = self._view_ids(batch_mvp_idx)
             # Incremental re-generation ("fixed point positions" in DMesh++'s layered stage): when
             # the geometry tensors, cameras and views are the SAME OBJECTS at the SAME VERSION as in the previous
             # call, only face_existence can have changed - binning and first hits are reused and the tet walk
-            # alone is redone.  In-place updates bump torch's version counter and invalidate the entry.
+            # alone is redone.  In-place updates bump torch's version counter and invalidate the entry.  The
+            # cache entry holds STRONG references to the geometry tensors and compares with `is`: a freed
+            # temporary's address (and version 0) can be handed to the next temporary by the caching allocator,
+            # an address of a tensor that is still alive cannot.
             geo = (verts, faces, tets, face_tets, tet_faces, self.mv, self.proj, self.ray_o, self.ray_d)
-            sig = (key, self.width, self.height) + tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in geo)
+            sig = (key, self.width, self.height)
+            vers = tuple(t._version for t in geo)
             prev = self.__dict__.get("_layer_cache") if getattr(self, "incremental", True) else None
-            reuse = prev[1] if prev is not None and prev[0] == sig else None
+            reuse = None
+            if (prev is not None and prev["sig"] == sig and prev["versions"] == vers
+                    and all(a is b for a, b in zip(prev["geo"], geo))):
+                reuse = prev["taps"]
             layers, cnt, taps = _C.generate_render_layers_cuda(
                 self.width, self.height,
                 verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),
                 tet_faces.to(dtype=i32), faces_existence.to(dtype=i32), None, None, self.ray_o, self.ray_d, num_layers,
                 fused=(self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
                        ray_view), return_taps=True, reuse=reuse)
-            self.__dict__["_layer_cache"] = (sig, taps)
+            self.__dict__["_layer_cache"] = dict(sig=sig, versions=vers, geo=geo, taps=taps)
             return layers, cnt
         verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])
         ray_o, ray_d = self.ray_o[batch_mvp_idx], self.ray_d[batch_mvp_idx]
