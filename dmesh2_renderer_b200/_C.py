@@ -5,10 +5,10 @@ error behaviour (RuntimeError with the reference's messages) - but the work is d
 hand-written sm_100a kernels in libdm2_b200.so through the C-ABI of include/dm2_renderer.h.
 
 Differences that are private to this implementation (allowed by SURVEY.md section 8b):
-  * the AA cache is ONE compact pool (28 bytes per partially covered (pixel, face) pair the forward
-    pass clipped) returned in the ``oarea`` slot of the reference's 10-tuple; the other three cache
-    tensors come back empty.  ``len_oarea_buffer == 0`` disables it (the backward pass then
-    recomputes every overlap area, as it does for pairs beyond the pool capacity);
+  * the reference's four AA cache tensors are ONE compact "shading cache" pool (16 bytes per touched and
+    24 bytes per partially covered (pixel, face) pair of the frame) returned in the ``oarea`` slot of the
+    reference's 10-tuple; the other three cache tensors come back empty.  ``len_oarea_buffer == 0``
+    disables it (the backward pass then recomputes, as it does for blocks beyond the pool capacity);
   * the three scratch buffers are laid out per DM2FaceLayout / DM2ImageLayout / DM2BinningLayout.
 """
 import ctypes as C
@@ -19,27 +19,34 @@ from . import _lib
 from ._lib import DM2BinningLayout, DM2FaceLayout, DM2ImageLayout, DM2LayerInputs, DM2RenderGrads, DM2RenderInputs
 
 
-# AA-cache sizing: pairs reserved per sorted (face, tile) instance, and a hard cap on the pool size
-AA_CACHE_PAIRS_PER_INSTANCE = 32
-AA_CACHE_MAX_BYTES = 8 << 30
+# Shading-cache sizing (include/dm2_renderer.h: 16 bytes per touched (pixel, face) pair + 24 bytes per
+# partially covered one, handed from the forward to the backward pass).  The pool is sized from what the
+# previous forward call of the same problem shape asked for (+ SHADE_CACHE_SLACK); a first call reserves
+# SHADE_CACHE_FIRST_BYTES_PER_INSTANCE per sorted (face, tile) instance.  Blocks that do not fit are simply
+# not cached (the backward pass recomputes them), so a pool that is too small costs time, never results.
+SHADE_CACHE_FIRST_BYTES_PER_INSTANCE = 512
+SHADE_CACHE_SLACK = 1.08
+SHADE_CACHE_MAX_BYTES = 48 << 30
+SHADE_CACHE_HEADER = 256
 
 
-def aa_cache_alloc(len_oarea_buffer, num_rendered, aa_temperature, device, want=True):
-    """Returns (pool tensor, capacity in pairs); (empty, 0) when the cache is off."""
-    cap = 0
-    if want and len_oarea_buffer > 0 and aa_temperature > 0 and num_rendered > 0:
-        cap = min(int(num_rendered) * AA_CACHE_PAIRS_PER_INSTANCE, AA_CACHE_MAX_BYTES // 28, (1 << 32) - (1 << 28))
-    if cap == 0:
-        return torch.empty((0,), dtype=torch.float32, device=device), 0
-    nb = C.c_size_t(0)
-    _lib.check(_lib.load_library().dm2_aa_cache_bytes(cap, C.byref(nb)))
-    return torch.empty(((nb.value + 3) // 4,), dtype=torch.float32, device=device), cap
+def shade_cache_alloc(len_oarea_buffer, num_rendered, aa_temperature, device, want=True, used_granules=None):
+    """Returns the pool tensor (uint8; empty when the cache is off: len_oarea_buffer == 0 - the reference's K -,
+    aa_temperature == 0, nothing to render, or no gradient wanted)."""
+    if not (want and len_oarea_buffer > 0 and aa_temperature > 0 and num_rendered > 0):
+        return torch.empty((0,), dtype=torch.uint8, device=device)
+    if used_granules is not None and used_granules > 0:
+        nbytes = int(used_granules * 16 * SHADE_CACHE_SLACK) + 4096
+    else:
+        nbytes = int(num_rendered) * SHADE_CACHE_FIRST_BYTES_PER_INSTANCE
+    nbytes = min(nbytes, SHADE_CACHE_MAX_BYTES)
+    nbytes = SHADE_CACHE_HEADER + (nbytes + 15) // 16 * 16
+    return torch.empty((nbytes,), dtype=torch.uint8, device=device)
 
 
-def aa_cache_capacity(pool):
-    """Capacity (pairs) of a pool returned by aa_cache_alloc - inverse of dm2_aa_cache_bytes."""
-    n = int(pool.numel()) * 4
-    return 0 if n == 0 else ((n - 512) // 28 // 64) * 64
+def shade_cache_used_granules(pool):
+    """16-byte granules the forward pass asked for (device -> host read: synchronises; tests / sizing only)."""
+    return int(pool[:4].view(torch.int32).item()) & 0xFFFFFFFF if pool.numel() >= 4 else 0
 
 
 def _err(msg):
@@ -201,14 +208,15 @@ def render_forward_cuda(background, patch_min, patch_width, patch_height, verts,
         out_depth = torch.empty((B, H, W), **f_opts)
         face_buffer = torch.empty((face_layout(B, s.F).total,), dtype=torch.uint8, device=dev)
         image_buffer = torch.empty((image_layout(B, H, W).total,), dtype=torch.uint8, device=dev)
-        num_rendered = C.c_int64(0)
+        num_rendered, longest = C.c_int64(0), C.c_int64(0)
         _lib.check(lib.dm2_render_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
-                                             C.byref(num_rendered), stream))
+                                             C.byref(num_rendered), C.byref(longest), stream))
         R = int(num_rendered.value)
         binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
-        oarea, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev, want_cache)
+        oarea = shade_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev, want_cache)
         _lib.check(lib.dm2_render_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
-                                          R, _ptr(out_color), _ptr(out_depth), _ptr(oarea), cap, stream))
+                                          R, int(longest.value), _ptr(out_color), _ptr(out_depth), _ptr(oarea),
+                                          int(oarea.numel()), stream))
         # the other AA cache tensors are placeholders, kept so the tuple has the reference's arity
         tri_id = torch.empty((B, H, W, 0), dtype=torch.int32, device=dev)
         tri_cnt = torch.empty((0,), dtype=torch.int32, device=dev)
@@ -246,11 +254,12 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
             nb = C.c_size_t(0)
             _lib.check(lib.dm2_backward_workspace_bytes(s.B, s.F, C.byref(nb)))
             grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
-            cap = aa_cache_capacity(oarea_buffer_oarea) if oarea_buffer_oarea is not None else 0
+            pool = oarea_buffer_oarea
+            nb_pool = int(pool.numel()) * pool.element_size() if pool is not None else 0
             _lib.check(lib.dm2_render_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
                                                _ptr(image_buffer), int(num_rendered), _ptr(gc), _ptr(gd),
                                                C.byref(g), _ptr(grad_ws),
-                                               _ptr(oarea_buffer_oarea) if cap else C.c_void_p(0), cap, _stream(dev)))
+                                               _ptr(pool) if nb_pool else C.c_void_p(0), nb_pool, _stream(dev)))
     return dL_dverts, dL_dverts_color, dL_dfaces_opacity, dL_dverts_ndc, dL_dfaces_intense, dL_daa_face_verts
 
 
@@ -333,14 +342,14 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
         geo_bytes = C.c_size_t(0)
         _lib.check(lib.dm2_layers_geo_bytes(F, T, C.byref(geo_bytes)))
         geo_buffer = torch.empty((geo_bytes.value,), dtype=torch.uint8, device=dev)
-        num_rendered = C.c_int64(0)
+        num_rendered, longest = C.c_int64(0), C.c_int64(0)
         _lib.check(lib.dm2_layers_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
-                                             C.byref(num_rendered), stream))
+                                             C.byref(num_rendered), C.byref(longest), stream))
         R = int(num_rendered.value)
         binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
         _lib.check(lib.dm2_generate_render_layers(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
-                                                  _ptr(image_buffer), _ptr(geo_buffer), R, _ptr(render_layers),
-                                                  _ptr(render_layers_cnt), stream))
+                                                  _ptr(image_buffer), _ptr(geo_buffer), R, int(longest.value),
+                                                  _ptr(render_layers), _ptr(render_layers_cnt), stream))
     if return_taps:
         return render_layers, render_layers_cnt, dict(num_rendered=R, face_buffer=face_buffer,
                                                       binning_buffer=binning_buffer, image_buffer=image_buffer,

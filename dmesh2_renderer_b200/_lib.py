@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -87,25 +87,30 @@ SYMBOLS = {
     "dm2_face_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P(DM2FaceLayout)]),
     "dm2_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(DM2ImageLayout)]),
     "dm2_binning_layout": (C.c_int, [C.c_int64, _P(DM2BinningLayout)]),
-    "dm2_render_preprocess": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
-    "dm2_render_forward": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+    "dm2_render_preprocess": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), _P(C.c_int64),
+                                        C.c_void_p]),
+    "dm2_render_forward": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "dm2_aa_cache_bytes": (C.c_int, [C.c_int64, _P(C.c_size_t)]),
     "dm2_backward_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "dm2_render_backward": (C.c_int, [_P(DM2RenderInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_void_p, _P(DM2RenderGrads), C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]),
-    "dm2_fused_preprocess": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
-    "dm2_fused_forward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+    "dm2_fused_preprocess": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), _P(C.c_int64),
+                                       C.c_void_p]),
+    "dm2_fused_forward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dm2_fused_forward_pipelined": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                              _P(C.c_int64), _P(C.c_int64), _P(C.c_int32), C.c_void_p]),
     "dm2_fused_backward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, _P(DM2FusedGrads), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p]),
     "dm2_peer_allreduce_sum": (C.c_int, [_P(C.c_void_p), C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
-    "dm2_layers_preprocess": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
+    "dm2_layers_preprocess": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), _P(C.c_int64),
+                                        C.c_void_p]),
     "dm2_layers_geo_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "dm2_generate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                             C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dm2_regenerate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p]),
     "dm2_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

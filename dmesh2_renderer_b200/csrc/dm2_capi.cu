@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "dm2_common.cuh"
@@ -25,8 +26,10 @@ void set_error(const char* fmt, ...) {
 void count_launch() { g_launches++; }
 
 // ---- optional per-stage timing (CUDA events on the launching stream) -------------------------
+// Shared by all threads of the process (one report); every access goes through g_prof_mu.
 struct ProfEntry { const char* name; cudaEvent_t a, b; };
-static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfEntry> g_prof_pending;
 static std::vector<cudaEvent_t> g_prof_pool;
 static std::map<std::string, std::pair<double, long long>> g_prof_acc;
@@ -35,17 +38,20 @@ static cudaEvent_t prof_event() {
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 int prof_begin(const char* name, cudaStream_t s) {
-    if (!g_prof_on) return -1;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return -1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfEntry p{name, prof_event(), prof_event()};
     cudaEventRecord(p.a, s);
     g_prof_pending.push_back(p);
     return (int)g_prof_pending.size() - 1;
 }
 void prof_end(int handle, cudaStream_t s) {
-    if (handle < 0 || handle >= (int)g_prof_pending.size()) return;     // scopes may nest
+    if (handle < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (handle >= (int)g_prof_pending.size()) return;     // collected in between (scopes may nest)
     cudaEventRecord(g_prof_pending[handle].b, s);
 }
-static void prof_collect() {
+static void prof_collect() {          // caller holds g_prof_mu
     for (auto& p : g_prof_pending) {
         float ms = 0.f;
         if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
@@ -138,7 +144,6 @@ static BinWs carve_bin(void* ws, long long R) {
     BinWs b;
     b.keys_unsorted = (uint64_t*)(p + L.keys_unsorted); b.vals_unsorted = (uint32_t*)(p + L.vals_unsorted);
     b.keys = (uint64_t*)(p + L.keys); b.vals = (uint32_t*)(p + L.vals);
-    b.sort_temp = p + L.sort_temp; b.sort_temp_bytes = 0;
     b.imask = (uint8_t*)(p + L.imask);
     b.meta = p + L.meta;
     b.R = R;
@@ -156,25 +161,52 @@ static int check_render_inputs(const DM2RenderInputs* in) {
     return 0;
 }
 
-// longest tile segment seen by the last preprocess call on a given image workspace (host-side hint that
-// lets the forward call skip the sort tiers nothing falls into; -1 / absent = unknown)
-static thread_local std::map<const void*, long long> g_longest;
+// Pinned read-back slot + event per (thread, device) for the 12-byte binning header.
+struct Readback { uint32_t* host = nullptr; std::map<int, cudaEvent_t> ev; };
+static thread_local Readback g_rb;
+static int readback_slot(uint32_t** host, cudaEvent_t* ev) {
+    if (!g_rb.host) DM2_CHECK(cudaHostAlloc((void**)&g_rb.host, 4 * sizeof(uint32_t), cudaHostAllocPortable));
+    int d = 0;
+    DM2_CHECK(cudaGetDevice(&d));
+    auto it = g_rb.ev.find(d);
+    if (it == g_rb.ev.end()) {
+        cudaEvent_t e;
+        DM2_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        it = g_rb.ev.emplace(d, e).first;
+    }
+    *host = g_rb.host; *ev = it->second;
+    return 0;
+}
 
-// shared tail of the preprocess entry points: per-tile counts -> tile ranges + read-back of num_rendered
-// The caller zeroes iw.tile_cursor[0 .. num_tiles + 1] BEFORE its preprocess kernel (which may raise
-// patch flags in the last word).
-static int count_and_scan(const FaceWs& fw, const ImageWs& iw, long long BF, int B, int F, int gx, int gy,
-                          int64_t* num_rendered_host, uint32_t* flags_host, cudaStream_t s) {
-    *num_rendered_host = 0;
+// shared tail of the preprocess entry points: per-tile counts -> tile ranges, then the read-back of the
+// binning header (num_rendered, input flags, longest segment) is ENQUEUED; wait_header() completes it.
+// The caller zeroes iw.tile_cursor[0 .. num_tiles + 2] BEFORE its preprocess kernel (which may raise
+// flags in hdr[1]).
+static int count_and_scan(const FaceWs& fw, const ImageWs& iw, long long BF, int B, int F, int gx, int gy, cudaStream_t s) {
     const int num_tiles = B * gx * gy;
     if (launch_tile_count_scan(BF, F, gx, gy, num_tiles, fw.tiles_touched, fw.rects, iw.ranges, iw.tile_cursor, s))
         return 1;
-    uint32_t r[3] = {0u, 0u, 0u};
-    DM2_CHECK(cudaMemcpyAsync(r, iw.tile_cursor + num_tiles, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    DM2_CHECK(cudaStreamSynchronize(s));
-    *num_rendered_host = (int64_t)r[0];
-    if (flags_host) *flags_host = r[1];
-    g_longest[iw.tile_cursor] = r[2];          // consumed by the matching forward call (bin_faces)
+    uint32_t* host; cudaEvent_t ev;
+    if (readback_slot(&host, &ev)) return 1;
+    DM2_CHECK(cudaMemcpyAsync(host, iw.tile_cursor + num_tiles, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    DM2_CHECK(cudaEventRecord(ev, s));
+    return 0;
+}
+static int wait_header(int64_t* num_rendered, uint32_t* flags, int64_t* longest) {
+    uint32_t* host; cudaEvent_t ev;
+    if (readback_slot(&host, &ev)) return 1;
+    DM2_CHECK(cudaEventSynchronize(ev));
+    *num_rendered = (int64_t)host[0];
+    *flags = host[1];
+    if (longest) *longest = (int64_t)host[2];
+    return 0;
+}
+static int check_flags(uint32_t flags) {
+    // same messages as the reference's host-side asserts (__init__.py:283-284)
+    DM2_REQUIRE(!(flags & kFlagPatchX), "Some b_patch_max_x exceed self.width");
+    DM2_REQUIRE(!(flags & kFlagPatchY), "Some b_patch_max_y exceed self.height");
+    DM2_REQUIRE(!(flags & kFlagPatchNeg), "negative patch_min is not supported by the fused route (set renderer.fused = False)");
+    DM2_REQUIRE(!(flags & kFlagVertexId), "faces reference a vertex id outside [0, P)");
     return 0;
 }
 static int zero_cursor(const ImageWs& iw, int B, int gx, int gy, cudaStream_t s) {
@@ -191,15 +223,13 @@ static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaSt
     return 0;
 }
 
-// shared middle of both pipelines: scatter into the tile segments + per-segment sort
+// shared middle of both pipelines: scatter into the tile segments + per-segment sort.  capacity: instances
+// the binning workspace was laid out for; longest: longest tile segment (-1 = unknown: every sort tier runs).
 static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* key_depths, const FaceWs& fw,
-                     const BinWs& bw, const ImageWs& iw, long long R, cudaStream_t s) {
-    if (R <= 0) return 0;
-    long long longest = -1;
-    auto it = g_longest.find(iw.tile_cursor);
-    if (it != g_longest.end()) { longest = it->second; g_longest.erase(it); }
+                     const BinWs& bw, const ImageWs& iw, long long longest, cudaStream_t s) {
+    if (bw.R <= 0) return 0;
     return launch_tile_sort(BF, F, gx, gy, B * gx * gy, key_depths, fw.tiles_touched, fw.rects, iw.ranges,
-                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, longest, s);
+                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, bw.R, longest, s);
 }
 
 }  // namespace dm2
@@ -212,12 +242,14 @@ const char* dm2_last_error(void) { return g_err; }
 int dm2_abi_version(void) { return DM2_ABI_VERSION; }
 uint32_t dm2_higher_msb(uint32_t n) { return higher_msb(n); }
 void dm2_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     prof_collect();
     g_prof_on = on != 0;
 }
-void dm2_profile_reset(void) { prof_collect(); g_prof_acc.clear(); }
+void dm2_profile_reset(void) { std::lock_guard<std::mutex> lk(g_prof_mu); prof_collect(); g_prof_acc.clear(); }
 // Writes "name total_ms count\n" lines into buf; returns the number of bytes needed.
 int64_t dm2_profile_report(char* buf, int64_t cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     prof_collect();
     std::string out;
     char line[256];
@@ -247,33 +279,48 @@ int dm2_binning_layout(int64_t num_rendered, DM2BinningLayout* out) {
 }
 
 int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
-                          void* stream) {
+                          int64_t* longest_host, void* stream) {
     if (check_render_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_render_preprocess: null workspace");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     *num_rendered_host = 0;
+    if (longest_host) *longest_host = 0;
     if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);    // reference render.cu:149
     FaceWs fw = carve_face(face_ws, BF, false);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
-    if (launch_render_preprocess(*in, fw, s)) return 1;
-    return count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, num_rendered_host, nullptr, s);
+    if (launch_render_preprocess(*in, fw, iw.tile_cursor + (size_t)in->B * gx * gy + 1, s)) return 1;
+    if (count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, s)) return 1;
+    uint32_t flags = 0;
+    if (wait_header(num_rendered_host, &flags, longest_host)) return 1;
+    return check_flags(flags);
+}
+
+// everything behind the scan: scatter + segment sort, classification, forward compositor
+static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, long long longest,
+                        float* out_color, float* out_depth, void* shade_cache, long long shade_cache_bytes,
+                        bool sort_too, cudaStream_t s) {
+    const long long BF = (long long)in->B * in->F;
+    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+    const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
+    if (sort_too && bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, longest, s)) return 1;
+    if (launch_classify(bw.keys, bw.R, iw.tile_cursor + (size_t)in->B * gx * gy, tm, s)) return 1;
+    return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0, s);
 }
 
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                       int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
-                       int64_t aa_cache_pairs, void* stream) {
+                       int64_t capacity, int64_t longest, float* out_color, float* out_depth, void* shade_cache,
+                       int64_t shade_cache_bytes, void* stream) {
     if (check_render_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && out_color && out_depth, "dm2_render_forward: null buffer");
-    DM2_REQUIRE(num_rendered >= 0 && num_rendered < (1ll << 31), "dm2_render_forward: bad num_rendered");
-    DM2_REQUIRE(aa_cache_pairs >= 0 && aa_cache_pairs <= (1ll << 32) - (1ll << 28), "dm2_render_forward: bad aa_cache_pairs");
+    DM2_REQUIRE(capacity >= 0 && capacity < (1ll << 31), "dm2_render_forward: bad num_rendered");
+    DM2_REQUIRE(shade_cache_bytes >= 0, "dm2_render_forward: bad shade_cache_bytes");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
-    const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     FaceWs fw = carve_face(face_ws, BF, false);
-    BinWs bw = carve_bin(binning_ws, num_rendered);
+    BinWs bw = carve_bin(binning_ws, capacity);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
     if (in->P == 0) {                                          // reference render.cu:128-129, 149: zeros
         const size_t npix = (size_t)in->B * in->H * in->W;
@@ -281,30 +328,26 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
         DM2_CHECK(cudaMemsetAsync(out_depth, 0, npix * sizeof(float), s));
         return 0;
     }
-    const long long R = num_rendered;
-    const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, R, s)) return 1;
-    if (launch_classify(bw.keys, R, tm, s)) return 1;
-    return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, aa_cache, aa_cache ? aa_cache_pairs : 0, s);
+    return forward_tail(in, fw, bw, iw, longest, out_color, out_depth, shade_cache, shade_cache_bytes, true, s);
 }
 
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
-                        const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
+                        const void* image_ws, int64_t capacity, const float* dL_dout_color,
                         const float* dL_dout_depth, const DM2RenderGrads* grads, void* grad_ws,
-                        const void* aa_cache, int64_t aa_cache_pairs, void* stream) {
+                        const void* shade_cache, int64_t shade_cache_bytes, void* stream) {
     if (check_render_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
                 "dm2_render_backward: null buffer");
     DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dverts_ndc &&
                 grads->dL_dfaces_intense && grads->dL_daa_face_verts, "dm2_render_backward: null gradient buffer");
-    if (in->F == 0 || num_rendered == 0) return 0;             // reference render.cu:320
+    if (in->F == 0 || capacity == 0) return 0;                 // reference render.cu:320
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
-    BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
+    BinWs bw = carve_bin(const_cast<void*>(binning_ws), capacity);
     ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
-    if (launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, aa_cache,
-                               aa_cache ? aa_cache_pairs : 0, s)) return 1;
+    if (launch_raster_backward(*in, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, shade_cache,
+                               shade_cache ? shade_cache_bytes : 0, s)) return 1;
     return launch_grad_scatter(*in, fw, *grads, grad_ws, s);
 }
 
@@ -332,67 +375,114 @@ static DM2RenderInputs as_render_inputs(const DM2FusedInputs& f) {
     return r;
 }
 
-int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
-                         void* stream) {
-    if (check_fused_inputs(in)) return 2;
-    DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_fused_preprocess: null workspace");
-    cudaStream_t s = (cudaStream_t)stream;
+static int fused_front(const DM2FusedInputs* in, void* face_ws, void* image_ws, cudaStream_t s) {
     const long long BF = (long long)in->B * in->F;
-    *num_rendered_host = 0;
-    if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);
     FaceWs fw = carve_face(face_ws, BF, false);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
     if (launch_fused_preprocess(*in, fw, iw.tile_cursor + (size_t)in->B * gx * gy + 1, s)) return 1;
+    return count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, s);
+}
+
+int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
+                         int64_t* longest_host, void* stream) {
+    if (check_fused_inputs(in)) return 2;
+    DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_fused_preprocess: null workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    *num_rendered_host = 0;
+    if (longest_host) *longest_host = 0;
+    if (in->P == 0 || BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, false, s);
+    if (fused_front(in, face_ws, image_ws, s)) return 1;
     uint32_t flags = 0;
-    if (count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, num_rendered_host, &flags, s)) return 1;
-    // same messages as the reference's host-side asserts (__init__.py:283-284)
-    DM2_REQUIRE(!(flags & 1u), "Some b_patch_max_x exceed self.width");
-    DM2_REQUIRE(!(flags & 2u), "Some b_patch_max_y exceed self.height");
-    return 0;
+    if (wait_header(num_rendered_host, &flags, longest_host)) return 1;
+    return check_flags(flags);
 }
 
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                      int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
-                      int64_t aa_cache_pairs, void* stream) {
+                      int64_t capacity, int64_t longest, float* out_color, float* out_depth, void* shade_cache,
+                      int64_t shade_cache_bytes, void* stream) {
     if (check_fused_inputs(in)) return 2;
     DM2_REQUIRE(in->ray_o && in->ray_d && in->ray_view, "dm2_fused_forward: null ray buffers");
     const DM2RenderInputs r = as_render_inputs(*in);
-    return dm2_render_forward(&r, face_ws, binning_ws, image_ws, num_rendered, out_color, out_depth, aa_cache,
-                              aa_cache_pairs, stream);
+    return dm2_render_forward(&r, face_ws, binning_ws, image_ws, capacity, longest, out_color, out_depth, shade_cache,
+                              shade_cache_bytes, stream);
+}
+
+// which sort tiers launch_tile_sort runs for a given `longest` (hint or exact): bit 1 = tier 1, bit 2 = tier 2
+static int tiers_for(long long longest) {
+    if (longest < 0) return 6;
+    return (longest > 2048 ? 2 : 0) | (longest > 8192 ? 4 : 0);
+}
+
+int dm2_fused_forward_pipelined(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                                int64_t capacity, int64_t longest_hint, float* out_color, float* out_depth,
+                                void* shade_cache, int64_t shade_cache_bytes, int64_t* num_rendered_host,
+                                int64_t* longest_host, int32_t* fits_host, void* stream) {
+    if (check_fused_inputs(in)) return 2;
+    DM2_REQUIRE(in->ray_o && in->ray_d && in->ray_view, "dm2_fused_forward_pipelined: null ray buffers");
+    DM2_REQUIRE(face_ws && binning_ws && image_ws && out_color && out_depth && num_rendered_host && longest_host && fits_host,
+                "dm2_fused_forward_pipelined: null buffer");
+    DM2_REQUIRE(capacity > 0 && capacity < (1ll << 31), "dm2_fused_forward_pipelined: bad capacity");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long BF = (long long)in->B * in->F;
+    *num_rendered_host = 0; *longest_host = 0; *fits_host = 1;
+    const DM2RenderInputs r = as_render_inputs(*in);
+    if (in->P == 0 || BF == 0) {
+        if (zero_ranges(image_ws, in->B, in->H, in->W, false, s)) return 1;
+        return dm2_render_forward(&r, face_ws, binning_ws, image_ws, 0, 0, out_color, out_depth, nullptr, 0, stream);
+    }
+    // 1. preprocess + per-tile counts + scan; the 12-byte header read-back is enqueued behind them
+    if (fused_front(in, face_ws, image_ws, s)) return 1;
+    // 2. the whole tail is enqueued on the workspace the caller sized from the previous frame: every kernel
+    //    checks the header on the device and returns at once if the frame does not fit
+    FaceWs fw = carve_face(face_ws, BF, false);
+    BinWs bw = carve_bin(binning_ws, capacity);
+    ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
+    if (forward_tail(&r, fw, bw, iw, longest_hint, out_color, out_depth, shade_cache, shade_cache_bytes, true, s)) return 1;
+    // 3. only now wait for the header (its event completed long before the raster kernel ends)
+    uint32_t flags = 0;
+    if (wait_header(num_rendered_host, &flags, longest_host)) return 1;
+    if (check_flags(flags)) return 2;
+    if (*num_rendered_host > capacity) { *fits_host = 0; return 0; }      // caller re-runs dm2_fused_forward
+    const int missing = tiers_for(*longest_host) & ~tiers_for(longest_hint);
+    if (missing) {
+        // a segment longer than the hinted sort tier: the scatter is valid (and must not run twice) - sort the
+        // long segments now and redo classification + compositing on the same workspace
+        const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
+        if (launch_tile_sort_tiers(in->B * gx * gy, iw.ranges, iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted,
+                                   bw.keys, bw.vals, bw.R, missing, s)) return 1;
+        if (forward_tail(&r, fw, bw, iw, *longest_host, out_color, out_depth, shade_cache, shade_cache_bytes, false, s))
+            return 1;
+    }
+    return 0;
 }
 
 int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void* binning_ws,
-                       const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
+                       const void* image_ws, int64_t capacity, const float* dL_dout_color,
                        const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws,
-                       const void* aa_cache, int64_t aa_cache_pairs, void* stream) {
+                       const void* shade_cache, int64_t shade_cache_bytes, void* stream) {
     if (check_fused_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && dL_dout_color && dL_dout_depth && grads && grad_ws,
                 "dm2_fused_backward: null buffer");
     DM2_REQUIRE(grads->dL_dverts && grads->dL_dverts_color && grads->dL_dfaces_opacity && grads->dL_dfaces_intense,
                 "dm2_fused_backward: null gradient buffer");
-    if (in->F == 0 || num_rendered == 0) return 0;
+    if (in->F == 0 || capacity == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     const DM2RenderInputs r = as_render_inputs(*in);
     FaceWs fw = carve_face(const_cast<void*>(face_ws), BF, false);
-    BinWs bw = carve_bin(const_cast<void*>(binning_ws), num_rendered);
+    BinWs bw = carve_bin(const_cast<void*>(binning_ws), capacity);
     ImageWs iw = carve_image(const_cast<void*>(image_ws), in->B, in->H, in->W, false);
-    if (launch_raster_backward(r, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, aa_cache,
-                               aa_cache ? aa_cache_pairs : 0, s)) return 1;
+    if (launch_raster_backward(r, fw, bw, iw, dL_dout_color, dL_dout_depth, grad_ws, shade_cache,
+                               shade_cache ? shade_cache_bytes : 0, s)) return 1;
     return launch_fused_grad_scatter(*in, fw, *grads, grad_ws, s);
 }
 
 int dm2_peer_allreduce_sum(const void* const* peer_ptrs, void* multicast_ptr, int32_t world, int32_t rank,
                            int64_t n_floats, void* stream) {
     return launch_peer_allreduce(peer_ptrs, multicast_ptr, world, rank, n_floats, (cudaStream_t)stream);
-}
-
-int dm2_aa_cache_bytes(int64_t capacity_pairs, size_t* bytes) {
-    DM2_REQUIRE(bytes && capacity_pairs >= 0 && capacity_pairs < (1ll << 32) - 1, "dm2_aa_cache_bytes: bad arguments");
-    *bytes = aa_cache_bytes(capacity_pairs);
-    return 0;
 }
 
 int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes) {
@@ -411,19 +501,23 @@ static int check_layer_inputs(const DM2LayerInputs* in) {
 }
 
 int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
-                          void* stream) {
+                          int64_t* longest_host, void* stream) {
     if (check_layer_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_layers_preprocess: null workspace");
     cudaStream_t s = (cudaStream_t)stream;
     const long long BF = (long long)in->B * in->F;
     *num_rendered_host = 0;
+    if (longest_host) *longest_host = 0;
     if (BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, true, s);
     FaceWs fw = carve_face(face_ws, BF, true);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
-    if (launch_layers_preprocess(*in, fw, s)) return 1;
-    return count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, num_rendered_host, nullptr, s);
+    if (launch_layers_preprocess(*in, fw, iw.tile_cursor + (size_t)in->B * gx * gy + 1, s)) return 1;
+    if (count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, s)) return 1;
+    uint32_t flags = 0;
+    if (wait_header(num_rendered_host, &flags, longest_host)) return 1;
+    return check_flags(flags);
 }
 
 int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes) {
@@ -433,7 +527,7 @@ int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes) {
 }
 
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                               void* geo_ws, int64_t num_rendered, int32_t* render_layers,
+                               void* geo_ws, int64_t num_rendered, int64_t longest, int32_t* render_layers,
                                int32_t* render_layers_cnt, void* stream) {
     if (check_layer_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && geo_ws && render_layers_cnt, "dm2_generate_render_layers: null buffer");
@@ -446,7 +540,7 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
     BinWs bw = carve_bin(binning_ws, num_rendered);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     // key = min depth (reference renderer.cu:603)
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, num_rendered, s)) return 1;
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, longest, s)) return 1;
     return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, false, s);
 }
 

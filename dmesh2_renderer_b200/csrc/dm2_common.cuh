@@ -13,6 +13,7 @@
 // The CPU oracle (oracle/dm2_oracle.cpp) restates the same sequences with fmaf().
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -57,17 +58,18 @@ struct ProfScope {
     } while (0)
 
 // cudaFuncSetAttribute applies to the CURRENT device: one-time kernel set-up is tracked per device, so that
-// renderers on several GPUs of one process all get their shared-memory opt-in.
+// renderers on several GPUs of one process all get their shared-memory opt-in.  Thread-safe: first() stays
+// true for a device until done() was called for it AFTER the attribute calls succeeded, so threads that race
+// on the first launch each perform the (idempotent) set-up themselves before they launch; none can skip it.
 struct PerDeviceOnce {
-    unsigned long long done = 0ull;
-    bool first() {
+    std::atomic<unsigned long long> ready{0ull};
+    static unsigned long long bit() {
         int d = 0;
-        if (cudaGetDevice(&d) != cudaSuccess) return true;
-        const unsigned long long bit = 1ull << (d & 63);
-        if (done & bit) return false;
-        done |= bit;
-        return true;
+        if (cudaGetDevice(&d) != cudaSuccess) return 0ull;
+        return 1ull << (d & 63);
     }
+    bool first() const { const unsigned long long b = bit(); return b == 0ull || !(ready.load(std::memory_order_acquire) & b); }
+    void done() { ready.fetch_or(bit(), std::memory_order_release); }
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -190,6 +192,21 @@ __device__ __forceinline__ float clamp01_depth(float z) {
     return d;
 }
 
+// ---------------------------------------------------------------- binning header + speculative launches
+// k_tile_scan leaves three words behind the per-tile cursors: hdr[0] = num_rendered, hdr[1] = input flags
+// raised by the preprocess kernel (kFlag*), hdr[2] = the longest tile segment.  Every kernel downstream of
+// the scan can be enqueued BEFORE the host has read them back (dm2_*_forward_pipelined): it receives the
+// capacity (in instances) of the binning workspace it was launched on and returns at once if the frame
+// turned out not to fit or the inputs were rejected - the host then re-runs the tail on a larger workspace.
+constexpr uint32_t kFlagPatchX = 1u;       // some patch_min.x + patch_width  > frame width  (reference __init__.py:283)
+constexpr uint32_t kFlagPatchY = 2u;       // some patch_min.y + patch_height > frame height (reference __init__.py:284)
+constexpr uint32_t kFlagPatchNeg = 4u;     // negative patch_min on the fused route (rays are read in place)
+constexpr uint32_t kFlagVertexId = 8u;     // a face references a vertex id outside [0, P)
+struct BinGuard { const uint32_t* hdr; uint32_t capacity; };
+__device__ __forceinline__ bool bin_invalid(const BinGuard g) {
+    return __ldg(g.hdr) > g.capacity || __ldg(g.hdr + 1) != 0u;
+}
+
 // ---------------------------------------------------------------- internal launchers
 struct FaceWs {
     float* depths; float* min_depths; float* max_depths;
@@ -203,9 +220,8 @@ struct ImageWs {
 };
 struct BinWs {
     uint64_t* keys_unsorted; uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
-    void* sort_temp; size_t sort_temp_bytes;
     uint8_t* imask;               // per sorted instance: bit w = footprint w has a touched pixel (render path)
-    long long R;                  // num_rendered
+    long long R;                  // capacity of this workspace in instances (>= num_rendered; = stride of meta)
     void* meta;                   // uint4[8][R]: per (footprint, instance) pixel classification (k_classify_instances)
 };
 struct TileMaskArgs {             // optional second output of the tile-range pass (render path)
@@ -213,8 +229,8 @@ struct TileMaskArgs {             // optional second output of the tile-range pa
     int F, gx, gy, use_bbox;
 };
 
-int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, cudaStream_t s);
-int launch_layers_preprocess(const DM2LayerInputs& in, const FaceWs& fw, cudaStream_t s);
+int launch_render_preprocess(const DM2RenderInputs& in, const FaceWs& fw, uint32_t* flags, cudaStream_t s);
+int launch_layers_preprocess(const DM2LayerInputs& in, const FaceWs& fw, uint32_t* flags, cudaStream_t s);
 int launch_scan(const uint32_t* in, uint32_t* out, long long n, uint32_t* partials, cudaStream_t s);
 long long scan_partials_count(long long n);
 int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, const uint32_t* tiles_touched,
@@ -222,18 +238,20 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
 int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
                      const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
                      uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
-                     long long longest, cudaStream_t s);
+                     long long capacity, long long longest, cudaStream_t s);
+int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
+                           const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
+                           cudaStream_t s);
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
                       long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
 size_t sort_temp_bytes(long long n);
-int launch_classify(const uint64_t* keys, long long R, const TileMaskArgs& tm, cudaStream_t s);
+int launch_classify(const uint64_t* keys, long long capacity, const uint32_t* hdr, const TileMaskArgs& tm, cudaStream_t s);
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
-                          const ImageWs& iw, float* out_color, float* out_depth, void* aa_cache,
-                          long long aa_cache_pairs, cudaStream_t s);
+                          const ImageWs& iw, float* out_color, float* out_depth, void* shade_cache,
+                          long long shade_cache_bytes, cudaStream_t s);
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
-                           void* grad_ws, const void* aa_cache, long long aa_cache_pairs, cudaStream_t s);
-size_t aa_cache_bytes(long long capacity_pairs);
+                           void* grad_ws, const void* shade_cache, long long shade_cache_bytes, cudaStream_t s);
 int launch_peer_allreduce(const void* const* peer_ptrs, void* multicast_ptr, int world, int rank, long long n_floats,
                           cudaStream_t s);
 int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,

@@ -5,14 +5,14 @@
 // Warp-autonomous like the forward kernel (dm2_raster_common.cuh): one warp per 8x4-pixel footprint, one
 // pixel per lane, the tile's sorted list scanned back to front.  Per sub-chunk of kBSub candidates a warp does:
 //   1. per-lane hit / partial bit masks from the staged classification words;
-//   2. a DENSE pass over the candidate-major list of all hit pairs: overlap area (read back from the AA cache
-//      the forward pass filled; clipped again only for pairs it did not cache), hit point, alpha and
-//      S = iC . dL/dC + iD . dL/dD into [candidate][pixel] tables;
+//   2. a DENSE pass over the candidate-major list of all hit pairs: the (uc, vc, ratio, code) record the forward
+//      pass left in the shading cache (recomputed - clip, hit point, clamp - only for blocks that are not
+//      cached), interpolation, alpha and S = iC . dL/dC + iD . dL/dD into [candidate][pixel] tables;
 //   3. the pixel-sequential walk (each lane its own hits, back to front): recovers T (T /= 1 - alpha)
 //      and computes dL/dalpha - the only order-dependent quantities - into the same tables;
-//   4. the face-parallel gradient phase over the same list: one THREAD per contribution recomputes the hit
-//      point and evaluates the 29 per-face gradient values (pixel constants are fetched from the owning
-//      lane with shuffles, d(area)/d(aa verts) from the AA cache); the warp transposes them through shared
+//   4. the face-parallel gradient phase over the same list: one THREAD per contribution evaluates the 29
+//      per-face gradient values (pixel constants are fetched from the owning lane with shuffles, the record and
+//      d(area)/d(aa verts) from the shading cache); the warp transposes them through shared
 //      memory, lane q sums column q over the run of one candidate and issues ONE coalesced 29-lane atomic
 //      per (warp, face) into the per-(view, face) 128-byte gradient record.
 // A second kernel scatters the records to the output tensors (or, on the fused path, chains them
@@ -71,14 +71,26 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 }
 
 
-// Recomputation of the clip for pairs the forward pass did not cache (K = 0 or pool overflow): kept out of
-// line so that the rarely taken path does not sit in the instruction stream of the hot loops (the kernel
-// showed "no instruction" fetch stalls with the clip inlined twice).
-__device__ __noinline__ bool clip_area_only(const float* rec, float pxmin, float pymin, unsigned inmask, float* area) {
-    float a;
-    const bool ok = aa_clip<false>(rec, pxmin, pymin, inmask, a, nullptr);
-    *area = a;
-    return ok;
+// Recomputation for pairs whose block is not in the shading cache (cache off, aa_temperature == 0, or pool
+// overflow): kept out of line so that the rarely taken path does not sit in the instruction stream of the hot
+// loops (the kernel showed "no instruction" fetch stalls with the clip inlined twice).  Returns the hit record
+// the forward pass would have written: (uc, vc, ratio, code), ratio == 0 = skip.
+__device__ __noinline__ float4 shade_recompute(const float* rec, float ox, float oy, float oz, float dx, float dy,
+                                               float dz, float pxmin, float pymin, float tau, int l, bool partial,
+                                               bool use_aa) {
+    Shade s;
+    s.area = use_aa ? 1.0f : 0.0f;
+    if (partial) {
+        const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
+        float a;
+        if (!aa_clip<false>(rec, pxmin, pymin, inm, a, nullptr)) return make_float4(0.f, 0.f, 0.f, 0.f);
+        s.area = a;
+    }
+    PixelGeom qg;
+    qg.pxmin = pxmin; qg.pymin = pymin;
+    qg.o = f3{ox, oy, oz}; qg.d = f3{dx, dy, dz};
+    if (!shade_tail(rec, qg, tau, s)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return make_float4(s.w1, s.w2, s.ratio, __int_as_float(s.code));
 }
 __device__ __noinline__ void clip_gradient(const float* rec, float pxmin, float pymin, unsigned inmask, float* g) {
     float a, gg[6];
@@ -96,23 +108,28 @@ constexpr int kRedWords = 8 * kRedGroup;
 
 // Candidates per sub-chunk.  Measured at cfg2 (ms): 8 candidates / 6 CTAs of 4 warps per SM 1.86;
 // 16 / 4 CTAs 1.69; 12 / 5 CTAs 1.66 - the dense passes want many pairs per sub-chunk (~110 here, 4
-// batches), the latency-bound walk wants warps; 45 KB of shared memory per CTA lets 5 CTAs share an SM.
-constexpr int kBSub = 12;
+// batches), the latency-bound walk wants warps.
+#ifndef DM2_BSUB
+#define DM2_BSUB 12
+#endif
+#ifndef DM2_BWD_MINBLOCKS
+#define DM2_BWD_MINBLOCKS 5
+#endif
+constexpr int kBSub = DM2_BSUB;
 constexpr int kBSlots = kBSub * 32;
 
 struct BwdWarpSmem {
     float srec[kBSub * kRecStride];         // staged records of the sub-chunk
     float tA[kBSlots];                      // [candidate][pixel]: alpha (or skip)  -> T before the contribution
     float tS[kBSlots];                      //                     iC.dC + iD.dD     -> dL/dalpha
-    float tArea[kBSlots];                   //                     overlap area
     float red[kRedWords];                   // half-warp transpose tile (layout: red_index)
     WarpQueue q;
     uint16_t plist[kBSlots];                // candidate-major list of all hit pairs: k | lane << 4 | partial << 9
 };
 
-__global__ void __launch_bounds__(kRasterThreads, 5)
+__global__ void __launch_bounds__(kRasterThreads, DM2_BWD_MINBLOCKS)
 k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                  const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R, AACache cache,
+                  const uint8_t* __restrict__ imask, const uint4* __restrict__ meta, uint32_t R, ShadeCache cache,
                   const uint2* __restrict__ ranges,
                   const float* __restrict__ final_T, const float* __restrict__ final_prev_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
@@ -181,20 +198,6 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
             return tc.inside && (int)ws.q.idx[(head + k) & (kQueue - 1)] < my_last;
         });
         if (__any_sync(0xffffffffu, hit != 0u)) {
-            // every lane prefetches the cached overlap area of ITS partially covered pixel (written by the
-            // forward pass) straight into the table; the copies fly while the pair list is built
-            if (cached) {
-                for (uint32_t pp = part; pp != 0u; pp &= pp - 1u) {
-                    const int k = __ffs(pp) - 1;
-                    const float* rec = ws.srec + k * kRecStride;
-                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
-                    if (poff == kNoCache) continue;
-                    const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & lt_mask);
-                    cp_async4(&ws.tArea[k * 32 + lane], cache.area + j);
-                }
-            }
-            cp_async_commit();
-
             // candidate-major list of all hit pairs (k | lane << 4 | partial << 9); the dense pass and the
             // gradient pass both run over it
             int npairs = 0;
@@ -204,46 +207,39 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                 if (h) ws.plist[npairs + __popc(m & lt_mask)] = (uint16_t)(k | (lane << 4) | (((part >> k) & 1u) << 9));
                 npairs += __popc(m);
             }
-            cp_async_wait0();
             __syncwarp();
 
-            // ====== 2. dense pass over every hit pair: area (cached, else clipped), hit point, alpha, S
+            // ====== 2. dense pass over every hit pair: hit record (cached, else recomputed), alpha, S
             for (int p0 = 0; p0 < npairs; p0 += 32) {
                 const int pid = p0 + lane;
                 const bool act = pid < npairs;
                 const unsigned e = act ? ws.plist[pid] : 0u;
                 const int k = e & 15, l = (e >> 4) & 31;
-                PixelGeom qg;
-                qg.o.x = __shfl_sync(0xffffffffu, pg.o.x, l); qg.o.y = __shfl_sync(0xffffffffu, pg.o.y, l);
-                qg.o.z = __shfl_sync(0xffffffffu, pg.o.z, l); qg.d.x = __shfl_sync(0xffffffffu, pg.d.x, l);
-                qg.d.y = __shfl_sync(0xffffffffu, pg.d.y, l); qg.d.z = __shfl_sync(0xffffffffu, pg.d.z, l);
-                const float qC0 = __shfl_sync(0xffffffffu, dC0, l), qC1 = __shfl_sync(0xffffffffu, dC1, l);
-                const float qC2 = __shfl_sync(0xffffffffu, dC2, l), qD = __shfl_sync(0xffffffffu, dD, l);
-                if (!act) continue;
-                qg.pxmin = tc.fx0 + (float)(l & 7);
-                qg.pymin = tc.fy0 + (float)(l >> 3);
                 const float* rec = ws.srec + k * kRecStride;
                 const int slot = k * 32 + l;
-                Shade s;
-                s.area = use_aa ? 1.0f : 0.0f;
-                bool ok = true;
-                if ((e >> 9) & 1u) {
-                    if (cached && __float_as_uint(rec[R_META + 3]) != kNoCache) {      // evaluated by the forward pass
-                        s.area = ws.tArea[slot];
-                        ok = !(s.area == -1.0f);
-                    } else {
-                        const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
-                        float at;
-                        ok = clip_area_only(rec, qg.pxmin, qg.pymin, inm, &at);
-                        s.area = at;
-                        ws.tArea[slot] = at;
-                    }
-                } else {
-                    ws.tArea[slot] = s.area;
+                // the record's load is issued first; the shuffles below cover part of its latency
+                const uint32_t poff = act ? __float_as_uint(rec[R_META + 3]) : kNoCache;
+                const bool from_cache = cached && poff != kNoCache;
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (from_cache)
+                    h = __ldg(cache.data + (size_t)poff + __popc(__float_as_uint(rec[R_META]) & ((1u << l) - 1u)));
+                const float qC0 = __shfl_sync(0xffffffffu, dC0, l), qC1 = __shfl_sync(0xffffffffu, dC1, l);
+                const float qC2 = __shfl_sync(0xffffffffu, dC2, l), qD = __shfl_sync(0xffffffffu, dD, l);
+                if (!__all_sync(0xffffffffu, from_cache || !act)) {
+                    const float ox = __shfl_sync(0xffffffffu, pg.o.x, l), oy = __shfl_sync(0xffffffffu, pg.o.y, l);
+                    const float oz = __shfl_sync(0xffffffffu, pg.o.z, l), dx = __shfl_sync(0xffffffffu, pg.d.x, l);
+                    const float dy = __shfl_sync(0xffffffffu, pg.d.y, l), dz = __shfl_sync(0xffffffffu, pg.d.z, l);
+                    if (act && !from_cache)
+                        h = shade_recompute(rec, ox, oy, oz, dx, dy, dz, tc.fx0 + (float)(l & 7), tc.fy0 + (float)(l >> 3),
+                                            tau, l, (e >> 9) & 1u, use_aa);
                 }
-                ok = ok && shade_tail(rec, qg, tau, s);
-                if (ok) {
-                    ws.tA[slot] = __fmul_rn(rec[R_MISC + 1], s.ratio);
+                if (!act) continue;
+                if (h.z != 0.0f) {
+                    Shade s;
+                    s.w1 = h.x; s.w2 = h.y;
+                    s.w0 = __fsub_rn(__fsub_rn(1.0f, h.x), h.y);
+                    shade_interp(rec, s);
+                    ws.tA[slot] = __fmul_rn(rec[R_MISC + 1], h.z);
                     ws.tS[slot] = s.iC[0] * qC0 + s.iC[1] * qC1 + s.iC[2] * qC2 + s.iD * qD;
                 } else {
                     ws.tA[slot] = __uint_as_float(kSkipBits);
@@ -302,17 +298,25 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     const int slot = k * 32 + src;
                     qg.pxmin = tc.fx0 + (float)(src & 7);
                     qg.pymin = tc.fy0 + (float)(src >> 3);
-                    // d(area)/d(aa verts) of a partially covered pixel: straight from the AA cache (global; the
-                    // loads are issued first and consumed last), else clipped again
+                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                    const bool from_cache = cached && poff != kNoCache;
+                    const uint32_t touched = __float_as_uint(rec[R_META]);
+                    // hit record and d(area)/d(aa verts) of a partially covered pixel: straight from the shading
+                    // cache (global; the loads are issued first and consumed last), else recomputed
+                    float4 h;
                     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if ((e >> 9) & 1u) {
-                        const uint32_t poff = __float_as_uint(rec[R_META + 3]);
-                        if (cached && poff != kNoCache) {
-                            const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << src) - 1u));
-                            const float2* gj = reinterpret_cast<const float2*>(cache.grad + (size_t)j * 6);
+                    if (from_cache) {
+                        h = __ldg(cache.data + (size_t)poff + __popc(touched & ((1u << src) - 1u)));
+                        if ((e >> 9) & 1u) {
+                            const uint32_t j = __popc(__float_as_uint(rec[R_PMASK]) & ((1u << src) - 1u));
+                            const float2* gj = reinterpret_cast<const float2*>(cache.data + (size_t)poff + __popc(touched)) + 3 * j;
                             const float2 g0 = __ldg(gj), g1 = __ldg(gj + 1), g2 = __ldg(gj + 2);
                             g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y; g[4] = g2.x; g[5] = g2.y;
-                        } else {
+                        }
+                    } else {
+                        h = shade_recompute(rec, qg.o.x, qg.o.y, qg.o.z, qg.d.x, qg.d.y, qg.d.z, qg.pxmin, qg.pymin, tau,
+                                            src, (e >> 9) & 1u, use_aa);
+                        if ((e >> 9) & 1u) {
                             const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), src);
                             float gt[6];
                             clip_gradient(rec, qg.pxmin, qg.pymin, inm, gt);
@@ -321,8 +325,8 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                         }
                     }
                     Shade s;
-                    s.area = ws.tArea[slot];
-                    shade_tail(rec, qg, tau, s);                   // succeeded in the dense pass: same function, same inputs
+                    s.w1 = h.x; s.w2 = h.y; s.ratio = h.z; s.code = __float_as_int(h.w);
+                    s.w0 = __fsub_rn(__fsub_rn(1.0f, h.x), h.y);
                     const float Tq = ws.tA[slot], dL_dalpha = ws.tS[slot];
                     const float opacity = rec[R_MISC + 1], intense = rec[R_MISC + 2];
                     const float alpha = __fmul_rn(opacity, s.ratio);
@@ -516,12 +520,6 @@ k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touch
 
 constexpr size_t kBwdSmem = sizeof(BwdWarpSmem) * (kRasterThreads / 32);
 
-size_t aa_cache_bytes(long long capacity_pairs) {
-    if (capacity_pairs <= 0) return 0;
-    const size_t c64 = (((size_t)capacity_pairs + 63) / 64) * 64;
-    return 256 + c64 * 4 + c64 * 24 + 256;
-}
-
 size_t backward_ws_bytes(long long BF) { return align_up((size_t)BF * kGradWords * 4, 256) + 256; }
 
 int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const DM2FusedGrads& g, void* grad_ws,
@@ -548,8 +546,8 @@ int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2Re
 
 // zero the per-face gradient records and run the tile kernel; the caller scatters afterwards
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                           const float* dL_dcolor, const float* dL_ddepth, void* grad_ws, const void* aa_cache,
-                           long long aa_cache_pairs, cudaStream_t s) {
+                           const float* dL_dcolor, const float* dL_ddepth, void* grad_ws, const void* shade_cache,
+                           long long shade_cache_bytes, cudaStream_t s) {
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     const long long BF = (long long)in.B * in.F;
@@ -558,6 +556,7 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_raster_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kBwdSmem));
+        attr_set.done();
     }
     float* gface = reinterpret_cast<float*>(grad_ws);
     {
@@ -568,7 +567,7 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
         ProfScope _ps("raster_backward", s);
         k_raster_backward<<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kBwdSmem, s>>>(
             in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R,
-            aa_cache_view(const_cast<void*>(aa_cache), aa_cache_pairs), iw.ranges, iw.final_T, iw.final_prev_T,
+            shade_cache_view(const_cast<void*>(shade_cache), shade_cache_bytes), iw.ranges, iw.final_T, iw.final_prev_T,
             iw.n_contrib, dL_dcolor, dL_ddepth, gface, gx, gy);
         DM2_LAUNCH_CHECK();
     }

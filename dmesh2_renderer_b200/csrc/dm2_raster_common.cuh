@@ -29,8 +29,6 @@ constexpr int kWarpsPerCta = 4;              // a CTA renders half a tile (4 of 
 constexpr int kRasterThreads = 32 * kWarpsPerCta;   // talk to each other, smaller CTAs free their SM slots sooner
 constexpr int kCtasPerTile = 8 / kWarpsPerCta;
 constexpr int kGradWords = 32;              // per-(view,face) gradient record (29 used)
-constexpr int kSub = 8;                     // candidates per sub-chunk (forward)
-constexpr int kSlots = kSub * 32;           // (candidate, pixel) table slots per warp (forward)
 constexpr int kQueue = 64;                  // candidate ring capacity (>= sub-chunk - 1 + 32)
 constexpr uint32_t kSkipBits = 0xFFFFFFFFu; // table marker: the reference skips this (pixel, face) pair
 
@@ -86,29 +84,40 @@ __device__ __forceinline__ void fill_queue(WarpQueue& q, int head, int& count, i
 // Stages the records of the first `ncs` queued candidates into slots 0..ncs-1; the 16th 16-byte chunk
 // of a slot receives the candidate's classification words (k_classify_instances) for this warp's
 // footprint.  tmeta: meta + warp * R + range.x (nullptr when aa_temperature == 0).
-constexpr int R_META = 60;                  // staged slot only: touched-pixel mask, corner grid lo / hi, AA-cache offset
+constexpr int R_META = 60;                  // staged slot only: touched-pixel mask, corner grid lo / hi, cache block offset
 constexpr int R_PMASK = 64;                 // staged slot only: partially-covered-pixel mask of the footprint
-constexpr uint32_t kNoCache = 0xFFFFFFFFu;  // AA-cache offset: this candidate's pairs are not cached
+constexpr uint32_t kNoCache = 0xFFFFFFFFu;  // cache offset: this candidate has no block in the shading cache
 
 // ------------------------------------------------------------------------------------------------
-// AA cache (the role of the reference's oarea buffers, render.cu:143-146, as a compact pool): the
-// forward pass stores the overlap area and its gradient of every partially covered (pixel, face)
-// pair it evaluates, the backward pass reads them back instead of clipping again.  Entries of one
-// (instance, footprint) are contiguous, ordered by pixel; the entry offset lives in the 4th
-// classification word.  Layout: [u32 counter | pad to 256 B][area f32 x C][grad f32 x 6C].
-struct AACache {
+// Shading cache (the role of the reference's four oarea buffers, render.cu:143-146 - a zero-filled
+// B*H*W*K*32-byte array there - as a compact pool, and more: HBM is ~90 % idle while these kernels are
+// instruction bound, so the forward pass also hands the backward pass everything it would otherwise
+// recompute per contribution).  For every staged (instance, footprint) the forward pass reserves ONE block
+//     [ n_t hit records : float4 (uc, vc, ratio, code) ]   n_t = touched pixels of the footprint
+//     [ n_p x 6 floats  : d(area)/d(aa verts)         ]   n_p = partially covered pixels
+// ordered by pixel inside each part; `ratio == 0` marks a pair the reference skips (AA error code, zero
+// overlap, denom == 0, zero coverage).  The block's offset (in 16-byte granules) lives in the 4th
+// classification word of the instance.  The backward pass reads the records back instead of re-running
+// Moeller-Trumbore, the barycentric clamp and the polygon clip, and falls back to recomputation for
+// blocks that did not fit (kNoCache) or when the cache is off.
+// Pool layout: [u32 granule counter | pad to 256 B][capacity granules of 16 bytes].
+struct ShadeCache {
     uint32_t* counter;
-    float* area;
-    float* grad;
-    uint32_t capacity;
+    float4* data;
+    uint32_t capacity;                      // granules
 };
-__host__ __device__ __forceinline__ AACache aa_cache_view(void* pool, long long capacity) {
-    AACache c;
+constexpr size_t kCacheHeader = 256;
+__host__ __device__ __forceinline__ ShadeCache shade_cache_view(void* pool, long long bytes) {
+    ShadeCache c;
     c.counter = reinterpret_cast<uint32_t*>(pool);
-    c.area = reinterpret_cast<float*>(reinterpret_cast<char*>(pool) + 256);
-    c.grad = c.area + (((size_t)capacity + 63) / 64) * 64;
-    c.capacity = pool ? (uint32_t)capacity : 0u;
+    c.data = reinterpret_cast<float4*>(reinterpret_cast<char*>(pool) + kCacheHeader);
+    long long cap = pool && bytes > (long long)kCacheHeader ? (bytes - (long long)kCacheHeader) / 16 : 0;
+    if (cap > (1ll << 32) - (1ll << 28)) cap = (1ll << 32) - (1ll << 28);       // the 32-bit counter must not wrap
+    c.capacity = (uint32_t)cap;
     return c;
+}
+__device__ __forceinline__ uint32_t cache_block_granules(uint32_t n_t, uint32_t n_p) {
+    return n_t + ((6u * n_p + 3u) >> 2);
 }
 
 // partially covered pixels of a footprint from its classification words (touched & not all 4 corners inside)
@@ -150,6 +159,21 @@ struct Shade {
     int code;
 };
 
+// Interpolated colour and NDC depth from the barycentric weights s.w0..w2 (forward.cu:383-395).
+__device__ __forceinline__ void shade_interp(const float* __restrict__ rec, Shade& s) {
+    const float4 c0 = *reinterpret_cast<const float4*>(rec + R_COL);        // c0.rgb c1.r
+    const float4 c1 = *reinterpret_cast<const float4*>(rec + R_COL + 4);    // c1.gb c2.rg
+    const float c2b = rec[R_COL + 8];
+    const float intense = rec[R_MISC + 2];
+    const float col0[3] = {c0.x, c0.y, c0.z}, col1[3] = {c0.w, c1.x, c1.y}, col2[3] = {c1.z, c1.w, c2b};
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float c = __fmaf_rn(s.w2, col2[ch], __fmaf_rn(s.w0, col0[ch], __fmul_rn(s.w1, col1[ch])));
+        s.iC[ch] = __fmul_rn(c, intense);
+    }
+    s.iD = __fmaf_rn(s.w2, rec[R_P2 + 3], __fmaf_rn(s.w0, rec[R_P0 + 3], __fmul_rn(s.w1, rec[R_P1 + 3])));
+}
+
 // Everything after the coverage area (s.area must be set): hit point, clamped barycentrics,
 // coverage ratio, interpolated colour and depth (forward.cu:354-395).
 __device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const PixelGeom& pg, float tau, Shade& s) {
@@ -168,17 +192,7 @@ __device__ __forceinline__ bool shade_tail(const float* __restrict__ rec, const 
     const float rt = __fmul_rn(s.area, tau);
     s.ratio = (s.code == 0) ? (float)((double)__fsub_rn(1.0f, tau) + (double)rt) : rt;
     if (s.ratio == 0.0f) return false;
-    const float4 c0 = *reinterpret_cast<const float4*>(rec + R_COL);        // c0.rgb c1.r
-    const float4 c1 = *reinterpret_cast<const float4*>(rec + R_COL + 4);    // c1.gb c2.rg
-    const float c2b = rec[R_COL + 8];
-    const float intense = rec[R_MISC + 2];
-    const float col0[3] = {c0.x, c0.y, c0.z}, col1[3] = {c0.w, c1.x, c1.y}, col2[3] = {c1.z, c1.w, c2b};
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        float c = __fmaf_rn(s.w2, col2[ch], __fmaf_rn(s.w0, col0[ch], __fmul_rn(s.w1, col1[ch])));
-        s.iC[ch] = __fmul_rn(c, intense);
-    }
-    s.iD = __fmaf_rn(s.w2, a2.w, __fmaf_rn(s.w0, a0.w, __fmul_rn(s.w1, a1.w)));
+    shade_interp(rec, s);
     return true;
 }
 
@@ -206,20 +220,6 @@ template <typename LaneOk>
 __device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec, int ncs, bool use_aa, int lane,
                                                   uint32_t& hit, uint32_t& part, LaneOk lane_ok) {
     hit = 0u; part = 0u;
-#ifdef DM2_CLASSIFY_OLD
-    for (int k = 0; k < ncs; k++) {
-        bool on = lane_ok(k);
-        unsigned inmask = 0xF;
-        if (use_aa) {
-            const uint4 m = *reinterpret_cast<const uint4*>(srec + k * kRecStride + R_META);    // broadcast
-            on = on && ((m.x >> lane) & 1u);
-            inmask = corner_mask_of(m, lane);
-        }
-        const bool p = on && (inmask != 0xF);
-        hit |= (on ? 1u : 0u) << k;
-        part |= (p ? 1u : 0u) << k;
-    }
-#else
     // bit `lane` of every candidate's touched-pixel and partially-covered-pixel masks (two broadcast reads)
     for (int k = 0; k < ncs; k++) {
         uint32_t touched = 0xFFFFFFFFu, pm = 0u;
@@ -231,7 +231,6 @@ __device__ __forceinline__ void classify_subchunk(const float* __restrict__ srec
         hit |= on << k;
         part |= (on & (pm >> lane)) << k;
     }
-#endif
 }
 
 struct TileCtx {

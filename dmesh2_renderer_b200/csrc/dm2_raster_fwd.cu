@@ -19,23 +19,26 @@ struct FwdWarpSmem {
     uint16_t plist[kFSlots];                // partially covered (pixel, face) pairs: k | lane << 4
 };
 
-// CACHE: also evaluate d(area)/d(aa verts) in the clip and store area + gradient in the AA cache.
+// CACHE: fill the shading cache for the backward pass (dm2_raster_common.cuh): d(area)/d(aa verts) of every
+// clipped pair and one (uc, vc, ratio, code) record per visited (pixel, face) pair.
 template <bool CACHE>
 #ifndef DM2_FWD_MINBLOCKS
 #define DM2_FWD_MINBLOCKS (3 * kCtasPerTile)
 #endif
 __global__ void __launch_bounds__(kRasterThreads, DM2_FWD_MINBLOCKS)
 k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const uint32_t* __restrict__ list,
-                 const uint8_t* __restrict__ imask, uint4* __restrict__ meta, uint32_t R, AACache cache,
-                 const uint2* __restrict__ ranges, float* __restrict__ final_T,
+                 const uint8_t* __restrict__ imask, uint4* __restrict__ meta, uint32_t R, ShadeCache cache,
+                 BinGuard guard, const uint2* __restrict__ ranges, float* __restrict__ final_T,
                  float* __restrict__ final_prev_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                  float* __restrict__ out_depth, int gx, int gy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (bin_invalid(guard)) return;          // speculative launch on a workspace that turned out too small
     const TileCtx tc = tile_ctx(in, gx, gy);
     const int warp = tc.warp, lane = tc.lane;
     FwdWarpSmem& ws = reinterpret_cast<FwdWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const float tau = in.aa_temperature;
     const bool use_aa = tau > 0.0f;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     PixelGeom pg;
     pg.pxmin = (float)((uint32_t)tc.px + (uint32_t)in.patch_min[2 * tc.b]);      // forward.cu:319-322
@@ -70,10 +73,12 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
 
         if (use_aa) store_partial_masks(ws.srec, ncs, lane);
         if (CACHE && use_aa) {
-            // reserve cache entries for every partially covered pixel of the staged candidates
-            uint32_t pm = 0u;
-            if (lane < ncs) pm = __float_as_uint(ws.srec[lane * kRecStride + R_PMASK]);
-            const uint32_t cnt = __popc(pm);
+            // reserve one cache block per staged candidate: a hit record for every touched pixel of the
+            // footprint + the area gradient of every partially covered one
+            uint32_t cnt = 0u;
+            if (lane < ncs)
+                cnt = cache_block_granules(__popc(__float_as_uint(ws.srec[lane * kRecStride + R_META])),
+                                           __popc(__float_as_uint(ws.srec[lane * kRecStride + R_PMASK])));
             uint32_t incl = cnt;
 #pragma unroll
             for (int o = 1; o < kFSub; o <<= 1) {
@@ -82,7 +87,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
             }
             const uint32_t tot = __shfl_sync(0xffffffffu, incl, ncs - 1);
             // (a warp that once found the pool full stops bumping it: every warp overshoots by at most one
-            // sub-chunk, so the 32-bit counter cannot wrap - the host keeps the capacity below 2^32 - 2^28)
+            // sub-chunk, so the 32-bit counter cannot wrap - the capacity stays below 2^32 - 2^28 granules)
             uint32_t base = cache.capacity;
             if (lane == 0 && tot > 0u && !pool_full) base = atomicAdd(cache.counter, tot);
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -132,9 +137,9 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                     if (CACHE) {
                         const uint32_t poff = __float_as_uint(rec[R_META + 3]);
                         if (poff != kNoCache) {
-                            const uint32_t j = poff + __popc(__float_as_uint(rec[R_PMASK]) & ((1u << l) - 1u));
-                            cache.area[j] = ok ? area : -1.0f;
-                            float2* gj = reinterpret_cast<float2*>(cache.grad + (size_t)j * 6);
+                            const uint32_t n_t = __popc(__float_as_uint(rec[R_META]));
+                            const uint32_t j = __popc(__float_as_uint(rec[R_PMASK]) & ((1u << l) - 1u));
+                            float2* gj = reinterpret_cast<float2*>(cache.data + (size_t)poff + n_t) + 3 * j;
                             gj[0] = make_float2(g[0], g[1]); gj[1] = make_float2(g[2], g[3]); gj[2] = make_float2(g[4], g[5]);
                         }
                     }
@@ -148,11 +153,16 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                 const float* rec = ws.srec + k * kRecStride;
                 Shade s;
                 s.area = use_aa ? 1.0f : 0.0f;
-                if ((part >> k) & 1u) {
-                    s.area = ws.parea[k * 32 + lane];
-                    if (s.area == -1.0f) continue;
+                if ((part >> k) & 1u) s.area = ws.parea[k * 32 + lane];
+                const bool ok = (s.area != -1.0f) && shade_tail(rec, pg, tau, s);
+                if (CACHE) {
+                    // the backward pass reads this instead of re-running the hit point and the clamp
+                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                    if (poff != kNoCache)
+                        cache.data[(size_t)poff + __popc(__float_as_uint(rec[R_META]) & lt_mask)] =
+                            ok ? make_float4(s.w1, s.w2, s.ratio, __int_as_float(s.code)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (!shade_tail(rec, pg, tau, s)) continue;
+                if (!ok) continue;
                 // forward.cu:398-415
                 const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
                 C0 = __fmaf_rn(__fmul_rn(s.iC[0], alpha), T, C0);   // C += iC*alpha*T
@@ -186,7 +196,8 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
 constexpr size_t kFwdSmem = sizeof(FwdWarpSmem) * (kRasterThreads / 32);
 
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                          float* out_color, float* out_depth, void* aa_cache, long long aa_cache_pairs, cudaStream_t s) {
+                          float* out_color, float* out_depth, void* shade_cache, long long shade_cache_bytes,
+                          cudaStream_t s) {
     const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
     const long long nblk = (long long)in.B * gx * gy;
     if (nblk == 0) return 0;
@@ -194,18 +205,20 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
     if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_raster_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
         DM2_CHECK(cudaFuncSetAttribute(k_raster_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        attr_set.done();
     }
-    const AACache cache = aa_cache_view(aa_cache, aa_cache_pairs);
+    const ShadeCache cache = shade_cache_view(shade_cache, shade_cache_bytes);
+    const BinGuard guard{iw.tile_cursor + nblk, (uint32_t)bw.R};
     const bool use_cache = cache.capacity > 0 && in.aa_temperature > 0.0f && bw.R > 0;
     if (use_cache) DM2_CHECK(cudaMemsetAsync(cache.counter, 0, sizeof(uint32_t), s));
     ProfScope _ps("raster_forward", s);
     if (use_cache)
         k_raster_forward<true><<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kFwdSmem, s>>>(
-            in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, iw.ranges,
+            in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, guard, iw.ranges,
             iw.final_T, iw.final_prev_T, iw.n_contrib, out_color, out_depth, gx, gy);
     else
         k_raster_forward<false><<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kFwdSmem, s>>>(
-            in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, iw.ranges,
+            in, fw.records, bw.vals, bw.imask, reinterpret_cast<uint4*>(bw.meta), (uint32_t)bw.R, cache, guard, iw.ranges,
             iw.final_T, iw.final_prev_T, iw.n_contrib, out_color, out_depth, gx, gy);
     DM2_LAUNCH_CHECK();
     return 0;

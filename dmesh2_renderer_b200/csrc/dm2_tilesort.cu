@@ -160,8 +160,10 @@ template <bool SMEM>
 __global__ void __launch_bounds__(kBinThreads)
 k_scatter_instances(int F, int fpt, int gx, int gy, const float* __restrict__ key_depths,
                     const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
-                    uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                    uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                    BinGuard guard) {
     extern __shared__ uint32_t s_cnt[];
+    if (bin_invalid(guard)) return;
     const int view = blockIdx.y, tiles = gx * gy, lane = threadIdx.x & 31;
     const uint32_t tbase = (uint32_t)view * (uint32_t)tiles;
     uint32_t* gcur = cursor + (size_t)tbase;
@@ -319,8 +321,9 @@ __device__ __forceinline__ void sort_segment_smem(const uint64_t* __restrict__ k
 template <int TIER>
 __global__ void __launch_bounds__(TIER == 0 ? 256 : 1024)
 k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, BinGuard guard) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
+    if (bin_invalid(guard)) return;
     constexpr int THREADS = TIER == 0 ? 256 : 1024;
     constexpr uint32_t LO = TIER == 0 ? 0u : (TIER == 1 ? kSortCap0 : kSortCap1);
     constexpr uint32_t HI = TIER == 0 ? kSortCap0 : (TIER == 1 ? kSortCap1 : 0xFFFFFFFFu);
@@ -370,6 +373,7 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
             DM2_CHECK(cudaFuncSetAttribute(k_count_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTiles * 4));
             DM2_CHECK(cudaFuncSetAttribute(k_scatter_instances<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kMaxSmemTiles * 4));
+            cattr.done();
         }
         ProfScope _ps("tile_count", s);
         const int tiles = gx * gy;
@@ -393,8 +397,9 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
 int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
                      const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
                      uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
-                     long long longest, cudaStream_t s) {
+                     long long capacity, long long longest, cudaStream_t s) {
     if (BF == 0 || num_tiles == 0) return 0;
+    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity};
     if (longest < 0) longest = 1ll << 40;            // unknown: launch every tier
     {
         ProfScope _ps("scatter_instances", s);
@@ -403,28 +408,41 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
         const dim3 grid(cdiv(F, kBinThreads * fpt), (unsigned)(BF / F));
         if (tiles <= kMaxSmemTiles)
             k_scatter_instances<true><<<grid, kBinThreads, (size_t)tiles * 4, s>>>(
-                F, fpt, gx, gy, key_depths, tiles_touched, rects, cursor, keys_unsorted, vals_unsorted);
+                F, fpt, gx, gy, key_depths, tiles_touched, rects, cursor, keys_unsorted, vals_unsorted, guard);
         else
             k_scatter_instances<false><<<grid, kBinThreads, 0, s>>>(F, fpt, gx, gy, key_depths, tiles_touched, rects,
-                                                                  cursor, keys_unsorted, vals_unsorted);
+                                                                  cursor, keys_unsorted, vals_unsorted, guard);
         DM2_LAUNCH_CHECK();
     }
+    const int tiers = 1 | (longest > kSortCap0 ? 2 : 0) | (longest > kSortCap1 ? 4 : 0);
+    return launch_tile_sort_tiers(num_tiles, ranges, cursor, keys_unsorted, vals_unsorted, keys, vals, capacity, tiers, s);
+}
+
+// the per-segment sort alone; tiers: bit t = run tier t (segments of <= 2048 / <= 8192 / more instances)
+int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
+                           const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
+                           cudaStream_t s) {
+    if (num_tiles == 0 || tiers == 0) return 0;
+    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity};
     static PerDeviceOnce attr_set;
     if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap1 * sizeof(uint64_t))));
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap2 * sizeof(uint64_t))));
+        attr_set.done();
     }
     ProfScope _ps("tile_sort", s);
-    k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
-    DM2_LAUNCH_CHECK();
-    if (longest > kSortCap0) {
-        k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
+    if (tiers & 1) {
+        k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard);
         DM2_LAUNCH_CHECK();
     }
-    if (longest > kSortCap1) {
-        k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals);
+    if (tiers & 2) {
+        k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard);
+        DM2_LAUNCH_CHECK();
+    }
+    if (tiers & 4) {
+        k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard);
         DM2_LAUNCH_CHECK();
     }
     return 0;

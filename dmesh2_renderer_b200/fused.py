@@ -15,8 +15,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._C import (_err, _prep, _ptr, _stream, aa_cache_alloc, aa_cache_capacity, binning_layout, face_layout,
-                 image_layout)
+from ._C import (_err, _prep, _ptr, _stream, binning_layout, face_layout, image_layout, shade_cache_alloc)
 from ._lib import DM2FusedGrads, DM2FusedInputs
 
 
@@ -64,23 +63,61 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
     return s, keep
 
 
+class _FrameHint:
+    """What the last forward call of one problem shape needed: num_rendered, the longest tile segment and the
+    shading-cache demand (read back asynchronously into pinned memory; consumed once its event has completed)."""
+
+    def __init__(self):
+        self.num_rendered = 0
+        self.longest = -1
+        self.cache_granules = 0
+        self._pinned = None
+        self._event = None
+
+    def note_cache_counter(self, pool, stream):
+        if pool.numel() < 4:
+            return
+        if self._pinned is None:
+            self._pinned = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self._pinned.copy_(pool[:4].view(torch.int32), non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(stream)
+
+    def poll(self):
+        if self._event is not None and self._event.query():
+            self.cache_granules = int(self._pinned[0]) & 0xFFFFFFFF
+            self._event = None
+
+
+class GradSink:
+    """Optional destination of the replicated-parameter gradients: when a sink is passed to
+    FusedRenderFunction, its backward ADDS dL/dverts, dL/dverts_color and dL/dfaces_opacity into these
+    (caller-zeroed, fp32, contiguous) tensors with the kernels' own atomics and returns None for the three
+    inputs - e.g. the views of a multiview.GradBucket, so that a multi-view step needs no gradient copies."""
+
+    def __init__(self, dverts, dverts_color, dfaces_opacity):
+        self.dverts, self.dverts_color, self.dfaces_opacity = dverts, dverts_color, dfaces_opacity
+
+
 class FusedRenderFunction(torch.autograd.Function):
     """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, mv [B,4,4], proj [B,4,4],
-    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer, depth_unit) -> (color [B,H,W,3],
-    depth [B,H,W]).  Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense.
-    len_oarea_buffer > 0 turns the forward -> backward AA cache on (see _C.py).  depth_unit = False: depth is
+    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer, depth_unit, grad_sink) -> (color
+    [B,H,W,3], depth [B,H,W]).  Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense.
+    len_oarea_buffer > 0 turns the forward -> backward shading cache on (see _C.py).  depth_unit = False: depth is
     the NDC depth render_forward_cuda returns; True: the kernels apply Renderer.forward's remap
-    1 - (depth_ndc + 1) / 2 (reference __init__.py:377-378) themselves, bit-identically, forward and backward."""
+    1 - (depth_ndc + 1) / 2 (reference __init__.py:377-378) themselves, bit-identically, forward and backward.
+    grad_sink: see GradSink."""
 
-    # num_rendered of the last call per problem shape: the binning workspace and the AA cache are allocated
-    # from it BEFORE the preprocess call, so that nothing but the comparison sits between the num_rendered
-    # read-back (the one host wait of the pipeline) and the launch of the remaining kernels
+    # Per problem shape: what the last call needed.  The binning workspace and the shading cache are allocated
+    # from it BEFORE anything is launched and the whole forward pass is enqueued in one library call
+    # (dm2_fused_forward_pipelined): the kernels check on the device that the frame fits; the host only waits
+    # for the 12-byte header after everything is in the queue and re-runs the tail in the rare case it does not.
     _size_hint = {}
 
     @staticmethod
     def forward(ctx, background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
                 mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer=20,
-                depth_unit=False):
+                depth_unit=False, grad_sink=None):
         lib = _lib.load_library()
         s, keep = _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
                                 faces_opacity, mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view,
@@ -95,30 +132,45 @@ class FusedRenderFunction(torch.autograd.Function):
             image_buffer = torch.empty((image_layout(B, H, W).total,), dtype=torch.uint8, device=dev)
             want_cache = any(ctx.needs_input_grad)
             hint_key = (B, s.P, s.F, H, W, dev.index)
-            hint = FusedRenderFunction._size_hint.get(hint_key, 0)
-            binning_buffer = pool = None
-            if hint > 0:
-                R_cap = hint + hint // 16 + 1024
-                binning_buffer = torch.empty((binning_layout(R_cap).total,), dtype=torch.uint8, device=dev)
-                pool, cap = aa_cache_alloc(int(len_oarea_buffer), R_cap, float(aa_temperature), dev, want_cache)
-            nr = C.c_int64(0)
-            _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer), C.byref(nr), stream))
+            hint = FusedRenderFunction._size_hint.setdefault(hint_key, _FrameHint())
+            hint.poll()
+            nr, longest, fits = C.c_int64(0), C.c_int64(-1), C.c_int32(0)
+            cap = 0
+            if hint.num_rendered > 0:
+                cap = hint.num_rendered + hint.num_rendered // 16 + 1024
+                binning_buffer = torch.empty((binning_layout(cap).total,), dtype=torch.uint8, device=dev)
+                pool = shade_cache_alloc(int(len_oarea_buffer), cap, float(aa_temperature), dev, want_cache,
+                                         hint.cache_granules)
+                lhint = -1 if hint.longest < 0 else hint.longest + hint.longest // 4
+                _lib.check(lib.dm2_fused_forward_pipelined(
+                    C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer), cap, lhint, _ptr(color),
+                    _ptr(depth), _ptr(pool), int(pool.numel()), C.byref(nr), C.byref(longest), C.byref(fits), stream))
+            else:
+                _lib.check(lib.dm2_fused_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer), C.byref(nr),
+                                                    C.byref(longest), stream))
             R = int(nr.value)
-            if hint <= 0 or R > R_cap:
-                # (the layout of R instances is a prefix-compatible carving of any larger workspace)
-                binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
-                pool, cap = aa_cache_alloc(int(len_oarea_buffer), R, float(aa_temperature), dev, want_cache)
-            _lib.check(lib.dm2_fused_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
-                                             R, _ptr(color), _ptr(depth), _ptr(pool), cap, stream))
-            FusedRenderFunction._size_hint[hint_key] = R
+            if not fits.value:
+                # first call of this shape, or the frame outgrew the previous one by more than the slack
+                # (the layout of R instances is what the kernels index with: it travels to the backward call)
+                cap = R
+                binning_buffer = torch.empty((binning_layout(cap).total,), dtype=torch.uint8, device=dev)
+                pool = shade_cache_alloc(int(len_oarea_buffer), cap, float(aa_temperature), dev, want_cache,
+                                         hint.cache_granules)
+                _lib.check(lib.dm2_fused_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
+                                                 cap, int(longest.value), _ptr(color), _ptr(depth), _ptr(pool),
+                                                 int(pool.numel()), stream))
+            hint.num_rendered, hint.longest = R, int(longest.value)
+            hint.note_cache_counter(pool, torch.cuda.current_stream(dev))
             if depth_unit and s.P == 0:
                 depth.fill_(0.5)          # the library's P == 0 shortcut writes depth_ndc = 0
         ctx.save_for_backward(*keep.values(), face_buffer, binning_buffer, image_buffer, pool)
         ctx.keys = list(keep.keys())
         ctx.num_rendered = R
+        ctx.capacity = cap
         ctx.patch = (patch_width, patch_height)
         ctx.aa_temperature = aa_temperature
         ctx.depth_unit = bool(depth_unit)
+        ctx.grad_sink = grad_sink
         return color, depth
 
     @staticmethod
@@ -134,10 +186,18 @@ class FusedRenderFunction(torch.autograd.Function):
         dev = keep["verts"].device
         gc = _prep(grad_color, torch.float32, "dL_dout_color")
         gd = _prep(grad_depth, torch.float32, "dL_dout_depth")
+        sink = ctx.grad_sink
         with torch.cuda.device(dev):
-            g_verts = torch.zeros_like(keep["verts"])
-            g_color = torch.zeros_like(keep["verts_color"])
-            g_opacity = torch.zeros_like(keep["faces_opacity"])
+            if sink is not None:
+                g_verts, g_color, g_opacity = sink.dverts, sink.dverts_color, sink.dfaces_opacity
+                for t, ref in ((g_verts, keep["verts"]), (g_color, keep["verts_color"]), (g_opacity, keep["faces_opacity"])):
+                    if not (t.is_cuda and t.device == dev and t.dtype == torch.float32 and t.is_contiguous()
+                            and t.numel() == ref.numel()):
+                        _err("grad_sink tensors must be contiguous fp32 CUDA tensors of the parameters' sizes")
+            else:
+                g_verts = torch.zeros_like(keep["verts"])
+                g_color = torch.zeros_like(keep["verts_color"])
+                g_opacity = torch.zeros_like(keep["faces_opacity"])
             g_intense = torch.zeros_like(keep["faces_intense"])
             if s.F != 0:
                 g = DM2FusedGrads(g_verts.data_ptr(), g_color.data_ptr(), g_opacity.data_ptr(), g_intense.data_ptr())
@@ -145,8 +205,10 @@ class FusedRenderFunction(torch.autograd.Function):
                 _lib.check(lib.dm2_backward_workspace_bytes(s.B, s.F, C.byref(nb)))
                 grad_ws = torch.empty((nb.value,), dtype=torch.uint8, device=dev)
                 _lib.check(lib.dm2_fused_backward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
-                                                  _ptr(image_buffer), ctx.num_rendered, _ptr(gc), _ptr(gd),
-                                                  C.byref(g), _ptr(grad_ws), _ptr(pool), aa_cache_capacity(pool),
+                                                  _ptr(image_buffer), ctx.capacity, _ptr(gc), _ptr(gd),
+                                                  C.byref(g), _ptr(grad_ws), _ptr(pool), int(pool.numel()),
                                                   _stream(dev)))
+        if sink is not None:
+            g_verts = g_color = g_opacity = None
         return (None, None, None, None, g_verts, None, g_color, g_opacity, None, None, g_intense, None, None, None,
-                None, None, None)
+                None, None, None, None)

@@ -55,8 +55,11 @@ class Renderer(torch.nn.Module):
     def __init__(self, mv, proj, width, height, device, aa_grad_buffer_size=20):
         super().__init__()
         self._setup(mv, proj, width, height, device)
-        # > 0: keep the forward pass's AA overlap areas + gradients for the backward pass (compact pool,
-        # _C.aa_cache_alloc); 0: recompute them in the backward pass
+        # > 0: the forward pass hands its per-contribution shading state (clamped barycentrics, coverage,
+        # d(area)/d(aa verts)) to the backward pass through a compact pool (_C.shade_cache_alloc - the role of
+        # the reference's K-deep per-pixel AA buffers); 0: the backward pass recomputes it
+        # self.grad_sink (optional, fused.GradSink): gradients of verts / verts_color / faces_opacity are added
+        # into the sink's tensors instead of being returned to autograd (multi-view steps: no gradient copies)
         self.aa_grad_buffer_size = aa_grad_buffer_size
 
     def _setup(self, mv, proj, width, height, device):
@@ -167,7 +170,7 @@ class Renderer(torch.nn.Module):
             verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
             self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
             faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view, self.aa_grad_buffer_size,
-            True)
+            True, getattr(self, "grad_sink", None))
 
     def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
                        faces_opacity, faces_intense, background, aa_temperature=1.0):

@@ -16,9 +16,11 @@
  *   - every pointer is a DEVICE pointer to a densely packed (contiguous) array unless the
  *     name ends in `_host`;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing in the
- *     library calls cudaDeviceSynchronize — the only host wait is the one in
- *     dm2_*_preprocess, which waits on `stream` for the 12-byte read-back (num_rendered, patch-bound
- *     flags, longest tile segment) - the reference performs the num_rendered one too (reference cuda_impl/renderer.cu:174-179);
+ *     library calls cudaDeviceSynchronize.  dm2_*_preprocess waits on an event behind the 12-byte
+ *     read-back of (num_rendered, input flags, longest tile segment) - the reference performs the
+ *     num_rendered one too, with a blocking copy (reference cuda_impl/renderer.cu:174-179);
+ *     dm2_fused_forward_pipelined enqueues the WHOLE forward pass before it waits for that event,
+ *     so the GPU never idles on the host;
  *   - workspaces are caller-allocated byte buffers (torch caching allocator on the host
  *     side); their sizes come from the dm2_*_bytes functions and their internal layout from
  *     DM2FaceLayout / DM2ImageLayout / DM2BinningLayout (used by the parity tests as the
@@ -40,7 +42,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 12
+#define DM2_ABI_VERSION 13
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -144,7 +146,7 @@ typedef struct DM2BinningLayout {     /* reference BinningState, state.h:41-51 *
     size_t vals_unsorted;        /* u32[R]  face id within the view, same order                 */
     size_t keys;                 /* u64[R]  sorted                                              */
     size_t vals;                 /* u32[R]  sorted  (= reference face_list)                     */
-    size_t sort_temp;            /* unused by the pipeline (scratch of dm2_sort_pairs)          */
+    size_t sort_temp;            /* zero-sized (the tile-segmented sort needs no scratch; kept for layout stability) */
     size_t imask;                /* u8[R]   render path: bit w = the face touches a pixel of the
                                   *         8x4-pixel footprint w of its tile (x = (w&1)*8, y = (w>>1)*4) */
     size_t meta;                 /* uint4[8][R] render path: per (footprint, instance) touched-pixel mask
@@ -163,40 +165,47 @@ int dm2_binning_layout(int64_t num_rendered, DM2BinningLayout* out);
 /* ---- Renderer: replaces render_forward_cuda / render_backward_cuda ---------------------- */
 /* Stage 1 (reference renderer.cu:150-179): per-face depth / tile bbox / tiles_touched, the
  * packed face records, the per-tile instance counts and their scan (= the tile ranges), and
- * the num_rendered read-back (waits on stream).                                              */
+ * the read-back of num_rendered and of the longest tile segment (waits on an event recorded on
+ * `stream`; longest_host may be NULL).  Fails (message in dm2_last_error) when a face references a
+ * vertex id outside [0, P) - the reference's torch indexing raises for that, raw pointers cannot. */
 int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_ws,
-                          int64_t* num_rendered_host, void* stream);
+                          int64_t* num_rendered_host, int64_t* longest_host, void* stream);
 /* Stage 2 (reference renderer.cu:181-266): key emission straight into the tile segments, per-
  * segment sort by (depth bits, face id) - together the reference's stable radix sort on the low
  * 32+bit key bits -, the per-instance pixel classification, then the forward tile compositor.
- * out_color (B,H,W,3) and out_depth (B,H,W) are fully overwritten.                           */
+ * out_color (B,H,W,3) and out_depth (B,H,W) are fully overwritten.
+ * capacity: the instance count binning_ws was laid out for by dm2_binning_layout (>= num_rendered; the
+ * actual count is read on the device); longest: what stage 1 returned, or -1 (= run every sort tier). */
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                       int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
-                       int64_t aa_cache_pairs, void* stream);
-/* Optional AA cache (the role of the reference's four oarea buffers, render.cu:143-146, as a compact
- * pool): when aa_cache != NULL the forward pass also evaluates d(area)/d(aa verts) and stores area +
- * gradient of every partially covered (pixel, face) pair it clips (28 bytes per pair, up to
- * aa_cache_pairs pairs; pairs beyond the capacity are simply not cached); the backward pass reads
- * them back instead of clipping again and falls back to recomputation for anything not cached.
- * The same buffer and capacity must be passed to the matching backward call.  Contents are private. */
-int dm2_aa_cache_bytes(int64_t capacity_pairs, size_t* bytes);
+                       int64_t capacity, int64_t longest, float* out_color, float* out_depth,
+                       void* shade_cache, int64_t shade_cache_bytes, void* stream);
+/* Optional shading cache (the role of the reference's four oarea buffers, render.cu:143-146 - a zero-
+ * filled B*H*W*K*32-byte array there - as a compact pool): when shade_cache != NULL (shade_cache_bytes
+ * >= 512, a multiple of 16) the forward pass leaves, for every (instance, 8x4-pixel footprint) it stages,
+ * one 16-byte record (clamped barycentrics, coverage ratio, clamp code) per touched pixel and
+ * d(area)/d(aa verts) (24 bytes) per partially covered pixel; the backward pass reads them back instead of
+ * re-running the hit point, the clamp and the polygon clip, and falls back to recomputation for blocks
+ * that did not fit.  The first 4 bytes hold the number of 16-byte granules the forward pass asked for
+ * (may exceed the capacity: size the next call's pool from it).  The same buffer and size must be passed
+ * to the matching backward call.  No initialisation needed; other contents are private.               */
 /* reference renderer.cu:271-392 / backward.cu:17-532.  grad_ws: scratch of
- * dm2_backward_workspace_bytes(B, F) bytes (per-(view,face) gradient records; zeroed inside).  */
+ * dm2_backward_workspace_bytes(B, F) bytes (per-(view,face) gradient records; zeroed inside).
+ * capacity: as passed to the forward call.                                                     */
 int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes);
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
-                        const void* image_ws, int64_t num_rendered,
+                        const void* image_ws, int64_t capacity,
                         const float* dL_dout_color, const float* dL_dout_depth,
-                        const DM2RenderGrads* grads, void* grad_ws, const void* aa_cache,
-                        int64_t aa_cache_pairs, void* stream);
+                        const DM2RenderGrads* grads, void* grad_ws, const void* shade_cache,
+                        int64_t shade_cache_bytes, void* stream);
 
 /* ---- LayeredRenderer: replaces generate_render_layers_cuda ------------------------------- */
 int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws,
-                          int64_t* num_rendered_host, void* stream);
+                          int64_t* num_rendered_host, int64_t* longest_host, void* stream);
 /* render_layers (B,H,W,L) must be pre-filled with -1 and render_layers_cnt (B,H,W) with 0 by
  * the caller (reference render.cu:437-438); geo_ws needs dm2_layers_geo_bytes(F,T) bytes.    */
 int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes);
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
-                               void* image_ws, void* geo_ws, int64_t num_rendered,
+                               void* image_ws, void* geo_ws, int64_t num_rendered, int64_t longest,
                                int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
 
 /* Incremental re-generation: when ONLY face_existence changed since a
@@ -248,14 +257,27 @@ typedef struct DM2FusedGrads {   /* caller-zeroed */
 } DM2FusedGrads;
 
 int dm2_fused_preprocess(const DM2FusedInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
-                         void* stream);
+                         int64_t* longest_host, void* stream);
 int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
-                      int64_t num_rendered, float* out_color, float* out_depth, void* aa_cache,
-                      int64_t aa_cache_pairs, void* stream);
+                      int64_t capacity, int64_t longest, float* out_color, float* out_depth, void* shade_cache,
+                      int64_t shade_cache_bytes, void* stream);
+/* dm2_fused_preprocess + dm2_fused_forward in ONE call without a host wait between them (the reference
+ * blocks on a device->host copy of num_rendered before it can size the binning scratch, reference
+ * cuda_impl/renderer.cu:174-183).  The caller sizes binning_ws for `capacity` instances from the previous
+ * frame of the same problem (and passes that frame's longest tile segment, or -1, as longest_hint); all
+ * kernels are enqueued at once - those behind the tile scan compare num_rendered with `capacity` ON THE
+ * DEVICE and return immediately if the frame does not fit - and only then the call waits for the 12-byte
+ * header.  *fits_host = 1: the outputs are valid.  *fits_host = 0: *num_rendered_host > capacity; the caller
+ * allocates a workspace for *num_rendered_host instances and calls dm2_fused_forward (the preprocess results
+ * in face_ws / image_ws stay valid).  A longest segment beyond the hinted sort tier is repaired inside.    */
+int dm2_fused_forward_pipelined(const DM2FusedInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                                int64_t capacity, int64_t longest_hint, float* out_color, float* out_depth,
+                                void* shade_cache, int64_t shade_cache_bytes, int64_t* num_rendered_host,
+                                int64_t* longest_host, int32_t* fits_host, void* stream);
 int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void* binning_ws,
-                       const void* image_ws, int64_t num_rendered, const float* dL_dout_color,
+                       const void* image_ws, int64_t capacity, const float* dL_dout_color,
                        const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws,
-                       const void* aa_cache, int64_t aa_cache_pairs, void* stream);
+                       const void* shade_cache, int64_t shade_cache_bytes, void* stream);
 
 /* ---- multi-view optimisation step: the gradient exchange ----------------
  * The reference is single-GPU; DMesh++'s multi-view step shards views over the GPUs of one box and

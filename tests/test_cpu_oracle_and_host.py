@@ -43,25 +43,25 @@ def test_workspace_layouts_are_aligned_and_disjoint(built):
     assert I.final_T >= I.ranges + 2 * 4 * 5 * 8 and I.total > I.n_contrib
 
 
-def test_aa_cache_sizing_roundtrip(built, monkeypatch):
-    """Host-side AA-cache policy: off for K = 0 / tau = 0 / no instances / no grad; capacity recovered from the
-    pool size (the backward call gets only the pool tensor back from autograd)."""
+def test_shade_cache_sizing_policy(built, monkeypatch):
+    """Host-side shading-cache policy: off for K = 0 / tau = 0 / no instances / no grad; a first call reserves a
+    fixed number of bytes per instance, later calls what the previous forward pass asked for plus slack; the
+    pool is a 256-byte header + a whole number of 16-byte granules, capped."""
     import torch
     from dmesh2_renderer_b200 import _C
     cpu = torch.device("cpu")
     for args in ((0, 1000, 1.0), (20, 1000, 0.0), (20, 0, 1.0)):
-        pool, cap = _C.aa_cache_alloc(*args, cpu)
-        assert cap == 0 and pool.numel() == 0 and _C.aa_cache_capacity(pool) == 0
-    pool, cap = _C.aa_cache_alloc(20, 1000, 1.0, cpu, want=False)
-    assert cap == 0
+        assert _C.shade_cache_alloc(*args, cpu).numel() == 0
+    assert _C.shade_cache_alloc(20, 1000, 1.0, cpu, want=False).numel() == 0
     for R in (1, 7, 1000, 12345):
-        pool, cap = _C.aa_cache_alloc(20, R, 0.5, cpu)
-        assert cap == R * _C.AA_CACHE_PAIRS_PER_INSTANCE
-        assert _C.aa_cache_capacity(pool) >= cap and _C.aa_cache_capacity(pool) - cap < 64
-        assert pool.numel() * 4 >= 256 + 28 * cap
-    monkeypatch.setattr(_C, "AA_CACHE_MAX_BYTES", 28 * 500)
-    _pool, cap = _C.aa_cache_alloc(20, 1000, 1.0, cpu)
-    assert cap == 500
+        pool = _C.shade_cache_alloc(20, R, 0.5, cpu)
+        assert pool.dtype == torch.uint8 and (pool.numel() - _C.SHADE_CACHE_HEADER) % 16 == 0
+        assert pool.numel() >= _C.SHADE_CACHE_HEADER + R * _C.SHADE_CACHE_FIRST_BYTES_PER_INSTANCE
+    used = 54321
+    pool = _C.shade_cache_alloc(20, 1000, 1.0, cpu, used_granules=used)
+    assert used * 16 * _C.SHADE_CACHE_SLACK <= pool.numel() - _C.SHADE_CACHE_HEADER <= used * 16 * 1.2 + 8192
+    monkeypatch.setattr(_C, "SHADE_CACHE_MAX_BYTES", 16 * 500)
+    assert _C.shade_cache_alloc(20, 1000, 1.0, cpu).numel() == _C.SHADE_CACHE_HEADER + 16 * 500
 
 
 def test_higher_msb_matches_reference_formula(built):

@@ -130,9 +130,9 @@ def test_render_matches_reference_cache_semantics(built):
 
 
 @pytest.mark.parametrize("fused", [False, True])
-def test_aa_cache_on_off_overflow_agree(built, fused, monkeypatch):
-    """Backward with the forward->backward AA cache (K > 0), without it (K = 0: every overlap area is
-    recomputed) and with a pool far too small (most pairs fall back to recomputation) must agree: the
+def test_shade_cache_on_off_overflow_agree(built, fused, monkeypatch):
+    """Backward with the forward->backward shading cache (K > 0), without it (K = 0: hit point, clamp and clip
+    are recomputed) and with a pool far too small (most blocks fall back to recomputation) must agree: the
     cached values ARE the recomputed values, so only the atomic order differs."""
     import dmesh2_renderer_b200 as dm
     from dmesh2_renderer_b200 import _C, scenes
@@ -140,8 +140,10 @@ def test_aa_cache_on_off_overflow_agree(built, fused, monkeypatch):
     sc = scenes.small(n_faces=1500, size=96, sigma=0.08, seed=21)
     st = scene_tensors(sc, dev)
 
-    def run(K, pairs_per_instance):
-        monkeypatch.setattr(_C, "AA_CACHE_PAIRS_PER_INSTANCE", pairs_per_instance)
+    def run(K, bytes_per_instance):
+        from dmesh2_renderer_b200.fused import FusedRenderFunction
+        FusedRenderFunction._size_hint.clear()          # first-call sizing policy for every run
+        monkeypatch.setattr(_C, "SHADE_CACHE_FIRST_BYTES_PER_INSTANCE", bytes_per_instance)
         r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev, aa_grad_buffer_size=K)
         r.fused = fused
         leaves = {k: st[k].detach().clone().requires_grad_(True)
@@ -152,9 +154,9 @@ def test_aa_cache_on_off_overflow_agree(built, fused, monkeypatch):
         ((color * st["w_color"][:1]).sum() + (depth * st["w_depth"][:1]).sum()).backward()
         return color.detach(), {k: v.grad.detach().cpu().numpy() for k, v in leaves.items()}
 
-    c_on, g_on = run(20, 32)
-    c_off, g_off = run(0, 32)
-    c_ovf, g_ovf = run(20, 1)
+    c_on, g_on = run(20, 4096)
+    c_off, g_off = run(0, 4096)
+    c_ovf, g_ovf = run(20, 24)
     assert torch.equal(c_on, c_off) and torch.equal(c_on, c_ovf), "the cache must not change the forward result"
     for k in g_on:
         assert np.abs(g_on[k]).max() > 0
@@ -862,3 +864,173 @@ def test_double_backward_call_and_no_grad_forward(built):
         c2, d2 = r([0], pm, sc.width, sc.height, p["verts"], st["faces"], p["verts_color"], p["faces_opacity"], fi,
                    st["background"])
     assert torch.equal(color.detach(), c2) and torch.equal(depth.detach(), d2)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: pipelined forward (no host wait before the raster kernels), input flags, gradient sink, layer cache
+def _public_step(r, st, sc, dev, views=(0,), sink=None):
+    leaves = {k: st[k].detach().clone().requires_grad_(True) for k in ("verts", "verts_color", "faces_opacity")}
+    fi = st["faces_intense"][list(views)].detach().clone().requires_grad_(True)
+    pm = torch.zeros((len(views), 2), dtype=torch.int32, device=dev)
+    if sink is not None:
+        r.grad_sink = sink
+    color, depth = r(list(views), pm, sc.width, sc.height, leaves["verts"], st["faces"], leaves["verts_color"],
+                     leaves["faces_opacity"], fi, st["background"])
+    ((color * st["w_color"][list(views)]).sum() + (depth * st["w_depth"][list(views)]).sum()).backward()
+    return color.detach(), depth.detach(), leaves, fi
+
+
+def test_pipelined_forward_equals_first_call(built):
+    """Call 1 of a problem shape goes preprocess -> host wait -> forward; call 2 is enqueued in one piece on a
+    workspace sized from call 1 (dm2_fused_forward_pipelined).  Same image bit for bit, same gradients."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    from dmesh2_renderer_b200.fused import FusedRenderFunction
+    dev = _dev()
+    sc = scenes.small(n_faces=3000, size=128, sigma=0.06, seed=41)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    FusedRenderFunction._size_hint.clear()
+    c1, d1, l1, f1 = _public_step(r, st, sc, dev)
+    hint = next(iter(FusedRenderFunction._size_hint.values()))
+    assert hint.num_rendered > 0 and hint.longest > 0
+    torch.cuda.synchronize()
+    c2, d2, l2, f2 = _public_step(r, st, sc, dev)
+    hint.poll()
+    assert hint.cache_granules > 0, "the shading-cache demand of the previous call must have been read back"
+    c3, d3, l3, f3 = _public_step(r, st, sc, dev)                       # pool now sized from the measured demand
+    for c, d in ((c2, d2), (c3, d3)):
+        assert torch.equal(c1, c) and torch.equal(d1, d)
+    for k in l1:
+        for other in (l2, l3):
+            assert rel_err(other[k].grad.cpu().numpy(), l1[k].grad.cpu().numpy()) <= 1e-5, k
+    assert rel_err(f3.grad.cpu().numpy(), f1.grad.cpu().numpy()) <= 1e-5
+
+
+def test_pipelined_forward_repairs_a_longer_segment_than_hinted(built):
+    """The hinted longest tile segment selects the sort tiers that are enqueued speculatively; when the frame
+    has a longer segment the missing tiers run afterwards and classification + compositing are redone."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    from dmesh2_renderer_b200.fused import FusedRenderFunction
+    dev = _dev()
+    sc = scenes.triangle_soup("long_lists", 45_000, 32, 0.01, seed=31)            # segments of > 8192 instances
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    FusedRenderFunction._size_hint.clear()
+    c1, d1, l1, _ = _public_step(r, st, sc, dev)
+    hint = next(iter(FusedRenderFunction._size_hint.values()))
+    assert hint.longest > 8192
+    hint.longest = 100                                   # pretend the previous frame had short lists only
+    c2, d2, l2, _ = _public_step(r, st, sc, dev)
+    assert hint.longest > 8192
+    assert torch.equal(c1, c2) and torch.equal(d1, d2)
+    assert rel_err(l2["verts"].grad.cpu().numpy(), l1["verts"].grad.cpu().numpy()) <= 1e-5
+
+
+def test_input_flags_vertex_ids_and_negative_patch(built):
+    """Out-of-range vertex ids raise (torch indexing raises for them in the reference's host prep; raw pointers
+    would read out of bounds) - on the first (synchronous) call and on a pipelined one; a negative patch_min is
+    rejected by the fused route and handled by the reference-shaped route as the reference does (wrap-around)."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    from dmesh2_renderer_b200.fused import FusedRenderFunction
+    dev = _dev()
+    sc = scenes.small(n_faces=200, size=64)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    rest = (st["verts_color"], st["faces_opacity"], st["faces_intense"][:1], st["background"])
+    bad = st["faces"].clone()
+    bad[17, 1] = st["verts"].shape[0] + 5
+    FusedRenderFunction._size_hint.clear()
+    with pytest.raises(RuntimeError, match="vertex id"):
+        r([0], pm, 64, 64, st["verts"], bad, *rest)
+    r([0], pm, 64, 64, st["verts"], st["faces"], *rest)                 # establishes the hint -> pipelined next
+    with pytest.raises(RuntimeError, match="vertex id"):
+        r([0], pm, 64, 64, st["verts"], bad, *rest)
+    color, _ = r([0], pm, 64, 64, st["verts"], st["faces"], *rest)      # and the renderer still works afterwards
+    assert bool(torch.isfinite(color).all())
+    neg = torch.tensor([[-3, 0]], dtype=torch.int32, device=dev)
+    with pytest.raises(RuntimeError, match="negative patch_min"):
+        r([0], neg, 32, 32, st["verts"], st["faces"], *rest)
+    # the reference-shaped entry point checks too (its torch prep would already have raised in the reference)
+    _r, _st, args = render_args(sc, dev)
+    args[5] = bad
+    with pytest.raises(RuntimeError, match="vertex id"):
+        dm.RenderFunction.apply(*args)
+
+
+def test_grad_sink_accumulates_in_place(built):
+    """Gradients of the replicated parameters land directly in caller-provided tensors (the views of a gradient
+    bucket) and accumulate over calls; autograd gets None for them."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    from dmesh2_renderer_b200.fused import GradSink
+    from dmesh2_renderer_b200.multiview import GradBucket
+    dev = _dev()
+    sc = scenes.small(n_faces=900, size=96, sigma=0.1, seed=13, n_views=2)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    _, _, la, fa = _public_step(r, st, sc, dev, views=(0,))
+    _, _, lb, fb = _public_step(r, st, sc, dev, views=(1,))
+    bucket = GradBucket(st["verts"].shape[0], st["faces"].shape[0], dev)
+    sink = GradSink(bucket.dverts, bucket.dverts_color, bucket.dfaces_opacity)
+    r2 = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    _, _, l0, f0 = _public_step(r2, st, sc, dev, views=(0,), sink=sink)
+    _, _, l1, f1 = _public_step(r2, st, sc, dev, views=(1,), sink=sink)
+    assert all(l0[k].grad is None and l1[k].grad is None for k in l0)
+    assert rel_err(f0.grad.cpu().numpy(), fa.grad.cpu().numpy()) <= 1e-5
+    for name, view in (("verts", bucket.dverts), ("verts_color", bucket.dverts_color), ("faces_opacity", bucket.dfaces_opacity)):
+        want = (la[name].grad + lb[name].grad).cpu().numpy()
+        assert rel_err(view.cpu().numpy(), want) <= 1e-5, name
+
+
+def test_layer_cache_is_not_fooled_by_recycled_temporaries(built):
+    """geometry passed as a fresh temporary each call (same shape, freed after the call - the caching
+    allocator hands the next temporary the same address at version 0) must never hit the incremental cache."""
+    from dmesh2_renderer_b200 import LayeredRenderer, scenes
+    dev = _dev()
+    sc = scenes.small_tets(n_points=400, size=64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    rest = [t(getattr(sc, k)) for k in ("faces", "tets", "face_tets", "tet_faces", "face_existence")]
+    base = t(sc.verts)
+    outs = []
+    for scale in (1.0, 0.8, 1.0):
+        layers, cnt = lr.generate([0], base * scale, *rest, sc.num_layers)       # temporary, freed right after
+        outs.append((layers.clone(), cnt.clone()))
+    full = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    full.incremental = False
+    for scale, (layers, cnt) in zip((1.0, 0.8, 1.0), outs):
+        want = full.generate([0], (base * scale).clone(), *rest, sc.num_layers)
+        assert torch.equal(layers, want[0]) and torch.equal(cnt, want[1]), scale
+    assert not torch.equal(outs[0][0], outs[1][0])
+    # same objects, same versions: the walk-only path is taken and agrees
+    kept = base * 0.9
+    a = lr.generate([0], kept, *rest, sc.num_layers)
+    b = lr.generate([0], kept, *rest, sc.num_layers)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_camera_gradients_use_the_reference_shaped_route(built):
+    """ADVICE r1: cameras that require grad get their gradient (through the torch prep, as in the reference);
+    negative view ids are accepted like `self.mv[idx]` does."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=300, size=48, n_views=3)
+    st = scene_tensors(sc, dev)
+    mv = st["mv"].clone().requires_grad_(True)
+    r = dm.Renderer(mv, st["proj"], sc.width, sc.height, dev)
+    pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+    rest = (st["verts"], st["faces"], st["verts_color"], st["faces_opacity"])
+    color, depth = r([1], pm, 48, 48, *rest, st["faces_intense"][[1]], st["background"])
+    (color.sum() + depth.sum()).backward()
+    assert mv.grad is not None and float(mv.grad[1].abs().max()) > 0 and float(mv.grad[0].abs().max()) == 0
+    r2 = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    a = r2([-1], pm, 48, 48, *rest, st["faces_intense"][[2]], st["background"])
+    b = r2([2], pm, 48, 48, *rest, st["faces_intense"][[2]], st["background"])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    with pytest.raises(IndexError):
+        r2([3], pm, 48, 48, *rest, st["faces_intense"][[2]], st["background"])
