@@ -106,6 +106,8 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, _P(DM2FusedGrads), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p]),
     "dm2_peer_allreduce_sum": (C.c_int, [_P(C.c_void_p), C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "dm2_peer_allreduce_sum_fused": (C.c_int, [_P(C.c_void_p), C.c_void_p, _P(C.c_void_p), C.c_int32, C.c_int32,
+                                               C.c_int64, C.c_uint32, C.c_void_p]),
     "dm2_layers_preprocess": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, _P(C.c_int64), _P(C.c_int64),
                                         C.c_void_p]),
     "dm2_layers_geo_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),

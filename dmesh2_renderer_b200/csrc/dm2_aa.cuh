@@ -11,12 +11,24 @@
 //   * the clipped polygon is never materialised: vertices are streamed into a fan accumulator
 //     (first / previous / current vertex), so there are no local-memory arrays (the reference keeps
 //     polygon[10][2] + two [10][4] Jacobian arrays on the stack);
-//   * the gradient is NOT chained through per-vertex 2x2 Jacobians (aa.h:280-294, 416-433).  For a
+//   * the gradient is normally NOT chained through per-vertex 2x2 Jacobians (aa.h:280-294, 416-433).  For a
 //     triangle edge whose part inside the pixel is the parameter interval [ta, tb], moving the edge
 //     end points sweeps area  dA/dp_start = n (tb-ta - (tb^2-ta^2)/2),  dA/dp_end = n (tb^2-ta^2)/2
 //     with n = (e.y, -e.x) the outward edge normal scaled by the edge length.  This is the same
 //     derivative (it agrees with the reference's analytic gradient to 1e-6 on the reference's own
-//     Python implementation, tests/golden/aa_overlap_golden.npz) at ~15 flops per edge.
+//     Python implementation, tests/golden/aa_overlap_golden.npz) at ~15 flops per edge - WHENEVER the
+//     polygon the reference builds is the true clip polygon.  Two situations make the reference's chained
+//     gradient differ from the true derivative, and there the clip asks for aa_grad_reference(), an
+//     out-of-line transcription of the reference's polygon + Jacobian chain:
+//       (a) a triangle vertex exactly ON a pixel boundary line (a kink of the area: the reference
+//           differentiates "the intersection slides along the pixel edge", a one-sided derivative);
+//       (b) an INCONSISTENT polygon: the inside-corner flags (half-plane tests, aa.h:103-149) and the
+//           edge / pixel-edge intersections (aa.h:230-262) are rounded independently, so for an edge that
+//           passes within an ulp of a pixel corner the run of inside corners behind an exit point can
+//           disagree with the pixel edge on which the next edge enters - the reference then appends
+//           spurious corners (or misses one), its area is off by ~1e-5 and its gradient by O(1)
+//           (measured: 1 pair in ~16 M at 1 M triangles @1024^2; found by the full-size parity test
+//           against the fp64-accumulated oracle).  Detected from the exit / entry pixel-edge indices.
 // Error semantics: the reference returns codes 1..6 and the caller skips the face for that pixel
 // on any non-zero code (forward.cu:337-338, backward.cu:286-289); here `false` = "skip".
 #pragma once
@@ -57,14 +69,19 @@ struct FanAcc {
 // (0, 1] (or NaN, which the reference also lets through); g[6] = d area / d tri verts when GRAD.
 // Straight-line predicated code: errors are accumulated in a flag instead of returning early (every
 // reference error code has the same consequence - the face is skipped for this pixel).
+// GRAD: *chain_needed (may be nullptr) is set when g must be replaced by aa_grad_reference() - see above.
 template <bool GRAD>
 __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxmin, float pymin, unsigned inmask,
-                                        float& area_out, float* __restrict__ g) {
+                                        float& area_out, float* __restrict__ g, bool* chain_needed = nullptr) {
     const float pxmax = __fadd_rn(pxmin, 1.0f);
     const float pymax = __fadd_rn(pymin, 1.0f);
     FanAcc fan;
     const unsigned zflags = __float_as_uint(rec[R_MISC + 3]);
     float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // consistency of the polygon's boundary walk (GRAD only): every exit point + its run of inside corners must
+    // lead to the pixel edge on which the next triangle edge enters
+    bool pend = false, odd = false, kink = false;
+    int pend_pe = 0, first_entry = -1;
 
 #ifndef DM2_CLIP_UNROLL
 #define DM2_CLIP_UNROLL 1
@@ -120,13 +137,24 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
         // covered pixel has at most 3 inside corners
         bool run = two | leave;
         const int final_pedge = two ? (swap ? pa : pb) : pa;
+        int run_len = 0;
 #pragma unroll
         for (int pvi = 0; pvi < 3; pvi++) {
             const int cur = (final_pedge + 1 + pvi) & 3;
             run = run & (((inmask >> cur) & 1u) != 0u);
             fan.push(run, (cur == 1 || cur == 2) ? pxmax : pxmin, (cur >= 2) ? pymax : pymin);
+            if (GRAD) run_len += run ? 1 : 0;
         }
         if (GRAD) {
+            kink |= in0 & ((p0.x == pxmin) | (p0.x == pxmax) | (p0.y == pymin) | (p0.y == pymax));
+            const bool e_in = two | enter, e_out = two | leave;
+            const int entry_pe = two ? (swap ? pb : pa) : pa;
+            odd |= e_in & (pend ? (entry_pe != pend_pe) : (first_entry >= 0));
+            first_entry = (e_in & !pend) ? entry_pe : first_entry;
+            pend = pend & !e_in;
+            pend_pe = e_out ? ((final_pedge + run_len) & 3) : pend_pe;
+            pend |= e_out;
+
             // part of the edge inside the pixel: [t_in, t_out]
             const bool covered = !none || whole;
             const float t_in  = two ? (swap ? tb : ta) : (enter ? ta : 0.0f);
@@ -146,8 +174,104 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
     if (GRAD) {
 #pragma unroll
         for (int k = 0; k < 6; k++) g[k] = gr[k];
+        odd |= pend ? (first_entry != pend_pe) : (first_entry >= 0);
+        if (chain_needed) *chain_needed = ok & (odd | kink);
     }
     return ok;
+}
+
+// Out-of-line transcription of the reference's polygon construction and Jacobian-chain gradient
+// (aa.h:151-441) for the rare pairs aa_clip flags (kinks, inconsistent polygons): d(area)/d(tri verts) exactly
+// as the reference chains it - polygon array, per-vertex 2x2 Jacobians d ip/d p0 and d ip/d p1 (aa.h:280-294;
+// the `1.0 - t` terms are evaluated in double there), fan triangles from polygon[0] (aa.h:403-433).  Only
+// called for pairs whose clip succeeded (no error code), so the error exits are not repeated.
+__device__ __noinline__ void aa_grad_reference(const float* __restrict__ rec, float pxmin, float pymin, unsigned inmask,
+                                               float* __restrict__ g) {
+    const float pxmax = __fadd_rn(pxmin, 1.0f), pymax = __fadd_rn(pymin, 1.0f);
+    const unsigned zflags = __float_as_uint(rec[R_MISC + 3]);
+    float px[10], py[10], j0[10][4], j1[10][4];
+    int pe[10], n = 0;
+    auto add = [&](float x, float y, int e, const float* a, const float* b) {
+        if (n >= 10) return;
+        px[n] = x; py[n] = y; pe[n] = e;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { j0[n][k] = a ? a[k] : 0.0f; j1[n][k] = b ? b[k] : 0.0f; }
+        n++;
+    };
+    const float eye[4] = {1.f, 0.f, 0.f, 1.f};
+    for (int ti = 0; ti < 3; ti++) {
+        const int tj = (ti == 2) ? 0 : ti + 1;
+        const float p0[2] = {rec[R_AAV + 2 * ti], rec[R_AAV + 2 * ti + 1]};
+        const float p1[2] = {rec[R_AAV + 2 * tj], rec[R_AAV + 2 * tj + 1]};
+        const float e[2] = {rec[R_AAE + 2 * ti], rec[R_AAE + 2 * ti + 1]};
+        const float r[2] = {rec[R_AAR + 2 * ti], rec[R_AAR + 2 * ti + 1]};
+        const bool vertical = (zflags >> (2 * ti)) & 1u, horizontal = (zflags >> (2 * ti + 1)) & 1u;
+        const bool in0 = p0[0] >= pxmin && p0[0] <= pxmax && p0[1] >= pymin && p0[1] <= pymax;
+        const bool in1 = p1[0] >= pxmin && p1[0] <= pxmax && p1[1] >= pymin && p1[1] <= pymax;
+        float ipx[2], ipy[2], it[2], g0[2][4], g1[2][4];
+        int ipe[2], ni = 0;
+        for (int pi = 0; pi < 4 && ni < 2; pi++) {
+            const bool ph = (pi == 0) || (pi == 2);
+            if ((horizontal && ph) || (vertical && !ph)) continue;
+            const int a0 = ph ? 1 : 0, a1 = 1 - a0;
+            const float lo = ph ? pxmin : pymin, hi = ph ? pxmax : pymax;
+            const float c = (pi == 0) ? pymin : (pi == 1) ? pxmax : (pi == 2) ? pymax : pxmin;
+            const float tt = __fmul_rn(__fsub_rn(c, p0[a0]), r[a0]);
+            const float i1 = __fmaf_rn(tt, e[a1], p0[a1]);
+            if (!((tt >= 0.0f) && (tt <= 1.0f) && (i1 >= lo) && (i1 <= hi))) continue;
+            ipx[ni] = ph ? i1 : c; ipy[ni] = ph ? c : i1; it[ni] = tt; ipe[ni] = pi;
+            float gt0[2] = {0.f, 0.f}, gt1[2] = {0.f, 0.f};
+            gt0[a0] = __fmul_rn(__fmul_rn(__fsub_rn(c, p1[a0]), r[a0]), r[a0]);
+            gt1[a0] = __fmul_rn(__fmul_rn(__fadd_rn(-c, p0[a0]), r[a0]), r[a0]);
+            g0[ni][0] = (float)((1.0 - (double)tt) + (double)__fmul_rn(gt0[0], e[0]));
+            g0[ni][1] = __fmul_rn(gt0[0], e[1]);
+            g0[ni][2] = __fmul_rn(gt0[1], e[0]);
+            g0[ni][3] = (float)((1.0 - (double)tt) + (double)__fmul_rn(gt0[1], e[1]));
+            g1[ni][0] = __fmaf_rn(gt1[0], e[0], tt);
+            g1[ni][1] = __fmul_rn(gt1[0], e[1]);
+            g1[ni][2] = __fmul_rn(gt1[1], e[0]);
+            g1[ni][3] = __fmaf_rn(gt1[1], e[1], tt);
+            ni++;
+        }
+        int final_pedge = -1;
+        if (ni == 2) {
+            const int s0 = (it[0] > it[1]) ? 1 : 0, s1 = 1 - s0;
+            add(ipx[s0], ipy[s0], ti, g0[s0], g1[s0]);
+            add(ipx[s1], ipy[s1], ti, g0[s1], g1[s1]);
+            final_pedge = ipe[s1];
+        } else if (ni == 1) {
+            add(ipx[0], ipy[0], ti, g0[0], g1[0]);
+            if (!in0 && in1) add(p1[0], p1[1], ti, nullptr, eye);
+            else if (in0 && !in1) final_pedge = ipe[0];
+        } else if (in0 && in1) {
+            add(p1[0], p1[1], ti, nullptr, eye);
+        }
+        if (final_pedge >= 0) {
+            for (int pvi = 0; pvi < 4; pvi++) {
+                const int cur = (final_pedge + 1 + pvi) & 3;
+                if (!((inmask >> cur) & 1u)) break;
+                add((cur == 1 || cur == 2) ? pxmax : pxmin, (cur >= 2) ? pymax : pymin, -1, nullptr, nullptr);
+            }
+        }
+    }
+    float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto upd = [&](int v, float gax, float gay) {            // aa.h:67-86
+        const int e = pe[v];
+        if (e < 0) return;
+        const int i0 = e, i1 = (e == 2) ? 0 : e + 1;
+        gr[2 * i0]     += __fmaf_rn(j0[v][0], gax, __fmul_rn(j0[v][1], gay));
+        gr[2 * i0 + 1] += __fmaf_rn(j0[v][2], gax, __fmul_rn(j0[v][3], gay));
+        gr[2 * i1]     += __fmaf_rn(j1[v][0], gax, __fmul_rn(j1[v][1], gay));
+        gr[2 * i1 + 1] += __fmaf_rn(j1[v][2], gax, __fmul_rn(j1[v][3], gay));
+    };
+    for (int si = 0; si + 2 < n; si++) {
+        const int a = 0, b = si + 1, c = si + 2;
+        upd(a, 0.5f * (py[b] - py[c]), 0.5f * (-px[b] + px[c]));
+        upd(b, 0.5f * (py[c] - py[a]), 0.5f * (-px[c] + px[a]));
+        upd(c, 0.5f * (py[a] - py[b]), 0.5f * (-px[a] + px[b]));
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) g[k] = gr[k];
 }
 
 }  // namespace dm2

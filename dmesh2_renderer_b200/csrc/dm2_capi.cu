@@ -482,7 +482,12 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
 
 int dm2_peer_allreduce_sum(const void* const* peer_ptrs, void* multicast_ptr, int32_t world, int32_t rank,
                            int64_t n_floats, void* stream) {
-    return launch_peer_allreduce(peer_ptrs, multicast_ptr, world, rank, n_floats, (cudaStream_t)stream);
+    return launch_peer_allreduce(peer_ptrs, multicast_ptr, nullptr, 0u, world, rank, n_floats, (cudaStream_t)stream);
+}
+int dm2_peer_allreduce_sum_fused(const void* const* peer_ptrs, void* multicast_ptr, const void* const* peer_flag_ptrs,
+                                 int32_t world, int32_t rank, int64_t n_floats, uint32_t epoch, void* stream) {
+    DM2_REQUIRE(peer_flag_ptrs != nullptr, "dm2_peer_allreduce_sum_fused: null flag pointer table");
+    return launch_peer_allreduce(peer_ptrs, multicast_ptr, peer_flag_ptrs, epoch, world, rank, n_floats, (cudaStream_t)stream);
 }
 
 int dm2_backward_workspace_bytes(int32_t B, int32_t F, size_t* bytes) {

@@ -252,8 +252,8 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
                            void* grad_ws, const void* shade_cache, long long shade_cache_bytes, cudaStream_t s);
-int launch_peer_allreduce(const void* const* peer_ptrs, void* multicast_ptr, int world, int rank, long long n_floats,
-                          cudaStream_t s);
+int launch_peer_allreduce(const void* const* peer_ptrs, void* multicast_ptr, const void* const* peer_flag_ptrs,
+                          uint32_t epoch, int world, int rank, long long n_floats, cudaStream_t s);
 int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,
                         cudaStream_t s);
 int launch_fused_preprocess(const DM2FusedInputs& in, const FaceWs& fw, uint32_t* patch_flags, cudaStream_t s);

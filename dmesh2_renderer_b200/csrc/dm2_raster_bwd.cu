@@ -94,7 +94,9 @@ __device__ __noinline__ float4 shade_recompute(const float* rec, float ox, float
 }
 __device__ __noinline__ void clip_gradient(const float* rec, float pxmin, float pymin, unsigned inmask, float* g) {
     float a, gg[6];
-    aa_clip<true>(rec, pxmin, pymin, inmask, a, gg);
+    bool chain = false;
+    aa_clip<true>(rec, pxmin, pymin, inmask, a, gg, &chain);
+    if (chain) aa_grad_reference(rec, pxmin, pymin, inmask, gg);
 #pragma unroll
     for (int q = 0; q < 6; q++) g[q] = gg[q];
 }

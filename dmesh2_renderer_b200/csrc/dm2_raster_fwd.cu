@@ -132,7 +132,10 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                     const float* rec = ws.srec + k * kRecStride;
                     const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
                     float area, g[6];
-                    const bool ok = aa_clip<CACHE>(rec, tc.fx0 + (float)(l & 7), tc.fy0 + (float)(l >> 3), inm, area, g);
+                    bool chain = false;
+                    const bool ok = aa_clip<CACHE>(rec, tc.fx0 + (float)(l & 7), tc.fy0 + (float)(l >> 3), inm, area, g, &chain);
+                    if (CACHE && chain)        // kink / inconsistent polygon: the reference's Jacobian chain (rare, out of line)
+                        aa_grad_reference(rec, tc.fx0 + (float)(l & 7), tc.fy0 + (float)(l >> 3), inm, g);
                     ws.parea[k * 32 + l] = ok ? area : -1.0f;
                     if (CACHE) {
                         const uint32_t poff = __float_as_uint(rec[R_META + 3]);

@@ -60,15 +60,20 @@ class GradBucket:
         return self
 
 
+PEER_FLAG_WORDS = 64          # DM2_PEER_FLAG_WORDS of include/dm2_renderer.h
+
+
 class PeerGradBucket(GradBucket):
     """GradBucket whose allreduce is this library's own kernel over NVLink peer memory
     (csrc/dm2_peer.cu) instead of a library collective.
 
     The flat buffer is a symmetric allocation (torch.distributed._symmetric_memory: every rank's
     buffer is mapped into every process, plus one NVSwitch multicast mapping when the fabric
-    supports it - plumbing only).  allreduce() = cross-GPU barrier, ONE kernel in which rank r sums
-    slice r of all buckets (multimem.ld_reduce: the add happens inside the switch; peer loads in
-    rank order without multicast) and writes the sum into every rank's bucket, cross-GPU barrier.
+    supports it - plumbing only).  allreduce() = ONE kernel launch per rank: rank r sums slice r of all
+    buckets (multimem.ld_reduce: the add happens inside the switch; peer loads in rank order without
+    multicast) and writes the sum into every rank's bucket; the two cross-GPU barriers around the data
+    movement are release / acquire flags in the same symmetric allocation, exchanged inside the kernel
+    (`fused_barriers=False`: the barriers are two extra symmetric-memory barrier launches, as in round 1).
     Requires CUDA tensors and an initialised NCCL process group on ONE node; use GradBucket
     (torch.distributed.all_reduce) anywhere else.  `use_multicast`: None = the switch reduction from 4
     ranks up when the fabric offers a multicast mapping (measured on 8 x B200, 76 MB bucket: 0.236 ms,
@@ -76,7 +81,7 @@ class PeerGradBucket(GradBucket):
     0.134 ms vs 0.22 ms, NCCL 0.170 ms); True / False force one kernel.
     """
 
-    def __init__(self, num_verts: int, num_faces: int, device, group=None, use_multicast=None):
+    def __init__(self, num_verts: int, num_faces: int, device, group=None, use_multicast=None, fused_barriers=True):
         import ctypes as C
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -86,9 +91,11 @@ class PeerGradBucket(GradBucket):
         n = 6 * self.P + self.F
         self._n_padded = (n + 3) // 4 * 4                      # the kernel moves 16-byte vectors
         self._group = group if group is not None else dist.group.WORLD
-        self._storage = symm_mem.empty(self._n_padded, dtype=torch.float32, device=device)
-        self._storage.zero_()
-        self._hdl = symm_mem.rendezvous(self._storage, self._group)
+        self._device = torch.device(device)
+        with torch.cuda.device(self._device):
+            self._storage = symm_mem.empty(self._n_padded + PEER_FLAG_WORDS, dtype=torch.float32, device=device)
+            self._storage.zero_()
+            self._hdl = symm_mem.rendezvous(self._storage, self._group)
         self.world, self.rank = int(self._hdl.world_size), int(self._hdl.rank)
         self.flat = self._storage[:n]
         self.dverts = self.flat[:3 * self.P].view(self.P, 3)
@@ -96,49 +103,87 @@ class PeerGradBucket(GradBucket):
         self.dfaces_opacity = self.flat[6 * self.P:]
         ptrs = [int(p) for p in self._hdl.buffer_ptrs]
         self._peer_ptrs = (C.c_void_p * self.world)(*ptrs)
+        self._flag_ptrs = (C.c_void_p * self.world)(*[p + 4 * self._n_padded for p in ptrs])
         if use_multicast is None:
             use_multicast = self.world >= 4
         mc = int(self._hdl.multicast_ptr) if (use_multicast and self._hdl.has_multicast_support) else 0
         self._multicast_ptr = C.c_void_p(mc)
         self.uses_multicast = mc != 0
+        self.fused_barriers = bool(fused_barriers)
+        self._epoch = 0
         self._lib = _lib
-        self._device = torch.device(device)
+        if self.world > 1:
+            with torch.cuda.device(self._device):
+                self._hdl.barrier(channel=0)           # every rank's zeroed flag area is in place
 
     def allreduce(self, group=None):
+        if group is not None and group is not self._group:
+            raise ValueError("PeerGradBucket.allreduce: the bucket was set up for a different process group")
         if self.world == 1:
             return self
         lib = self._lib.load_library()
-        stream = torch.cuda.current_stream(self._device)
-        self._hdl.barrier(channel=0)                    # every rank's bucket is complete
-        self._lib.check(lib.dm2_peer_allreduce_sum(self._peer_ptrs, self._multicast_ptr, self.world, self.rank,
-                                                   self._n_padded, stream.cuda_stream))
-        self._hdl.barrier(channel=1)                    # every rank's stores have landed
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device)
+            if self.fused_barriers:
+                self._epoch = self._epoch % 0x7FFFFFFF + 1
+                self._lib.check(lib.dm2_peer_allreduce_sum_fused(self._peer_ptrs, self._multicast_ptr, self._flag_ptrs,
+                                                                 self.world, self.rank, self._n_padded, self._epoch,
+                                                                 stream.cuda_stream))
+            else:
+                self._hdl.barrier(channel=0)                    # every rank's bucket is complete
+                self._lib.check(lib.dm2_peer_allreduce_sum(self._peer_ptrs, self._multicast_ptr, self.world, self.rank,
+                                                           self._n_padded, stream.cuda_stream))
+                self._hdl.barrier(channel=1)                    # every rank's stores have landed
         return self
 
 
 def make_grad_bucket(num_verts: int, num_faces: int, device, peer: bool = True, group=None):
-    """PeerGradBucket on a multi-GPU NCCL job (falls back to GradBucket + NCCL allreduce if the symmetric
-    allocation cannot be set up, with the reason on stderr), GradBucket otherwise."""
+    """PeerGradBucket on a multi-GPU NCCL job, GradBucket otherwise.  Setting up the symmetric allocation is a
+    collective: if it fails on ANY rank (reason on stderr), ALL ranks agree - through an all_reduce(MIN) of a
+    success flag - to fall back to GradBucket + NCCL all_reduce, so no rank is left waiting in a rendezvous."""
     dev = torch.device(device)
     if (peer and dev.type == "cuda" and dist.is_available() and dist.is_initialized()
             and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl"):
+        bucket, ok = None, 1
         try:
-            return PeerGradBucket(num_verts, num_faces, dev, group)
-        except Exception as ex:      # noqa: BLE001 - any set-up failure means "no peer mapping on this box"
-            import sys
-            print(f"dmesh2_renderer_b200: peer-memory bucket unavailable ({ex}); using NCCL all_reduce", file=sys.stderr)
+            import torch.distributed._symmetric_memory  # noqa: F401  (absent / unsupported: same verdict on every rank)
+        except Exception as ex:      # noqa: BLE001
+            ok = 0
+            reason = ex
+        if ok:
+            flag = torch.ones((1,), dtype=torch.int32, device=dev)
+            try:
+                bucket = PeerGradBucket(num_verts, num_faces, dev, group)
+            except Exception as ex:  # noqa: BLE001 - any set-up failure means "no peer mapping on this box"
+                flag.zero_()
+                reason = ex
+            # (a rank that failed BEFORE the rendezvous leaves the others inside it: the rendezvous itself has a
+            #  store timeout and raises there, which lands in the except branch above on those ranks too)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            ok = int(flag.item())
+        if ok and bucket is not None:
+            return bucket
+        import sys
+        why = locals().get("reason", "another rank could not set it up")
+        print(f"dmesh2_renderer_b200: peer-memory bucket unavailable ({why}); using NCCL all_reduce", file=sys.stderr)
     return GradBucket(num_verts, num_faces, dev)
 
 
 def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts: torch.Tensor,
                    verts_color: torch.Tensor, faces_opacity: torch.Tensor, bucket: Optional[GradBucket] = None,
-                   micro_batch: int = 8, world_size: Optional[int] = None, rank: Optional[int] = None, group=None):
+                   micro_batch: int = 8, world_size: Optional[int] = None, rank: Optional[int] = None, group=None,
+                   renderer=None):
     """One optimisation step's gradient over `all_views`, sharded over the process group.
 
     `render_view_batch(views, verts, verts_color, faces_opacity) -> scalar loss tensor` renders the
     given views (a list of global view ids) and returns their summed loss; it is called once per
     micro-batch on this rank's shard.  Returns (local_loss_sum, bucket) where the bucket holds the
     gradients summed over ALL views of ALL ranks.
+
+    `renderer` (optional): the dmesh2_renderer_b200.Renderer that render_view_batch uses.  Its fused route
+    then ADDS the three replicated-parameter gradients straight into the bucket's views (fused.GradSink) - no
+    per-micro-batch gradient tensors, no accumulate pass, no pack copy; without it the gradients come back
+    through autograd and are added to the bucket here.
     """
     if world_size is None:
         world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -149,13 +194,22 @@ def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts:
     bucket.zero_()
     mine = shard_views(len(all_views), world_size, rank)
     local_loss = torch.zeros((), dtype=torch.float32, device=verts.device)
-    for mb in micro_batches([all_views[i] for i in mine], micro_batch):
-        v = verts.detach().requires_grad_(True)
-        c = verts_color.detach().requires_grad_(True)
-        o = faces_opacity.detach().requires_grad_(True)
-        loss = render_view_batch(mb, v, c, o)
-        loss.backward()
-        bucket.accumulate(v.grad, c.grad, o.grad)
-        local_loss = local_loss + loss.detach().to(local_loss.dtype)
+    sink_on = False
+    if renderer is not None and verts.is_cuda and getattr(renderer, "fused", True):
+        from .fused import GradSink
+        renderer.grad_sink = GradSink(bucket.dverts, bucket.dverts_color, bucket.dfaces_opacity)
+        sink_on = True
+    try:
+        for mb in micro_batches([all_views[i] for i in mine], micro_batch):
+            v = verts.detach().requires_grad_(True)
+            c = verts_color.detach().requires_grad_(True)
+            o = faces_opacity.detach().requires_grad_(True)
+            loss = render_view_batch(mb, v, c, o)
+            loss.backward()
+            bucket.accumulate(v.grad, c.grad, o.grad)      # all None when the sink took them
+            local_loss = local_loss + loss.detach().to(local_loss.dtype)
+    finally:
+        if sink_on:
+            renderer.grad_sink = None
     bucket.allreduce(group)
     return local_loss, bucket

@@ -292,6 +292,15 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
  * dmesh2_renderer_b200/multiview.py:PeerGradBucket.                                                   */
 int dm2_peer_allreduce_sum(const void* const* peer_ptrs, void* multicast_ptr, int32_t world, int32_t rank,
                            int64_t n_floats, void* stream);
+/* The same exchange with BOTH cross-GPU barriers inside the kernel (one launch per optimisation step instead of
+ * three): peer_flag_ptrs[q] = rank q's flag area as mapped into this process - DM2_PEER_FLAG_WORDS u32 words of
+ * the same symmetric allocation, zeroed once before the first call (and made visible to all ranks by one
+ * barrier) -, epoch = 1, 2, 3, ... the same on every rank for the same step.  Ranks signal arrival / departure
+ * with st.release.sys into their peers' flag areas and spin on their own with ld.acquire.sys (bounded: a peer
+ * that never arrives makes the kernel trap after ~20 s instead of hanging the job).                          */
+#define DM2_PEER_FLAG_WORDS 64
+int dm2_peer_allreduce_sum_fused(const void* const* peer_ptrs, void* multicast_ptr, const void* const* peer_flag_ptrs,
+                                 int32_t world, int32_t rank, int64_t n_floats, uint32_t epoch, void* stream);
 
 /* ---- binning primitives exposed on their own (sort keys/s metric, parity tests) ---------- */
 /* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit): a stand-alone
