@@ -21,14 +21,17 @@
 //     gradient differ from the true derivative, and there the clip asks for aa_grad_reference(), an
 //     out-of-line transcription of the reference's polygon + Jacobian chain:
 //       (a) a triangle vertex exactly ON a pixel boundary line (a kink of the area: the reference
-//           differentiates "the intersection slides along the pixel edge", a one-sided derivative);
+//           differentiates "the intersection slides along the pixel edge", a one-sided derivative) - flagged
+//           per face by the preprocess kernels (bit 9 of the record's flag word: some screen coordinate of
+//           the face is an integer), conservatively;
 //       (b) an INCONSISTENT polygon: the inside-corner flags (half-plane tests, aa.h:103-149) and the
 //           edge / pixel-edge intersections (aa.h:230-262) are rounded independently, so for an edge that
 //           passes within an ulp of a pixel corner the run of inside corners behind an exit point can
 //           disagree with the pixel edge on which the next edge enters - the reference then appends
 //           spurious corners (or misses one), its area is off by ~1e-5 and its gradient by O(1)
 //           (measured: 1 pair in ~16 M at 1 M triangles @1024^2; found by the full-size parity test
-//           against the fp64-accumulated oracle).  Detected from the exit / entry pixel-edge indices.
+//           against the fp64-accumulated oracle).  Detected by counting corner pushes: in a true clip
+//           polygon every inside corner is a vertex exactly once.
 // Error semantics: the reference returns codes 1..6 and the caller skips the face for that pixel
 // on any non-zero code (forward.cu:337-338, backward.cu:286-289); here `false` = "skip".
 #pragma once
@@ -78,10 +81,7 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
     FanAcc fan;
     const unsigned zflags = __float_as_uint(rec[R_MISC + 3]);
     float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    // consistency of the polygon's boundary walk (GRAD only): every exit point + its run of inside corners must
-    // lead to the pixel edge on which the next triangle edge enters
-    bool pend = false, odd = false, kink = false;
-    int pend_pe = 0, first_entry = -1;
+    int corner_pushes = 0;        // GRAD only: see the consistency test at the end
 
 #ifndef DM2_CLIP_UNROLL
 #define DM2_CLIP_UNROLL 1
@@ -137,23 +137,14 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
         // covered pixel has at most 3 inside corners
         bool run = two | leave;
         const int final_pedge = two ? (swap ? pa : pb) : pa;
-        int run_len = 0;
 #pragma unroll
         for (int pvi = 0; pvi < 3; pvi++) {
             const int cur = (final_pedge + 1 + pvi) & 3;
             run = run & (((inmask >> cur) & 1u) != 0u);
             fan.push(run, (cur == 1 || cur == 2) ? pxmax : pxmin, (cur >= 2) ? pymax : pymin);
-            if (GRAD) run_len += run ? 1 : 0;
+            if (GRAD) corner_pushes += run ? 1 : 0;
         }
         if (GRAD) {
-            kink |= in0 & ((p0.x == pxmin) | (p0.x == pxmax) | (p0.y == pymin) | (p0.y == pymax));
-            const bool e_in = two | enter, e_out = two | leave;
-            const int entry_pe = two ? (swap ? pb : pa) : pa;
-            odd |= e_in & (pend ? (entry_pe != pend_pe) : (first_entry >= 0));
-            first_entry = (e_in & !pend) ? entry_pe : first_entry;
-            pend = pend & !e_in;
-            pend_pe = e_out ? ((final_pedge + run_len) & 3) : pend_pe;
-            pend |= e_out;
 
             // part of the edge inside the pixel: [t_in, t_out]
             const bool covered = !none || whole;
@@ -174,8 +165,11 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
     if (GRAD) {
 #pragma unroll
         for (int k = 0; k < 6; k++) g[k] = gr[k];
-        odd |= pend ? (first_entry != pend_pe) : (first_entry >= 0);
-        if (chain_needed) *chain_needed = ok & (odd | kink);
+        // In the true clip polygon every inside pixel corner is a vertex exactly once.  The reference's corner
+        // runs (aa.h:359-379) can push a corner twice / not at all when flags and intersections disagree, and a
+        // face with a vertex on an integer pixel line (flag bit 9, set by the preprocess kernels) has kinks.
+        if (chain_needed)
+            *chain_needed = ok & ((corner_pushes != (int)__popc(inmask & 0xFu)) | (((zflags >> 9) & 1u) != 0u));
     }
     return ok;
 }
@@ -185,7 +179,7 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
 // as the reference chains it - polygon array, per-vertex 2x2 Jacobians d ip/d p0 and d ip/d p1 (aa.h:280-294;
 // the `1.0 - t` terms are evaluated in double there), fan triangles from polygon[0] (aa.h:403-433).  Only
 // called for pairs whose clip succeeded (no error code), so the error exits are not repeated.
-__device__ __noinline__ void aa_grad_reference(const float* __restrict__ rec, float pxmin, float pymin, unsigned inmask,
+static __device__ __noinline__ void aa_grad_reference(const float* __restrict__ rec, float pxmin, float pymin, unsigned inmask,
                                                float* __restrict__ g) {
     const float pxmax = __fadd_rn(pxmin, 1.0f), pymax = __fadd_rn(pymin, 1.0f);
     const unsigned zflags = __float_as_uint(rec[R_MISC + 3]);

@@ -128,8 +128,10 @@ __device__ __forceinline__ bool render_preprocess_one(const DM2RenderInputs& in,
     }
     const float c0 = ac[0], c1 = ac[1], c2 = ac[2];
     uint32_t flags = 0;
+    bool on_grid = false;         // some screen coordinate is an integer: possible kink of the overlap area (dm2_aa.cuh)
 #pragma unroll
-    for (int k = 0; k < 6; k++) flags |= (az[k] ? 1u : 0u) << k;
+    for (int k = 0; k < 6; k++) { flags |= (az[k] ? 1u : 0u) << k; on_grid |= a[k] == floorf(a[k]); }
+    flags |= on_grid ? 0x200u : 0u;
     const float txmin = nanmin(nanmin(a[0], a[2]), a[4]), txmax = nanmax(nanmax(a[0], a[2]), a[4]);
     const float tymin = nanmin(nanmin(a[1], a[3]), a[5]), tymax = nanmax(nanmax(a[1], a[3]), a[5]);
     const float* p0 = in.verts + 3 * (size_t)v0;
@@ -272,6 +274,9 @@ __device__ __forceinline__ bool fused_preprocess_one(const DM2FusedInputs& in, i
         r[k] = __fdiv_rn(1.0f, e[k]);
         flags |= (fabsf(e[k]) < 1e-3f ? 1u : 0u) << k;
     }
+    // some screen coordinate is an integer: possible kink of the overlap area (dm2_aa.cuh)
+    if (p0x == floorf(p0x) || p0y == floorf(p0y) || p1x == floorf(p1x) || p1y == floorf(p1y) || p2x == floorf(p2x) ||
+        p2y == floorf(p2y)) flags |= 0x200u;
     // n_k = (-e_k.y, e_k.x), c_k = n_k . anchor_k  (two rounded products, one add)
     const float n[6] = {-e[1], e[0], -e[3], e[2], -e[5], e[4]};
     const float c0 = __fadd_rn(__fmul_rn(n[0], p0x), __fmul_rn(n[1], p0y));

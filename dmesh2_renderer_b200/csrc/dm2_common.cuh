@@ -86,7 +86,8 @@ constexpr int kRecBytes   = kRecWords * 4;
 constexpr int R_BBOX      = 0;    // txmin txmax tymin tymax      (min/max of aa_face_verts)
 constexpr int R_N01       = 4;    // n0.x n0.y n1.x n1.y          (aa_face_edges_normal)
 constexpr int R_N2C       = 8;    // n2.x n2.y c0 c1              (…, aa_face_edges_normal_c)
-constexpr int R_MISC      = 12;   // c2, opacity, intense, flags (bits 0..5: edges_iszero[e][k] at bit 2e+k)
+constexpr int R_MISC      = 12;   // c2, opacity, intense, flags (bits 0..5: edges_iszero[e][k] at bit 2e+k; bit 8: the fused
+                                  // preprocess flipped the face to CCW; bit 9: some screen coordinate is an integer)
 constexpr int R_P0        = 16;   // p0.xyz (world), z0 (ndc)
 constexpr int R_P1        = 20;
 constexpr int R_P2        = 24;

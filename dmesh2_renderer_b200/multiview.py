@@ -146,7 +146,8 @@ def make_grad_bucket(num_verts: int, num_faces: int, device, peer: bool = True, 
             and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl"):
         bucket, ok = None, 1
         try:
-            import torch.distributed._symmetric_memory  # noqa: F401  (absent / unsupported: same verdict on every rank)
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")     # absent: same verdict on every rank
         except Exception as ex:      # noqa: BLE001
             ok = 0
             reason = ex

@@ -434,9 +434,9 @@ def test_layers_incremental_regenerate(built):
             assert "_layer_cache" in lr.__dict__
         if step == 2:                      # move the points in place: version bump -> full path again
             geo[0].mul_(0.97)
-    sig_before = lr.__dict__["_layer_cache"][0]
-    lr.generate([0], *geo, ex, 3)          # a different layer count reuses the same cache entry
-    assert lr.__dict__["_layer_cache"][0] == sig_before
+    taps_before = lr.__dict__["_layer_cache"]["taps"]
+    lr.generate([0], *geo, ex, 3)          # a different layer count reuses the same cache entry (walk only)
+    assert lr.__dict__["_layer_cache"]["taps"] is taps_before
 
 
 def test_layers_properties(built):
