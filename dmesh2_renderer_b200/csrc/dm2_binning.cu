@@ -776,12 +776,13 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
     if (i < R) imask[i] = (uint8_t)s_im[t];
 }
 
-int launch_classify(const uint64_t* keys, long long capacity, const uint32_t* hdr, const TileMaskArgs& tm, cudaStream_t s) {
+int launch_classify(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr, const TileMaskArgs& tm,
+                    cudaStream_t s) {
     if (capacity <= 0) return 0;
     ProfScope _ps("classify", s);
     // (the grid covers the workspace capacity; blocks past the actual num_rendered exit at once)
     k_classify_instances<<<cdiv(capacity, kClsThreads), kClsThreads, 0, s>>>(
-        keys, tm.vals, (uint32_t)capacity, BinGuard{hdr, (uint32_t)capacity}, tm.records, tm.patch_min, tm.F, tm.gx, tm.gy,
+        keys, tm.vals, (uint32_t)capacity, BinGuard{hdr, (uint32_t)capacity, (uint32_t)longest_cap}, tm.records, tm.patch_min, tm.F, tm.gx, tm.gy,
         tm.use_bbox, tm.imask, reinterpret_cast<uint4*>(tm.meta));
     DM2_LAUNCH_CHECK();
     return 0;

@@ -299,14 +299,16 @@ int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_
 }
 
 // everything behind the scan: scatter + segment sort, classification, forward compositor
-static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, long long longest,
+static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, BinWs bw, const ImageWs& iw, long long longest,
                         float* out_color, float* out_depth, void* shade_cache, long long shade_cache_bytes,
                         bool sort_too, cudaStream_t s) {
+    // kernels that read the SORTED lists return at once if a segment is longer than the enqueued sort tiers cover
+    bw.longest_cap = sort_too ? sort_tiers_longest_cap(longest) : 0xFFFFFFFFll;
     const long long BF = (long long)in->B * in->F;
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
     if (sort_too && bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, longest, s)) return 1;
-    if (launch_classify(bw.keys, bw.R, iw.tile_cursor + (size_t)in->B * gx * gy, tm, s)) return 1;
+    if (launch_classify(bw.keys, bw.R, bw.longest_cap, iw.tile_cursor + (size_t)in->B * gx * gy, tm, s)) return 1;
     return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0, s);
 }
 

@@ -203,9 +203,11 @@ constexpr uint32_t kFlagPatchX = 1u;       // some patch_min.x + patch_width  > 
 constexpr uint32_t kFlagPatchY = 2u;       // some patch_min.y + patch_height > frame height (reference __init__.py:284)
 constexpr uint32_t kFlagPatchNeg = 4u;     // negative patch_min on the fused route (rays are read in place)
 constexpr uint32_t kFlagVertexId = 8u;     // a face references a vertex id outside [0, P)
-struct BinGuard { const uint32_t* hdr; uint32_t capacity; };
+// longest_cap: the longest tile segment the sort tiers that were enqueued can handle (kernels that read the
+// SORTED lists must not run on segments no launched tier has sorted; 0xFFFFFFFF for the binning kernels themselves)
+struct BinGuard { const uint32_t* hdr; uint32_t capacity; uint32_t longest_cap; };
 __device__ __forceinline__ bool bin_invalid(const BinGuard g) {
-    return __ldg(g.hdr) > g.capacity || __ldg(g.hdr + 1) != 0u;
+    return __ldg(g.hdr) > g.capacity || __ldg(g.hdr + 1) != 0u || __ldg(g.hdr + 2) > g.longest_cap;
 }
 
 // ---------------------------------------------------------------- internal launchers
@@ -223,6 +225,7 @@ struct BinWs {
     uint64_t* keys_unsorted; uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
     uint8_t* imask;               // per sorted instance: bit w = footprint w has a touched pixel (render path)
     long long R;                  // capacity of this workspace in instances (>= num_rendered; = stride of meta)
+    long long longest_cap = 0xFFFFFFFFll;   // longest tile segment the enqueued sort tiers cover (speculative launches)
     void* meta;                   // uint4[8][R]: per (footprint, instance) pixel classification (k_classify_instances)
 };
 struct TileMaskArgs {             // optional second output of the tile-range pass (render path)
@@ -246,7 +249,9 @@ int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* c
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
                       long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
 size_t sort_temp_bytes(long long n);
-int launch_classify(const uint64_t* keys, long long capacity, const uint32_t* hdr, const TileMaskArgs& tm, cudaStream_t s);
+int launch_classify(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr, const TileMaskArgs& tm,
+                    cudaStream_t s);
+long long sort_tiers_longest_cap(long long longest_hint);
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                           const ImageWs& iw, float* out_color, float* out_depth, void* shade_cache,
                           long long shade_cache_bytes, cudaStream_t s);

@@ -193,6 +193,19 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
 
         if (use_aa) store_partial_masks(ws.srec, ncs, lane);
+        // the candidates' cache blocks (written by the forward kernel: DRAM by now) are pulled into L2 while the
+        // masks and the pair list are built: lane k asks for candidate k's block, one request per 128-byte line
+        if (cached && lane < ncs) {
+            const float* rec = ws.srec + lane * kRecStride;
+            const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+            if (poff != kNoCache) {
+                const uint32_t bytes = 16u * cache_block_granules(__popc(__float_as_uint(rec[R_META])),
+                                                                  __popc(__float_as_uint(rec[R_PMASK])));
+                const char* base = reinterpret_cast<const char*>(cache.data + (size_t)poff);
+                for (uint32_t off = 0; off < bytes; off += 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            }
+        }
 
         // ====== 1. per-lane hit / partial masks from the classification words
         uint32_t hit, part;

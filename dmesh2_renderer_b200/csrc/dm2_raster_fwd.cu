@@ -156,16 +156,21 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                 const float* rec = ws.srec + k * kRecStride;
                 Shade s;
                 s.area = use_aa ? 1.0f : 0.0f;
-                if ((part >> k) & 1u) s.area = ws.parea[k * 32 + lane];
-                const bool ok = (s.area != -1.0f) && shade_tail(rec, pg, tau, s);
-                if (CACHE) {
-                    // the backward pass reads this instead of re-running the hit point and the clamp
-                    const uint32_t poff = __float_as_uint(rec[R_META + 3]);
-                    if (poff != kNoCache)
-                        cache.data[(size_t)poff + __popc(__float_as_uint(rec[R_META]) & lt_mask)] =
-                            ok ? make_float4(s.w1, s.w2, s.ratio, __int_as_float(s.code)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // the backward pass reads the pair's record instead of re-running the hit point and the clamp;
+                // pairs the reference skips leave a zero record (rare: out of the straight path)
+                auto leave_record = [&](const float4 r4) {
+                    if (CACHE) {
+                        const uint32_t poff = __float_as_uint(rec[R_META + 3]);
+                        if (poff != kNoCache)
+                            cache.data[(size_t)poff + __popc(__float_as_uint(rec[R_META]) & lt_mask)] = r4;
+                    }
+                };
+                if ((part >> k) & 1u) {
+                    s.area = ws.parea[k * 32 + lane];
+                    if (s.area == -1.0f) { leave_record(make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
                 }
-                if (!ok) continue;
+                if (!shade_tail(rec, pg, tau, s)) { leave_record(make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
+                leave_record(make_float4(s.w1, s.w2, s.ratio, __int_as_float(s.code)));
                 // forward.cu:398-415
                 const float alpha = __fmul_rn(rec[R_MISC + 1], s.ratio);
                 C0 = __fmaf_rn(__fmul_rn(s.iC[0], alpha), T, C0);   // C += iC*alpha*T
@@ -211,7 +216,7 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
         attr_set.done();
     }
     const ShadeCache cache = shade_cache_view(shade_cache, shade_cache_bytes);
-    const BinGuard guard{iw.tile_cursor + nblk, (uint32_t)bw.R};
+    const BinGuard guard{iw.tile_cursor + nblk, (uint32_t)bw.R, (uint32_t)bw.longest_cap};
     const bool use_cache = cache.capacity > 0 && in.aa_temperature > 0.0f && bw.R > 0;
     if (use_cache) DM2_CHECK(cudaMemsetAsync(cache.counter, 0, sizeof(uint32_t), s));
     ProfScope _ps("raster_forward", s);

@@ -399,7 +399,7 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
                      uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
                      long long capacity, long long longest, cudaStream_t s) {
     if (BF == 0 || num_tiles == 0) return 0;
-    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity};
+    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity, 0xFFFFFFFFu};
     if (longest < 0) longest = 1ll << 40;            // unknown: launch every tier
     {
         ProfScope _ps("scatter_instances", s);
@@ -418,12 +418,18 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
     return launch_tile_sort_tiers(num_tiles, ranges, cursor, keys_unsorted, vals_unsorted, keys, vals, capacity, tiers, s);
 }
 
+// longest segment covered by the tiers launch_tile_sort enqueues for a given hint (-1: all of them)
+long long sort_tiers_longest_cap(long long longest_hint) {
+    if (longest_hint < 0 || longest_hint > kSortCap1) return 0xFFFFFFFFll;
+    return longest_hint > kSortCap0 ? (long long)kSortCap1 : (long long)kSortCap0;
+}
+
 // the per-segment sort alone; tiers: bit t = run tier t (segments of <= 2048 / <= 8192 / more instances)
 int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
                            cudaStream_t s) {
     if (num_tiles == 0 || tiers == 0) return 0;
-    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity};
+    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity, 0xFFFFFFFFu};
     static PerDeviceOnce attr_set;
     if (attr_set.first()) {
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
