@@ -168,6 +168,10 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
         // In the true clip polygon every inside pixel corner is a vertex exactly once.  The reference's corner
         // runs (aa.h:359-379) can push a corner twice / not at all when flags and intersections disagree, and a
         // face with a vertex on an integer pixel line (flag bit 9, set by the preprocess kernels) has kinks.
+#ifdef DM2_EXP_NO_CHAINDET                /* timing experiment only */
+        if (chain_needed) *chain_needed = false;
+        else
+#endif
         if (chain_needed)
             *chain_needed = ok & ((corner_pushes != (int)__popc(inmask & 0xFu)) | (((zflags >> 9) & 1u) != 0u));
     }

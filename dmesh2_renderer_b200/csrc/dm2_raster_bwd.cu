@@ -190,7 +190,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
         fill_queue<true, kBSub>(ws.q, head, count, cursor, warp_last, tmask, tlist, warp, lane);
         if (count == 0) break;
         const int ncs = min(count, kBSub);
-        stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
+        stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane, count - ncs);
 
         if (use_aa) store_partial_masks(ws.srec, ncs, lane);
         // the candidates' cache blocks (written by the forward kernel: DRAM by now) are pulled into L2 while the

@@ -131,9 +131,20 @@ __device__ __forceinline__ uint32_t partial_mask(const uint4 m) {
     }
     return m.x & ~full;
 }
+// `ahead`: candidates already queued behind these (the next sub-chunk): their records (2 lines each) and
+// classification words are requested into L2 now, a whole sub-chunk of work before they are staged.
 __device__ __forceinline__ void stage_candidates(float* __restrict__ srec, const float* __restrict__ records,
                                                  const uint4* __restrict__ tmeta, const WarpQueue& q, int head, int ncs,
-                                                 size_t view_base, int lane) {
+                                                 size_t view_base, int lane, int ahead = 0) {
+#ifndef DM2_NO_STAGE_PREFETCH
+    if (lane < ahead) {
+        const int pos = (head + ncs + lane) & (kQueue - 1);
+        const float* r = records + (view_base + q.fid[pos]) * kRecWords;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 32));
+        if (tmeta) asm volatile("prefetch.global.L2 [%0];" ::"l"(tmeta + q.idx[pos]));
+    }
+#endif
     for (int t = lane; t < ncs * 16; t += 32) {
         const int slot = t >> 4, chunk = t & 15;
         const int pos = (head + slot) & (kQueue - 1);

@@ -69,7 +69,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
         fill_queue<false, kFSub>(ws.q, head, count, cursor, total, tmask, tlist, warp, lane);
         if (count == 0) break;
         const int ncs = min(count, kFSub);
-        stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane);
+        stage_candidates(ws.srec, records, tmeta, ws.q, head, ncs, view_base, lane, count - ncs);
 
         if (use_aa) store_partial_masks(ws.srec, ncs, lane);
         if (CACHE && use_aa) {
@@ -159,6 +159,9 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
                 // the backward pass reads the pair's record instead of re-running the hit point and the clamp;
                 // pairs the reference skips leave a zero record (rare: out of the straight path)
                 auto leave_record = [&](const float4 r4) {
+#ifdef DM2_EXP_NO_HITREC                 /* timing experiment only: the backward pass then reads garbage */
+                    return;
+#endif
                     if (CACHE) {
                         const uint32_t poff = __float_as_uint(rec[R_META + 3]);
                         if (poff != kNoCache)
