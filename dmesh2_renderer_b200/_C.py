@@ -265,7 +265,7 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
 
 def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, tet_faces, face_existence, verts_ndc,
                                 verts_image, image_ray_o, image_ray_d, num_layers, return_taps=False, fused=None,
-                                reuse=None):
+                                reuse=None, ray_spec=None):
     """reference render.h:101-119 / render.cu:378-476.  Returns (render_layers, render_layers_cnt).
 
     fused = (mv [B,4,4], proj [B,4,4], ray_view [B] int32): the fused host prep - the preprocess kernel
@@ -274,8 +274,14 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
 
     reuse = the `taps` dict of an earlier call with IDENTICAL geometry, views and rays (return_taps=True):
     only face_existence may differ - binning and first hits are reused, the tet walk alone is redone
-    (dm2_regenerate_render_layers).  The caller vouches for the condition."""
+    (dm2_regenerate_render_layers).  The caller vouches for the condition.
+
+    ray_spec = (recipe, params [V,32], (V, H, W)) (fused only): the kernels generate the rays themselves;
+    image_ray_o / image_ray_d may then be None."""
     lib = _lib.load_library()
+    use_ray_spec = ray_spec is not None and fused is not None
+    if use_ray_spec and image_ray_o is None:        # shape-only placeholders (never dereferenced)
+        image_ray_o = image_ray_d = verts.new_empty((0, int(height), int(width), 3))
     if fused is not None:       # shape-only placeholders (never dereferenced: the kernel projects the vertices itself)
         nb = int(fused[0].size(0))
         verts_ndc = verts.new_empty((nb, 0, 3))
@@ -307,7 +313,8 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
                 face_tets=_prep(face_tets, i32, "face_tets"), tet_faces=_prep(tet_faces, i32, "tet_faces"),
                 face_existence=_prep(face_existence, i32, "face_existence"),
                 verts_ndc=_prep(verts_ndc, f32, "verts_ndc"), verts_image=_prep(verts_image, f32, "verts_image"),
-                image_ray_o=_prep(image_ray_o, f32, "image_ray_o"), image_ray_d=_prep(image_ray_d, f32, "image_ray_d"))
+                image_ray_o=image_ray_o if use_ray_spec else _prep(image_ray_o, f32, "image_ray_o"),
+                image_ray_d=image_ray_d if use_ray_spec else _prep(image_ray_d, f32, "image_ray_d"))
     B, P, F, T = int(verts_ndc.size(0)), int(verts.size(0)), int(faces.size(0)), int(tets.size(0))
     H, W, L = int(height), int(width), int(num_layers)
     if face_tets.size(0) != F or tet_faces.size(0) != T:
@@ -328,6 +335,10 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
             _err("mv / proj must have dimensions (B, 4, 4)")
         s.mv, s.proj, s.ray_view = keep["mv"].data_ptr(), keep["proj"].data_ptr(), keep["ray_view"].data_ptr()
         s.verts_ndc = s.verts_image = 0
+        if use_ray_spec:
+            keep["ray_params"] = _prep(ray_spec[1], f32, "ray_params")
+            s.ray_params, s.ray_recipe, s.ray_v = keep["ray_params"].data_ptr(), int(ray_spec[0]), int(ray_spec[2][0])
+            s.image_ray_o = s.image_ray_d = 0
     dev = keep["verts"].device
     with torch.cuda.device(dev):
         stream = _stream(dev)

@@ -8,7 +8,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
+RAY_RECIPES = 36        # DM2_RAY_RECIPES
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
 
@@ -24,7 +25,8 @@ class DM2RenderInputs(C.Structure):
         ("aa_face_edges_normal", C.c_void_p), ("aa_face_edges_normal_c", C.c_void_p),
         ("image_ray_o", C.c_void_p), ("image_ray_d", C.c_void_p),
         ("ray_view", C.c_void_p), ("ray_h", C.c_int32), ("ray_w", C.c_int32),
-        ("depth_unit", C.c_int32), ("reserved_", C.c_int32),
+        ("depth_unit", C.c_int32), ("ray_recipe", C.c_int32), ("ray_params", C.c_void_p),
+        ("ray_v", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -35,7 +37,8 @@ class DM2FusedInputs(C.Structure):
         ("background", C.c_void_p), ("patch_min", C.c_void_p), ("verts", C.c_void_p), ("faces", C.c_void_p),
         ("verts_color", C.c_void_p), ("faces_opacity", C.c_void_p), ("mv", C.c_void_p), ("proj", C.c_void_p),
         ("faces_intense", C.c_void_p), ("ray_o", C.c_void_p), ("ray_d", C.c_void_p), ("ray_view", C.c_void_p),
-        ("depth_unit", C.c_int32), ("reserved_", C.c_int32),
+        ("depth_unit", C.c_int32), ("ray_recipe", C.c_int32), ("ray_params", C.c_void_p),
+        ("ray_v", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -61,6 +64,7 @@ class DM2LayerInputs(C.Structure):
         ("tet_faces", C.c_void_p), ("face_existence", C.c_void_p), ("verts_ndc", C.c_void_p),
         ("verts_image", C.c_void_p), ("image_ray_o", C.c_void_p), ("image_ray_d", C.c_void_p),
         ("mv", C.c_void_p), ("proj", C.c_void_p), ("ray_view", C.c_void_p),
+        ("ray_params", C.c_void_p), ("ray_recipe", C.c_int32), ("ray_v", C.c_int32),
     ]
 
 
@@ -105,6 +109,8 @@ SYMBOLS = {
     "dm2_fused_backward": (C.c_int, [_P(DM2FusedInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, _P(DM2FusedGrads), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p]),
+    "dm2_generate_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "dm2_peer_allreduce_sum": (C.c_int, [_P(C.c_void_p), C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "dm2_peer_allreduce_sum_fused": (C.c_int, [_P(C.c_void_p), C.c_void_p, _P(C.c_void_p), C.c_int32, C.c_int32,
                                                C.c_int64, C.c_uint32, C.c_void_p]),

@@ -360,6 +360,7 @@ static int check_fused_inputs(const DM2FusedInputs* in) {
     DM2_REQUIRE(in->image_h >= in->H && in->image_w >= in->W, "patch larger than the frame");
     DM2_REQUIRE(in->B == 0 || (in->mv && in->proj), "mv / proj must not be null");
     DM2_REQUIRE(in->aa_temperature >= 0.0f && in->aa_temperature <= 1.0f, "aa_temperature must be in the range [0, 1]");
+    DM2_REQUIRE(in->ray_recipe >= 0 && in->ray_recipe <= DM2_RAY_RECIPES, "ray_recipe out of range");
     DM2_REQUIRE((long long)in->B * in->F < (1ll << 31), "B*F must be < 2^31");
     DM2_REQUIRE((long long)in->B * in->H * in->W < (1ll << 31), "B*H*W must be < 2^31");
     DM2_REQUIRE(cdiv(in->W, kTile) < 65536 && cdiv(in->H, kTile) < 65536, "patch too large");
@@ -374,6 +375,9 @@ static DM2RenderInputs as_render_inputs(const DM2FusedInputs& f) {
     r.verts_color = f.verts_color; r.faces_opacity = f.faces_opacity; r.faces_intense = f.faces_intense;
     r.image_ray_o = f.ray_o; r.image_ray_d = f.ray_d; r.ray_view = f.ray_view; r.ray_h = f.image_h; r.ray_w = f.image_w;
     r.depth_unit = f.depth_unit;
+    r.ray_recipe = f.ray_params ? f.ray_recipe : 0;
+    r.ray_params = f.ray_params;
+    r.ray_v = f.ray_v;
     return r;
 }
 
@@ -406,7 +410,8 @@ int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws,
                       int64_t capacity, int64_t longest, float* out_color, float* out_depth, void* shade_cache,
                       int64_t shade_cache_bytes, void* stream) {
     if (check_fused_inputs(in)) return 2;
-    DM2_REQUIRE(in->ray_o && in->ray_d && in->ray_view, "dm2_fused_forward: null ray buffers");
+    DM2_REQUIRE(in->ray_view && ((in->ray_o && in->ray_d) || (in->ray_params && in->ray_recipe > 0)),
+                "dm2_fused_forward: null ray buffers");
     const DM2RenderInputs r = as_render_inputs(*in);
     return dm2_render_forward(&r, face_ws, binning_ws, image_ws, capacity, longest, out_color, out_depth, shade_cache,
                               shade_cache_bytes, stream);
@@ -423,7 +428,8 @@ int dm2_fused_forward_pipelined(const DM2FusedInputs* in, void* face_ws, void* b
                                 void* shade_cache, int64_t shade_cache_bytes, int64_t* num_rendered_host,
                                 int64_t* longest_host, int32_t* fits_host, void* stream) {
     if (check_fused_inputs(in)) return 2;
-    DM2_REQUIRE(in->ray_o && in->ray_d && in->ray_view, "dm2_fused_forward_pipelined: null ray buffers");
+    DM2_REQUIRE(in->ray_view && ((in->ray_o && in->ray_d) || (in->ray_params && in->ray_recipe > 0)),
+                "dm2_fused_forward_pipelined: null ray buffers");
     DM2_REQUIRE(face_ws && binning_ws && image_ws && out_color && out_depth && num_rendered_host && longest_host && fits_host,
                 "dm2_fused_forward_pipelined: null buffer");
     DM2_REQUIRE(capacity > 0 && capacity < (1ll << 31), "dm2_fused_forward_pipelined: bad capacity");
@@ -482,6 +488,14 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
     return launch_fused_grad_scatter(*in, fw, *grads, grad_ws, s);
 }
 
+int dm2_generate_rays(const float* ray_params, int32_t V, int32_t H, int32_t W, int32_t recipe, float* out_o,
+                      float* out_d, void* stream) {
+    DM2_REQUIRE(ray_params && out_o && out_d && V >= 0 && H >= 0 && W >= 0, "dm2_generate_rays: bad arguments");
+    DM2_REQUIRE(recipe >= 1 && recipe <= DM2_RAY_RECIPES, "dm2_generate_rays: recipe out of range");
+    DM2_REQUIRE((long long)V * H * W < (1ll << 31), "dm2_generate_rays: V*H*W must be < 2^31");
+    return launch_generate_rays(ray_params, V, H, W, recipe, out_o, out_d, (cudaStream_t)stream);
+}
+
 int dm2_peer_allreduce_sum(const void* const* peer_ptrs, void* multicast_ptr, int32_t world, int32_t rank,
                            int64_t n_floats, void* stream) {
     return launch_peer_allreduce(peer_ptrs, multicast_ptr, nullptr, 0u, world, rank, n_floats, (cudaStream_t)stream);
@@ -502,6 +516,8 @@ static int check_layer_inputs(const DM2LayerInputs* in) {
     DM2_REQUIRE(in != nullptr, "inputs must not be null");
     DM2_REQUIRE(in->B >= 0 && in->P >= 0 && in->F >= 0 && in->T >= 0 && in->H >= 0 && in->W >= 0, "negative dimension");
     DM2_REQUIRE(in->num_layers >= 0, "num_layers must be non-negative");
+    DM2_REQUIRE(in->ray_recipe >= 0 && in->ray_recipe <= DM2_RAY_RECIPES, "ray_recipe out of range");
+    DM2_REQUIRE(in->ray_recipe == 0 || (in->ray_params && in->ray_view), "ray_recipe needs ray_params and ray_view");
     DM2_REQUIRE((long long)in->B * in->F < (1ll << 31), "B*F must be < 2^31");
     DM2_REQUIRE((long long)in->B * in->H * in->W < (1ll << 31), "B*H*W must be < 2^31");
     return 0;

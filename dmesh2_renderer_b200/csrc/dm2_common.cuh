@@ -186,6 +186,54 @@ __device__ __forceinline__ float4 clip_vertex(const float* __restrict__ v, const
     return make_float4(c[0], c[1], c[2], c[3]);
 }
 
+// Pixel ray of frame pixel (x, y) of view `view` from prm = [inv(proj) | inv(mv)] of that view (reference
+// __init__.py:198-237), with the rounding choices of recipe r in [1, 36]: r - 1 = 18 * T + 9 * D + 3 * M + N
+//   D: centre / size as an IEEE division (0) or as centre * rn(1 / size) (1: what torch's CUDA division by a
+//      host scalar does);
+//   M: accumulation of the two K = 4 products: fma chain k = 0..3 after a plain first product (0: what cuBLAS
+//      runs for them), fma chain k = 3..0 (1), two fma pairs added (2);
+//   N: squared norm: fma chain x, y, z (0), (rn(x^2) + rn(y^2)) + rn(z^2) (1), (rn(x^2) + rn(z^2)) + rn(y^2)
+//      (2: torch's reduction kernel on sm_100);
+//   T: 1 = the last (V H W) mod 65535 pixels of the whole ray tensor use (rn(p0) + rn(p2)) + (rn(p1) + rn(p3))
+//      for both products: torch runs the (V H W)-batch matmul in chunks of 65535 (the grid limit), and cuBLAS
+//      picks another kernel for a small last chunk (measured on B200, tools/probe_ray_stages.py).
+__device__ __forceinline__ float ray_dot4(const float c0, const float c1, const float c2, const float c3,
+                                          const float* __restrict__ m, int M) {
+    if (M == 0) return __fmaf_rn(c3, m[3], __fmaf_rn(c2, m[2], __fmaf_rn(c1, m[1], __fmul_rn(c0, m[0]))));
+    if (M == 1) return __fmaf_rn(c0, m[0], __fmaf_rn(c1, m[1], __fmaf_rn(c2, m[2], __fmul_rn(c3, m[3]))));
+    if (M == 2) return __fadd_rn(__fmaf_rn(c1, m[1], __fmul_rn(c0, m[0])), __fmaf_rn(c3, m[3], __fmul_rn(c2, m[2])));
+    return __fadd_rn(__fadd_rn(__fmul_rn(c0, m[0]), __fmul_rn(c2, m[2])), __fadd_rn(__fmul_rn(c1, m[1]), __fmul_rn(c3, m[3])));
+}
+__device__ __forceinline__ void make_ray(const float* __restrict__ prm, int view, int x, int y, int W, int H, int V,
+                                         int recipe, f3& o, f3& d) {
+    const int r = recipe - 1;
+    const int T = r / 18, D = (r / 9) % 2, N = r % 3;
+    int M = (r / 3) % 3;
+    if (T) {
+        const long long total = (long long)V * H * W, row = ((long long)view * H + y) * W + x;
+        if (row >= total - total % 65535) M = 3;
+    }
+    const float cx = (float)x + 0.5f, cy = (float)y + 0.5f;
+    const float fx = D ? __fmul_rn(cx, __fdiv_rn(1.0f, (float)W)) : __fdiv_rn(cx, (float)W);
+    const float fy = D ? __fmul_rn(cy, __fdiv_rn(1.0f, (float)H)) : __fdiv_rn(cy, (float)H);
+    const float nx = __fsub_rn(__fmul_rn(fx, 2.0f), 1.0f), ny = __fsub_rn(__fmul_rn(fy, 2.0f), 1.0f);
+    const float* ip = prm;            // inv(proj), row-major: view[j] = sum_k clip[k] * ip[4 j + k]
+    const float* im = prm + 16;       // inv(mv)
+    float v[4], w[3];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = ray_dot4(nx, ny, -1.0f, 1.0f, ip + 4 * j, M);
+#pragma unroll
+    for (int j = 0; j < 3; j++) w[j] = ray_dot4(v[0], v[1], v[2], v[3], im + 4 * j, M);
+    o = f3{im[3], im[7], im[11]};
+    const float dx = __fsub_rn(w[0], o.x), dy = __fsub_rn(w[1], o.y), dz = __fsub_rn(w[2], o.z);
+    float n2;
+    if (N == 0) n2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    else if (N == 1) n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    else n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz)), __fmul_rn(dy, dy));
+    const float len = __fadd_rn(__fsqrt_rn(n2), 1e-6f);
+    d = f3{__fdiv_rn(dx, len), __fdiv_rn(dy, len), __fdiv_rn(dz, len)};
+}
+
 __device__ __forceinline__ float clamp01_depth(float z) {
     float d = __fmul_rn(__fadd_rn(z, 1.0f), 0.5f);
     if (d < 0.0f) d = 0.0f;
@@ -258,6 +306,7 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
                            void* grad_ws, const void* shade_cache, long long shade_cache_bytes, cudaStream_t s);
+int launch_generate_rays(const float* ray_params, int V, int H, int W, int recipe, float* out_o, float* out_d, cudaStream_t s);
 int launch_peer_allreduce(const void* const* peer_ptrs, void* multicast_ptr, const void* const* peer_flag_ptrs,
                           uint32_t epoch, int world, int rank, long long n_floats, cudaStream_t s);
 int launch_grad_scatter(const DM2RenderInputs& in, const FaceWs& fw, const DM2RenderGrads& g, void* grad_ws,

@@ -141,11 +141,15 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
     const size_t pix = inside ? ((size_t)b * in.H + py) * in.W + px : 0;
     f3 ro{0, 0, 0}, rd{0, 0, 0};
     if (inside) {
-        const size_t rix = in.ray_view ? ((size_t)in.ray_view[b] * in.H + py) * in.W + px : pix;
-        const float* o = in.image_ray_o + rix * 3;
-        const float* d = in.image_ray_d + rix * 3;
-        ro = f3{o[0], o[1], o[2]};
-        rd = f3{d[0], d[1], d[2]};
+        if (in.ray_view && in.ray_recipe > 0) {
+            make_ray(in.ray_params + 32 * (size_t)in.ray_view[b], in.ray_view[b], px, py, in.W, in.H, in.ray_v, in.ray_recipe, ro, rd);
+        } else {
+            const size_t rix = in.ray_view ? ((size_t)in.ray_view[b] * in.H + py) * in.W + px : pix;
+            const float* o = in.image_ray_o + rix * 3;
+            const float* d = in.image_ray_d + rix * 3;
+            ro = f3{o[0], o[1], o[2]};
+            rd = f3{d[0], d[1], d[2]};
+        }
     }
     const uint2 range = ranges[blockIdx.x];
     const int total = (int)(range.y - range.x);
@@ -248,6 +252,26 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
         curr_tet = next_tet;
     }
     layers_cnt[pix] = n_done;
+}
+
+__global__ void __launch_bounds__(256)
+k_generate_rays(const float* __restrict__ prm, int V, int H, int W, int recipe, float* __restrict__ out_o,
+                float* __restrict__ out_d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)V * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), v = (int)(i / ((long long)W * H));
+    f3 o, d;
+    make_ray(prm + 32 * (size_t)v, v, x, y, W, H, V, recipe, o, d);
+    out_o[3 * i] = o.x; out_o[3 * i + 1] = o.y; out_o[3 * i + 2] = o.z;
+    out_d[3 * i] = d.x; out_d[3 * i + 1] = d.y; out_d[3 * i + 2] = d.z;
+}
+
+int launch_generate_rays(const float* ray_params, int V, int H, int W, int recipe, float* out_o, float* out_d, cudaStream_t s) {
+    const long long n = (long long)V * H * W;
+    if (n == 0) return 0;
+    k_generate_rays<<<cdiv(n, 256), 256, 0, s>>>(ray_params, V, H, W, recipe, out_o, out_d);
+    DM2_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, void* geo_ws,

@@ -159,11 +159,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
     float T_final = 0.0f, prev_T_final = 0.0f;
     int my_last = 0;
     if (tc.inside) {
-        const size_t rix = ray_index(in, tc);
-        const float* ro = in.image_ray_o + rix * 3;
-        const float* rd = in.image_ray_d + rix * 3;
-        pg.o = f3{ro[0], ro[1], ro[2]};
-        pg.d = f3{rd[0], rd[1], rd[2]};
+        load_ray(in, tc, pg.o, pg.d);
         dC0 = dL_dcolor[tc.pix * 3 + 0]; dC1 = dL_dcolor[tc.pix * 3 + 1]; dC2 = dL_dcolor[tc.pix * 3 + 2];
         dD = dL_ddepth[tc.pix];
         if (in.depth_unit) dD = -0.5f * dD;      // d(1 - (z + 1) / 2)/dz, exact

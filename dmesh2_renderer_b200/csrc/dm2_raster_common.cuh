@@ -276,12 +276,25 @@ __device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, i
                        (blockIdx.x % kCtasPerTile) * kWarpsPerCta + (threadIdx.x >> 5));
 }
 
-// index of this pixel's ray: patch-local (B,H,W,3) buffers, or the renderer's full-resolution
-// (V,ray_h,ray_w,3) buffers addressed through ray_view + patch_min (fused path)
-__device__ __forceinline__ size_t ray_index(const DM2RenderInputs& in, const TileCtx& tc) {
-    if (in.ray_view == nullptr) return tc.pix;
-    const int pmx = in.patch_min[2 * tc.b], pmy = in.patch_min[2 * tc.b + 1];
-    return ((size_t)in.ray_view[tc.b] * in.ray_h + (tc.py + pmy)) * in.ray_w + (tc.px + pmx);
+// This pixel's ray: from patch-local (B,H,W,3) buffers, from the renderer's full-resolution
+// (V,ray_h,ray_w,3) buffers addressed through ray_view + patch_min (fused path), or - ray_recipe > 0 -
+// computed from the view's 32 ray parameters (make_ray: bit-identical to the buffers by construction,
+// verified by the host before it selects a recipe).
+__device__ __forceinline__ void load_ray(const DM2RenderInputs& in, const TileCtx& tc, f3& o, f3& d) {
+    size_t rix = tc.pix;
+    if (in.ray_view != nullptr) {
+        const int pmx = in.patch_min[2 * tc.b], pmy = in.patch_min[2 * tc.b + 1];
+        const int view = in.ray_view[tc.b];
+        if (in.ray_recipe > 0) {
+            make_ray(in.ray_params + 32 * (size_t)view, view, tc.px + pmx, tc.py + pmy, in.ray_w, in.ray_h, in.ray_v, in.ray_recipe, o, d);
+            return;
+        }
+        rix = ((size_t)view * in.ray_h + (tc.py + pmy)) * in.ray_w + (tc.px + pmx);
+    }
+    const float* ro = in.image_ray_o + rix * 3;
+    const float* rd = in.image_ray_d + rix * 3;
+    o = f3{ro[0], ro[1], ro[2]};
+    d = f3{rd[0], rd[1], rd[2]};
 }
 
 }  // namespace dm2

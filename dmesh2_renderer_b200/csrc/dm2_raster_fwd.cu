@@ -45,11 +45,7 @@ k_raster_forward(DM2RenderInputs in, const float* __restrict__ records, const ui
     pg.pymin = (float)((uint32_t)tc.py + (uint32_t)in.patch_min[2 * tc.b + 1]);
     pg.o = f3{0, 0, 0}; pg.d = f3{0, 0, 0};
     if (tc.inside) {
-        const size_t rix = ray_index(in, tc);
-        const float* ro = in.image_ray_o + rix * 3;
-        const float* rd = in.image_ray_d + rix * 3;
-        pg.o = f3{ro[0], ro[1], ro[2]};
-        pg.d = f3{rd[0], rd[1], rd[2]};
+        load_ray(in, tc, pg.o, pg.d);
     }
 
     const uint2 range = ranges[tc.tile];

@@ -20,7 +20,7 @@ from ._lib import DM2FusedGrads, DM2FusedInputs
 
 
 def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
-                  mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, depth_unit=False):
+                  mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, depth_unit=False, ray_spec=None):
     f32, i32 = torch.float32, torch.int32
     keep = dict(background=_prep(background, f32, "background"), patch_min=_prep(patch_min, i32, "patch_min"),
                 verts=_prep(verts, f32, "verts"), faces=_prep(faces, i32, "faces"),
@@ -28,8 +28,12 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
                 faces_opacity=_prep(faces_opacity, f32, "faces_opacity"),
                 mv=_prep(mv, f32, "mv"), proj=_prep(proj, f32, "proj"),
                 faces_intense=_prep(faces_intense, f32, "faces_intense"),
-                ray_o=_prep(ray_o, f32, "ray_o"), ray_d=_prep(ray_d, f32, "ray_d"),
                 ray_view=_prep(ray_view, i32, "ray_view"))
+    if ray_spec is None:
+        keep["ray_o"], keep["ray_d"] = _prep(ray_o, f32, "ray_o"), _prep(ray_d, f32, "ray_d")
+    else:
+        # the kernels generate the rays (recipe verified bit-identical by Renderer._init_rays): no ray tensors
+        keep["ray_params"] = _prep(ray_spec[1], f32, "ray_params")
     if keep["background"].dim() != 1 or keep["background"].size(0) != 3:
         _err("background must have dimensions (3,)")
     if keep["verts"].dim() != 2 or keep["verts"].size(1) != 3:
@@ -48,16 +52,24 @@ def _fused_struct(background, patch_min, patch_width, patch_height, verts, faces
         _err("faces_intense must have dimensions (B, F,)")
     if tuple(keep["patch_min"].shape) != (B, 2) or keep["ray_view"].numel() != B:
         _err("patch_min must have dimensions (B, 2)")
-    ro, rd = keep["ray_o"], keep["ray_d"]
-    if ro.dim() != 4 or ro.size(3) != 3 or ro.shape != rd.shape:
-        _err("image_ray_o must have dimensions (B, H, W, 3)")
+    if ray_spec is None:
+        ro, rd = keep["ray_o"], keep["ray_d"]
+        if ro.dim() != 4 or ro.size(3) != 3 or ro.shape != rd.shape:
+            _err("image_ray_o must have dimensions (B, H, W, 3)")
+        frame = (int(ro.size(1)), int(ro.size(2)))
+    else:
+        if tuple(keep["ray_params"].shape) != (ray_spec[2][0], 32):
+            _err("ray_params must have dimensions (V, 32)")
+        frame = (int(ray_spec[2][1]), int(ray_spec[2][2]))
     if aa_temperature < 0 or aa_temperature > 1:
         _err("aa_temperature must be in the range [0, 1]")
     s = DM2FusedInputs()
     s.B, s.P, s.F, s.H, s.W = B, P, F, int(patch_height), int(patch_width)
-    s.image_h, s.image_w = int(ro.size(1)), int(ro.size(2))
+    s.image_h, s.image_w = frame
     s.aa_temperature = float(aa_temperature)
     s.depth_unit = 1 if depth_unit else 0
+    s.ray_recipe = int(ray_spec[0]) if ray_spec is not None else 0
+    s.ray_v = int(ray_spec[2][0]) if ray_spec is not None else 0
     for k, t in keep.items():
         setattr(s, k, t.data_ptr() if t.numel() > 0 else 0)
     return s, keep
@@ -101,12 +113,13 @@ class GradSink:
 
 class FusedRenderFunction(torch.autograd.Function):
     """(background, patch_min, pw, ph, verts, faces, verts_color, faces_opacity, mv [B,4,4], proj [B,4,4],
-    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer, depth_unit, grad_sink) -> (color
+    faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer, depth_unit, grad_sink, ray_spec) -> (color
     [B,H,W,3], depth [B,H,W]).  Differentiable w.r.t. verts, verts_color, faces_opacity, faces_intense.
     len_oarea_buffer > 0 turns the forward -> backward shading cache on (see _C.py).  depth_unit = False: depth is
     the NDC depth render_forward_cuda returns; True: the kernels apply Renderer.forward's remap
     1 - (depth_ndc + 1) / 2 (reference __init__.py:377-378) themselves, bit-identically, forward and backward.
-    grad_sink: see GradSink."""
+    grad_sink: see GradSink.  ray_spec: (recipe, params [V,32], (V, H, W)) from Renderer._ray_spec() - the kernels
+    then generate the rays themselves and ray_o / ray_d are ignored (may be None)."""
 
     # Per problem shape: what the last call needed.  The binning workspace and the shading cache are allocated
     # from it BEFORE anything is launched and the whole forward pass is enqueued in one library call
@@ -117,11 +130,11 @@ class FusedRenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, background, patch_min, patch_width, patch_height, verts, faces, verts_color, faces_opacity,
                 mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view, len_oarea_buffer=20,
-                depth_unit=False, grad_sink=None):
+                depth_unit=False, grad_sink=None, ray_spec=None):
         lib = _lib.load_library()
         s, keep = _fused_struct(background, patch_min, patch_width, patch_height, verts, faces, verts_color,
                                 faces_opacity, mv, proj, faces_intense, aa_temperature, ray_o, ray_d, ray_view,
-                                depth_unit)
+                                depth_unit, ray_spec)
         dev = keep["verts"].device
         B, H, W = s.B, s.H, s.W
         with torch.cuda.device(dev):
@@ -171,6 +184,7 @@ class FusedRenderFunction(torch.autograd.Function):
         ctx.aa_temperature = aa_temperature
         ctx.depth_unit = bool(depth_unit)
         ctx.grad_sink = grad_sink
+        ctx.ray_spec = None if ray_spec is None else (ray_spec[0], None, ray_spec[2])
         return color, depth
 
     @staticmethod
@@ -179,10 +193,11 @@ class FusedRenderFunction(torch.autograd.Function):
         saved = ctx.saved_tensors
         keep = dict(zip(ctx.keys, saved[:len(ctx.keys)]))
         face_buffer, binning_buffer, image_buffer, pool = saved[len(ctx.keys):]
+        ray_spec = None if ctx.ray_spec is None else (ctx.ray_spec[0], keep["ray_params"], ctx.ray_spec[2])
         s, keep = _fused_struct(keep["background"], keep["patch_min"], ctx.patch[0], ctx.patch[1], keep["verts"],
                                 keep["faces"], keep["verts_color"], keep["faces_opacity"], keep["mv"], keep["proj"],
-                                keep["faces_intense"], ctx.aa_temperature, keep["ray_o"], keep["ray_d"],
-                                keep["ray_view"], ctx.depth_unit)
+                                keep["faces_intense"], ctx.aa_temperature, keep.get("ray_o"), keep.get("ray_d"),
+                                keep["ray_view"], ctx.depth_unit, ray_spec)
         dev = keep["verts"].device
         gc = _prep(grad_color, torch.float32, "dL_dout_color")
         gd = _prep(grad_depth, torch.float32, "dL_dout_depth")
@@ -211,4 +226,4 @@ class FusedRenderFunction(torch.autograd.Function):
         if sink is not None:
             g_verts = g_color = g_opacity = None
         return (None, None, None, None, g_verts, None, g_color, g_opacity, None, None, g_intense, None, None, None,
-                None, None, None, None)
+                None, None, None, None, None)

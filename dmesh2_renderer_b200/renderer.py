@@ -46,7 +46,42 @@ def _unproject_pixel_rays(mv, proj, width, height, device):
     target = world[..., :3].squeeze(-2)                                                      # [B, H, W, 3]
     direction = target - origin
     length = torch.norm(direction, dim=-1, keepdim=True) + 1e-6
-    return origin, direction / length
+    return origin, direction / length, inv_mv, inv_proj
+
+
+def _find_ray_recipe(ray_o, ray_d, inv_mv, inv_proj):
+    """In-kernel ray generation (include/dm2_renderer.h `dm2_generate_rays`).
+
+    The rays are a function of 32 floats per view, but the rounding of the torch ops that produced ray_o /
+    ray_d depends on library choices (division by a host scalar, cuBLAS accumulation order, the norm's reduction
+    order).  The library implements a small family of arithmetic "recipes"; this probe generates ALL rays with
+    each of them once and returns (recipe, params [V, 32]) for the first one whose output equals the torch
+    tensors BIT FOR BIT - only then do the kernels compute rays instead of reading them.  (0, None) otherwise:
+    the kernels keep reading the tensors, which is always correct."""
+    import ctypes as C
+
+    from . import _lib
+    if not (ray_o.is_cuda and ray_o.dtype == torch.float32 and inv_mv.dtype == torch.float32 and ray_o.numel() > 0):
+        return 0, None
+    V, H, W = int(ray_o.shape[0]), int(ray_o.shape[1]), int(ray_o.shape[2])
+    if V * H * W >= 2 ** 31:
+        return 0, None
+    lib = _lib.load_library()
+    params = torch.cat((inv_proj.reshape(V, 16), inv_mv.reshape(V, 16)), dim=1).contiguous()
+    dev = ray_o.device
+    with torch.cuda.device(dev):
+        o = torch.empty_like(ray_o)
+        d = torch.empty_like(ray_d)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        ro, rd = ray_o.contiguous(), ray_d.contiguous()
+        # (the combinations measured on B200 first: D = 1, M = 0, N = 2, with and without the small-last-chunk rule)
+        first = [18 * 1 + 9 * 1 + 0 + 2 + 1, 9 * 1 + 0 + 2 + 1]
+        for recipe in first + [q for q in range(1, _lib.RAY_RECIPES + 1) if q not in first]:
+            _lib.check(lib.dm2_generate_rays(C.c_void_p(params.data_ptr()), V, H, W, recipe, C.c_void_p(o.data_ptr()),
+                                             C.c_void_p(d.data_ptr()), stream))
+            if torch.equal(d, rd) and torch.equal(o, ro):
+                return recipe, params
+    return 0, None
 
 
 class Renderer(torch.nn.Module):
@@ -74,7 +109,24 @@ class Renderer(torch.nn.Module):
         self._init_rays()
 
     def _init_rays(self):
-        self.ray_o, self.ray_d = _unproject_pixel_rays(self.mv, self.proj, self.width, self.height, self.device)
+        self.ray_o, self.ray_d, inv_mv, inv_proj = _unproject_pixel_rays(self.mv, self.proj, self.width, self.height,
+                                                                         self.device)
+        # kernels compute the rays themselves when a recipe reproduces these tensors bit for bit (fused routes)
+        self._ray_recipe, self._ray_params = 0, None
+        if getattr(self, "kernel_rays", True) and self.ray_o.is_cuda:
+            try:
+                self._ray_recipe, self._ray_params = _find_ray_recipe(self.ray_o, self.ray_d, inv_mv.detach(),
+                                                                      inv_proj.detach())
+            except RuntimeError:
+                self._ray_recipe, self._ray_params = 0, None
+
+    def release_ray_buffers(self):
+        """Drops the resident (V, H, W, 3) ray tensors (24 bytes per pixel and view) once the kernels generate
+        the rays themselves.  Only the fused routes keep working afterwards; raises if no ray recipe matched."""
+        if not self._ray_recipe:
+            raise RuntimeError("in-kernel ray generation is not active for this renderer: the ray tensors are needed")
+        self._ray_shape = tuple(self.ray_o.shape)
+        self.ray_o = self.ray_d = None
 
     def _view_ids(self, batch_mvp_idx):
         """(key, ray_view int32 [B], view_idx int64 [B]) for the fused routes.  Python-style negative view ids
@@ -90,12 +142,18 @@ class Renderer(torch.nn.Module):
         key = tuple(key)
         cache = self.__dict__.setdefault("_view_cache", {})
         if key not in cache:
-            idx = torch.tensor(list(key), dtype=torch.int64, device=self.ray_o.device)
+            idx = torch.tensor(list(key), dtype=torch.int64, device=self.mv.device)
             cache[key] = (idx.to(torch.int32), idx)
         return (key,) + cache[key]
 
     def _cameras_need_grad(self):
         return torch.is_grad_enabled() and (self.mv.requires_grad or self.proj.requires_grad)
+
+    def _ray_spec(self):
+        """(recipe, params, (V, H, W)) for the kernels' own ray generation, or None (read the ray tensors)."""
+        if not getattr(self, "_ray_recipe", 0):
+            return None
+        return self._ray_recipe, self._ray_params, (self.num_batch, self.height, self.width)
 
     def compute_verts_ndc_image(self, verts, mv, proj):
         """verts [P,3], mv/proj [B,4,4] -> (verts_ndc [B,P,3], verts_image [B,P,2]) (reference :239-262)."""
@@ -170,7 +228,7 @@ class Renderer(torch.nn.Module):
             verts.to(dtype=f32), faces.to(dtype=torch.int32), verts_color.to(dtype=f32), faces_opacity.to(dtype=f32),
             self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
             faces_intense.to(dtype=f32), aa_temperature, self.ray_o, self.ray_d, ray_view, self.aa_grad_buffer_size,
-            True, getattr(self, "grad_sink", None))
+            True, getattr(self, "grad_sink", None), self._ray_spec())
 
     def prepare_inputs(self, batch_mvp_idx, batch_patch_min, patch_width, patch_height, verts, faces, verts_color,
                        faces_opacity, faces_intense, background, aa_temperature=1.0):
@@ -234,7 +292,8 @@ class LayeredRenderer(Renderer):
             # cache entry holds STRONG references to the geometry tensors and compares with `is`: a freed
             # temporary's address (and version 0) can be handed to the next temporary by the caching allocator,
             # an address of a tensor that is still alive cannot.
-            geo = (verts, faces, tets, face_tets, tet_faces, self.mv, self.proj, self.ray_o, self.ray_d)
+            geo = (verts, faces, tets, face_tets, tet_faces, self.mv, self.proj) + \
+                ((self.ray_o, self.ray_d) if self.ray_o is not None else ())
             sig = (key, self.width, self.height)
             vers = tuple(t._version for t in geo)
             prev = self.__dict__.get("_layer_cache") if getattr(self, "incremental", True) else None
@@ -247,7 +306,7 @@ class LayeredRenderer(Renderer):
                 verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),
                 tet_faces.to(dtype=i32), faces_existence.to(dtype=i32), None, None, self.ray_o, self.ray_d, num_layers,
                 fused=(self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
-                       ray_view), return_taps=True, reuse=reuse)
+                       ray_view), return_taps=True, reuse=reuse, ray_spec=self._ray_spec())
             self.__dict__["_layer_cache"] = dict(sig=sig, versions=vers, geo=geo, taps=taps)
             return layers, cnt
         verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 13
+#define DM2_ABI_VERSION 14
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -77,6 +77,13 @@ typedef struct DM2RenderInputs {
      * ops, so bit-identical), and dL_dout_depth is the gradient w.r.t. THAT value (the backward pass
      * applies the exact factor -1/2).  0: out_depth = depth_ndc, as render_forward_cuda returns it.   */
     int32_t depth_unit;
+    /* In-kernel ray generation: ray_recipe > 0 and ray_params != NULL - the kernels
+     * compute the ray of frame pixel (x, y) of view ray_view[b] from ray_params[view] = [inv(proj) | inv(mv)]
+     * (2 x 16 floats, row-major) with the arithmetic of recipe `ray_recipe` (dm2_generate_rays) instead of
+     * reading image_ray_o / image_ray_d (which may then be NULL).  Needs ray_view / ray_h / ray_w.              */
+    int32_t ray_recipe;
+    const float* ray_params;
+    int32_t ray_v;               /* number of views V behind ray_params / the ray buffers */
     int32_t reserved_;
 } DM2RenderInputs;
 
@@ -113,6 +120,9 @@ typedef struct DM2LayerInputs {
     const float*   mv;                       /* (B,4,4) */
     const float*   proj;                     /* (B,4,4) */
     const int32_t* ray_view;                 /* (B)     */
+    const float*   ray_params;               /* (V,32), as DM2RenderInputs.ray_params (needs ray_view)   */
+    int32_t ray_recipe;                      /* as DM2RenderInputs.ray_recipe                            */
+    int32_t ray_v;                           /* V                                                        */
 } DM2LayerInputs;
 
 /* Byte offsets inside the three workspaces (all 256-byte aligned).                         */
@@ -246,6 +256,9 @@ typedef struct DM2FusedInputs {
     const float*   ray_d;
     const int32_t* ray_view;     /* (B) row of ray_o/ray_d used by batch entry b                   */
     int32_t depth_unit;          /* as DM2RenderInputs.depth_unit                                  */
+    int32_t ray_recipe;          /* as DM2RenderInputs.ray_recipe (0: read ray_o / ray_d)          */
+    const float* ray_params;     /* (V,32) [inv(proj) | inv(mv)] per view, or NULL                 */
+    int32_t ray_v;               /* V                                                              */
     int32_t reserved_;
 } DM2FusedInputs;
 
@@ -278,6 +291,22 @@ int dm2_fused_backward(const DM2FusedInputs* in, const void* face_ws, const void
                        const void* image_ws, int64_t capacity, const float* dL_dout_color,
                        const float* dL_dout_depth, const DM2FusedGrads* grads, void* grad_ws,
                        const void* shade_cache, int64_t shade_cache_bytes, void* stream);
+
+/* ---- pixel rays -------------------------------------------------------------
+ * The reference keeps one origin and one direction per pixel of EVERY view resident (Renderer._init_rays,
+ * reference dmesh2_renderer/__init__.py:198-237: 24 bytes per pixel and view) and gathers patches of them per
+ * call (:264-302).  A ray is a function of 32 floats per view: dm2_generate_rays evaluates it - pixel centre ->
+ * NDC -> inv(proj) -> inv(mv) -> minus the camera position -> normalise with the reference's `+ 1e-6` - and the
+ * tile kernels can do the same in their prologue.  The torch ops of _init_rays fix the ROUNDING only up to
+ * choices the libraries make (division by the frame size as a multiplication by its reciprocal on CUDA, the
+ * accumulation order of the two K = 4 products in cuBLAS - which differs for the last (V H W) mod 65535 pixels,
+ * a separate small batch -, of the squared norm in the reduction kernel), so the
+ * arithmetic is parameterised by a recipe id in [1, DM2_RAY_RECIPES]; the host generates the rays with every
+ * recipe once at construction time and only uses in-kernel rays with a recipe whose output is BIT-IDENTICAL to
+ * the tensors torch produced (dmesh2_renderer_b200/renderer.py).  out_o / out_d: (V, H, W, 3).              */
+#define DM2_RAY_RECIPES 36
+int dm2_generate_rays(const float* ray_params, int32_t V, int32_t H, int32_t W, int32_t recipe, float* out_o,
+                      float* out_d, void* stream);
 
 /* ---- multi-view optimisation step: the gradient exchange ----------------
  * The reference is single-GPU; DMesh++'s multi-view step shards views over the GPUs of one box and

@@ -330,7 +330,7 @@ def test_bench_reference_arm_prints_one_json_line_without_a_gpu(built):
     if torch.cuda.is_available():
         pytest.skip("GPU box: the reference arm runs the reference's CUDA extension there")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--faces", "3000",
-                          "--size", "128", "--cpu-sample-patch", "64"], capture_output=True, text=True, timeout=600)
+                          "--size", "128"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -338,6 +338,8 @@ def test_bench_reference_arm_prints_one_json_line_without_a_gpu(built):
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "frames/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # the CPU oracle is also timed on cfg1, for real
+    assert d["cpu_baseline"]["cfg1"]["value"] > 0 and "cfg1" in d["cpu_baseline"]["cfg1"]["sample"]
 
 
 def test_bench_algorithmic_bytes_follow_survey_8d():

@@ -1066,3 +1066,61 @@ def test_camera_gradients_use_the_reference_shaped_route(built):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     with pytest.raises(IndexError):
         r2([3], pm, 48, 48, *rest, st["faces_intense"][[2]], st["background"])
+
+
+# ------------------------------------------------------------------------------------------------
+# in-kernel ray generation
+@pytest.mark.parametrize("size,n_views", [(64, 3), (96, 2), (200, 1)])
+def test_kernel_rays_are_bit_identical_to_the_torch_ray_tensors(built, size, n_views):
+    """A ray recipe is only selected when it reproduces torch's ray_o / ray_d bit for bit (power-of-two and other
+    frame sizes: torch's CUDA division by the frame size is a multiplication by its reciprocal); with it the
+    kernels generate the rays themselves: same image, same layer ids, same gradients - also after the ray
+    tensors have been released."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import _lib, scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=500, size=size, sigma=0.12, seed=9, n_views=n_views)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], size, size, dev)
+    assert 1 <= r._ray_recipe <= _lib.RAY_RECIPES, "no ray recipe reproduces torch's rays on this box"
+    off = dm.Renderer.__new__(dm.Renderer)
+    torch.nn.Module.__init__(off)
+    off.kernel_rays = False                       # the renderer that reads the tensors
+    off._setup(st["mv"], st["proj"], size, size, dev)
+    off.aa_grad_buffer_size = 20
+    assert off._ray_recipe == 0
+    views = list(range(n_views))
+    a = _public_step(r, st, sc, dev, views=views)
+    b = _public_step(off, st, sc, dev, views=views)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in a[2]:
+        assert rel_err(a[2][k].grad.cpu().numpy(), b[2][k].grad.cpu().numpy()) <= 1e-5, k
+    # patches (rays addressed through patch_min) and released tensors
+    pm = torch.tensor([[5, 9]] * n_views, dtype=torch.int32, device=dev)
+    args = (st["verts"], st["faces"], st["verts_color"], st["faces_opacity"], st["faces_intense"][views], st["background"])
+    p0 = off(views, pm, 40, 33, *args)
+    r.release_ray_buffers()
+    assert r.ray_o is None
+    p1 = r(views, pm, 40, 33, *args)
+    assert torch.equal(p0[0], p1[0]) and torch.equal(p0[1], p1[1])
+    with pytest.raises(RuntimeError):
+        off.release_ray_buffers()
+
+
+def test_kernel_rays_layered(built):
+    from dmesh2_renderer_b200 import LayeredRenderer, scenes
+    dev = _dev()
+    sc = scenes.small_tets(n_points=400, size=80)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    a = [t(getattr(sc, k)) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")]
+    lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    assert lr._ray_recipe > 0
+    off = LayeredRenderer.__new__(LayeredRenderer)
+    off.kernel_rays = False
+    off._setup(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    x, y = lr.generate([0], *a, sc.num_layers), off.generate([0], *a, sc.num_layers)
+    assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
+    lr.release_ray_buffers()
+    lr.incremental = False
+    z = lr.generate([0], *a, sc.num_layers)
+    assert torch.equal(z[0], y[0]) and torch.equal(z[1], y[1])
