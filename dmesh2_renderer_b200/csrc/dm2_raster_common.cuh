@@ -276,6 +276,14 @@ __device__ __forceinline__ TileCtx tile_ctx(const DM2RenderInputs& in, int gx, i
                        (blockIdx.x % kCtasPerTile) * kWarpsPerCta + (threadIdx.x >> 5));
 }
 
+// (out of line: once per thread, and the tile kernels' register allocation must not depend on this prologue)
+static __device__ __noinline__ void make_ray_outlined(const float* prm, int view, int x, int y, int W, int H, int V,
+                                                      int recipe, float* out6) {
+    f3 o, d;
+    make_ray(prm, view, x, y, W, H, V, recipe, o, d);
+    out6[0] = o.x; out6[1] = o.y; out6[2] = o.z; out6[3] = d.x; out6[4] = d.y; out6[5] = d.z;
+}
+
 // This pixel's ray: from patch-local (B,H,W,3) buffers, from the renderer's full-resolution
 // (V,ray_h,ray_w,3) buffers addressed through ray_view + patch_min (fused path), or - ray_recipe > 0 -
 // computed from the view's 32 ray parameters (make_ray: bit-identical to the buffers by construction,
@@ -285,10 +293,16 @@ __device__ __forceinline__ void load_ray(const DM2RenderInputs& in, const TileCt
     if (in.ray_view != nullptr) {
         const int pmx = in.patch_min[2 * tc.b], pmy = in.patch_min[2 * tc.b + 1];
         const int view = in.ray_view[tc.b];
+#ifndef DM2_EXP_NO_KERNEL_RAYS
         if (in.ray_recipe > 0) {
-            make_ray(in.ray_params + 32 * (size_t)view, view, tc.px + pmx, tc.py + pmy, in.ray_w, in.ray_h, in.ray_v, in.ray_recipe, o, d);
+            float r6[6];
+            make_ray_outlined(in.ray_params + 32 * (size_t)view, view, tc.px + pmx, tc.py + pmy, in.ray_w, in.ray_h, in.ray_v,
+                              in.ray_recipe, r6);
+            o = f3{r6[0], r6[1], r6[2]};
+            d = f3{r6[3], r6[4], r6[5]};
             return;
         }
+#endif
         rix = ((size_t)view * in.ray_h + (tc.py + pmy)) * in.ray_w + (tc.px + pmx);
     }
     const float* ro = in.image_ray_o + rix * 3;

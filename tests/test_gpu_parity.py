@@ -1082,13 +1082,9 @@ def test_kernel_rays_are_bit_identical_to_the_torch_ray_tensors(built, size, n_v
     sc = scenes.small(n_faces=500, size=size, sigma=0.12, seed=9, n_views=n_views)
     st = scene_tensors(sc, dev)
     r = dm.Renderer(st["mv"], st["proj"], size, size, dev)
-    assert 1 <= r._ray_recipe <= _lib.RAY_RECIPES, "no ray recipe reproduces torch's rays on this box"
-    off = dm.Renderer.__new__(dm.Renderer)
-    torch.nn.Module.__init__(off)
-    off.kernel_rays = False                       # the renderer that reads the tensors
-    off._setup(st["mv"], st["proj"], size, size, dev)
-    off.aa_grad_buffer_size = 20
-    assert off._ray_recipe == 0
+    assert r._ray_recipe == 0, "in-kernel rays are opt-in"
+    assert r.enable_kernel_rays() and 1 <= r._ray_recipe <= _lib.RAY_RECIPES, "no ray recipe reproduces torch's rays"
+    off = dm.Renderer(st["mv"], st["proj"], size, size, dev)      # the renderer that reads the tensors
     views = list(range(n_views))
     a = _public_step(r, st, sc, dev, views=views)
     b = _public_step(off, st, sc, dev, views=views)
@@ -1103,8 +1099,11 @@ def test_kernel_rays_are_bit_identical_to_the_torch_ray_tensors(built, size, n_v
     assert r.ray_o is None
     p1 = r(views, pm, 40, 33, *args)
     assert torch.equal(p0[0], p1[0]) and torch.equal(p0[1], p1[1])
+    # a renderer whose rays no recipe reproduces keeps its tensors
+    off.ray_d = off.ray_d * 1.0000001
     with pytest.raises(RuntimeError):
         off.release_ray_buffers()
+    assert off.ray_o is not None
 
 
 def test_kernel_rays_layered(built):
@@ -1114,10 +1113,8 @@ def test_kernel_rays_layered(built):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     a = [t(getattr(sc, k)) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")]
     lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
-    assert lr._ray_recipe > 0
-    off = LayeredRenderer.__new__(LayeredRenderer)
-    off.kernel_rays = False
-    off._setup(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    assert lr.enable_kernel_rays()
+    off = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
     x, y = lr.generate([0], *a, sc.num_layers), off.generate([0], *a, sc.num_layers)
     assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
     lr.release_ray_buffers()
