@@ -121,6 +121,8 @@ SYMBOLS = {
                                              C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dm2_regenerate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p]),
+    "dm2_layers_composite_forward": (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 9),
+    "dm2_layers_composite_backward": (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 13),
     "dm2_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "dm2_sort_temp_bytes": (C.c_int, [C.c_int64, _P(C.c_size_t)]),

@@ -578,6 +578,35 @@ int dm2_regenerate_render_layers(const DM2LayerInputs* in, void* image_ws, void*
     return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, true, (cudaStream_t)stream);
 }
 
+int dm2_layers_composite_forward(int32_t B, int32_t H, int32_t W, int32_t L, int32_t F, const int32_t* render_layers,
+                                 const int32_t* render_layers_cnt, const float* faces_color, const float* faces_opacity,
+                                 const float* faces_intense, const float* background, float* out_color, float* out_alpha,
+                                 void* stream) {
+    DM2_REQUIRE(B >= 0 && H >= 0 && W >= 0 && L >= 0 && F >= 0, "dm2_layers_composite_forward: negative dimension");
+    DM2_REQUIRE((long long)B * H * W < (1ll << 31), "B*H*W must be < 2^31");
+    if ((long long)B * H * W == 0) return 0;
+    DM2_REQUIRE(render_layers_cnt && (render_layers || L == 0) && background && out_color && out_alpha &&
+                (F == 0 || (faces_color && faces_opacity)), "dm2_layers_composite_forward: null buffer");
+    return launch_layers_composite_forward(B, H, W, L, F, render_layers, render_layers_cnt, faces_color, faces_opacity,
+                                           faces_intense, background, out_color, out_alpha, (cudaStream_t)stream);
+}
+int dm2_layers_composite_backward(int32_t B, int32_t H, int32_t W, int32_t L, int32_t F, const int32_t* render_layers,
+                                  const int32_t* render_layers_cnt, const float* faces_color, const float* faces_opacity,
+                                  const float* faces_intense, const float* background, const float* dL_dout_color,
+                                  const float* dL_dout_alpha, void* grad_ws, float* dL_dfaces_color,
+                                  float* dL_dfaces_opacity, float* dL_dfaces_intense, void* stream) {
+    DM2_REQUIRE(B >= 0 && H >= 0 && W >= 0 && L >= 0 && F >= 0, "dm2_layers_composite_backward: negative dimension");
+    DM2_REQUIRE((long long)B * H * W < (1ll << 31), "B*H*W must be < 2^31");
+    if (F == 0) return 0;
+    DM2_REQUIRE(render_layers_cnt && (render_layers || L == 0) && background && dL_dout_color && grad_ws && faces_color &&
+                faces_opacity && dL_dfaces_color && dL_dfaces_opacity, "dm2_layers_composite_backward: null buffer");
+    DM2_REQUIRE((faces_intense == nullptr) == (dL_dfaces_intense == nullptr) || dL_dfaces_intense == nullptr,
+                "dm2_layers_composite_backward: dL_dfaces_intense without faces_intense");
+    return launch_layers_composite_backward(B, H, W, L, F, render_layers, render_layers_cnt, faces_color, faces_opacity,
+                                            faces_intense, background, dL_dout_color, dL_dout_alpha, grad_ws, dL_dfaces_color,
+                                            dL_dfaces_opacity, dL_dfaces_intense, (cudaStream_t)stream);
+}
+
 int dm2_sort_temp_bytes(int64_t n, size_t* bytes) {
     DM2_REQUIRE(bytes && n >= 0, "dm2_sort_temp_bytes: bad arguments");
     *bytes = sort_temp_bytes(n);

@@ -318,5 +318,12 @@ size_t backward_ws_bytes(long long BF);
 int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
                   void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, cudaStream_t s);
 size_t layers_geo_bytes(int F, int T);
+int launch_layers_composite_forward(int B, int H, int W, int L, int F, const int32_t* layers, const int32_t* cnt,
+                                    const float* color, const float* opacity, const float* intense, const float* background,
+                                    float* out_color, float* out_alpha, cudaStream_t s);
+int launch_layers_composite_backward(int B, int H, int W, int L, int F, const int32_t* layers, const int32_t* cnt,
+                                     const float* color, const float* opacity, const float* intense, const float* background,
+                                     const float* g_color, const float* g_alpha, void* grad_ws, float* d_color,
+                                     float* d_opacity, float* d_intense, cudaStream_t s);
 
 }  // namespace dm2

@@ -300,4 +300,118 @@ int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, c
     return 0;
 }
 
+// =====================================================================================================
+// Layer consumer: the step DMesh++ runs after LayeredRenderer.generate() - gather the
+// attributes of the faces recorded per ray and composite them front to back - as ONE kernel per direction
+// instead of L gathers + a cumulative product in torch (the reference returns ids only, __init__.py:404-451).
+//   T_0 = 1;  a_l = opacity[f_l];  c_l = color[f_l] * intense[b, f_l] (intense optional)
+//   C = sum_l T_l a_l c_l + T_L background;  T_{l+1} = T_l (1 - a_l);  alpha = 1 - T_L;   l < min(cnt, L)
+// Backward: dL/dc_l = T_l a_l g;  dL/da_l = T_l (c_l . g) - (R_l - T_L g_alpha) / (1 - a_l) with
+// R_l = sum_{m>l} T_m a_m (c_m . g) + T_L (background . g); per (ray, layer) ONE 16-byte vector reduction into a
+// packed per-face record (d color, d opacity), unpacked by a second kernel.
+constexpr int kCompMaxL = 32;
+
+__global__ void __launch_bounds__(256)
+k_layers_composite_fwd(long long npix, int HW, int L, int F, const int32_t* __restrict__ layers,
+                       const int32_t* __restrict__ cnt, const float* __restrict__ color, const float* __restrict__ opacity,
+                       const float* __restrict__ intense, const float* __restrict__ background,
+                       float* __restrict__ out_color, float* __restrict__ out_alpha) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int n = min(cnt[i], L);
+    const size_t vb = (size_t)(i / HW) * F;
+    float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int l = 0; l < n; l++) {
+        const int f = layers[i * L + l];
+        if ((unsigned)f >= (unsigned)F) continue;
+        const float a = opacity[f];
+        const float w = T * a * (intense ? intense[vb + f] : 1.0f);
+        c0 = fmaf(w, color[3 * (size_t)f], c0);
+        c1 = fmaf(w, color[3 * (size_t)f + 1], c1);
+        c2 = fmaf(w, color[3 * (size_t)f + 2], c2);
+        T *= 1.0f - a;
+    }
+    out_color[3 * i] = fmaf(T, background[0], c0);
+    out_color[3 * i + 1] = fmaf(T, background[1], c1);
+    out_color[3 * i + 2] = fmaf(T, background[2], c2);
+    out_alpha[i] = 1.0f - T;
+}
+
+__global__ void __launch_bounds__(256)
+k_layers_composite_bwd(long long npix, int HW, int L, int F, const int32_t* __restrict__ layers,
+                       const int32_t* __restrict__ cnt, const float* __restrict__ color, const float* __restrict__ opacity,
+                       const float* __restrict__ intense, const float* __restrict__ background,
+                       const float* __restrict__ g_color, const float* __restrict__ g_alpha, float* __restrict__ gface,
+                       float* __restrict__ g_intense) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int n = min(min(cnt[i], L), kCompMaxL);
+    const size_t vb = (size_t)(i / HW) * F;
+    const float g0 = g_color[3 * i], g1 = g_color[3 * i + 1], g2 = g_color[3 * i + 2], ga = g_alpha ? g_alpha[i] : 0.0f;
+    float Ts[kCompMaxL];
+    float T = 1.0f;
+    for (int l = 0; l < n; l++) {
+        Ts[l] = T;
+        const int f = layers[i * L + l];
+        if ((unsigned)f < (unsigned)F) T *= 1.0f - opacity[f];
+    }
+    // R = everything behind layer l as seen through dL/dC, minus the alpha output's share
+    float R = T * (background[0] * g0 + background[1] * g1 + background[2] * g2) - T * ga;
+    for (int l = n - 1; l >= 0; l--) {
+        const int f = layers[i * L + l];
+        if ((unsigned)f >= (unsigned)F) continue;
+        const float a = opacity[f], it = intense ? intense[vb + f] : 1.0f;
+        const float q0 = color[3 * (size_t)f], q1 = color[3 * (size_t)f + 1], q2 = color[3 * (size_t)f + 2];
+        const float cg = q0 * g0 + q1 * g1 + q2 * g2;           // (colour . g), without the intensity
+        const float Tl = Ts[l];
+        const float w = Tl * a * it;
+        const float da = Tl * it * cg - R / (1.0f - a);
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(gface + 4 * (size_t)f), "f"(w * g0), "f"(w * g1),
+                     "f"(w * g2), "f"(da) : "memory");
+        if (g_intense) atomicAdd(g_intense + vb + f, Tl * a * cg);
+        R += w * cg;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_layers_composite_unpack(int F, const float* __restrict__ gface, float* __restrict__ d_color, float* __restrict__ d_opacity) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const float4 g = reinterpret_cast<const float4*>(gface)[f];
+    d_color[3 * (size_t)f] = g.x; d_color[3 * (size_t)f + 1] = g.y; d_color[3 * (size_t)f + 2] = g.z;
+    d_opacity[f] = g.w;
+}
+
+int launch_layers_composite_forward(int B, int H, int W, int L, int F, const int32_t* layers, const int32_t* cnt,
+                                    const float* color, const float* opacity, const float* intense, const float* background,
+                                    float* out_color, float* out_alpha, cudaStream_t s) {
+    const long long npix = (long long)B * H * W;
+    if (npix == 0) return 0;
+    ProfScope _ps("layers_composite_forward", s);
+    k_layers_composite_fwd<<<cdiv(npix, 256), 256, 0, s>>>(npix, H * W, L, F, layers, cnt, color, opacity, intense, background,
+                                                          out_color, out_alpha);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_layers_composite_backward(int B, int H, int W, int L, int F, const int32_t* layers, const int32_t* cnt,
+                                     const float* color, const float* opacity, const float* intense, const float* background,
+                                     const float* g_color, const float* g_alpha, void* grad_ws, float* d_color,
+                                     float* d_opacity, float* d_intense, cudaStream_t s) {
+    const long long npix = (long long)B * H * W;
+    if (F == 0) return 0;
+    DM2_REQUIRE(L <= kCompMaxL, "dm2_layers_composite_backward: at most 32 layers");
+    float* gface = reinterpret_cast<float*>(grad_ws);
+    ProfScope _ps("layers_composite_backward", s);
+    DM2_CHECK(cudaMemsetAsync(gface, 0, (size_t)F * 16, s));
+    if (npix > 0) {
+        k_layers_composite_bwd<<<cdiv(npix, 256), 256, 0, s>>>(npix, H * W, L, F, layers, cnt, color, opacity, intense,
+                                                              background, g_color, g_alpha, gface, d_intense);
+        DM2_LAUNCH_CHECK();
+    }
+    k_layers_composite_unpack<<<cdiv(F, 256), 256, 0, s>>>(F, gface, d_color, d_opacity);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace dm2

@@ -226,6 +226,24 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
 int dm2_regenerate_render_layers(const DM2LayerInputs* in, void* image_ws, void* geo_ws,
                                  int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
 
+/* ---- layer consumer ----------------------------------------------------------------
+ * The reference's LayeredRenderer returns face ids only (reference dmesh2_renderer/__init__.py:404-451); DMesh++
+ * then gathers per-layer face attributes and composites them in torch (L gathers + a cumulative product).  One
+ * kernel per direction: front-to-back compositing of the first min(cnt, L) recorded faces of every ray,
+ *     C = sum_l T_l a_l c_l + T_L background,  T_{l+1} = T_l (1 - a_l),  alpha = 1 - T_L,
+ * a_l = faces_opacity[f_l], c_l = faces_color[f_l] (* faces_intense[b, f_l] if faces_intense != NULL).
+ * Backward: dL/dfaces_color (F,3), dL/dfaces_opacity (F) are fully overwritten; dL/dfaces_intense (B,F) is
+ * accumulated into a caller-zeroed buffer (NULL: not wanted); grad_ws: 16 * F bytes of scratch; L <= 32.       */
+int dm2_layers_composite_forward(int32_t B, int32_t H, int32_t W, int32_t L, int32_t F, const int32_t* render_layers,
+                                 const int32_t* render_layers_cnt, const float* faces_color, const float* faces_opacity,
+                                 const float* faces_intense, const float* background, float* out_color, float* out_alpha,
+                                 void* stream);
+int dm2_layers_composite_backward(int32_t B, int32_t H, int32_t W, int32_t L, int32_t F, const int32_t* render_layers,
+                                  const int32_t* render_layers_cnt, const float* faces_color, const float* faces_opacity,
+                                  const float* faces_intense, const float* background, const float* dL_dout_color,
+                                  const float* dL_dout_alpha, void* grad_ws, float* dL_dfaces_color,
+                                  float* dL_dfaces_opacity, float* dL_dfaces_intense, void* stream);
+
 /* ---- Renderer, fused host prep ----------------------------------------
  * Renderer.forward of the reference spends ~25 torch kernels per call on host-side prep
  * (reference dmesh2_renderer/__init__.py:239-262, 335-347 and pyrenderer.py:6-30): the w clamp and

@@ -1121,3 +1121,59 @@ def test_kernel_rays_layered(built):
     lr.incremental = False
     z = lr.generate([0], *a, sc.num_layers)
     assert torch.equal(z[0], y[0]) and torch.equal(z[1], y[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# layer consumer: fused gather + front-to-back composite of the generated layers
+@pytest.mark.parametrize("with_intense", [False, True])
+def test_composite_layers_matches_torch(built, with_intense):
+    """Forward within 1e-5 and all gradients within 1e-4 (atomic order) of the plain-torch statement of the op,
+    on real layers of a tet scene (ragged counts, -1 padding, two views)."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    dev = _dev()
+    sc = scenes.delaunay_tets("comp", 1500, 96, seed=19, p_exist=0.3, num_layers=6,
+                              eyes=[tuple(e) for e in scenes.fibonacci_eyes(64)[:2]])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lr = dm.LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    layers, cnt = lr.generate([0, 1], t(sc.verts), t(sc.faces), t(sc.tets), t(sc.face_tets), t(sc.tet_faces),
+                              t(sc.face_existence), sc.num_layers)
+    assert int(cnt.max()) == sc.num_layers and int(cnt.min()) == 0
+    F = sc.faces.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(2)
+    mk = lambda *s_: torch.rand(*s_, generator=g).to(dev)
+    base = dict(color=mk(F, 3), opacity=mk(F) * 0.9 + 0.05, intense=mk(2, F) * 0.5 + 0.5)
+    bg = torch.tensor([0.2, 0.5, 0.9], device=dev)
+    wc, wa = mk(2, sc.height, sc.width, 3) - 0.5, mk(2, sc.height, sc.width) - 0.5
+    res = []
+    for fn in (dm.composite_layers, dm.composite_layers_torch):
+        p = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        color, alpha = fn(layers, cnt, p["color"], p["opacity"], bg, p["intense"] if with_intense else None)
+        ((color * wc).sum() + (alpha * wa).sum()).backward()
+        res.append((color.detach(), alpha.detach(), p))
+    (c0, a0, p0), (c1, a1, p1) = res
+    assert float((c0 - c1).abs().max()) <= 1e-5 and float((a0 - a1).abs().max()) <= 1e-5
+    for k in ("color", "opacity") + (("intense",) if with_intense else ()):
+        e = float((p0[k].grad - p1[k].grad).abs().max()) / (float(p1[k].grad.abs().max()) + 1e-30)
+        assert e <= 1e-4, (k, e)
+    assert with_intense or p0["intense"].grad is None
+
+
+def test_composite_layers_edge_cases(built):
+    import dmesh2_renderer_b200 as dm
+    dev = _dev()
+    bg = torch.tensor([1.0, 0.0, 0.5], device=dev)
+    col = torch.rand(4, 3, device=dev)
+    op = torch.tensor([0.5, 0.25, 0.0, 0.9], device=dev)
+    layers = torch.tensor([[[[0, 1, -1], [-1, -1, -1], [3, 3, 3]]]], dtype=torch.int32, device=dev)      # (1,1,3,3)
+    cnt = torch.tensor([[[2, 0, 5]]], dtype=torch.int32, device=dev)                                       # cnt > L is clamped
+    color, alpha = dm.composite_layers(layers, cnt, col, op, bg)
+    want_c, want_a = dm.composite_layers_torch(layers, cnt, col, op, bg)
+    assert torch.allclose(color, want_c, atol=1e-6) and torch.allclose(alpha, want_a, atol=1e-6)
+    assert torch.allclose(color[0, 0, 1], bg) and float(alpha[0, 0, 1]) == 0.0
+    empty = dm.composite_layers(layers[:, :, :0], cnt[:, :, :0], col, op, bg)
+    assert empty[0].shape == (1, 1, 0, 3)
+    with pytest.raises(RuntimeError):
+        dm.composite_layers(layers, cnt, col[:3], op, bg)
+    with pytest.raises(RuntimeError):
+        dm.composite_layers(layers.cpu(), cnt.cpu(), col.cpu(), op.cpu(), bg.cpu())
