@@ -22,23 +22,31 @@ from ._lib import DM2BinningLayout, DM2FaceLayout, DM2ImageLayout, DM2LayerInput
 # Shading-cache sizing (include/dm2_renderer.h: 16 bytes per touched (pixel, face) pair + 24 bytes per
 # partially covered one, handed from the forward to the backward pass).  The pool is sized from what the
 # previous forward call of the same problem shape asked for (+ SHADE_CACHE_SLACK); a first call reserves
-# SHADE_CACHE_FIRST_BYTES_PER_INSTANCE per sorted (face, tile) instance.  Blocks that do not fit are simply
-# not cached (the backward pass recomputes them), so a pool that is too small costs time, never results.
+# SHADE_CACHE_FIRST_BYTES_PER_INSTANCE per sorted (face, tile) instance, at most SHADE_CACHE_FIRST_MAX_BYTES
+# (deep scenes terminate early and stage a fraction of their instances: 10 M triangles @2048^2 need 100 bytes per
+# instance, 1 M @1024^2 360).  Blocks that do not fit are simply not cached (the backward pass recomputes them),
+# so a pool that is too small costs time, never results; a pool that overflowed under-reports its demand (warps
+# stop asking once it is full), so the next one is twice as large.
 SHADE_CACHE_FIRST_BYTES_PER_INSTANCE = 512
+SHADE_CACHE_FIRST_MAX_BYTES = 2 << 30
 SHADE_CACHE_SLACK = 1.08
 SHADE_CACHE_MAX_BYTES = 48 << 30
 SHADE_CACHE_HEADER = 256
 
 
-def shade_cache_alloc(len_oarea_buffer, num_rendered, aa_temperature, device, want=True, used_granules=None):
+def shade_cache_alloc(len_oarea_buffer, num_rendered, aa_temperature, device, want=True, used_granules=None,
+                      prev_capacity_bytes=0):
     """Returns the pool tensor (uint8; empty when the cache is off: len_oarea_buffer == 0 - the reference's K -,
-    aa_temperature == 0, nothing to render, or no gradient wanted)."""
+    aa_temperature == 0, nothing to render, or no gradient wanted).  used_granules / prev_capacity_bytes: demand
+    counter and pool size of the previous forward call of this problem shape."""
     if not (want and len_oarea_buffer > 0 and aa_temperature > 0 and num_rendered > 0):
         return torch.empty((0,), dtype=torch.uint8, device=device)
     if used_granules is not None and used_granules > 0:
         nbytes = int(used_granules * 16 * SHADE_CACHE_SLACK) + 4096
+        if prev_capacity_bytes and used_granules * 16 > prev_capacity_bytes - SHADE_CACHE_HEADER:
+            nbytes = max(nbytes, 2 * int(prev_capacity_bytes))            # overflowed: the demand is a lower bound
     else:
-        nbytes = int(num_rendered) * SHADE_CACHE_FIRST_BYTES_PER_INSTANCE
+        nbytes = min(int(num_rendered) * SHADE_CACHE_FIRST_BYTES_PER_INSTANCE, SHADE_CACHE_FIRST_MAX_BYTES)
     nbytes = min(nbytes, SHADE_CACHE_MAX_BYTES)
     nbytes = SHADE_CACHE_HEADER + (nbytes + 15) // 16 * 16
     return torch.empty((nbytes,), dtype=torch.uint8, device=device)

@@ -41,25 +41,51 @@ namespace dm2 {
 
 // Fan accumulator with PREDICATED pushes: every lane executes the same instruction stream whatever
 // its polygon looks like (the branchy formulation ran at 2-3 active lanes per instruction).
+// Instruction-count reductions of the clip that were measured SLOWER on B200 in same-box A/Bs (ptxas' register
+// allocation for the forward kernel is the binding constraint, not the instruction count) stay switchable:
+//   DM2_CLIP_RELFAN  previous fan vertex kept relative to the first one (2 FADD less per push)
+//   DM2_CLIP_CARRY   an edge's end-point inside test carried over to the next edge (4 compares less per edge)
+//   DM2_CLIP_NCHECK  "more than two intersections" tested once per edge instead of once per pixel edge
+#ifndef DM2_CLIP_RELFAN
+#define DM2_CLIP_RELFAN 0
+#endif
+#ifndef DM2_CLIP_CARRY
+#define DM2_CLIP_CARRY 0
+#endif
+#ifndef DM2_CLIP_NCHECK
+#define DM2_CLIP_NCHECK 0
+#endif
 struct FanAcc {
     int np = 0;
     float area = 0.0f;
-    float fx = 0.f, fy = 0.f, qx = 0.f, qy = 0.f;       // first and previous polygon vertex
+    // first polygon vertex, and the previous one RELATIVE to it (qx - fx, qy - fy): exactly the two differences
+    // the next fan triangle needs - they were computed as (x - fx, y - fy) when that vertex was pushed
+    float fx = 0.f, fy = 0.f, qx = 0.f, qy = 0.f;
     bool bad = false;     // negative fan-triangle area (aa.h:410-412); polygon overflow is checked at the end
     __device__ __forceinline__ void push(bool cond, float x, float y) {
         const bool is_first = cond & (np == 0);
         const bool is_tri = cond & (np >= 2);
         // _tri_area(first, prev, v), aa.h:88-94
+#if DM2_CLIP_RELFAN
+        const float ax = qx, dy = qy;
+        const float cx = __fsub_rn(x, fx), by = __fsub_rn(y, fy);
+#else
         const float ax = __fsub_rn(qx, fx), by = __fsub_rn(y, fy);
         const float cx = __fsub_rn(x, fx),  dy = __fsub_rn(qy, fy);
+#endif
         const float s = __fmul_rn(0.5f, __fmaf_rn(ax, by, -__fmul_rn(cx, dy)));
         bad |= is_tri & (s < 0.0f);
         area = is_tri ? __fadd_rn(area, s) : area;
         fx = is_first ? x : fx;
         fy = is_first ? y : fy;
         const bool set_prev = cond & (np >= 1);
+#if DM2_CLIP_RELFAN
+        qx = set_prev ? cx : qx;
+        qy = set_prev ? by : qy;
+#else
         qx = set_prev ? x : qx;
         qy = set_prev ? y : qy;
+#endif
         np += cond ? 1 : 0;
     }
     // aa.h:45-48: adding a vertex to a polygon that already holds 10 is an error; np only grows on
@@ -87,6 +113,14 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
 #define DM2_CLIP_UNROLL 1
 #endif
     constexpr int kClipUnroll = DM2_CLIP_UNROLL;
+#if DM2_CLIP_CARRY
+    // (an edge's end point is the next edge's start point: its inside test is carried over)
+    bool in_next;
+    {
+        const float2 v0 = *reinterpret_cast<const float2*>(rec + R_AAV);
+        in_next = (v0.x >= pxmin) & (v0.x <= pxmax) & (v0.y >= pymin) & (v0.y <= pymax);
+    }
+#endif
 #pragma unroll kClipUnroll
     for (int ti = 0; ti < 3; ti++) {
         const int tj = (ti == 2) ? 0 : ti + 1;
@@ -96,8 +130,14 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
         const float2 rc = *reinterpret_cast<const float2*>(rec + R_AAR + 2 * ti);
         const bool edge_vertical   = (zflags >> (2 * ti)) & 1u;      // edges_iszero[ti][0]
         const bool edge_horizontal = (zflags >> (2 * ti + 1)) & 1u;  // edges_iszero[ti][1]
+#if DM2_CLIP_CARRY
+        const bool in0 = in_next;
+        const bool in1 = (p1.x >= pxmin) & (p1.x <= pxmax) & (p1.y >= pymin) & (p1.y <= pymax);
+        in_next = in1;
+#else
         const bool in0 = (p0.x >= pxmin) & (p0.x <= pxmax) & (p0.y >= pymin) & (p0.y <= pymax);
         const bool in1 = (p1.x >= pxmin) & (p1.x <= pxmax) & (p1.y >= pymin) & (p1.y <= pymax);
+#endif
 
         float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;     // up to two intersections, pixel-edge order
         float ta = 0.f, tb = 0.f;
@@ -117,13 +157,20 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
             const float i1 = __fmaf_rn(t, ea1, p0a1);                // aa.h:252
             const bool valid = (t >= 0.0f) & (t <= 1.0f) & (i1 >= lo1) & (i1 <= hi1) & !parallel;
             // error 1: hits a pixel corner; error 2: more than two intersections
+#if DM2_CLIP_NCHECK
+            fan.bad |= valid & ((i1 == lo1) | (i1 == hi1));           // (error 2: n > 2 after the loop)
+#else
             fan.bad |= valid & ((i1 == lo1) | (i1 == hi1) | (n >= 2));
+#endif
             const float qx = horiz ? i1 : cst, qy = horiz ? cst : i1;
             const bool is_a = valid & (n == 0), is_b = valid & (n == 1);
             ax = is_a ? qx : ax; ay = is_a ? qy : ay; ta = is_a ? t : ta; pa = is_a ? pi : pa;
             bx = is_b ? qx : bx; by = is_b ? qy : by; tb = is_b ? t : tb; pb = is_b ? pi : pb;
             n += valid ? 1 : 0;
         }
+#if DM2_CLIP_NCHECK
+        fan.bad |= n > 2;
+#endif
         // aa.h:299-400 as predicates
         const bool two = (n >= 2), one = (n == 1), none = (n == 0);
         const bool swap = two & (ta > tb);                           // sort by t; strict '>' keeps order on ties

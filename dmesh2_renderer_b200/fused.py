@@ -83,6 +83,8 @@ class _FrameHint:
         self.num_rendered = 0
         self.longest = -1
         self.cache_granules = 0
+        self.cache_bytes = 0          # size of the pool the demand counter above was measured on
+        self._pending_bytes = 0
         self._pinned = None
         self._event = None
 
@@ -92,12 +94,14 @@ class _FrameHint:
         if self._pinned is None:
             self._pinned = torch.zeros((1,), dtype=torch.int32).pin_memory()
         self._pinned.copy_(pool[:4].view(torch.int32), non_blocking=True)
+        self._pending_bytes = int(pool.numel())
         self._event = torch.cuda.Event()
         self._event.record(stream)
 
     def poll(self):
         if self._event is not None and self._event.query():
             self.cache_granules = int(self._pinned[0]) & 0xFFFFFFFF
+            self.cache_bytes = self._pending_bytes
             self._event = None
 
 
@@ -153,7 +157,7 @@ class FusedRenderFunction(torch.autograd.Function):
                 cap = hint.num_rendered + hint.num_rendered // 16 + 1024
                 binning_buffer = torch.empty((binning_layout(cap).total,), dtype=torch.uint8, device=dev)
                 pool = shade_cache_alloc(int(len_oarea_buffer), cap, float(aa_temperature), dev, want_cache,
-                                         hint.cache_granules)
+                                         hint.cache_granules, hint.cache_bytes)
                 lhint = -1 if hint.longest < 0 else hint.longest + hint.longest // 4
                 _lib.check(lib.dm2_fused_forward_pipelined(
                     C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer), cap, lhint, _ptr(color),
@@ -168,7 +172,7 @@ class FusedRenderFunction(torch.autograd.Function):
                 cap = R
                 binning_buffer = torch.empty((binning_layout(cap).total,), dtype=torch.uint8, device=dev)
                 pool = shade_cache_alloc(int(len_oarea_buffer), cap, float(aa_temperature), dev, want_cache,
-                                         hint.cache_granules)
+                                         hint.cache_granules, hint.cache_bytes)
                 _lib.check(lib.dm2_fused_forward(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer),
                                                  cap, int(longest.value), _ptr(color), _ptr(depth), _ptr(pool),
                                                  int(pool.numel()), stream))

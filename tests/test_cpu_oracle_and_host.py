@@ -60,6 +60,11 @@ def test_shade_cache_sizing_policy(built, monkeypatch):
     used = 54321
     pool = _C.shade_cache_alloc(20, 1000, 1.0, cpu, used_granules=used)
     assert used * 16 * _C.SHADE_CACHE_SLACK <= pool.numel() - _C.SHADE_CACHE_HEADER <= used * 16 * 1.2 + 8192
+    # a pool that overflowed under-reports its demand: the next one doubles
+    pool = _C.shade_cache_alloc(20, 1000, 1.0, cpu, used_granules=1000, prev_capacity_bytes=_C.SHADE_CACHE_HEADER + 16 * 900)
+    assert pool.numel() >= 2 * (_C.SHADE_CACHE_HEADER + 16 * 900)
+    monkeypatch.setattr(_C, "SHADE_CACHE_FIRST_MAX_BYTES", 16 * 700)
+    assert _C.shade_cache_alloc(20, 1000, 1.0, cpu).numel() == _C.SHADE_CACHE_HEADER + 16 * 700
     monkeypatch.setattr(_C, "SHADE_CACHE_MAX_BYTES", 16 * 500)
     assert _C.shade_cache_alloc(20, 1000, 1.0, cpu).numel() == _C.SHADE_CACHE_HEADER + 16 * 500
 

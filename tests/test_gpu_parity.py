@@ -600,8 +600,8 @@ def test_peer_allreduce_matches_nccl_two_gpus(built):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
-    for k in ("small_p2p", "cfg2_p2p"):
-        assert res[k]["max_rel_err_vs_nccl"] < 1e-6 and res[k]["same_on_all_ranks"]
+    for k in ("small_p2p_fused", "tiny_p2p_fused", "cfg2_p2p_fused", "small_p2p_unfused", "cfg2_p2p_unfused"):
+        assert res[k]["max_rel_err_vs_nccl"] < 1e-6 and res[k]["same_on_all_ranks"], (k, res[k])
 
 
 def test_fused_workspace_hint_survives_a_much_larger_frame(built):

@@ -41,9 +41,15 @@ def main():
     from dmesh2_renderer_b200.multiview import PeerGradBucket
     load_library()
     out = {"world": world}
-    for label, (P, F, mc) in {"small_p2p": (1001, 333, False), "small_mc": (1001, 333, True),
-                              "cfg2_p2p": (3_000_000, 1_000_000, False), "cfg2_mc": (3_000_000, 1_000_000, True)}.items():
-        b = PeerGradBucket(P, F, dev, use_multicast=mc)
+    cases = {}
+    for fused in (True, False):
+        tag = "fused" if fused else "unfused"
+        cases.update({f"small_p2p_{tag}": (1001, 333, False, fused), f"small_mc_{tag}": (1001, 333, True, fused),
+                      f"tiny_p2p_{tag}": (1, 2, False, fused),          # fewer 16-byte vectors than ranks: empty slices
+                      f"cfg2_p2p_{tag}": (3_000_000, 1_000_000, False, fused),
+                      f"cfg2_mc_{tag}": (3_000_000, 1_000_000, True, fused)})
+    for label, (P, F, mc, fused) in cases.items():
+        b = PeerGradBucket(P, F, dev, use_multicast=mc, fused_barriers=fused)
         if mc and not b.uses_multicast:
             out[label] = "no multicast support"
             continue
@@ -52,7 +58,7 @@ def main():
         ref = data.clone()
         dist.all_reduce(ref)
         worst = 0.0
-        for _ in range(3):                       # repeated use of the same bucket / barriers
+        for _ in range(5):                       # repeated use of the same bucket / barriers (epochs)
             b.flat.copy_(data)
             b.allreduce()
             torch.cuda.synchronize()

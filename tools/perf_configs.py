@@ -21,14 +21,19 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+PEAKS = {}
+
+
 def t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def time_it(fn, iters, warmup=2):
+def time_it(fn, iters, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    PEAKS["first_calls"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    torch.cuda.reset_peak_memory_stats()
     ts = []
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -124,7 +129,8 @@ def main():
                 st = _lib.profile_report(); _lib.profile_enable(False)
                 print(json.dumps({"config": sc.name, "stages_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in st.items()}}), flush=True)
             print(json.dumps({"config": sc.name, "impl": name, "ms": ms, "views_or_frames_per_s": unit,
-                              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "scene_gen_s": gen_s}),
+                              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                              "peak_mem_first_calls_gb": PEAKS.get("first_calls"), "scene_gen_s": gen_s}),
                   flush=True)
         if args.check and len(res) == 2:
             a, b = res["b200"], res["reference"]
