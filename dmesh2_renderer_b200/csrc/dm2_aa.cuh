@@ -55,6 +55,16 @@ namespace dm2 {
 #ifndef DM2_CLIP_NCHECK
 #define DM2_CLIP_NCHECK 0
 #endif
+// DM2_CLIP_PFADD: conditional float moves written as predicated `x + 0.0f` (FMA pipe) instead of selects (ALU pipe,
+// the pipe that limits the forward kernel: 72 % busy against 26 % for the FMA pipe)
+#ifndef DM2_CLIP_PFADD
+#define DM2_CLIP_PFADD 0
+#endif
+#if DM2_CLIP_PFADD
+#define DM2_CMOV(p, dst, src) do { if (p) dst = __fadd_rn(src, 0.0f); } while (0)
+#else
+#define DM2_CMOV(p, dst, src) do { dst = (p) ? (src) : dst; } while (0)
+#endif
 struct FanAcc {
     int np = 0;
     float area = 0.0f;
@@ -76,15 +86,15 @@ struct FanAcc {
         const float s = __fmul_rn(0.5f, __fmaf_rn(ax, by, -__fmul_rn(cx, dy)));
         bad |= is_tri & (s < 0.0f);
         area = is_tri ? __fadd_rn(area, s) : area;
-        fx = is_first ? x : fx;
-        fy = is_first ? y : fy;
+        DM2_CMOV(is_first, fx, x);
+        DM2_CMOV(is_first, fy, y);
         const bool set_prev = cond & (np >= 1);
 #if DM2_CLIP_RELFAN
-        qx = set_prev ? cx : qx;
-        qy = set_prev ? by : qy;
+        DM2_CMOV(set_prev, qx, cx);
+        DM2_CMOV(set_prev, qy, by);
 #else
-        qx = set_prev ? x : qx;
-        qy = set_prev ? y : qy;
+        DM2_CMOV(set_prev, qx, x);
+        DM2_CMOV(set_prev, qy, y);
 #endif
         np += cond ? 1 : 0;
     }
@@ -164,8 +174,8 @@ __device__ __forceinline__ bool aa_clip(const float* __restrict__ rec, float pxm
 #endif
             const float qx = horiz ? i1 : cst, qy = horiz ? cst : i1;
             const bool is_a = valid & (n == 0), is_b = valid & (n == 1);
-            ax = is_a ? qx : ax; ay = is_a ? qy : ay; ta = is_a ? t : ta; pa = is_a ? pi : pa;
-            bx = is_b ? qx : bx; by = is_b ? qy : by; tb = is_b ? t : tb; pb = is_b ? pi : pb;
+            DM2_CMOV(is_a, ax, qx); DM2_CMOV(is_a, ay, qy); DM2_CMOV(is_a, ta, t); pa = is_a ? pi : pa;
+            DM2_CMOV(is_b, bx, qx); DM2_CMOV(is_b, by, qy); DM2_CMOV(is_b, tb, t); pb = is_b ? pi : pb;
             n += valid ? 1 : 0;
         }
 #if DM2_CLIP_NCHECK
