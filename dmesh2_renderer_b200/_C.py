@@ -12,6 +12,7 @@ Differences that are private to this implementation (allowed by SURVEY.md sectio
   * the three scratch buffers are laid out per DM2FaceLayout / DM2ImageLayout / DM2BinningLayout.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -317,6 +318,14 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
     if num_layers < 0:
         _err("num_layers must be non-negative")
     f32, i32 = torch.float32, torch.int32
+    if os.environ.get("DM2_VALIDATE_INDICES", "0") != "0":
+        # debug aid (synchronises): the kernels follow tets / tet_faces / face_tets through raw pointers, where
+        # torch indexing in the reference would raise for out-of-range ids
+        P_, F_, T_ = int(verts.size(0)), int(faces.size(0)), int(tets.size(0))
+        for name, t, lo, hi in (("faces", faces, 0, P_), ("tets", tets, 0, P_), ("tet_faces", tet_faces, 0, F_),
+                                ("face_tets", face_tets, -1, T_)):
+            if t.numel() and (int(t.min()) < lo or int(t.max()) >= hi):
+                _err(f"{name} holds an index outside [{lo}, {hi})")
     keep = dict(verts=_prep(verts, f32, "verts"), faces=_prep(faces, i32, "faces"), tets=_prep(tets, i32, "tets"),
                 face_tets=_prep(face_tets, i32, "face_tets"), tet_faces=_prep(tet_faces, i32, "tet_faces"),
                 face_existence=_prep(face_existence, i32, "face_existence"),

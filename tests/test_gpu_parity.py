@@ -1177,3 +1177,70 @@ def test_composite_layers_edge_cases(built):
         dm.composite_layers(layers, cnt, col[:3], op, bg)
     with pytest.raises(RuntimeError):
         dm.composite_layers(layers.cpu(), cnt.cpu(), col.cpu(), op.cpu(), bg.cpu())
+
+
+@pytest.mark.parametrize("n_views,n_faces", [(1, 700), (8, 700), (1, 1_000_000), (8, 1_000_000)])
+def test_fused_projection_is_bit_identical_to_torch_matmul(built, n_views, n_faces):
+    """The fused preprocess kernel reproduces the two K = 4 matmuls of compute_verts_ndc_image as the fma chain
+    cuBLAS runs for them (dm2_common.cuh: clip_vertex) - for B in {1, 8} and P in {2 k, 3 M} (different cuBLAS
+    kernels: gemv / batched).  Checked on what the projection feeds: tiles_touched, the three depth keys, and the
+    packed records (NDC z, screen-space AA vertices / edges / reciprocals / normals) must be bit-identical between
+    the fused preprocess and the reference-shaped one, which consumes torch's tensors."""
+    import ctypes as C
+    from dmesh2_renderer_b200 import _C, _lib, scenes
+    from dmesh2_renderer_b200.fused import _fused_struct
+    dev = _dev()
+    sc = scenes.cfg4(n_views=n_views, size=256, n_faces=n_faces)
+    r, st, args = render_args(sc, dev)
+    with torch.no_grad():
+        res = _C.render_forward_cuda(*args)
+    R, fb = res[0], res[7]
+    B, F = n_views, n_faces
+    lib = _lib.load_library()
+    key = tuple(range(n_views))
+    _k, ray_view, view_idx = r._view_ids(key)
+    pm = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    s, keep = _fused_struct(st["background"], pm, sc.width, sc.height, st["verts"], st["faces"], st["verts_color"],
+                            st["faces_opacity"], r.mv.index_select(0, view_idx), r.proj.index_select(0, view_idx),
+                            st["faces_intense"], 1.0, r.ray_o, r.ray_d, ray_view, False)
+    fb2 = torch.empty_like(fb)
+    ib2 = torch.empty((_C.image_layout(B, sc.height, sc.width).total,), dtype=torch.uint8, device=dev)
+    nr, longest = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.dm2_fused_preprocess(C.byref(s), _C._ptr(fb2), _C._ptr(ib2), C.byref(nr), C.byref(longest),
+                                        _C._stream(dev)))
+    assert int(nr.value) == R
+    a, b = _C.face_taps(fb, B, F), _C.face_taps(fb2, B, F)
+    live = a["tiles_touched"] > 0
+    assert torch.equal(a["tiles_touched"], b["tiles_touched"]) and int(live.sum()) > 0
+    for k in ("depths", "min_depths", "max_depths"):
+        assert torch.equal(a[k].view(torch.int32)[live], b[k].view(torch.int32)[live]), k
+    L = _C.face_layout(B, F)
+    ra = fb[L.records:L.records + B * F * L.record_stride].view(torch.int32).view(B * F, -1)[live]
+    rb = fb2[L.records:L.records + B * F * L.record_stride].view(torch.int32).view(B * F, -1)[live]
+    # words 0..58: bbox, normals, offsets, opacity / intensity, 3-D vertices + NDC z, colours, vertex ids, AA verts /
+    # edges / reciprocals, face id; word 15 (flags) differs by design: the fused kernel records the CCW flip in bit 8
+    same = (ra[:, :59] == rb[:, :59])
+    same[:, 15] |= ((ra[:, 15] ^ rb[:, 15]) & ~0x100) == 0
+    assert bool(same.all()), f"{int((~same).sum())} record words differ"
+
+
+def test_layered_index_validation_debug_switch(built, monkeypatch):
+    """DM2_VALIDATE_INDICES=1: out-of-range tet / face ids raise instead of being followed through raw pointers."""
+    from dmesh2_renderer_b200 import LayeredRenderer, scenes
+    dev = _dev()
+    sc = scenes.small_tets(n_points=200, size=48)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lr = LayeredRenderer(t(sc.mv), t(sc.proj), sc.width, sc.height, dev)
+    a = {k: t(getattr(sc, k)) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")}
+    monkeypatch.setenv("DM2_VALIDATE_INDICES", "1")
+    lr.generate([0], *a.values(), sc.num_layers)
+    bad = dict(a)
+    bad["tet_faces"] = a["tet_faces"].clone()
+    bad["tet_faces"][3, 2] = a["faces"].shape[0] + 7
+    with pytest.raises(RuntimeError, match="tet_faces"):
+        lr.generate([0], *bad.values(), sc.num_layers)
+    bad = dict(a)
+    bad["face_tets"] = a["face_tets"].clone()
+    bad["face_tets"][5, 0] = -2
+    with pytest.raises(RuntimeError, match="face_tets"):
+        lr.generate([0], *bad.values(), sc.num_layers)
