@@ -11,6 +11,7 @@ micro-batches of 8 views through the public Renderer API, accumulates the replic
 gradients in a flat bucket and the ranks sum the bucket ONCE per step with the library's peer-memory
 allreduce kernel over NVLink (dmesh2_renderer_b200.multiview.PeerGradBucket, csrc/dm2_peer.cu).  STRONG scaling: the 64 views are fixed, N grows.  Timed with CUDA
 events between barriers, max over ranks; rank 0 prints one JSON line (views/s over the whole job).
+(`bench.py --workload cfg4` is the driver-facing version of this workload, with the e2e feed and the allreduce check.)
 """
 import argparse
 import json
@@ -71,7 +72,7 @@ def main():
 
     def step():
         return multiview.multiview_step(render_view_batch, list(range(a.views)), verts, colour, opacity, bucket,
-                                        micro_batch=a.micro_batch, world_size=world, rank=rank)
+                                        micro_batch=a.micro_batch, world_size=world, rank=rank, renderer=renderer)
 
     def timed(n):
         if world > 1:
