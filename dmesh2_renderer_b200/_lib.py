@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 RAY_RECIPES = 36        # DM2_RAY_RECIPES
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
@@ -131,6 +131,7 @@ SYMBOLS = {
     "dm2_higher_msb": (C.c_uint32, [C.c_uint32]),
     "dm2_launch_count": (C.c_int64, [C.c_int32]),
     "dm2_profile_enable": (None, [C.c_int32]),
+    "dm2_set_forward_rounds": (None, [C.c_int64, C.c_int64]),
     "dm2_profile_reset": (None, []),
     "dm2_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
 }

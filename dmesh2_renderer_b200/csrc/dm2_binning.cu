@@ -683,21 +683,46 @@ __device__ __forceinline__ uint32_t corner_row_mask(float nx, float ylo, float c
 }
 
 constexpr int kClsThreads = 256;
+constexpr uint32_t kClsRoundBlocks = 4;     // blocks per tile of a classification round
 
+// ROUND: kClsRoundBlocks blocks per tile classify entries [round_begin, round_begin + 256 chunks) of the tile's list,
+// 256 at a time, only for the footprints of the tile that have not finished compositing (warp_done).  work == nullptr:
+// every tile (grid = kClsRoundBlocks x tiles, the first round); else a grid-stride loop over the list of tiles that
+// are still running (k_round_worklist) - a round in which (nearly) every tile has finished must not cost a launch of
+// tiles x 4 blocks (92 us at 2048^2).  The flat variant covers every instance.
+template <bool ROUND>
 __global__ void __launch_bounds__(kClsThreads)
 k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t cap, BinGuard guard,
                      const float* __restrict__ records, const int32_t* __restrict__ patch_min, int F, int gx, int gy,
-                     int use_bbox, uint8_t* __restrict__ imask, uint4* __restrict__ meta) {
+                     int use_bbox, uint8_t* __restrict__ imask, uint4* __restrict__ meta,
+                     const uint2* __restrict__ ranges, const uint8_t* __restrict__ warp_done, int round_begin, int chunks,
+                     const uint32_t* __restrict__ work, const uint32_t* __restrict__ work_n) {
     __shared__ float s_f[13][kClsThreads];
     __shared__ uint32_t s_o[2][kClsThreads];
     __shared__ uint32_t s_im[kClsThreads];
     __shared__ uint16_t s_pairs[kClsThreads * 8];
     const int t = threadIdx.x;
-    const uint32_t i = blockIdx.x * kClsThreads + t;
     if (bin_invalid(guard)) return;
-    const uint32_t R = __ldg(guard.hdr);            // num_rendered (<= cap, the stride of meta)
-    if (blockIdx.x * kClsThreads >= R) return;
-    if (!use_bbox) { if (i < R) imask[i] = 0xFF; return; }
+    const uint32_t n_items = !ROUND ? blockIdx.x + 1u : work ? *work_n * kClsRoundBlocks : gridDim.x;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    uint32_t R = __ldg(guard.hdr);                  // num_rendered (<= cap, the stride of meta)
+    uint32_t base = blockIdx.x * kClsThreads, active = 0xFFu;
+    if (ROUND) {
+        const uint32_t tile = work ? work[item / kClsRoundBlocks] : item / kClsRoundBlocks;
+        const uint2 r = ranges[tile];
+        base = r.x + (uint32_t)round_begin + (item % kClsRoundBlocks) * kClsThreads;
+        R = min(r.y, r.x + (uint32_t)round_begin + (uint32_t)chunks * kClsThreads);
+        const uint2 wd = *reinterpret_cast<const uint2*>(warp_done + (size_t)tile * 8);
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            if ((wd.x >> (8 * w)) & 0xFFu) active &= ~(1u << w);
+            if ((wd.y >> (8 * w)) & 0xFFu) active &= ~(16u << w);
+        }
+        if (active == 0u) continue;
+    }
+    for (; base < R; base += kClsRoundBlocks * kClsThreads) {           // (one trip in the flat variant)
+    const uint32_t i = base + t;
+    if (!use_bbox) { if (i < R) imask[i] = (uint8_t)active; if (ROUND) continue; return; }
     unsigned bm = 0u;
     if (i < R) {
         const uint32_t cur = (uint32_t)(keys[i] >> 32);
@@ -720,6 +745,7 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
             const bool hit = !((fx0 + 8.0f < bb.x) || (fx0 > bb.y) || (fy0 + 4.0f < bb.z) || (fy0 > bb.w));
             bm |= (hit ? 1u : 0u) << w;
         }
+        bm &= active;
     }
     s_im[t] = 0u;
     uint32_t total;
@@ -768,12 +794,35 @@ k_classify_instances(const uint64_t* __restrict__ keys, const uint32_t* __restri
         const unsigned long long corners = (unsigned long long)allc[0] | ((unsigned long long)allc[1] << 9) |
                                            ((unsigned long long)allc[2] << 18) | ((unsigned long long)allc[3] << 27) |
                                            ((unsigned long long)allc[4] << 36);
-        const uint32_t gi = blockIdx.x * kClsThreads + it;
+        const uint32_t gi = base + it;
         meta[(size_t)w * cap + gi] = make_uint4(hit, (uint32_t)corners, (uint32_t)(corners >> 32), 0xFFFFFFFFu);
         if (hit) atomicOr(&s_im[it], 1u << w);
     }
     __syncthreads();
     if (i < R) imask[i] = (uint8_t)s_im[t];
+    if (!ROUND) return;
+    __syncthreads();                      // s_f / s_pairs are rewritten by the next chunk
+    }
+    }
+}
+
+// Tiles that still have an unfinished footprint and list entries at / behind `next_begin`: their ids go to
+// cls_list (counter n[0]); their unfinished half tiles (tile * 2 + half) go to fwd_list (counter n[1]).
+__global__ void __launch_bounds__(256)
+k_round_worklist(const uint2* __restrict__ ranges, const uint8_t* __restrict__ warp_done, int num_tiles, BinGuard guard,
+                 uint32_t next_begin, uint32_t* __restrict__ n, uint32_t* __restrict__ cls_list,
+                 uint32_t* __restrict__ fwd_list) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= num_tiles || bin_invalid(guard)) return;
+    const uint2 r = ranges[tile];
+    if (r.y - r.x <= next_begin) return;
+    const uint2 wd = *reinterpret_cast<const uint2*>(warp_done + (size_t)tile * 8);
+    const bool lo = (wd.x & 0x01010101u) != 0x01010101u, hi = (wd.y & 0x01010101u) != 0x01010101u;
+    if (!lo && !hi) return;
+    cls_list[atomicAdd(n, 1u)] = (uint32_t)tile;
+    const uint32_t at = atomicAdd(n + 1, (lo ? 1u : 0u) + (hi ? 1u : 0u));
+    if (lo) fwd_list[at] = 2u * tile;
+    if (hi) fwd_list[at + (lo ? 1u : 0u)] = 2u * tile + 1u;
 }
 
 int launch_classify(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr, const TileMaskArgs& tm,
@@ -781,9 +830,34 @@ int launch_classify(const uint64_t* keys, long long capacity, long long longest_
     if (capacity <= 0) return 0;
     ProfScope _ps("classify", s);
     // (the grid covers the workspace capacity; blocks past the actual num_rendered exit at once)
-    k_classify_instances<<<cdiv(capacity, kClsThreads), kClsThreads, 0, s>>>(
+    k_classify_instances<false><<<cdiv(capacity, kClsThreads), kClsThreads, 0, s>>>(
         keys, tm.vals, (uint32_t)capacity, BinGuard{hdr, (uint32_t)capacity, (uint32_t)longest_cap}, tm.records, tm.patch_min, tm.F, tm.gx, tm.gy,
-        tm.use_bbox, tm.imask, reinterpret_cast<uint4*>(tm.meta));
+        tm.use_bbox, tm.imask, reinterpret_cast<uint4*>(tm.meta), nullptr, nullptr, 0, 1, nullptr, nullptr);
+    DM2_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_classify_round(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr,
+                          const TileMaskArgs& tm, const uint2* ranges, const uint8_t* warp_done, int num_tiles,
+                          int round_begin, int round_len, const RoundWork& work, cudaStream_t s) {
+    if (capacity <= 0 || num_tiles <= 0) return 0;
+    const BinGuard guard{hdr, (uint32_t)capacity, (uint32_t)longest_cap};
+    const bool listed = round_begin > 0;
+    if (listed) {
+        // the tiles / half tiles still running after the rounds so far
+        DM2_CHECK(cudaMemsetAsync(work.n, 0, 4 * sizeof(uint32_t), s));
+        k_round_worklist<<<cdiv(num_tiles, 256), 256, 0, s>>>(ranges, warp_done, num_tiles, guard, (uint32_t)round_begin,
+                                                              work.n, work.cls_list, work.fwd_list);
+        DM2_LAUNCH_CHECK();
+    }
+    ProfScope _ps("classify", s);
+    const int chunks = cdiv(round_len, kClsThreads);
+    const long long grid = listed ? std::min<long long>((long long)num_tiles * kClsRoundBlocks, 4ll * sm_count())
+                                  : (long long)num_tiles * kClsRoundBlocks;
+    k_classify_instances<true><<<(unsigned)grid, kClsThreads, 0, s>>>(
+        keys, tm.vals, (uint32_t)capacity, guard, tm.records, tm.patch_min, tm.F, tm.gx, tm.gy,
+        tm.use_bbox, tm.imask, reinterpret_cast<uint4*>(tm.meta), ranges, warp_done, round_begin, chunks,
+        listed ? work.cls_list : nullptr, listed ? work.n : nullptr);
     DM2_LAUNCH_CHECK();
     return 0;
 }

@@ -87,13 +87,20 @@ static void face_layout(long long BF, bool layered, DM2FaceLayout* L) {
     L->total         = off + 256;
 }
 
+// tile_cursor area: u32[nt + 3] (cursors + the 12-byte header), padded to 16 bytes, then - used when the forward
+// pass runs in rounds - u8[8 nt]: one "this footprint's compositing is finished" flag per (tile, 8x4 footprint), and
+// u32[4 + 3 nt]: the work lists of a round (RoundWork)
+static size_t cursor_words(size_t nt) { return (nt + 3 + 3) / 4 * 4; }
+static size_t cursor_zero_bytes(size_t nt) { return cursor_words(nt) * 4 + nt * 8; }     // zeroed every frame
+static size_t cursor_area_bytes(size_t nt) { return cursor_zero_bytes(nt) + (4 + 3 * nt) * 4; }
+
 static void image_layout(long long B, int H, int W, bool layered, DM2ImageLayout* L) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const long long tiles = (long long)cdiv(W, kTile) * cdiv(H, kTile);
     const size_t npix = (size_t)B * H * W;
     L->ranges = take((size_t)B * tiles * 8);
-    L->tile_cursor = take(((size_t)B * tiles + 3) * 4);
+    L->tile_cursor = take(cursor_area_bytes((size_t)B * tiles));
     if (layered) {
         L->final_T = L->final_prev_T = L->n_contrib = 0;
         L->first_face = take(npix * 4);
@@ -134,6 +141,9 @@ static ImageWs carve_image(void* ws, long long B, int H, int W, bool layered) {
     char* p = reinterpret_cast<char*>(ws);
     ImageWs i;
     i.ranges = (uint2*)(p + L.ranges); i.tile_cursor = (uint32_t*)(p + L.tile_cursor); i.final_T = (float*)(p + L.final_T);
+    const size_t nt = (size_t)B * cdiv(W, kTile) * cdiv(H, kTile);
+    i.warp_done = (uint8_t*)(i.tile_cursor + cursor_words(nt));
+    i.round_work = (uint32_t*)(i.warp_done + nt * 8);
     i.final_prev_T = (float*)(p + L.final_prev_T); i.n_contrib = (uint32_t*)(p + L.n_contrib);
     i.first_face = (int*)(p + L.first_face); i.first_tet = (int*)(p + L.first_tet);
     return i;
@@ -210,7 +220,7 @@ static int check_flags(uint32_t flags) {
     return 0;
 }
 static int zero_cursor(const ImageWs& iw, int B, int gx, int gy, cudaStream_t s) {
-    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, ((size_t)B * gx * gy + 3) * sizeof(uint32_t), s));
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, cursor_zero_bytes((size_t)B * gx * gy), s));
     return 0;
 }
 
@@ -219,7 +229,7 @@ static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaSt
     ImageWs iw = carve_image(image_ws, B, H, W, layered);
     const size_t nt = (size_t)B * cdiv(W, kTile) * cdiv(H, kTile);
     DM2_CHECK(cudaMemsetAsync(iw.ranges, 0, nt * sizeof(uint2), s));
-    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, (nt + 3) * sizeof(uint32_t), s));
+    DM2_CHECK(cudaMemsetAsync(iw.tile_cursor, 0, cursor_zero_bytes(nt), s));
     return 0;
 }
 
@@ -239,7 +249,23 @@ using namespace dm2;
 extern "C" {
 
 const char* dm2_last_error(void) { return g_err; }
+// Measured (tools/perf_configs.py --rounds-ab, profiles/r02_forward_rounds.md): doubling rounds beat equal ones (the
+// launches of rounds in which every tile has finished are not free); 512 / 4096 keeps the 8-view 512^2 micro-batch
+// (longest list 3 824, almost no early termination) on the single pass, where rounds cost 3 %.
+static long long kRoundLen = 512, kRoundThreshold = 4096;
+static void round_knobs() {             // DM2_ROUND_LEN (multiple of 256) / DM2_ROUND_THRESHOLD: measurement knobs
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (const char* e = getenv("DM2_ROUND_LEN")) kRoundLen = std::max(256ll, atoll(e) / 256 * 256);
+        if (const char* e = getenv("DM2_ROUND_THRESHOLD")) kRoundThreshold = atoll(e);
+    });
+}
 int dm2_abi_version(void) { return DM2_ABI_VERSION; }
+void dm2_set_forward_rounds(int64_t round_len, int64_t threshold) {
+    round_knobs();                      // (the environment is read first so that it cannot override this call later)
+    kRoundLen = std::max<long long>(256, round_len / 256 * 256);
+    kRoundThreshold = threshold;
+}
 uint32_t dm2_higher_msb(uint32_t n) { return higher_msb(n); }
 void dm2_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -298,18 +324,57 @@ int dm2_render_preprocess(const DM2RenderInputs* in, void* face_ws, void* image_
     return check_flags(flags);
 }
 
-// everything behind the scan: scatter + segment sort, classification, forward compositor
+// everything behind the scan: scatter + segment sort, classification, forward compositor.
+// Deep scenes (a tile segment longer than kRoundThreshold instances) run classification + compositing in ROUNDS of
+// kRoundLen, then doubling, list entries per tile: the forward pass terminates long before the end of such lists (T < 1e-4), and
+// classifying entries nobody composites is the most expensive stage there (10 M triangles @2048^2: 2.9 of 10.8 ms).
+// A round classifies entries [k C, (k + 1) C) of every tile that still has an unfinished footprint, then the
+// compositor resumes from the per-pixel state it left in the output / image-state buffers.
+static long long round_end(long long k) {        // list position behind round k
+    return kRoundLen << std::min(k, 40ll);
+}
+// longest: the segment length the launch has to cover (a hint with slack in the pipelined path); basis: the length
+// the rounds-or-not decision is taken on (without slack, so that it does not depend on the calling path)
+static long long rounds_for(long long longest, long long basis) {
+    round_knobs();
+    if (longest < 0 || basis <= kRoundThreshold) return 1;             // unknown / shallow: one pass over everything
+    long long n = 1;
+    while (round_end(n - 1) < longest) n++;
+    return n;
+}
+// longest tile segment a forward_tail launched for (longest, basis) handles correctly
+static long long tail_longest_cap(long long longest, long long basis, bool sort_too) {
+    long long cap = sort_too ? sort_tiers_longest_cap(longest) : 0xFFFFFFFFll;
+    const long long rounds = rounds_for(longest, basis);
+    if (rounds > 1) cap = std::min(cap, round_end(rounds - 1));
+    return cap;
+}
 static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, BinWs bw, const ImageWs& iw, long long longest,
-                        float* out_color, float* out_depth, void* shade_cache, long long shade_cache_bytes,
-                        bool sort_too, cudaStream_t s) {
-    // kernels that read the SORTED lists return at once if a segment is longer than the enqueued sort tiers cover
-    bw.longest_cap = sort_too ? sort_tiers_longest_cap(longest) : 0xFFFFFFFFll;
+                        long long basis, float* out_color, float* out_depth, void* shade_cache,
+                        long long shade_cache_bytes, bool sort_too, cudaStream_t s) {
+    // kernels that read the SORTED lists return at once if a segment is longer than what was enqueued covers
+    bw.longest_cap = tail_longest_cap(longest, basis, sort_too);
     const long long BF = (long long)in->B * in->F;
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
     if (sort_too && bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, longest, s)) return 1;
-    if (launch_classify(bw.keys, bw.R, bw.longest_cap, iw.tile_cursor + (size_t)in->B * gx * gy, tm, s)) return 1;
-    return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0, s);
+    const uint32_t* hdr = iw.tile_cursor + (size_t)in->B * gx * gy;
+    const long long rounds = rounds_for(longest, basis);
+    if (rounds == 1) {
+        if (launch_classify(bw.keys, bw.R, bw.longest_cap, hdr, tm, s)) return 1;
+        return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0,
+                                     0, 0, RoundWork{nullptr, nullptr, nullptr}, s);
+    }
+    const long long nt = (long long)in->B * gx * gy;
+    const RoundWork work{iw.round_work, iw.round_work + 4, iw.round_work + 4 + nt};
+    for (long long k = 0; k < rounds; k++) {
+        const int rb = k ? (int)round_end(k - 1) : 0, re = (int)round_end(k);
+        if (launch_classify_round(bw.keys, bw.R, bw.longest_cap, hdr, tm, iw.ranges, iw.warp_done, (int)nt,
+                                  rb, re - rb, work, s)) return 1;
+        if (launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0,
+                                  rb, re, work, s)) return 1;
+    }
+    return 0;
 }
 
 int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_ws, void* image_ws,
@@ -330,7 +395,7 @@ int dm2_render_forward(const DM2RenderInputs* in, void* face_ws, void* binning_w
         DM2_CHECK(cudaMemsetAsync(out_depth, 0, npix * sizeof(float), s));
         return 0;
     }
-    return forward_tail(in, fw, bw, iw, longest, out_color, out_depth, shade_cache, shade_cache_bytes, true, s);
+    return forward_tail(in, fw, bw, iw, longest, longest, out_color, out_depth, shade_cache, shade_cache_bytes, true, s);
 }
 
 int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const void* binning_ws,
@@ -448,20 +513,23 @@ int dm2_fused_forward_pipelined(const DM2FusedInputs* in, void* face_ws, void* b
     FaceWs fw = carve_face(face_ws, BF, false);
     BinWs bw = carve_bin(binning_ws, capacity);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, false);
-    if (forward_tail(&r, fw, bw, iw, longest_hint, out_color, out_depth, shade_cache, shade_cache_bytes, true, s)) return 1;
+    // (the previous frame's longest segment + 25 %: a little growth must not cost a repair)
+    const long long covered = longest_hint < 0 ? -1 : longest_hint + longest_hint / 4;
+    if (forward_tail(&r, fw, bw, iw, covered, longest_hint, out_color, out_depth, shade_cache, shade_cache_bytes, true, s)) return 1;
     // 3. only now wait for the header (its event completed long before the raster kernel ends)
     uint32_t flags = 0;
     if (wait_header(num_rendered_host, &flags, longest_host)) return 1;
     if (check_flags(flags)) return 2;
     if (*num_rendered_host > capacity) { *fits_host = 0; return 0; }      // caller re-runs dm2_fused_forward
-    const int missing = tiers_for(*longest_host) & ~tiers_for(longest_hint);
-    if (missing) {
-        // a segment longer than the hinted sort tier: the scatter is valid (and must not run twice) - sort the
-        // long segments now and redo classification + compositing on the same workspace
+    const int missing = tiers_for(*longest_host) & ~tiers_for(covered);
+    if (missing || *longest_host > tail_longest_cap(covered, longest_hint, true)) {
+        // a segment longer than the hinted sort tier / the enqueued rounds: the scatter is valid (and must not run
+        // twice) - sort the long segments now and redo classification + compositing on the same workspace
         const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
-        if (launch_tile_sort_tiers(in->B * gx * gy, iw.ranges, iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted,
-                                   bw.keys, bw.vals, bw.R, missing, s)) return 1;
-        if (forward_tail(&r, fw, bw, iw, *longest_host, out_color, out_depth, shade_cache, shade_cache_bytes, false, s))
+        if (missing && launch_tile_sort_tiers(in->B * gx * gy, iw.ranges, iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted,
+                                              bw.keys, bw.vals, bw.R, missing, s)) return 1;
+        DM2_CHECK(cudaMemsetAsync(iw.warp_done, 0, (size_t)in->B * gx * gy * 8, s));
+        if (forward_tail(&r, fw, bw, iw, *longest_host, *longest_host, out_color, out_depth, shade_cache, shade_cache_bytes, false, s))
             return 1;
     }
     return 0;

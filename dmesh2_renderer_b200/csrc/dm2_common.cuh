@@ -72,6 +72,19 @@ struct PerDeviceOnce {
     void done() { ready.fetch_or(bit(), std::memory_order_release); }
 };
 
+// SMs of the current device (persistent grids)
+static inline int sm_count() {
+    static std::atomic<int> cached[64];
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return 148;
+    int v = cached[d & 63].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) return 148;
+        cached[d & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -267,8 +280,13 @@ struct FaceWs {
 };
 struct ImageWs {
     uint2* ranges; uint32_t* tile_cursor; float* final_T; float* final_prev_T; uint32_t* n_contrib;
+    uint8_t* warp_done;           // u8[8 * tiles]: footprint finished (forward pass in rounds)
+    uint32_t* round_work;         // u32[4 + 3 * tiles]: work lists of a round (RoundWork)
     int* first_face; int* first_tet;
 };
+// tiles (cls_list, n[0] entries) and half tiles (tile * 2 + half: fwd_list, n[1] entries) still running in a round;
+// n[2]: next fwd_list item to hand out
+struct RoundWork { uint32_t* n; uint32_t* cls_list; uint32_t* fwd_list; };
 struct BinWs {
     uint64_t* keys_unsorted; uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
     uint8_t* imask;               // per sorted instance: bit w = footprint w has a touched pixel (render path)
@@ -300,9 +318,15 @@ size_t sort_temp_bytes(long long n);
 int launch_classify(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr, const TileMaskArgs& tm,
                     cudaStream_t s);
 long long sort_tiers_longest_cap(long long longest_hint);
+int launch_classify_round(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr,
+                          const TileMaskArgs& tm, const uint2* ranges, const uint8_t* warp_done, int num_tiles,
+                          int round_begin, int round_len, const RoundWork& work, cudaStream_t s);
+// round_end == 0: one pass over the whole lists; else list entries [round_begin, round_end) of every tile, resuming
+// from / leaving the per-pixel state in out_color / out_depth / final_T / final_prev_T / n_contrib (iw.warp_done)
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                           const ImageWs& iw, float* out_color, float* out_depth, void* shade_cache,
-                          long long shade_cache_bytes, cudaStream_t s);
+                          long long shade_cache_bytes, int round_begin, int round_end, const RoundWork& work,
+                          cudaStream_t s);
 int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,
                            const ImageWs& iw, const float* dL_dcolor, const float* dL_ddepth,
                            void* grad_ws, const void* shade_cache, long long shade_cache_bytes, cudaStream_t s);

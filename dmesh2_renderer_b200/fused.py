@@ -158,7 +158,7 @@ class FusedRenderFunction(torch.autograd.Function):
                 binning_buffer = torch.empty((binning_layout(cap).total,), dtype=torch.uint8, device=dev)
                 pool = shade_cache_alloc(int(len_oarea_buffer), cap, float(aa_temperature), dev, want_cache,
                                          hint.cache_granules, hint.cache_bytes)
-                lhint = -1 if hint.longest < 0 else hint.longest + hint.longest // 4
+                lhint = -1 if hint.longest < 0 else hint.longest       # (the library adds its own slack)
                 _lib.check(lib.dm2_fused_forward_pipelined(
                     C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer), cap, lhint, _ptr(color),
                     _ptr(depth), _ptr(pool), int(pool.numel()), C.byref(nr), C.byref(longest), C.byref(fits), stream))

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 14
+#define DM2_ABI_VERSION 15
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -295,7 +295,8 @@ int dm2_fused_forward(const DM2FusedInputs* in, void* face_ws, void* binning_ws,
 /* dm2_fused_preprocess + dm2_fused_forward in ONE call without a host wait between them (the reference
  * blocks on a device->host copy of num_rendered before it can size the binning scratch, reference
  * cuda_impl/renderer.cu:174-183).  The caller sizes binning_ws for `capacity` instances from the previous
- * frame of the same problem (and passes that frame's longest tile segment, or -1, as longest_hint); all
+ * frame of the same problem (and passes that frame's longest tile segment, or -1, as longest_hint - the
+ * library covers 25 % more than the hint); all
  * kernels are enqueued at once - those behind the tile scan compare num_rendered with `capacity` ON THE
  * DEVICE and return immediately if the frame does not fit - and only then the call waits for the 12-byte
  * header.  *fits_host = 1: the outputs are valid.  *fits_host = 0: *num_rendered_host > capacity; the caller
@@ -373,6 +374,13 @@ int64_t dm2_launch_count(int32_t reset);
  * raster_backward, ...).  dm2_profile_report fills buf with "name total_ms count" lines
  * (it waits for the recorded events) and returns the buffer size needed.                      */
 void dm2_profile_enable(int32_t on);
+/* Deep scenes: when the longest tile list exceeds `threshold` instances, classification + forward compositing run
+ * in rounds - list entries [0, round_len), [round_len, 2 round_len), [2 round_len, 4 round_len), ... of every tile
+ * (round_len a multiple of 256) - and tiles whose pixels have all terminated are not classified any further.  The
+ * reference classifies nothing ahead of time (forward.cu:139-432); this is where its early termination is recovered
+ * for the classification pre-pass.  Results do not depend on these values.  Defaults 512 / 4096; process-wide; not
+ * thread safe against running calls. */
+void dm2_set_forward_rounds(int64_t round_len, int64_t threshold);
 void dm2_profile_reset(void);
 int64_t dm2_profile_report(char* buf, int64_t cap);
 

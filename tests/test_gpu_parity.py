@@ -960,6 +960,50 @@ def test_pipelined_forward_repairs_a_longer_segment_than_hinted(built):
     assert rel_err(l2["verts"].grad.cpu().numpy(), l1["verts"].grad.cpu().numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("round_len,pool_bytes", [(256, None), (512, None), (1024, 1 << 20)])
+def test_forward_in_rounds_equals_single_pass(built, round_len, pool_bytes):
+    """Deep scenes composite in rounds of `round_len` list entries per tile with classification only for the tiles
+    that are still running (dm2_set_forward_rounds): images bit-identical to the single pass, same gradients -
+    synchronous first call, pipelined second call, repaired call (hint shorter than the rounds needed), and with
+    a shading cache too small for the frame (blocks that do not fit fall back to recomputation)."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes, _lib
+    from dmesh2_renderer_b200 import fused as _C
+    from dmesh2_renderer_b200.fused import FusedRenderFunction
+    dev = _dev()
+    sc = scenes.triangle_soup("deep", 80_000, 64, 0.02, seed=77)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    lib = _lib.load_library()
+    real_alloc = _C.shade_cache_alloc
+    try:
+        if pool_bytes is not None:
+            def tiny(*a, **k):
+                t = real_alloc(*a, **k)
+                return t[: pool_bytes] if t is not None and t.numel() > pool_bytes else t
+            _C.shade_cache_alloc = tiny
+        lib.dm2_set_forward_rounds(1024, 1 << 40)            # never in rounds
+        FusedRenderFunction._size_hint.clear()
+        c0, d0, l0, f0 = _public_step(r, st, sc, dev)
+        hint = next(iter(FusedRenderFunction._size_hint.values()))
+        assert hint.longest > 4096, hint.longest             # (also above the default threshold)
+        lib.dm2_set_forward_rounds(round_len, 0)             # always in rounds
+        FusedRenderFunction._size_hint.clear()
+        runs = [_public_step(r, st, sc, dev), _public_step(r, st, sc, dev)]
+        hint = next(iter(FusedRenderFunction._size_hint.values()))
+        hint.longest = round_len                             # the speculative launch covers one round only -> repair
+        runs.append(_public_step(r, st, sc, dev))
+        for c, d, l, f in runs:
+            assert torch.equal(c0, c) and torch.equal(d0, d)
+            for k in l0:
+                assert rel_err(l[k].grad.cpu().numpy(), l0[k].grad.cpu().numpy()) <= 1e-5, k
+            assert rel_err(f.grad.cpu().numpy(), f0.grad.cpu().numpy()) <= 1e-5
+    finally:
+        _C.shade_cache_alloc = real_alloc
+        lib.dm2_set_forward_rounds(512, 4096)
+        FusedRenderFunction._size_hint.clear()
+
+
 def test_input_flags_vertex_ids_and_negative_patch(built):
     """Out-of-range vertex ids raise (torch indexing raises for them in the reference's host prep; raw pointers
     would read out of bounds) - on the first (synchronous) call and on a pipelined one; a negative patch_min is

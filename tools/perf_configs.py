@@ -84,6 +84,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--stages", action="store_true", help="also print this library's per-stage CUDA-event times")
+    ap.add_argument("--rounds-ab", default="", help="same-process A/B of dm2_set_forward_rounds settings, e.g. "
+                    "'1024,1e12;1024,2048;512,1024' (round_len,threshold; a huge threshold = single pass)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     import dmesh2_renderer_b200 as dm
@@ -127,7 +129,19 @@ def main():
                 for _ in range(n):
                     (run_soup if kind == "soup" else run_layers)(*((pkg, sc, dev, views, 1) if kind == "soup" else (pkg, sc, dev, 1)))
                 st = _lib.profile_report(); _lib.profile_enable(False)
-                print(json.dumps({"config": sc.name, "stages_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in st.items()}}), flush=True)
+                steps = n * 4                       # time_it: 3 warm-up calls + 1 timed one
+                print(json.dumps({"config": sc.name, "stages_ms_per_step": {k: round(v[0] / steps, 4) for k, v in st.items()},
+                                  "launches_per_step": {k: v[1] / steps for k, v in st.items()}}), flush=True)
+            if args.rounds_ab and name == "b200" and kind == "soup":
+                from dmesh2_renderer_b200 import _lib
+                lib = _lib.load_library()
+                settings = [tuple(int(float(x)) for x in e.split(",")) for e in args.rounds_ab.split(";")]
+                for rep in range(2):
+                    for L, thr in settings:
+                        lib.dm2_set_forward_rounds(L, thr)
+                        ms_ab, _ = run_soup(pkg, sc, dev, views, args.iters)
+                        print(json.dumps({"config": sc.name, "round_len": L, "threshold": thr, "rep": rep, "ms": round(ms_ab, 4)}), flush=True)
+                lib.dm2_set_forward_rounds(512, 4096)
             print(json.dumps({"config": sc.name, "impl": name, "ms": ms, "views_or_frames_per_s": unit,
                               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                               "peak_mem_first_calls_gb": PEAKS.get("first_calls"), "scene_gen_s": gen_s}),
