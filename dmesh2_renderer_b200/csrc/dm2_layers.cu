@@ -19,7 +19,12 @@ namespace dm2 {
 
 constexpr int kLStage = 256;
 constexpr int kFGeoWords = 16;     // p0.xyz E1.xyz E2.xyz n.xyz (unit normal, not yet oriented) face_tets[2] existence pad
-constexpr int kTGeoWords = 8;      // centroid sum.xyz, flip bits (slot i: the face normal points INTO the tet), tet_faces[4]
+// per tet, 192 bytes: [0] centroid sum.xyz, flip bits (slot i: the face normal points INTO the tet); [1] tet_faces[4];
+// [2] id of the vertex opposite the face in slot i (-1: not a face of this tet); [3] the tet behind the face in slot i
+// (the reference's rule, forward.cu:985-992); [4 + i] position of that opposite vertex, L1 length of the longest edge;
+// [8 + i] stored (not yet oriented) unit normal of the face in slot i.  One record = everything a fast walk step reads
+// except the existence flag of the face it leaves through.
+constexpr int kTGeoWords = 48;
 
 size_t layers_geo_bytes(int F, int T) {
     return align_up((size_t)F * kFGeoWords * 4, 256) + align_up((size_t)T * kTGeoWords * 4, 256) + 256;
@@ -52,8 +57,9 @@ k_face_geo(int F, const float* __restrict__ verts, const int32_t* __restrict__ f
 // (runs after k_face_geo: the orientation test of auxiliary.h:421-427 - is the face normal on the
 // centroid's side? - does not depend on the ray either and is evaluated here once per (tet, face slot))
 __global__ void __launch_bounds__(256)
-k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ tets,
-          const int32_t* __restrict__ tet_faces, const float* __restrict__ fgeo, int F, float* __restrict__ tgeo) {
+k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ tets, const int32_t* __restrict__ faces,
+          const int32_t* __restrict__ tet_faces, const int32_t* __restrict__ face_tets, const float* __restrict__ fgeo, int F,
+          int P, float* __restrict__ tgeo) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int4 q = *reinterpret_cast<const int4*>(tets + 4 * (size_t)t);
@@ -77,9 +83,53 @@ k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ te
         const f3 dd{__fmaf_rn(sx, 0.25f, -fa.x), __fmaf_rn(sy, 0.25f, -fa.y), __fmaf_rn(sz, 0.25f, -fa.z)};
         if (dot3(f3{fc.y, fc.z, fc.w}, dd) > 0.0f) flip |= 1u << i;
     }
+    // walk fast path: the tet vertex opposite each face slot (exactly three of the four tet vertices must be the
+    // face's three distinct vertices), and the L1 length of the longest edge (scale of the robustness margin)
+    const int qv[4] = {q.x, q.y, q.z, q.w};
+    int opp[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        opp[i] = -1;
+        if (tfi[i] < 0 || tfi[i] >= F) continue;
+        const int f0 = faces[3 * (size_t)tfi[i]], f1 = faces[3 * (size_t)tfi[i] + 1], f2 = faces[3 * (size_t)tfi[i] + 2];
+        if (f0 == f1 || f1 == f2 || f0 == f2) continue;
+        int n_in = 0, out = -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool on = qv[k] == f0 || qv[k] == f1 || qv[k] == f2;
+            n_in += on ? 1 : 0;
+            if (!on) out = qv[k];
+        }
+        if (n_in == 3 && out >= 0 && out < P) opp[i] = out;
+    }
+    if (q.x == q.y || q.x == q.z || q.x == q.w || q.y == q.z || q.y == q.w || q.z == q.w) opp[0] = opp[1] = opp[2] = opp[3] = -1;
+    const float* pv[4] = {a, b, c, d};
+    float lmax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int k = i + 1; k < 4; k++)
+            lmax = fmaxf(lmax, fabsf(pv[i][0] - pv[k][0]) + fabsf(pv[i][1] - pv[k][1]) + fabsf(pv[i][2] - pv[k][2]));
     float4* o = reinterpret_cast<float4*>(tgeo + (size_t)t * kTGeoWords);
     o[0] = make_float4(sx, sy, sz, __uint_as_float(flip));
     o[1] = make_float4(__int_as_float(tf.x), __int_as_float(tf.y), __int_as_float(tf.z), __int_as_float(tf.w));
+    o[2] = make_float4(__int_as_float(opp[0]), __int_as_float(opp[1]), __int_as_float(opp[2]), __int_as_float(opp[3]));
+    int nb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        nb[i] = -1;
+        float4 ov = make_float4(0.f, 0.f, 0.f, lmax), nv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tfi[i] >= 0 && tfi[i] < F) {
+            const int ft0 = face_tets[2 * (size_t)tfi[i]], ft1 = face_tets[2 * (size_t)tfi[i] + 1];
+            nb[i] = ft0 != t ? ft0 : ft1 != t ? ft1 : -1;
+            const float4 fc = reinterpret_cast<const float4*>(fgeo + (size_t)tfi[i] * kFGeoWords)[2];
+            nv = make_float4(fc.y, fc.z, fc.w, 0.0f);
+        }
+        if (opp[i] >= 0) ov = make_float4(verts[3 * (size_t)opp[i]], verts[3 * (size_t)opp[i] + 1], verts[3 * (size_t)opp[i] + 2], lmax);
+        o[4 + i] = ov;
+        o[8 + i] = nv;
+    }
+    o[3] = make_float4(__int_as_float(nb[0]), __int_as_float(nb[1]), __int_as_float(nb[2]), __int_as_float(nb[3]));
 }
 
 struct FGeo { f3 p0, e1, e2, n; int ft0, ft1, exist; };
@@ -121,15 +171,68 @@ __device__ __forceinline__ float outward_dot_geo(const FGeo& g, const float4 tsu
     return (dot3(g.n, d) > 0.0f) ? -nd : nd;
 }
 
-// WALK_ONLY: the geometry (and hence the binning and every pixel's first hit / entry tet) is unchanged
-// since an earlier full call on the same workspaces - only face_existence moved: start from the stored
-// first_face / first_tet.
-template <bool WALK_ONLY>
-__global__ void __launch_bounds__(256, 3)
-k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __restrict__ list,
-         const uint2* __restrict__ ranges, const float* __restrict__ fgeo, const float* __restrict__ tgeo,
-         int* __restrict__ first_face_out, int* __restrict__ first_tet_out, int32_t* __restrict__ layers,
-         int32_t* __restrict__ layers_cnt, int gx, int gy) {
+#ifdef DM2_WALK_STATS          /* debug build (tools/build_variant.py walkstats -DDM2_WALK_STATS): step counters */
+__device__ unsigned long long g_walk_stats[8];
+#define DM2_WSTAT(i) atomicAdd(&g_walk_stats[i], 1ull)
+extern "C" void dm2_debug_walk_stats(unsigned long long* out8, int reset) {
+    cudaMemcpyFromSymbol(out8, g_walk_stats, sizeof(g_walk_stats));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_walk_stats, z, sizeof(z)); }
+}
+#else
+#define DM2_WSTAT(i) do { } while (0)
+#endif
+
+// State of the walk's fast path: the entry face's vertices, ordered so that the ray sees them counter-clockwise
+// ([d, a-o, b-o], [d, b-o, c-o], [d, c-o, a-o] > 0), their ids, and the magnitudes of those three edge functions.
+#ifndef DM2_WALK_K
+#define DM2_WALK_K 24.0f
+#endif
+constexpr float kWalkMargin = DM2_WALK_K * 5.9604645e-8f;
+struct WalkFace { f3 a, b, c; int ia, ib, ic; float mab, mbc, mca, zmin; bool ok; };
+__device__ __forceinline__ void walk_face_init(WalkFace& wf, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                                               int face, int P, const f3& ro, const f3& rd) {
+    wf.ok = false;
+    int i0 = __ldg(faces + 3 * (size_t)face), i1 = __ldg(faces + 3 * (size_t)face + 1), i2 = __ldg(faces + 3 * (size_t)face + 2);
+    if ((unsigned)i0 >= (unsigned)P || (unsigned)i1 >= (unsigned)P || (unsigned)i2 >= (unsigned)P) return;
+    f3 a{__ldg(verts + 3 * (size_t)i0), __ldg(verts + 3 * (size_t)i0 + 1), __ldg(verts + 3 * (size_t)i0 + 2)};
+    f3 b{__ldg(verts + 3 * (size_t)i1), __ldg(verts + 3 * (size_t)i1 + 1), __ldg(verts + 3 * (size_t)i1 + 2)};
+    f3 c{__ldg(verts + 3 * (size_t)i2), __ldg(verts + 3 * (size_t)i2 + 1), __ldg(verts + 3 * (size_t)i2 + 2)};
+    // [d, x - o, y - o] = (d x (x - o)) . (y - x)
+    const f3 ao = sub3(a, ro), bo = sub3(b, ro), co = sub3(c, ro);
+    float eab = dot3(cross3(rd, ao), sub3(b, a));
+    float ebc = dot3(cross3(rd, bo), sub3(c, b));
+    float eca = dot3(cross3(rd, co), sub3(a, c));
+    wf.zmin = fminf(dot3(rd, ao), fminf(dot3(rd, bo), dot3(rd, co)));       // smallest depth (x - o) . d of a vertex
+    if (eab < 0.0f && ebc < 0.0f && eca < 0.0f) {            // seen clockwise: swap b and c
+        const f3 t = b; b = c; c = t;
+        const int ti = i1; i1 = i2; i2 = ti;
+        const float e = eab; eab = -eca; eca = -e; ebc = -ebc;
+    }
+    if (!(eab > 0.0f && ebc > 0.0f && eca > 0.0f)) return;
+    wf.a = a; wf.b = b; wf.c = c; wf.ia = i0; wf.ib = i1; wf.ic = i2;
+    wf.mab = eab; wf.mbc = ebc; wf.mca = eca;
+    wf.ok = true;
+}
+
+__device__ __forceinline__ void load_layer_ray(const DM2LayerInputs& in, int b, int px, int py, size_t pix, f3& ro, f3& rd) {
+    if (in.ray_view && in.ray_recipe > 0) {
+        make_ray(in.ray_params + 32 * (size_t)in.ray_view[b], in.ray_view[b], px, py, in.W, in.H, in.ray_v, in.ray_recipe, ro, rd);
+    } else {
+        const size_t rix = in.ray_view ? ((size_t)in.ray_view[b] * in.H + py) * in.W + px : pix;
+        const float* o = in.image_ray_o + rix * 3;
+        const float* d = in.image_ray_d + rix * 3;
+        ro = f3{o[0], o[1], o[2]};
+        rd = f3{d[0], d[1], d[2]};
+    }
+}
+
+// First hit over the min-depth-sorted tile list + choice of the entry tet: one CTA per 16x16 tile (the list is staged
+// through shared memory by all 256 threads); results go to first_face / first_tet (also the state an incremental
+// re-generate starts from).
+__global__ void __launch_bounds__(256)
+k_layers_first_hit(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __restrict__ list,
+                   const uint2* __restrict__ ranges, const float* __restrict__ fgeo, const float* __restrict__ tgeo,
+                   int* __restrict__ first_face_out, int* __restrict__ first_tet_out, int gx, int gy) {
     __shared__ __align__(16) float srec[kLStage * kLRecWords];
     const int tiles = gx * gy;
     const int b = blockIdx.x / tiles, t_in = blockIdx.x % tiles;
@@ -140,17 +243,7 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
     const bool inside = px < in.W && py < in.H;
     const size_t pix = inside ? ((size_t)b * in.H + py) * in.W + px : 0;
     f3 ro{0, 0, 0}, rd{0, 0, 0};
-    if (inside) {
-        if (in.ray_view && in.ray_recipe > 0) {
-            make_ray(in.ray_params + 32 * (size_t)in.ray_view[b], in.ray_view[b], px, py, in.W, in.H, in.ray_v, in.ray_recipe, ro, rd);
-        } else {
-            const size_t rix = in.ray_view ? ((size_t)in.ray_view[b] * in.H + py) * in.W + px : pix;
-            const float* o = in.image_ray_o + rix * 3;
-            const float* d = in.image_ray_d + rix * 3;
-            ro = f3{o[0], o[1], o[2]};
-            rd = f3{d[0], d[1], d[2]};
-        }
-    }
+    if (inside) load_layer_ray(in, b, px, py, pix, ro, rd);
     const uint2 range = ranges[blockIdx.x];
     const int total = (int)(range.y - range.x);
     const size_t view_base = (size_t)b * in.F;
@@ -159,7 +252,7 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
     bool done = !inside;
     float min_T = -1.0f, min_T_max_depth = -1.0f;
     int first_face = -1;
-    for (int base = 0; !WALK_ONLY && base < total; base += kLStage) {
+    for (int base = 0; base < total; base += kLStage) {
         if (__syncthreads_count(done) == 256) break;
         const int cnt = min(kLStage, total - base);
         for (int q = threadIdx.x; q < cnt * 3; q += 256) {
@@ -189,44 +282,96 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
 
     // ---------------- entry tet (forward.cu:683-708)
     int first_tet = -1;
-    FGeo cur{};
-    if (WALK_ONLY) {
-        first_face = first_face_out[pix];
-        first_tet = first_tet_out[pix];
-        if (first_face >= 0) cur = load_fgeo(fgeo, first_face);
-    } else {
-        if (first_face >= 0) {
-            cur = load_fgeo(fgeo, first_face);
+    if (first_face >= 0) {
+        const FGeo cur = load_fgeo(fgeo, first_face);
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int tet = i == 0 ? cur.ft0 : cur.ft1;
-                if (tet < 0) continue;
-                const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords);
-                const float4 ts = __ldg(tp), tfw = __ldg(tp + 1);
-                const int sl = slot_of(tfw, first_face);
-                const float od = sl >= 0 ? outward_dot(cur, __float_as_uint(ts.w), sl, rd) : outward_dot_geo(cur, ts, rd);
-                if (od < 0.0f) first_tet = tet;
-            }
+        for (int i = 0; i < 2; i++) {
+            const int tet = i == 0 ? cur.ft0 : cur.ft1;
+            if (tet < 0) continue;
+            const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords);
+            const float4 ts = __ldg(tp), tfw = __ldg(tp + 1);
+            const int sl = slot_of(tfw, first_face);
+            const float od = sl >= 0 ? outward_dot(cur, __float_as_uint(ts.w), sl, rd) : outward_dot_geo(cur, ts, rd);
+            if (od < 0.0f) first_tet = tet;
         }
-        first_face_out[pix] = first_face;
-        first_tet_out[pix] = first_tet;
     }
+    first_face_out[pix] = first_face;
+    first_tet_out[pix] = first_tet;
+}
 
-    // ---------------- walk (forward.cu:842-999); `cur` is the record of curr_face
+// The walk: one WARP per 8x4-pixel footprint, CTAs of kWalkThreads (the rays of a tile take 0 .. 100+ steps: with one
+// 256-thread CTA per tile a third of the SM's warp slots waited for the slowest warp of their CTA).
+constexpr int kWalkThreads = 64;
+#ifndef DM2_WALK_MINB
+#define DM2_WALK_MINB 16
+#endif
+__global__ void __launch_bounds__(kWalkThreads, DM2_WALK_MINB)
+k_layers_walk(DM2LayerInputs in, const float* __restrict__ fgeo, const float* __restrict__ tgeo,
+              const int* __restrict__ first_face_in, const int* __restrict__ first_tet_in, int32_t* __restrict__ layers,
+              int32_t* __restrict__ layers_cnt, int gx, int gy) {
+    const int tiles = gx * gy;
+    const int fp_id = blockIdx.x * (kWalkThreads / 32) + (threadIdx.x >> 5);      // global footprint: tile * 8 + footprint
+    const int tile = fp_id >> 3, warp = fp_id & 7, lane = threadIdx.x & 31;
+    if (tile >= in.B * tiles) return;
+    const int b = tile / tiles, t_in = tile % tiles;
+    const int tile_x = t_in % gx, tile_y = t_in / gx;
+    const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
+    const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    if (!(px < in.W && py < in.H)) return;
+    const size_t pix = ((size_t)b * in.H + py) * in.W + px;
+    f3 ro, rd;
+    load_layer_ray(in, b, px, py, pix, ro, rd);
+    const int first_face = first_face_in[pix], first_tet = first_tet_in[pix];
+    float4 c2 = make_float4(0.f, 0.f, 0.f, 0.f), c3 = c2;
+    if (first_face >= 0) {
+        const float4* fp = reinterpret_cast<const float4*>(fgeo + (size_t)first_face * kFGeoWords);
+        c2 = __ldg(fp + 2); c3 = __ldg(fp + 3);
+    }
+    struct { f3 n; int exist; } cur{f3{c2.y, c2.z, c2.w}, __float_as_int(c3.z)};
+
+    // ---------------- walk (forward.cu:842-999)
+    // The reference decides every step with three Moeller-Trumbore tests (the three other faces of the tet) and
+    // stops unless exactly one of them is hit with the ray leaving the tet through it.  FAST PATH: with the entry
+    // face (a, b, c) ordered so that the ray sees it counter-clockwise and w the tet's fourth vertex, the signs of
+    //     s_x = [d, w - o, x - o] = (d x (w - o)) . (x - w),   x = a, b, c
+    // name the face the ray leaves through - 24 flops instead of 3 x 45 + an IEEE division each.  The three
+    // numerators of a Moeller-Trumbore test ARE these edge functions (u, v, 1-u-v = [d, x-o, y-o] / denom for the
+    // face's three edges), evaluated with an absolute error below ~6 eps |d| |T| |e|; the fast path is taken only
+    // when every edge function it relies on (three new ones, and the three of the entry face, which it carries
+    // along) exceeds kWalkMargin = 24 u |d|_1 (|w - o|_1 + l) l (u = 2^-24, l = L1 length of the longest tet edge; the
+    // worst-case bound of the two evaluations together is 14 u in L2 norms) and every vertex of the exit face lies
+    // clearly in front of the ray origin.  Then the reference's test of the exit face passes and its tests of the two other faces fail
+    // whatever their rounding (each of those has one robustly positive and one robustly negative edge function, so
+    // one of u, v, 1-u-v is robustly negative for either sign of the denominator).  The orientation test of the
+    // exit face (outward normal . d > 0) is evaluated exactly as the reference does.  Anything else - a margin
+    // not met, an irregular tet, an unexpected sign pattern - takes the reference's three tests (SLOW PATH) for
+    // that step, and the fast-path state is rebuilt from the face it arrives at.
     const int L = in.num_layers;
     int curr_face = first_face, curr_tet = first_tet, n_done = 0;
     bool wdone = (curr_face == -1 || curr_tet == -1);
     long long guard = (long long)in.T + in.F + 16;          // safety net against cyclic walks
+    float nd_cur = 0.0f;                                     // dot(stored normal of curr_face, ray_d)
+    int exist_cur = 0;
+    WalkFace wf;
+    wf.ok = false;
+    const float rd1 = fabsf(rd.x) + fabsf(rd.y) + fabsf(rd.z);
+    if (!wdone) {
+        nd_cur = dot3(cur.n, rd);
+        exist_cur = cur.exist;
+        walk_face_init(wf, in.verts, in.faces, curr_face, in.P, ro, rd);
+    }
+    // (the record of the tet a step enters is requested at the end of the step before, together with the existence
+    // flag of the face it arrives at: one memory round trip per step instead of two)
+    const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)max(curr_tet, 0) * kTGeoWords);
+    float4 ts = make_float4(0.f, 0.f, 0.f, 0.f), tfw = ts, tov = ts, tnb = ts;
+    if (!wdone) { ts = __ldg(tp); tfw = __ldg(tp + 1); tov = __ldg(tp + 2); tnb = __ldg(tp + 3); }
     while (!wdone && guard-- > 0) {
-        if (cur.exist) {
+        if (exist_cur) {
             if (n_done < L) layers[pix * L + n_done] = curr_face;
             n_done++;
             if (n_done >= L) break;
         }
         if (curr_tet == -1) break;
-        const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)curr_tet * kTGeoWords);
-        const float4 ts = __ldg(tp);
-        const float4 tfw = __ldg(tp + 1);
         const int tf[4] = {__float_as_int(tfw.x), __float_as_int(tfw.y), __float_as_int(tfw.z), __float_as_int(tfw.w)};
         const unsigned flip = __float_as_uint(ts.w);
         // the 3 other faces of the tet, in slot order (forward.cu:880-893: stop unless curr_face appears
@@ -234,22 +379,80 @@ k_layers(DM2LayerInputs in, const float* __restrict__ lrec, const uint32_t* __re
         const int m0 = tf[0] == curr_face, m1 = tf[1] == curr_face, m2 = tf[2] == curr_face, m3 = tf[3] == curr_face;
         if (m0 + m1 + m2 + m3 != 1) break;
         const int cslot = m0 ? 0 : m1 ? 1 : m2 ? 2 : 3;
-        const int oslot[3] = {cslot == 0 ? 1 : 0, cslot <= 1 ? 2 : 1, cslot <= 2 ? 3 : 2};
-        const int others[3] = {cslot == 0 ? tf[1] : tf[0], cslot <= 1 ? tf[2] : tf[1], cslot <= 2 ? tf[3] : tf[2]};
-        if (outward_dot(cur, flip, cslot, rd) >= 0.0f) break;
-        int next_cnt = 0, next_face = -1;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const FGeo g = load_fgeo(fgeo, others[i]);
-            if (hit_test(ro, rd, g) && outward_dot(g, flip, oslot[i], rd) > 0.0f) { next_face = others[i]; next_cnt++; }
+        if ((((flip >> cslot) & 1u) ? -nd_cur : nd_cur) >= 0.0f) break;        // outward_dot(curr_face) >= 0
+        int next_face = -1, next_tet = -1;
+        bool stepped = false;
+        DM2_WSTAT(0);                                         // steps
+        if (!wf.ok) DM2_WSTAT(1);                             // no fast state
+        if (wf.ok) {
+            const int ov[4] = {__float_as_int(tov.x), __float_as_int(tov.y), __float_as_int(tov.z), __float_as_int(tov.w)};
+            const int wid = m0 ? ov[0] : m1 ? ov[1] : m2 ? ov[2] : ov[3];
+            if (wid >= 0) {
+                const float4 wq = __ldg(tp + 4 + cslot);      // opposite vertex, longest edge
+                const f3 w{wq.x, wq.y, wq.z};
+                const float lmax = wq.w;
+                const f3 wo = sub3(w, ro);
+                const f3 m = cross3(rd, wo);
+                const float sa = dot3(m, sub3(wf.a, w)), sb = dot3(m, sub3(wf.b, w)), sc = dot3(m, sub3(wf.c, w));
+                const float thr = kWalkMargin * rd1 * (fabsf(wo.x) + fabsf(wo.y) + fabsf(wo.z) + lmax) * lmax;
+                const float lo = fminf(fminf(fabsf(sa), fabsf(sb)), fminf(fabsf(sc), fminf(wf.mab, fminf(wf.mbc, wf.mca))));
+                // leaves through (a, b, w): drop c; through (b, c, w): drop a; through (c, a, w): drop b
+                const bool dc = sa > 0.0f && sb < 0.0f, da = sb > 0.0f && sc < 0.0f, db = sc > 0.0f && sa < 0.0f;
+                // every vertex of the exit face lies in front of the ray origin by more than the error of the
+                // reference's hit distance (~0.1 lmax |d| at this margin): its `t >= 0` holds
+                const float zmin = fminf(wf.zmin, dot3(rd, wo));
+                const bool front = zmin > 0.25f * rd1 * rd1 * lmax;
+                if (!(lo > thr)) DM2_WSTAT(2);                // margin
+                else if (!front) DM2_WSTAT(3);
+                else if ((int)dc + (int)da + (int)db != 1) DM2_WSTAT(4);
+                if (lo > thr && front && ((int)dc + (int)da + (int)db == 1)) {
+                    const int drop = dc ? wf.ic : da ? wf.ia : wf.ib;
+                    const int e0 = ov[0] == drop, e1 = ov[1] == drop, e2 = ov[2] == drop, e3 = ov[3] == drop;
+                    const int eslot = e0 ? 0 : e1 ? 1 : e2 ? 2 : 3;
+                    const int ef = e0 ? tf[0] : e1 ? tf[1] : e2 ? tf[2] : tf[3];
+                    if (e0 + e1 + e2 + e3 == 1 && eslot != cslot && ef >= 0 && ef < in.F) {
+                        const float4 nq = __ldg(tp + 8 + eslot);
+                        const float nd = dot3(f3{nq.x, nq.y, nq.z}, rd);
+                        if ((((flip >> eslot) & 1u) ? -nd : nd) > 0.0f) {
+                            next_face = ef;
+                            next_tet = e0 ? __float_as_int(tnb.x) : e1 ? __float_as_int(tnb.y) : e2 ? __float_as_int(tnb.z) : __float_as_int(tnb.w);
+                            nd_cur = nd;
+                            exist_cur = __ldg(in.face_existence + ef);
+                            stepped = true;
+                            DM2_WSTAT(5);                     // fast steps
+                            wf.zmin = zmin;
+                            // the dropped vertex is replaced in place: (a, b, w), (w, b, c), (a, w, c) keep the orientation
+                            if (dc) { wf.c = w; wf.ic = wid; wf.mbc = fabsf(sb); wf.mca = fabsf(sa); }
+                            if (da) { wf.a = w; wf.ia = wid; wf.mab = fabsf(sb); wf.mca = fabsf(sc); }
+                            if (db) { wf.b = w; wf.ib = wid; wf.mab = fabsf(sa); wf.mbc = fabsf(sc); }
+                        }
+                    }
+                }
+            }
         }
-        if (next_cnt != 1) break;
-        cur = load_fgeo(fgeo, next_face);                   // just read: an L1 hit, cheaper than 15 selects x 2
-        int next_tet = -1;
-        if (cur.ft0 != curr_tet) next_tet = cur.ft0;
-        else if (cur.ft1 != curr_tet) next_tet = cur.ft1;
+        if (!stepped) {
+            const int oslot[3] = {cslot == 0 ? 1 : 0, cslot <= 1 ? 2 : 1, cslot <= 2 ? 3 : 2};
+            const int others[3] = {cslot == 0 ? tf[1] : tf[0], cslot <= 1 ? tf[2] : tf[1], cslot <= 2 ? tf[3] : tf[2]};
+            int next_cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const FGeo g = load_fgeo(fgeo, others[i]);
+                if (hit_test(ro, rd, g) && outward_dot(g, flip, oslot[i], rd) > 0.0f) { next_face = others[i]; next_cnt++; }
+            }
+            if (next_cnt != 1) { DM2_WSTAT(6); break; }
+            const float4* fp = reinterpret_cast<const float4*>(fgeo + (size_t)next_face * kFGeoWords);
+            const float4 nrec2 = __ldg(fp + 2), nrec3 = __ldg(fp + 3);       // just read: L1 hits
+            nd_cur = dot3(f3{nrec2.y, nrec2.z, nrec2.w}, rd);
+            exist_cur = __float_as_int(nrec3.z);
+            const int ft0 = __float_as_int(nrec3.x), ft1 = __float_as_int(nrec3.y);
+            if (ft0 != curr_tet) next_tet = ft0;
+            else if (ft1 != curr_tet) next_tet = ft1;
+            walk_face_init(wf, in.verts, in.faces, next_face, in.P, ro, rd);
+        }
         curr_face = next_face;
         curr_tet = next_tet;
+        tp = reinterpret_cast<const float4*>(tgeo + (size_t)max(curr_tet, 0) * kTGeoWords);
+        ts = __ldg(tp); tfw = __ldg(tp + 1); tov = __ldg(tp + 2); tnb = __ldg(tp + 3);
     }
     layers_cnt[pix] = n_done;
 }
@@ -287,15 +490,16 @@ int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, c
         DM2_LAUNCH_CHECK();
     }
     if (in.T > 0 && !walk_only) {
-        k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.tet_faces, fgeo, in.F, tgeo);
+        k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.faces, in.tet_faces, in.face_tets, fgeo, in.F, in.P, tgeo);
         DM2_LAUNCH_CHECK();
     }
-    if (walk_only)
-        k_layers<true><<<(unsigned)nblk, 256, 0, s>>>(in, nullptr, nullptr, iw.ranges, fgeo, tgeo, iw.first_face,
-                                                      iw.first_tet, render_layers, render_layers_cnt, gx, gy);
-    else
-        k_layers<false><<<(unsigned)nblk, 256, 0, s>>>(in, fw.records, bw.vals, iw.ranges, fgeo, tgeo, iw.first_face,
-                                                       iw.first_tet, render_layers, render_layers_cnt, gx, gy);
+    if (!walk_only) {
+        k_layers_first_hit<<<(unsigned)nblk, 256, 0, s>>>(in, fw.records, bw.vals, iw.ranges, fgeo, tgeo, iw.first_face,
+                                                          iw.first_tet, gx, gy);
+        DM2_LAUNCH_CHECK();
+    }
+    k_layers_walk<<<(unsigned)cdiv(nblk * 8, kWalkThreads / 32), kWalkThreads, 0, s>>>(
+        in, fgeo, tgeo, iw.first_face, iw.first_tet, render_layers, render_layers_cnt, gx, gy);
     DM2_LAUNCH_CHECK();
     return 0;
 }
