@@ -19,12 +19,19 @@ namespace dm2 {
 
 constexpr int kLStage = 256;
 constexpr int kFGeoWords = 16;     // p0.xyz E1.xyz E2.xyz n.xyz (unit normal, not yet oriented) face_tets[2] existence pad
-// per tet, 192 bytes: [0] centroid sum.xyz, flip bits (slot i: the face normal points INTO the tet); [1] tet_faces[4];
-// [2] id of the vertex opposite the face in slot i (-1: not a face of this tet); [3] the tet behind the face in slot i
-// (the reference's rule, forward.cu:985-992); [4 + i] position of that opposite vertex, L1 length of the longest edge;
-// [8 + i] stored (not yet oriented) unit normal of the face in slot i.  One record = everything a fast walk step reads
-// except the existence flag of the face it leaves through.
-constexpr int kTGeoWords = 48;
+// per tet, 256 bytes (float4 units):
+//   [0] centroid sum.xyz, flip bits (slot i: the stored face normal points INTO the tet)   } entry-tet choice and the
+//   [1] tet_faces[4]                                                                        } reference-shaped step
+//   [2] id of the vertex opposite the face in slot i (-1: slot i is not a proper face of this tet)
+//   [4 + i]  position of that opposite vertex, L1 length of the longest tet edge (+inf: no fast steps in this tet)
+//   [8 + i]  stored (not yet oriented) unit normal of the face in slot i
+//   [12 + i] int4: face id of slot i, the tet behind it (the reference's rule, forward.cu:985-992), link word,
+//            existence flag of the face (refreshed by k_tet_exist on every call)
+//            link word: bits 0-7 slot j of this tet -> slot of the same vertex in the tet behind (2 bits each),
+//            bits 8-9 slot of the shared face in the tet behind, bit 10 flip bit of that slot, bit 12 flip bit of slot i
+// A fast walk step reads [4 + entry slot], then [8 + exit slot] and [12 + exit slot] - all it needs besides the
+// existence flag of the face it leaves through.
+constexpr int kTGeoWords = 64;
 
 size_t layers_geo_bytes(int F, int T) {
     return align_up((size_t)F * kFGeoWords * 4, 256) + align_up((size_t)T * kTGeoWords * 4, 256) + 256;
@@ -84,7 +91,7 @@ k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ te
         if (dot3(f3{fc.y, fc.z, fc.w}, dd) > 0.0f) flip |= 1u << i;
     }
     // walk fast path: the tet vertex opposite each face slot (exactly three of the four tet vertices must be the
-    // face's three distinct vertices), and the L1 length of the longest edge (scale of the robustness margin)
+    // face's three distinct vertices), and the length of the longest edge (scale of the robustness margin)
     const int qv[4] = {q.x, q.y, q.z, q.w};
     int opp[4];
 #pragma unroll
@@ -109,19 +116,17 @@ k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ te
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int k = i + 1; k < 4; k++)
-            lmax = fmaxf(lmax, fabsf(pv[i][0] - pv[k][0]) + fabsf(pv[i][1] - pv[k][1]) + fabsf(pv[i][2] - pv[k][2]));
+            lmax = fmaxf(lmax, (pv[i][0] - pv[k][0]) * (pv[i][0] - pv[k][0]) + (pv[i][1] - pv[k][1]) * (pv[i][1] - pv[k][1]) +
+                                   (pv[i][2] - pv[k][2]) * (pv[i][2] - pv[k][2]));
+    lmax = sqrtf(lmax) * 1.000001f;          // Euclidean length of the longest edge, rounded up
     float4* o = reinterpret_cast<float4*>(tgeo + (size_t)t * kTGeoWords);
     o[0] = make_float4(sx, sy, sz, __uint_as_float(flip));
     o[1] = make_float4(__int_as_float(tf.x), __int_as_float(tf.y), __int_as_float(tf.z), __int_as_float(tf.w));
     o[2] = make_float4(__int_as_float(opp[0]), __int_as_float(opp[1]), __int_as_float(opp[2]), __int_as_float(opp[3]));
-    int nb[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        nb[i] = -1;
         float4 ov = make_float4(0.f, 0.f, 0.f, lmax), nv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tfi[i] >= 0 && tfi[i] < F) {
-            const int ft0 = face_tets[2 * (size_t)tfi[i]], ft1 = face_tets[2 * (size_t)tfi[i] + 1];
-            nb[i] = ft0 != t ? ft0 : ft1 != t ? ft1 : -1;
             const float4 fc = reinterpret_cast<const float4*>(fgeo + (size_t)tfi[i] * kFGeoWords)[2];
             nv = make_float4(fc.y, fc.z, fc.w, 0.0f);
         }
@@ -129,7 +134,71 @@ k_tet_geo(int T, const float* __restrict__ verts, const int32_t* __restrict__ te
         o[4 + i] = ov;
         o[8 + i] = nv;
     }
-    o[3] = make_float4(__int_as_float(nb[0]), __int_as_float(nb[1]), __int_as_float(nb[2]), __int_as_float(nb[3]));
+    o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Second pass over the tets (needs [1], [2] of the neighbours): the per-slot link records [12 + i], and +inf as the
+// longest edge of every tet that is not REGULAR - four distinct valid faces, four distinct opposite vertices, and
+// behind every face either nothing or a tet that lists the face exactly once and each of its three vertices
+// exactly once among its own (valid, distinct) opposite vertices.  In a regular tet the reference's "curr_face
+// appears exactly once" (forward.cu:880-893) holds by construction and slots can be carried instead of searched.
+__device__ __forceinline__ bool tet_self_valid(const int tf[4], const int ov[4], int F) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ok &= tf[i] >= 0 && tf[i] < F && ov[i] >= 0;
+#pragma unroll
+        for (int k = i + 1; k < 4; k++) ok &= tf[i] != tf[k] && ov[i] != ov[k];
+    }
+    return ok;
+}
+__global__ void __launch_bounds__(256)
+k_tet_link(int T, int F, const int32_t* __restrict__ face_tets, float* __restrict__ tgeo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    float4* o = reinterpret_cast<float4*>(tgeo + (size_t)t * kTGeoWords);
+    const float4 q0 = o[0], q1 = o[1], q2 = o[2];
+    const int tf[4] = {__float_as_int(q1.x), __float_as_int(q1.y), __float_as_int(q1.z), __float_as_int(q1.w)};
+    const int ov[4] = {__float_as_int(q2.x), __float_as_int(q2.y), __float_as_int(q2.z), __float_as_int(q2.w)};
+    const unsigned flip = __float_as_uint(q0.w);
+    bool regular = tet_self_valid(tf, ov, F);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        int nb = -1;
+        unsigned link = ((flip >> e) & 1u) << 12;
+        if (tf[e] >= 0 && tf[e] < F) {
+            const int ft0 = face_tets[2 * (size_t)tf[e]], ft1 = face_tets[2 * (size_t)tf[e] + 1];
+            nb = ft0 != t ? ft0 : ft1 != t ? ft1 : -1;
+        }
+        if (nb < -1 || nb >= T) { regular = false; }
+        else if (nb >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(tgeo + (size_t)nb * kTGeoWords);
+            const float4 n0 = p[0], n1 = p[1], n2 = p[2];
+            const int tf2[4] = {__float_as_int(n1.x), __float_as_int(n1.y), __float_as_int(n1.z), __float_as_int(n1.w)};
+            const int ov2[4] = {__float_as_int(n2.x), __float_as_int(n2.y), __float_as_int(n2.z), __float_as_int(n2.w)};
+            bool ok = tet_self_valid(tf2, ov2, F);
+            int cnt = 0, bs = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (tf2[k] == tf[e]) { cnt++; bs = k; }
+            ok &= cnt == 1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j == e) continue;
+                int c2 = 0, jj = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (ov2[k] == ov[j]) { c2++; jj = k; }
+                ok &= c2 == 1 && jj != bs;
+                link |= (unsigned)jj << (2 * j);
+            }
+            link |= (unsigned)bs << 8 | ((__float_as_uint(n0.w) >> bs) & 1u) << 10;
+            regular &= ok;
+        }
+        reinterpret_cast<int4*>(o)[12 + e] = make_int4(tf[e], nb, (int)link, 0);
+    }
+    if (!regular) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[4 + e].w = __int_as_float(0x7f800000);
+    }
 }
 
 struct FGeo { f3 p0, e1, e2, n; int ft0, ft1, exist; };
@@ -185,10 +254,10 @@ extern "C" void dm2_debug_walk_stats(unsigned long long* out8, int reset) {
 // State of the walk's fast path: the entry face's vertices, ordered so that the ray sees them counter-clockwise
 // ([d, a-o, b-o], [d, b-o, c-o], [d, c-o, a-o] > 0), their ids, and the magnitudes of those three edge functions.
 #ifndef DM2_WALK_K
-#define DM2_WALK_K 24.0f
+#define DM2_WALK_K 16.0f
 #endif
 constexpr float kWalkMargin = DM2_WALK_K * 5.9604645e-8f;
-struct WalkFace { f3 a, b, c; int ia, ib, ic; float mab, mbc, mca, zmin; bool ok; };
+struct WalkFace { f3 a, b, c; int ia, ib, ic; float mab, mbc, mca, zmin; bool ok; int cslot, pa, pb, pc; unsigned eflip; };
 __device__ __forceinline__ void walk_face_init(WalkFace& wf, const float* __restrict__ verts, const int32_t* __restrict__ faces,
                                                int face, int P, const f3& ro, const f3& rd) {
     wf.ok = false;
@@ -224,6 +293,34 @@ __device__ __forceinline__ void load_layer_ray(const DM2LayerInputs& in, int b, 
         ro = f3{o[0], o[1], o[2]};
         rd = f3{d[0], d[1], d[2]};
     }
+}
+
+// Every call (face_existence is the one input an incremental re-generate changes): the existence flag of the face in
+// each slot, next to the link record the fast step reads anyway.
+__global__ void __launch_bounds__(256)
+k_tet_exist(int T, int F, const int32_t* __restrict__ face_existence, float* __restrict__ tgeo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // (tet, slot)
+    if (i >= 4 * T) return;
+    int4* r = reinterpret_cast<int4*>(tgeo + (size_t)(i >> 2) * kTGeoWords) + 12 + (i & 3);
+    const int f = r->x;
+    r->w = (f >= 0 && f < F) ? face_existence[f] : 0;
+}
+
+// Completes the fast-path state for the step that enters tet `tet` through `face`: the slot of the entry face and
+// the slots (position among the tet's opposite vertices) of the entry face's three vertices.
+__device__ __forceinline__ void walk_enter_tet(WalkFace& wf, const float* __restrict__ tgeo, int tet, int face) {
+    if (!wf.ok) return;
+    wf.ok = false;
+    if (tet < 0) return;
+    const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)tet * kTGeoWords);
+    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+    if (!(__ldg(reinterpret_cast<const float*>(tp + 4) + 3) < 3.0e38f)) return;          // not a regular tet
+    const int cs = slot_of(q1, face);
+    const int pa = slot_of(q2, wf.ia), pb = slot_of(q2, wf.ib), pc = slot_of(q2, wf.ic);
+    if (cs < 0 || pa < 0 || pb < 0 || pc < 0) return;
+    wf.cslot = cs; wf.pa = pa; wf.pb = pb; wf.pc = pc;
+    wf.eflip = (__float_as_uint(q0.w) >> cs) & 1u;
+    wf.ok = true;
 }
 
 // First hit over the min-depth-sorted tile list + choice of the entry tet: one CTA per 16x16 tile (the list is staged
@@ -338,8 +435,8 @@ k_layers_walk(DM2LayerInputs in, const float* __restrict__ fgeo, const float* __
     // numerators of a Moeller-Trumbore test ARE these edge functions (u, v, 1-u-v = [d, x-o, y-o] / denom for the
     // face's three edges), evaluated with an absolute error below ~6 eps |d| |T| |e|; the fast path is taken only
     // when every edge function it relies on (three new ones, and the three of the entry face, which it carries
-    // along) exceeds kWalkMargin = 24 u |d|_1 (|w - o|_1 + l) l (u = 2^-24, l = L1 length of the longest tet edge; the
-    // worst-case bound of the two evaluations together is 14 u in L2 norms) and every vertex of the exit face lies
+    // along) exceeds kWalkMargin = 16 u |d|_1 (|w - o|_1 + l) l (u = 2^-24, l = length of the longest tet edge; the
+    // worst-case bound of the two evaluations together is 14 u in Euclidean norms, and |.|_1 >= |.|_2) and every vertex of the exit face lies
     // clearly in front of the ray origin.  Then the reference's test of the exit face passes and its tests of the two other faces fail
     // whatever their rounding (each of those has one robustly positive and one robustly negative edge function, so
     // one of u, v, 1-u-v is robustly negative for either sign of the denominator).  The orientation test of the
@@ -348,89 +445,94 @@ k_layers_walk(DM2LayerInputs in, const float* __restrict__ fgeo, const float* __
     // that step, and the fast-path state is rebuilt from the face it arrives at.
     const int L = in.num_layers;
     int curr_face = first_face, curr_tet = first_tet, n_done = 0;
-    bool wdone = (curr_face == -1 || curr_tet == -1);
-    long long guard = (long long)in.T + in.F + 16;          // safety net against cyclic walks
+    const bool wdone = (curr_face == -1 || curr_tet == -1);
+    unsigned guard = (unsigned)min((long long)in.T + in.F + 16, 0x7fffffffll);   // safety net against cyclic walks
     float nd_cur = 0.0f;                                     // dot(stored normal of curr_face, ray_d)
     int exist_cur = 0;
     WalkFace wf;
     wf.ok = false;
+    wf.cslot = 0;
     const float rd1 = fabsf(rd.x) + fabsf(rd.y) + fabsf(rd.z);
+    int32_t* const lp = layers + pix * L;
     if (!wdone) {
         nd_cur = dot3(cur.n, rd);
         exist_cur = cur.exist;
         walk_face_init(wf, in.verts, in.faces, curr_face, in.P, ro, rd);
+        walk_enter_tet(wf, tgeo, curr_tet, curr_face);
     }
-    // (the record of the tet a step enters is requested at the end of the step before, together with the existence
-    // flag of the face it arrives at: one memory round trip per step instead of two)
+    // (the apex record of the tet a step enters is requested at the end of the step before, together with the
+    // existence flag of the face it arrives at: one memory round trip per step)
     const float4* tp = reinterpret_cast<const float4*>(tgeo + (size_t)max(curr_tet, 0) * kTGeoWords);
-    float4 ts = make_float4(0.f, 0.f, 0.f, 0.f), tfw = ts, tov = ts, tnb = ts;
-    if (!wdone) { ts = __ldg(tp); tfw = __ldg(tp + 1); tov = __ldg(tp + 2); tnb = __ldg(tp + 3); }
-    while (!wdone && guard-- > 0) {
+    float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!wdone) wq = __ldg(tp + 4 + wf.cslot);
+    while (!wdone && guard-- > 0u) {
         if (exist_cur) {
-            if (n_done < L) layers[pix * L + n_done] = curr_face;
+            if (n_done < L) lp[n_done] = curr_face;
             n_done++;
             if (n_done >= L) break;
         }
         if (curr_tet == -1) break;
-        const int tf[4] = {__float_as_int(tfw.x), __float_as_int(tfw.y), __float_as_int(tfw.z), __float_as_int(tfw.w)};
-        const unsigned flip = __float_as_uint(ts.w);
-        // the 3 other faces of the tet, in slot order (forward.cu:880-893: stop unless curr_face appears
-        // exactly once); written with selects - indexed local arrays cost a quarter of this kernel
-        const int m0 = tf[0] == curr_face, m1 = tf[1] == curr_face, m2 = tf[2] == curr_face, m3 = tf[3] == curr_face;
-        if (m0 + m1 + m2 + m3 != 1) break;
-        const int cslot = m0 ? 0 : m1 ? 1 : m2 ? 2 : 3;
-        if ((((flip >> cslot) & 1u) ? -nd_cur : nd_cur) >= 0.0f) break;        // outward_dot(curr_face) >= 0
         int next_face = -1, next_tet = -1;
         bool stepped = false;
         DM2_WSTAT(0);                                         // steps
         if (!wf.ok) DM2_WSTAT(1);                             // no fast state
         if (wf.ok) {
-            const int ov[4] = {__float_as_int(tov.x), __float_as_int(tov.y), __float_as_int(tov.z), __float_as_int(tov.w)};
-            const int wid = m0 ? ov[0] : m1 ? ov[1] : m2 ? ov[2] : ov[3];
-            if (wid >= 0) {
-                const float4 wq = __ldg(tp + 4 + cslot);      // opposite vertex, longest edge
-                const f3 w{wq.x, wq.y, wq.z};
-                const float lmax = wq.w;
-                const f3 wo = sub3(w, ro);
-                const f3 m = cross3(rd, wo);
-                const float sa = dot3(m, sub3(wf.a, w)), sb = dot3(m, sub3(wf.b, w)), sc = dot3(m, sub3(wf.c, w));
-                const float thr = kWalkMargin * rd1 * (fabsf(wo.x) + fabsf(wo.y) + fabsf(wo.z) + lmax) * lmax;
-                const float lo = fminf(fminf(fabsf(sa), fabsf(sb)), fminf(fabsf(sc), fminf(wf.mab, fminf(wf.mbc, wf.mca))));
-                // leaves through (a, b, w): drop c; through (b, c, w): drop a; through (c, a, w): drop b
-                const bool dc = sa > 0.0f && sb < 0.0f, da = sb > 0.0f && sc < 0.0f, db = sc > 0.0f && sa < 0.0f;
-                // every vertex of the exit face lies in front of the ray origin by more than the error of the
-                // reference's hit distance (~0.1 lmax |d| at this margin): its `t >= 0` holds
-                const float zmin = fminf(wf.zmin, dot3(rd, wo));
-                const bool front = zmin > 0.25f * rd1 * rd1 * lmax;
-                if (!(lo > thr)) DM2_WSTAT(2);                // margin
-                else if (!front) DM2_WSTAT(3);
-                else if ((int)dc + (int)da + (int)db != 1) DM2_WSTAT(4);
-                if (lo > thr && front && ((int)dc + (int)da + (int)db == 1)) {
-                    const int drop = dc ? wf.ic : da ? wf.ia : wf.ib;
-                    const int e0 = ov[0] == drop, e1 = ov[1] == drop, e2 = ov[2] == drop, e3 = ov[3] == drop;
-                    const int eslot = e0 ? 0 : e1 ? 1 : e2 ? 2 : 3;
-                    const int ef = e0 ? tf[0] : e1 ? tf[1] : e2 ? tf[2] : tf[3];
-                    if (e0 + e1 + e2 + e3 == 1 && eslot != cslot && ef >= 0 && ef < in.F) {
-                        const float4 nq = __ldg(tp + 8 + eslot);
-                        const float nd = dot3(f3{nq.x, nq.y, nq.z}, rd);
-                        if ((((flip >> eslot) & 1u) ? -nd : nd) > 0.0f) {
-                            next_face = ef;
-                            next_tet = e0 ? __float_as_int(tnb.x) : e1 ? __float_as_int(tnb.y) : e2 ? __float_as_int(tnb.z) : __float_as_int(tnb.w);
-                            nd_cur = nd;
-                            exist_cur = __ldg(in.face_existence + ef);
-                            stepped = true;
-                            DM2_WSTAT(5);                     // fast steps
-                            wf.zmin = zmin;
-                            // the dropped vertex is replaced in place: (a, b, w), (w, b, c), (a, w, c) keep the orientation
-                            if (dc) { wf.c = w; wf.ic = wid; wf.mbc = fabsf(sb); wf.mca = fabsf(sa); }
-                            if (da) { wf.a = w; wf.ia = wid; wf.mab = fabsf(sb); wf.mca = fabsf(sc); }
-                            if (db) { wf.b = w; wf.ib = wid; wf.mab = fabsf(sa); wf.mbc = fabsf(sc); }
-                        }
-                    }
+            // (a regular tet lists curr_face exactly once, in slot wf.cslot)
+            if ((wf.eflip ? -nd_cur : nd_cur) >= 0.0f) break;                  // outward_dot(curr_face) >= 0
+            const f3 w{wq.x, wq.y, wq.z};
+            const float lmax = wq.w;
+            const f3 wo = sub3(w, ro);
+            const f3 m = cross3(rd, wo);
+            const float sa = dot3(m, sub3(wf.a, w)), sb = dot3(m, sub3(wf.b, w)), sc = dot3(m, sub3(wf.c, w));
+            const float thr = kWalkMargin * rd1 * (fabsf(wo.x) + fabsf(wo.y) + fabsf(wo.z) + lmax) * lmax;
+            const float lo = fminf(fminf(fabsf(sa), fabsf(sb)), fminf(fabsf(sc), fminf(wf.mab, fminf(wf.mbc, wf.mca))));
+            // leaves through (a, b, w): drop c; through (b, c, w): drop a; through (c, a, w): drop b
+            const bool dc = sa > 0.0f && sb < 0.0f, da = sb > 0.0f && sc < 0.0f, db = sc > 0.0f && sa < 0.0f;
+            // every vertex of the exit face lies in front of the ray origin by more than the error of the
+            // reference's hit distance (~0.1 lmax |d| at this margin): its `t >= 0` holds
+            const float zmin = fminf(wf.zmin, dot3(rd, wo));
+            const bool front = zmin > 0.25f * rd1 * rd1 * lmax;
+            if (!(lo > thr)) DM2_WSTAT(2);                    // margin (or not a regular tet: lmax = inf)
+            else if (!front) DM2_WSTAT(3);
+            else if (!(dc | da | db)) DM2_WSTAT(4);
+            if (lo > thr && front && (dc | da | db)) {        // (the three patterns exclude each other)
+                const int eslot = dc ? wf.pc : da ? wf.pa : wf.pb;
+                const int4 sr = __ldg(reinterpret_cast<const int4*>(tp) + 12 + eslot);
+                const float4 nq = __ldg(tp + 8 + eslot);
+                const unsigned link = (unsigned)sr.z;
+                const float nd = dot3(f3{nq.x, nq.y, nq.z}, rd);
+                if ((((link >> 12) & 1u) ? -nd : nd) > 0.0f) {
+                    next_face = sr.x;
+                    next_tet = sr.y;
+                    nd_cur = nd;
+                    exist_cur = sr.w;
+                    stepped = true;
+                    DM2_WSTAT(5);                             // fast steps
+                    wf.zmin = zmin;
+                    // the dropped vertex is replaced in place by w (slot cslot of this tet): (a, b, w), (w, b, c),
+                    // (a, w, c) keep the orientation; then the three slots are renamed for the tet behind
+                    if (dc) { wf.c = w; wf.pc = wf.cslot; wf.mbc = fabsf(sb); wf.mca = fabsf(sa); }
+                    if (da) { wf.a = w; wf.pa = wf.cslot; wf.mab = fabsf(sb); wf.mca = fabsf(sc); }
+                    if (db) { wf.b = w; wf.pb = wf.cslot; wf.mab = fabsf(sa); wf.mbc = fabsf(sc); }
+                    wf.pa = (link >> (2 * wf.pa)) & 3u;
+                    wf.pb = (link >> (2 * wf.pb)) & 3u;
+                    wf.pc = (link >> (2 * wf.pc)) & 3u;
+                    wf.cslot = (link >> 8) & 3u;
+                    wf.eflip = (link >> 10) & 1u;
                 }
             }
         }
         if (!stepped) {
+            // the reference's step: the 3 other faces of the tet, in slot order (forward.cu:880-893: stop unless
+            // curr_face appears exactly once), three hit tests, exactly one of them leaving the tet
+            const float4* tq = reinterpret_cast<const float4*>(tgeo + (size_t)curr_tet * kTGeoWords);
+            const float4 ts = __ldg(tq), tfw = __ldg(tq + 1);
+            const int tf[4] = {__float_as_int(tfw.x), __float_as_int(tfw.y), __float_as_int(tfw.z), __float_as_int(tfw.w)};
+            const unsigned flip = __float_as_uint(ts.w);
+            const int m0 = tf[0] == curr_face, m1 = tf[1] == curr_face, m2 = tf[2] == curr_face, m3 = tf[3] == curr_face;
+            if (m0 + m1 + m2 + m3 != 1) break;
+            const int cslot = m0 ? 0 : m1 ? 1 : m2 ? 2 : 3;
+            if ((((flip >> cslot) & 1u) ? -nd_cur : nd_cur) >= 0.0f) break;    // outward_dot(curr_face) >= 0
             const int oslot[3] = {cslot == 0 ? 1 : 0, cslot <= 1 ? 2 : 1, cslot <= 2 ? 3 : 2};
             const int others[3] = {cslot == 0 ? tf[1] : tf[0], cslot <= 1 ? tf[2] : tf[1], cslot <= 2 ? tf[3] : tf[2]};
             int next_cnt = 0;
@@ -448,11 +550,12 @@ k_layers_walk(DM2LayerInputs in, const float* __restrict__ fgeo, const float* __
             if (ft0 != curr_tet) next_tet = ft0;
             else if (ft1 != curr_tet) next_tet = ft1;
             walk_face_init(wf, in.verts, in.faces, next_face, in.P, ro, rd);
+            walk_enter_tet(wf, tgeo, next_tet, next_face);
         }
         curr_face = next_face;
         curr_tet = next_tet;
         tp = reinterpret_cast<const float4*>(tgeo + (size_t)max(curr_tet, 0) * kTGeoWords);
-        ts = __ldg(tp); tfw = __ldg(tp + 1); tov = __ldg(tp + 2); tnb = __ldg(tp + 3);
+        wq = __ldg(tp + 4 + wf.cslot);
     }
     layers_cnt[pix] = n_done;
 }
@@ -491,6 +594,12 @@ int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, c
     }
     if (in.T > 0 && !walk_only) {
         k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.faces, in.tet_faces, in.face_tets, fgeo, in.F, in.P, tgeo);
+        DM2_LAUNCH_CHECK();
+        k_tet_link<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.F, in.face_tets, tgeo);
+        DM2_LAUNCH_CHECK();
+    }
+    if (in.T > 0) {
+        k_tet_exist<<<cdiv(4ll * in.T, 256), 256, 0, s>>>(in.T, in.F, in.face_existence, tgeo);
         DM2_LAUNCH_CHECK();
     }
     if (!walk_only) {
