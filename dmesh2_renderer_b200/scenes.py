@@ -132,11 +132,14 @@ class TetScene:
     num_layers: int = 8
 
 
-def delaunay_tets(name, n_points, size, seed, p_exist=0.15, num_layers=8, eyes=((0.0, 0.0, 3.0),)):
+def delaunay_tets(name, n_points, size, seed, p_exist=0.15, num_layers=8, eyes=((0.0, 0.0, 3.0),), points=None,
+                  qhull_options=None):
+    """points: use these (n, 3) points instead of n_points uniform ones (e.g. a lattice: cospherical points, flat
+    slivers, rays through vertices and along faces); qhull_options: e.g. "QJ" for such degenerate input."""
     from scipy.spatial import Delaunay
     rng = np.random.default_rng(seed)
-    pts = rng.uniform(-1.0, 1.0, size=(n_points, 3))
-    tri = Delaunay(pts)
+    pts = rng.uniform(-1.0, 1.0, size=(n_points, 3)) if points is None else np.asarray(points, dtype=np.float64)
+    tri = Delaunay(pts) if qhull_options is None else Delaunay(pts, qhull_options=qhull_options)
     tets = tri.simplices.astype(np.int32)                                      # [T, 4]
     combos = np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]])
     all_faces = np.sort(tets[:, combos].reshape(-1, 3), axis=1)                # [4T, 3]

@@ -413,6 +413,55 @@ def test_layers_ragged_multiview(built):
     _layers_both(sc, views=[1, 0])
 
 
+@pytest.mark.parametrize("n,size,eye", [(5, 64, (0.0, 0.0, 3.0)), (6, 96, (0.0, 0.0, 3.0)), (5, 80, (3.0, 0.0, 0.0)),
+                                        (4, 64, (1.7, 1.7, 1.7))])
+def test_layers_lattice_degenerate_rays(built, n, size, eye):
+    """Points on a regular lattice seen along an axis / the space diagonal: cospherical points (flat slivers in the
+    joggled Delaunay mesh), many rays through vertices, along edges and inside faces.  The walk's fast path (signs of
+    edge functions with a robustness margin) must hand every such step to the reference's three hit tests: ids and
+    counts equal the oracle's on every ray."""
+    from dmesh2_renderer_b200 import scenes
+    g = np.linspace(-1.0, 1.0, n)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    sc = scenes.delaunay_tets(f"lattice_{n}", 0, size, seed=2, p_exist=0.35, num_layers=6, eyes=[eye], points=pts,
+                              qhull_options="QJ Qbb Qc")
+    layers, cnt = _layers_both(sc)
+    assert int(cnt.max()) > 0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_layers_inconsistent_adjacency(built, seed):
+    """Adjacency tensors that contradict the geometry - a face id repeated inside a tet, a face listed by a tet it
+    does not belong to, wrong / missing face_tets entries, a tet with a repeated vertex: the reference's walk stops
+    (or wanders) in a defined way on such input (forward.cu:880-893, 985-992); tets that are not regular never take
+    the fast path, so the result is the oracle's on every ray."""
+    from dmesh2_renderer_b200 import scenes
+    sc = scenes.small_tets(n_points=250, size=64, seed=21 + seed, num_layers=5)
+    rng = np.random.default_rng(100 + seed)
+    T, F = sc.tets.shape[0], sc.faces.shape[0]
+    tf, ft, tets = sc.tet_faces.copy(), sc.face_tets.copy(), sc.tets.copy()
+    for t in rng.choice(T, 25, replace=False):
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            tf[t, rng.integers(0, 4)] = tf[t, rng.integers(0, 4)]            # repeated face id
+        elif kind == 1:
+            tf[t, rng.integers(0, 4)] = rng.integers(0, F)                    # a face of some other tet
+        elif kind == 2:
+            tets[t, rng.integers(0, 4)] = tets[t, rng.integers(0, 4)]        # repeated vertex
+        else:
+            tets[t, rng.integers(0, 4)] = rng.integers(0, sc.verts.shape[0])  # a vertex that is not on its faces
+    for f in rng.choice(F, 40, replace=False):
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            ft[f, rng.integers(0, 2)] = rng.integers(0, T)                    # wrong neighbour
+        elif kind == 1:
+            ft[f, rng.integers(0, 2)] = -1                                    # missing neighbour
+        else:
+            ft[f] = ft[f, ::-1]                                               # swapped
+    sc.tet_faces, sc.face_tets, sc.tets = tf, ft, tets
+    _layers_both(sc)
+
+
 def test_layers_incremental_regenerate(built):
     """Same geometry, new face_existence: the walk-only path must give what a full generate gives, and
     an in-place geometry update must invalidate the cache."""
