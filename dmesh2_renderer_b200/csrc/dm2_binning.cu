@@ -197,7 +197,10 @@ __device__ __forceinline__ ProjVert project_vertex(const float4 c, float img_w, 
     return o;
 }
 
-__global__ void __launch_bounds__(kPreThreads)
+#ifndef DM2_PRE_MINB
+#define DM2_PRE_MINB 1
+#endif
+__global__ void __launch_bounds__(kPreThreads, DM2_PRE_MINB)
 k_fused_preprocess(DM2FusedInputs in, int gx, int gy, float* __restrict__ depths, float* __restrict__ min_depths,
                    float* __restrict__ max_depths, uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
                    float* __restrict__ records, uint32_t* __restrict__ patch_flags) {

@@ -477,7 +477,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef DM2_GS_MINB
+#define DM2_GS_MINB 4
+#endif
+__global__ void __launch_bounds__(256, DM2_GS_MINB)
 k_fused_grad_scatter(DM2FusedInputs in, const uint32_t* __restrict__ tiles_touched, const float* __restrict__ records,
                      const float* __restrict__ gface, DM2FusedGrads gr) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -212,7 +212,8 @@ int dm2_render_backward(const DM2RenderInputs* in, const void* face_ws, const vo
 int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws,
                           int64_t* num_rendered_host, int64_t* longest_host, void* stream);
 /* render_layers (B,H,W,L) must be pre-filled with -1 and render_layers_cnt (B,H,W) with 0 by
- * the caller (reference render.cu:437-438); geo_ws needs dm2_layers_geo_bytes(F,T) bytes.    */
+ * the caller (reference render.cu:437-438); geo_ws needs dm2_layers_geo_bytes(F,T) bytes (64 bytes per face +
+ * 256 bytes per tet: the ray-independent geometry and adjacency records of the walk, built once per geometry). */
 int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes);
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
                                void* image_ws, void* geo_ws, int64_t num_rendered, int64_t longest,
