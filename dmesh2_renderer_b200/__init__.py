@@ -9,7 +9,7 @@ Host code is Python/PyTorch; all device work is hand-written CUDA in lib/libdm2_
 C-ABI of include/dm2_renderer.h.  There is no CPU fallback: without the built library every call
 raises RuntimeError.
 """
-from ._lib import launch_count, load_library           # noqa: F401
+from ._lib import launch_count, load_library, set_exact_clip   # noqa: F401
 from .function import RenderFunction                   # noqa: F401
 from .layers_composite import composite_layers, composite_layers_torch   # noqa: F401
 from .renderer import LayeredRenderer, Renderer        # noqa: F401

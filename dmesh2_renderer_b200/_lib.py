@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 RAY_RECIPES = 36        # DM2_RAY_RECIPES
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
@@ -132,6 +132,8 @@ SYMBOLS = {
     "dm2_launch_count": (C.c_int64, [C.c_int32]),
     "dm2_profile_enable": (None, [C.c_int32]),
     "dm2_set_forward_rounds": (None, [C.c_int64, C.c_int64]),
+    "dm2_set_exact_clip": (None, [C.c_int32]),
+    "dm2_get_exact_clip": (C.c_int32, []),
     "dm2_profile_reset": (None, []),
     "dm2_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
 }
@@ -164,6 +166,16 @@ def check(status):
     if status != 0:
         msg = load_library().dm2_last_error().decode("utf-8", "replace")
         raise RuntimeError(msg or f"libdm2_b200 call failed with status {status}")
+
+
+def set_exact_clip(on=True):
+    """True: every partially covered (pixel, face) pair takes the reference's polygon construction (forward images
+    bit-identical to the reference's); False (default): the polygon-free overlap area of csrc/dm2_aa_fast.cuh where it
+    provably yields the same value to ~1e-7, the construction elsewhere.  Process-wide.  Returns the previous setting."""
+    lib = load_library()
+    prev = bool(lib.dm2_get_exact_clip())
+    lib.dm2_set_exact_clip(1 if on else 0)
+    return prev
 
 
 def profile_enable(on=True):

@@ -36,6 +36,7 @@
 // on any non-zero code (forward.cu:337-338, backward.cu:286-289); here `false` = "skip".
 #pragma once
 #include "dm2_common.cuh"
+#include "dm2_aa_fast.cuh"
 
 namespace dm2 {
 
@@ -327,6 +328,45 @@ static __device__ __noinline__ void aa_grad_reference(const float* __restrict__ 
     }
 #pragma unroll
     for (int k = 0; k < 6; k++) g[k] = gr[k];
+}
+
+// The exact construction for one pair, OUT OF LINE: aa_clip (+ the reference's Jacobian chain where it asks for it).
+// The tile kernels call it for the pairs aa_area_fast() declines (~0.5 % at 1 M triangles @1024^2) and for every pair
+// when the exact clip was requested (dm2_set_exact_clip).  gs: the caller's scratch array - its address escapes into
+// this call, so it lives in local memory; callers copy it into registers instead of handing over their own g[].
+template <bool GRAD>
+static __device__ __noinline__ bool aa_clip_exact(const float* __restrict__ rec, float pxmin, float pymin, unsigned inmask,
+                                                  float* __restrict__ area_out, float* __restrict__ gs) {
+    float a, g[6];
+    bool chain = false;
+    const bool ok = aa_clip<GRAD>(rec, pxmin, pymin, inmask, a, g, GRAD ? &chain : nullptr);
+    if (GRAD) {
+        if (chain) aa_grad_reference(rec, pxmin, pymin, inmask, g);
+#pragma unroll
+        for (int k = 0; k < 6; k++) gs[k] = g[k];
+    }
+    *area_out = a;
+    return ok;
+}
+
+// Overlap area (+ gradient) of one partially covered (pixel, face) pair: the polygon-free evaluation where it is
+// provably the reference's result (dm2_aa_fast.cuh), the exact construction otherwise.  inmask_of(): the 4-bit
+// inside-corner mask, only evaluated on the exact path.  Returns false = the reference skips the face for this pixel.
+template <bool GRAD, typename InMask>
+__device__ __forceinline__ bool aa_overlap(const float* __restrict__ rec, float pxmin, float pymin, bool exact_only,
+                                           InMask inmask_of, float& area, float* __restrict__ g) {
+    if (!exact_only &&
+        aa_area_fast<GRAD>(rec + R_AAV, rec + R_AAE, rec + R_AAR, __float_as_uint(rec[R_MISC + 3]), __float_as_uint(rec[R_SAFE]),
+                           pxmin, pymin, area, g))
+        return true;
+    float as, gs[6];
+    const bool ok = aa_clip_exact<GRAD>(rec, pxmin, pymin, inmask_of(), &as, gs);
+    area = as;
+    if (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) g[k] = gs[k];
+    }
+    return ok;
 }
 
 }  // namespace dm2

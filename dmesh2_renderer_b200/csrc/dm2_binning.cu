@@ -3,6 +3,7 @@
 // the reference's CUB calls.  Replaces reference cuda_impl/forward.cu:16-137 (preprocessFaceCUDA);
 // the tile binning itself (reference renderer.cu:165-218, 415-492) lives in dm2_tilesort.cu.
 #include "dm2_common.cuh"
+#include "dm2_aa_fast.cuh"
 
 namespace dm2 {
 
@@ -132,6 +133,8 @@ __device__ __forceinline__ bool render_preprocess_one(const DM2RenderInputs& in,
 #pragma unroll
     for (int k = 0; k < 6; k++) { flags |= (az[k] ? 1u : 0u) << k; on_grid |= a[k] == floorf(a[k]); }
     flags |= on_grid ? 0x200u : 0u;
+    uint32_t safe_word = 0u;
+    flags |= aaf_face_safety(a, e, r, flags, &safe_word);
     const float txmin = nanmin(nanmin(a[0], a[2]), a[4]), txmax = nanmax(nanmax(a[0], a[2]), a[4]);
     const float tymin = nanmin(nanmin(a[1], a[3]), a[5]), tymax = nanmax(nanmax(a[1], a[3]), a[5]);
     const float* p0 = in.verts + 3 * (size_t)v0;
@@ -158,7 +161,7 @@ __device__ __forceinline__ bool render_preprocess_one(const DM2RenderInputs& in,
     rec[11] = make_float4(a[4], a[5], e[0], e[1]);
     rec[12] = make_float4(e[2], e[3], e[4], e[5]);
     rec[13] = make_float4(r[0], r[1], r[2], r[3]);
-    rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
+    rec[14] = make_float4(r[4], r[5], __int_as_float(f), __uint_as_float(safe_word));
     return true;
 }
 
@@ -280,6 +283,11 @@ __device__ __forceinline__ bool fused_preprocess_one(const DM2FusedInputs& in, i
     // some screen coordinate is an integer: possible kink of the overlap area (dm2_aa.cuh)
     if (p0x == floorf(p0x) || p0y == floorf(p0y) || p1x == floorf(p1x) || p1y == floorf(p1y) || p2x == floorf(p2x) ||
         p2y == floorf(p2y)) flags |= 0x200u;
+    uint32_t safe_word = 0u;
+    {
+        const float av[6] = {p0x, p0y, p1x, p1y, p2x, p2y};
+        flags |= aaf_face_safety(av, e, r, flags, &safe_word);
+    }
     // n_k = (-e_k.y, e_k.x), c_k = n_k . anchor_k  (two rounded products, one add)
     const float n[6] = {-e[1], e[0], -e[3], e[2], -e[5], e[4]};
     const float c0 = __fadd_rn(__fmul_rn(n[0], p0x), __fmul_rn(n[1], p0y));
@@ -308,7 +316,7 @@ __device__ __forceinline__ bool fused_preprocess_one(const DM2FusedInputs& in, i
     rec[11] = make_float4(p2x, p2y, e[0], e[1]);
     rec[12] = make_float4(e[2], e[3], e[4], e[5]);
     rec[13] = make_float4(r[0], r[1], r[2], r[3]);
-    rec[14] = make_float4(r[4], r[5], __int_as_float(f), 0.0f);
+    rec[14] = make_float4(r[4], r[5], __int_as_float(f), __uint_as_float(safe_word));
     return true;
 }
 

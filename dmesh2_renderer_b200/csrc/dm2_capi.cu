@@ -244,10 +244,27 @@ static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* ke
 
 }  // namespace dm2
 
+namespace dm2 {
+static std::atomic<int> g_exact_clip{-1};          // -1: not set yet (DM2_EXACT_CLIP in the environment decides)
+bool exact_clip_requested() {
+    int v = g_exact_clip.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("DM2_EXACT_CLIP");
+        v = (e && atoi(e) != 0) ? 1 : 0;
+        int expected = -1;
+        g_exact_clip.compare_exchange_strong(expected, v);
+        v = g_exact_clip.load(std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+}  // namespace dm2
+
 using namespace dm2;
 
 extern "C" {
 
+void dm2_set_exact_clip(int32_t on) { g_exact_clip.store(on != 0 ? 1 : 0, std::memory_order_relaxed); }
+int32_t dm2_get_exact_clip(void) { return exact_clip_requested() ? 1 : 0; }
 const char* dm2_last_error(void) { return g_err; }
 // Measured (tools/perf_configs.py --rounds-ab, profiles/r02_forward_rounds.md): doubling rounds beat equal ones (the
 // launches of rounds in which every tile has finished are not free); 512 / 4096 keeps the 8-view 512^2 micro-batch

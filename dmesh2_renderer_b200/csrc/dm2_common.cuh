@@ -72,6 +72,10 @@ struct PerDeviceOnce {
     void done() { ready.fetch_or(bit(), std::memory_order_release); }
 };
 
+// dm2_set_exact_clip(): every partially covered (pixel, face) pair takes the reference's polygon construction
+// (dm2_aa.cuh) instead of the polygon-free area (dm2_aa_fast.cuh) - process-wide, defined in dm2_capi.cu
+bool exact_clip_requested();
+
 // SMs of the current device (persistent grids)
 static inline int sm_count() {
     static std::atomic<int> cached[64];
@@ -100,7 +104,8 @@ constexpr int R_BBOX      = 0;    // txmin txmax tymin tymax      (min/max of aa
 constexpr int R_N01       = 4;    // n0.x n0.y n1.x n1.y          (aa_face_edges_normal)
 constexpr int R_N2C       = 8;    // n2.x n2.y c0 c1              (…, aa_face_edges_normal_c)
 constexpr int R_MISC      = 12;   // c2, opacity, intense, flags (bits 0..5: edges_iszero[e][k] at bit 2e+k; bit 8: the fused
-                                  // preprocess flipped the face to CCW; bit 9: some screen coordinate is an integer)
+                                  // preprocess flipped the face to CCW; bit 9: some screen coordinate is an integer;
+                                  // bits 10, 11: kAafNearInt, kAafNever of dm2_aa_fast.cuh)
 constexpr int R_P0        = 16;   // p0.xyz (world), z0 (ndc)
 constexpr int R_P1        = 20;
 constexpr int R_P2        = 24;
@@ -110,6 +115,7 @@ constexpr int R_AAV       = 40;   // aa_face_verts   3 x (x,y)   40..45
 constexpr int R_AAE       = 46;   // aa_face_edges   3 x (x,y)   46..51
 constexpr int R_AAR       = 52;   // aa_face_edges_recip         52..57
 constexpr int R_FID       = 58;   // face id (int)
+constexpr int R_SAFE      = 59;   // thresholds of the polygon-free overlap area (dm2_aa_fast.cuh: err | tau_v as bf16)
 
 // packed record of the layered path: 12 words = 48 bytes per (view, face)
 constexpr int kLRecWords  = 12;   // p0.xyz p1.xyz p2.xyz min_depth max_depth face_id

@@ -398,7 +398,10 @@ k_layers_first_hit(DM2LayerInputs in, const float* __restrict__ lrec, const uint
 
 // The walk: one WARP per 8x4-pixel footprint, CTAs of kWalkThreads (the rays of a tile take 0 .. 100+ steps: with one
 // 256-thread CTA per tile a third of the SM's warp slots waited for the slowest warp of their CTA).
-constexpr int kWalkThreads = 64;
+#ifndef DM2_WALK_THREADS
+#define DM2_WALK_THREADS 64
+#endif
+constexpr int kWalkThreads = DM2_WALK_THREADS;
 #ifndef DM2_WALK_MINB
 #define DM2_WALK_MINB 16
 #endif

@@ -77,13 +77,14 @@ __device__ __forceinline__ f3 comb3(float a, const f3& x, float b, const f3& y) 
 // the forward pass would have written: (uc, vc, ratio, code), ratio == 0 = skip.
 __device__ __noinline__ float4 shade_recompute(const float* rec, float ox, float oy, float oz, float dx, float dy,
                                                float dz, float pxmin, float pymin, float tau, int l, bool partial,
-                                               bool use_aa) {
+                                               bool use_aa, bool exact_clip) {
     Shade s;
     s.area = use_aa ? 1.0f : 0.0f;
     if (partial) {
-        const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l);
         float a;
-        if (!aa_clip<false>(rec, pxmin, pymin, inm, a, nullptr)) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!aa_overlap<false>(rec, pxmin, pymin, exact_clip,
+                               [&]() { return corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), l); }, a, nullptr))
+            return make_float4(0.f, 0.f, 0.f, 0.f);
         s.area = a;
     }
     PixelGeom qg;
@@ -92,11 +93,9 @@ __device__ __noinline__ float4 shade_recompute(const float* rec, float ox, float
     if (!shade_tail(rec, qg, tau, s)) return make_float4(0.f, 0.f, 0.f, 0.f);
     return make_float4(s.w1, s.w2, s.ratio, __int_as_float(s.code));
 }
-__device__ __noinline__ void clip_gradient(const float* rec, float pxmin, float pymin, unsigned inmask, float* g) {
+__device__ __noinline__ void clip_gradient(const float* rec, float pxmin, float pymin, unsigned inmask, bool exact_clip, float* g) {
     float a, gg[6];
-    bool chain = false;
-    aa_clip<true>(rec, pxmin, pymin, inmask, a, gg, &chain);
-    if (chain) aa_grad_reference(rec, pxmin, pymin, inmask, gg);
+    aa_overlap<true>(rec, pxmin, pymin, exact_clip, [&]() { return inmask; }, a, gg);
 #pragma unroll
     for (int q = 0; q < 6; q++) g[q] = gg[q];
 }
@@ -242,7 +241,7 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                     const float dy = __shfl_sync(0xffffffffu, pg.d.y, l), dz = __shfl_sync(0xffffffffu, pg.d.z, l);
                     if (act && !from_cache)
                         h = shade_recompute(rec, ox, oy, oz, dx, dy, dz, tc.fx0 + (float)(l & 7), tc.fy0 + (float)(l >> 3),
-                                            tau, l, (e >> 9) & 1u, use_aa);
+                                            tau, l, (e >> 9) & 1u, use_aa, cache.exact_clip != 0u);
                 }
                 if (!act) continue;
                 if (h.z != 0.0f) {
@@ -326,11 +325,11 @@ k_raster_backward(DM2RenderInputs in, const float* __restrict__ records, const u
                         }
                     } else {
                         h = shade_recompute(rec, qg.o.x, qg.o.y, qg.o.z, qg.d.x, qg.d.y, qg.d.z, qg.pxmin, qg.pymin, tau,
-                                            src, (e >> 9) & 1u, use_aa);
+                                            src, (e >> 9) & 1u, use_aa, cache.exact_clip != 0u);
                         if ((e >> 9) & 1u) {
                             const unsigned inm = corner_mask_of(*reinterpret_cast<const uint4*>(rec + R_META), src);
                             float gt[6];
-                            clip_gradient(rec, qg.pxmin, qg.pymin, inm, gt);
+                            clip_gradient(rec, qg.pxmin, qg.pymin, inm, cache.exact_clip != 0u, gt);
 #pragma unroll
                             for (int q = 0; q < 6; q++) g[q] = gt[q];
                         }
@@ -579,9 +578,11 @@ int launch_raster_backward(const DM2RenderInputs& in, const FaceWs& fw, const Bi
     }
     {
         ProfScope _ps("raster_backward", s);
+        ShadeCache cache = shade_cache_view(const_cast<void*>(shade_cache), shade_cache_bytes);
+        cache.exact_clip = exact_clip_requested() ? 1u : 0u;
         k_raster_backward<<<(unsigned)(nblk * kCtasPerTile), kRasterThreads, kBwdSmem, s>>>(
             in, fw.records, bw.vals, bw.imask, reinterpret_cast<const uint4*>(bw.meta), (uint32_t)bw.R,
-            shade_cache_view(const_cast<void*>(shade_cache), shade_cache_bytes), iw.ranges, iw.final_T, iw.final_prev_T,
+            cache, iw.ranges, iw.final_T, iw.final_prev_T,
             iw.n_contrib, dL_dcolor, dL_ddepth, gface, gx, gy);
         DM2_LAUNCH_CHECK();
     }

@@ -105,6 +105,7 @@ struct ShadeCache {
     uint32_t* counter;
     float4* data;
     uint32_t capacity;                      // granules
+    uint32_t exact_clip;                    // 1: every partially covered pair takes the exact polygon clip (dm2_set_exact_clip)
 };
 constexpr size_t kCacheHeader = 256;
 __host__ __device__ __forceinline__ ShadeCache shade_cache_view(void* pool, long long bytes) {
@@ -114,6 +115,7 @@ __host__ __device__ __forceinline__ ShadeCache shade_cache_view(void* pool, long
     long long cap = pool && bytes > (long long)kCacheHeader ? (bytes - (long long)kCacheHeader) / 16 : 0;
     if (cap > (1ll << 32) - (1ll << 28)) cap = (1ll << 32) - (1ll << 28);       // the 32-bit counter must not wrap
     c.capacity = (uint32_t)cap;
+    c.exact_clip = 0u;
     return c;
 }
 __device__ __forceinline__ uint32_t cache_block_granules(uint32_t n_t, uint32_t n_p) {

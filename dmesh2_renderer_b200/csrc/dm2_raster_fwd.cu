@@ -107,7 +107,8 @@ int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const Bin
         DM2_CHECK(cudaFuncSetAttribute(k_raster_forward_listed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
         attr_set.done();
     }
-    const ShadeCache cache = shade_cache_view(shade_cache, shade_cache_bytes);
+    ShadeCache cache = shade_cache_view(shade_cache, shade_cache_bytes);
+    cache.exact_clip = exact_clip_requested() ? 1u : 0u;
     const BinGuard guard{iw.tile_cursor + nblk, (uint32_t)bw.R, (uint32_t)bw.longest_cap};
     const bool use_cache = cache.capacity > 0 && in.aa_temperature > 0.0f && bw.R > 0;
     const bool rounds = round_end > 0;

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 15
+#define DM2_ABI_VERSION 16
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -382,6 +382,13 @@ void dm2_profile_enable(int32_t on);
  * for the classification pre-pass.  Results do not depend on these values.  Defaults 512 / 4096; process-wide; not
  * thread safe against running calls. */
 void dm2_set_forward_rounds(int64_t round_len, int64_t threshold);
+/* Overlap area of a partially covered (pixel, face) pair (reference aa.h:151-441).  Default (0): the polygon-free
+ * evaluation of dm2_aa_fast.cuh wherever it provably yields the reference's value (same rounded polygon vertices, area
+ * equal to ~1e-7), the reference's polygon construction for the other ~0.5 % of the pairs.  1: the polygon construction
+ * for every pair - forward images then are bit-identical to the reference's (tests), at ~0.3 ms per 1 M-triangle frame.
+ * Process-wide; DM2_EXACT_CLIP=1 in the environment sets the initial value. */
+void dm2_set_exact_clip(int32_t on);
+int32_t dm2_get_exact_clip(void);
 void dm2_profile_reset(void);
 int64_t dm2_profile_report(char* buf, int64_t cap);
 

@@ -1337,3 +1337,30 @@ def test_layered_index_validation_debug_switch(built, monkeypatch):
     bad["face_tets"][5, 0] = -2
     with pytest.raises(RuntimeError, match="face_tets"):
         lr.generate([0], *bad.values(), sc.num_layers)
+
+
+@pytest.mark.parametrize("n_faces,size,sigma", [(3000, 128, 0.06), (40_000, 256, 0.02)])
+def test_fast_overlap_area_agrees_with_the_exact_clip(built, n_faces, size, sigma):
+    """dm2_set_exact_clip: the polygon-free overlap area (csrc/dm2_aa_fast.cuh, the default) against the reference's
+    polygon construction for every pair - images equal to 2e-6, the same contributors, gradients equal to 1e-4 of
+    their largest entry (the contract itself is checked pair by pair on the CPU, tests/test_aa_fast.py)."""
+    import dmesh2_renderer_b200 as dm
+    from dmesh2_renderer_b200 import scenes
+    dev = _dev()
+    sc = scenes.small(n_faces=n_faces, size=size, sigma=sigma, seed=43)
+    st = scene_tensors(sc, dev)
+    r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
+    prev = dm.set_exact_clip(True)
+    try:
+        c0, d0, l0, f0 = _public_step(r, st, sc, dev)
+        torch.cuda.synchronize()
+        assert dm.set_exact_clip(False) is True
+        c1, d1, l1, f1 = _public_step(r, st, sc, dev)
+        torch.cuda.synchronize()
+    finally:
+        dm.set_exact_clip(prev)
+    assert float((c0 - c1).abs().max()) <= 2e-6 and float((d0 - d1).abs().max()) <= 2e-6
+    assert float((c0 - c1).abs().max()) > 0.0 or n_faces < 10_000, "the two settings must run different code"
+    for k in l0:
+        assert rel_err(l1[k].grad.cpu().numpy(), l0[k].grad.cpu().numpy()) <= 1e-4, k
+    assert rel_err(f1.grad.cpu().numpy(), f0.grad.cpu().numpy()) <= 1e-4
