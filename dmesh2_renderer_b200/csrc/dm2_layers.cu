@@ -402,6 +402,9 @@ k_layers_first_hit(DM2LayerInputs in, const float* __restrict__ lrec, const uint
 #define DM2_WALK_THREADS 64
 #endif
 constexpr int kWalkThreads = DM2_WALK_THREADS;
+// register budget: measured at cfg3 (ms per walk-only generate, through the public API) 16 CTAs / SM (64 registers)
+// 0.595, 24 CTAs 0.623, 8 CTAs (128 registers) 0.635 in a same-box A/B (an earlier A/B had shown 0.571 for 8: not
+// reproducible); CTAs of 32 / 128 threads 0.597 / 0.597
 #ifndef DM2_WALK_MINB
 #define DM2_WALK_MINB 16
 #endif

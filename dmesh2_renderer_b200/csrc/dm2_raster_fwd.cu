@@ -9,14 +9,18 @@ namespace dm2 {
 
 // Candidates per sub-chunk.  Measured at cfg2 (ms, CTAs of 4 warps): 12 candidates / 7 CTAs per SM 1.23;
 // 16 / 6 CTAs 1.155; 20 / 5 CTAs 1.17; 24 / 4 CTAs 1.21.
-constexpr int kFSub = 16;
+#ifndef DM2_FSUB
+#define DM2_FSUB 16
+#endif
+constexpr int kFSub = DM2_FSUB;
+constexpr int kFSubBits = kFSub > 16 ? 5 : 4;      // candidate field of a pair-list entry
 constexpr int kFSlots = kFSub * 32;
 
 struct FwdWarpSmem {
     float srec[kFSub * kRecStride];         // staged records of the sub-chunk
     float parea[kFSlots];                   // [candidate][pixel]: overlap area of a partially covered pixel (-1: skip)
     WarpQueue q;
-    uint16_t plist[kFSlots];                // partially covered (pixel, face) pairs: k | lane << 4
+    uint16_t plist[kFSlots];                // partially covered (pixel, face) pairs: k | lane << kFSubBits
 };
 
 // CACHE: fill the shading cache for the backward pass (dm2_raster_common.cuh): d(area)/d(aa verts) of every

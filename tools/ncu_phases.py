@@ -15,7 +15,7 @@ import csv
 import os
 from collections import OrderedDict, defaultdict
 
-PRIO = ["dm2_aa.cuh", "dm2_common.cuh", "dm2_raster_common.cuh"]
+PRIO = ["dm2_aa_fast.cuh", "dm2_aa.cuh", "dm2_common.cuh", "dm2_raster_common.cuh"]
 
 
 def rank(fname):

@@ -65,8 +65,9 @@ def run_soup(pkg, sc, dev, views, iters):
     return ms, out
 
 
-def run_layers(pkg, sc, dev, iters):
+def run_layers(pkg, sc, dev, iters, incremental=True):
     lr = pkg.LayeredRenderer(t(sc.mv, dev), t(sc.proj, dev), sc.width, sc.height, dev)
+    lr.incremental = incremental            # this package only: False = binning + first hit + geometry records every call
     a = [t(getattr(sc, k), dev) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")]
     out = {}
 
@@ -118,6 +119,10 @@ def main():
                 else:
                     ms, out = run_layers(pkg, sc, dev, args.iters)
                     unit = 1000.0 / ms
+                    if name == "b200":      # the reference has no incremental path: its number is a full generate
+                        ms_full, _ = run_layers(pkg, sc, dev, args.iters, incremental=False)
+                        print(json.dumps({"config": sc.name, "impl": name, "ms_full_generate": ms_full,
+                                          "ms_walk_only_regenerate": ms}), flush=True)
             except Exception as ex:          # e.g. the reference running out of memory at cfg5
                 print(json.dumps({"config": cfg, "impl": name, "error": str(ex)[:200]}), flush=True)
                 continue
@@ -127,7 +132,7 @@ def main():
                 _lib.profile_reset(); _lib.profile_enable(True)
                 n = 3
                 for _ in range(n):
-                    (run_soup if kind == "soup" else run_layers)(*((pkg, sc, dev, views, 1) if kind == "soup" else (pkg, sc, dev, 1)))
+                    (run_soup if kind == "soup" else run_layers)(*((pkg, sc, dev, views, 1) if kind == "soup" else (pkg, sc, dev, 1, False)))
                 st = _lib.profile_report(); _lib.profile_enable(False)
                 steps = n * 4                       # time_it: 3 warm-up calls + 1 timed one
                 print(json.dumps({"config": sc.name, "stages_ms_per_step": {k: round(v[0] / steps, 4) for k, v in st.items()},
