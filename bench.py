@@ -14,7 +14,8 @@ the public API (and, for N > 1, ONE sum of [dverts | dverts_color | dfaces_opaci
 library's peer-memory allreduce kernel over NVLink, csrc/dm2_peer.cu - the gradients are accumulated by the
 backward kernels straight into the bucket, and the summed bucket is checked against torch.distributed.all_reduce
 after the timed region; the reference arm uses NCCL).  --workload cfg4: a step renders all 64 views at 512^2,
-8 views per micro-batch, view i on rank i % N (multiview.multiview_step).
+8 views per micro-batch, views assigned to the ranks by measured per-view cost (multiview.balanced_shards;
+--no-balance: view i on rank i % N).
 `value` is measured with the scene parameters resident in HBM; `e2e` additionally copies every step's
 inputs (verts, colours, opacity, intensity) from pinned host memory inside the timed region (copy stream,
 double buffered: the copy for step i+1 overlaps the compute of step i) and copies the loss back to pinned
@@ -49,6 +50,8 @@ def parse():
                     help="N > 1: peer-memory kernel with in-kernel barriers (default), with two separate barrier "
                          "launches, or torch.distributed.all_reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="cfg4, N > 1: keep view i on rank i %% N instead of balancing the shards by measured per-view cost")
     ap.add_argument("--clock-window-s", type=float, default=1.2,
                     help="untimed repeat of the timed loop during which nvidia-smi samples the clocks")
     return ap.parse_args()
@@ -313,6 +316,39 @@ def main():
                 bucket.allreduce()        # ONE exchange per optimisation step
         return total
 
+    # cfg4, N > 1: the 64 cameras see the scene from different directions and do not cost the same; view i on rank
+    # i % N leaves the exchange waiting ~1 ms of a 13 ms step for the slowest rank at 8 GPUs.  The cameras are fixed
+    # for the whole run, so every view is timed ONCE here, before the warm-up (a single-view fwd+bwd frame on the
+    # rank that owns it round-robin, CUDA events), the costs are shared, and every rank derives the same ownership
+    # table (multiview.balanced_shards: longest first, same number of views per rank).  Both arms.
+    view_balance = None
+    if cfg4 and world > 1 and not args.no_balance:
+        from dmesh2_renderer_b200.multiview import balanced_shards
+        costs = torch.zeros(n_views, dtype=torch.float32, device=dev)
+        patch_min.setdefault(1, torch.zeros((1, 2), dtype=torch.int32, device=dev))
+        for v in my_views:
+            batches[:] = [[v]]
+            compute(params, exchange=False)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            compute(params, exchange=False)
+            compute(params, exchange=False)
+            e1.record()
+            torch.cuda.synchronize()
+            costs[v] = e0.elapsed_time(e1) / 2
+        dist.all_reduce(costs)
+        c = costs.tolist()
+        shards = balanced_shards(c, world)
+        rr = [sum(c[v] for v in range(r, n_views, world)) for r in range(world)]
+        bal = [sum(c[v] for v in sh) for sh in shards]
+        view_balance = {"per_view_ms_min": round(min(c), 4), "per_view_ms_max": round(max(c), 4),
+                        "round_robin_rank_ms_max_over_mean": round(max(rr) / (sum(rr) / world), 4),
+                        "balanced_rank_ms_max_over_mean": round(max(bal) / (sum(bal) / world), 4)}
+        my_views = shards[rank]
+        batches[:] = [my_views[i:i + args.micro_batch] for i in range(0, len(my_views), args.micro_batch)]
+        for b in batches:
+            patch_min.setdefault(len(b), torch.zeros((len(b), 2), dtype=torch.int32, device=dev))
+
     # e2e input feed (both arms): every step's parameters are copied from pinned host memory inside the
     # timed region, on a copy stream and double buffered - a prefetching loader: the copy for step i+1
     # runs while step i computes; the compute stream waits on the copy's event, the copy waits on the
@@ -438,7 +474,8 @@ def main():
     if cfg4:
         workload = (f"{sc.name}: DMesh++ multi-view step, {n_views} views at {W}x{H} of {F} random semi-transparent triangles "
                     f"(SURVEY 8d cfg4: cfg2's scene, Fibonacci-sphere cameras), {args.micro_batch} views per Renderer call, "
-                    f"view i on rank i % {world}")
+                    + (f"views assigned to the ranks by measured per-view cost (multiview.balanced_shards)"
+                       if view_balance is not None else f"view i on rank i % {world}"))
     else:
         workload = (f"{sc.name}: Renderer fwd+bwd, {F} random semi-transparent triangles, {W}x{H}, "
                     f"1 view per GPU (SURVEY 8d cfg2, seed 2, sigma 0.0115, aa_temperature 1.0)")
@@ -457,6 +494,8 @@ def main():
     }
     if allreduce_check is not None:
         out["allreduce_check"] = allreduce_check
+    if view_balance is not None:
+        out["view_balance"] = view_balance
     if args.impl == "reference":
         out["impl"] = "reference"
         out["cpu_baseline"] = {"value": value, "unit": unit, "cores": 0, "kind": "reference",

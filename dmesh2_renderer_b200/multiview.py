@@ -22,6 +22,27 @@ def shard_views(num_views: int, world_size: int, rank: int) -> List[int]:
     return list(range(rank, num_views, world_size))
 
 
+def balanced_shards(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Cost-aware ownership of the views of a step: costs[i] = what view i costs to render (any consistent unit -
+    milliseconds of a single-view frame, instances, ...; cameras do not move between optimisation steps, so one
+    measurement serves the whole run).  Views are dealt out longest first, in rounds of `world_size`, the most
+    expensive view of a round to the least loaded rank - every rank gets the same NUMBER of views (+-1), which keeps
+    the micro-batches the same shape on all ranks.  Deterministic: every rank computes the same table from the same
+    costs.  Returns the view lists of ranks 0 .. world_size-1 (ascending view ids)."""
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    n = len(costs)
+    order = sorted(range(n), key=lambda i: (-float(costs[i]), i))
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    load = [0.0] * world_size
+    for r0 in range(0, n, world_size):
+        ranks = sorted(range(world_size), key=lambda r: (load[r], r))
+        for v, r in zip(order[r0:r0 + world_size], ranks):
+            shards[r].append(v)
+            load[r] += float(costs[v])
+    return [sorted(sh) for sh in shards]
+
+
 def micro_batches(views: Sequence[int], size: int) -> List[List[int]]:
     if size <= 0:
         raise ValueError("micro-batch size must be positive")
@@ -173,7 +194,7 @@ def make_grad_bucket(num_verts: int, num_faces: int, device, peer: bool = True, 
 def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts: torch.Tensor,
                    verts_color: torch.Tensor, faces_opacity: torch.Tensor, bucket: Optional[GradBucket] = None,
                    micro_batch: int = 8, world_size: Optional[int] = None, rank: Optional[int] = None, group=None,
-                   renderer=None):
+                   renderer=None, shards: Optional[Sequence[Sequence[int]]] = None):
     """One optimisation step's gradient over `all_views`, sharded over the process group.
 
     `render_view_batch(views, verts, verts_color, faces_opacity) -> scalar loss tensor` renders the
@@ -185,6 +206,9 @@ def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts:
     then ADDS the three replicated-parameter gradients straight into the bucket's views (fused.GradSink) - no
     per-micro-batch gradient tensors, no accumulate pass, no pack copy; without it the gradients come back
     through autograd and are added to the bucket here.
+
+    `shards` (optional): the ownership table of balanced_shards() - shards[r] = positions in `all_views` that rank r
+    renders - instead of round-robin.
     """
     if world_size is None:
         world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -193,7 +217,7 @@ def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts:
     if bucket is None:
         bucket = GradBucket(verts.shape[0], faces_opacity.shape[0], verts.device)
     bucket.zero_()
-    mine = shard_views(len(all_views), world_size, rank)
+    mine = list(shards[rank]) if shards is not None else shard_views(len(all_views), world_size, rank)
     local_loss = torch.zeros((), dtype=torch.float32, device=verts.device)
     sink_on = False
     if renderer is not None and verts.is_cuda and getattr(renderer, "fused", True):

@@ -562,14 +562,25 @@ def test_layers_match_reference_goldens(built, name):
     assert np.array_equal(cnt.cpu().numpy(), g["render_layers_cnt"])
 
 
-def test_live_reference_mid_size(built):
-    """200k triangles at 512x512 through BOTH public APIs on the same GPU (skipped without baseline/_ref)."""
+@pytest.mark.parametrize("exact_clip", [False, True])
+def test_live_reference_mid_size(built, exact_clip):
+    """200k triangles at 512x512 through BOTH public APIs on the same GPU (skipped without baseline/_ref).  With the
+    exact polygon clip for every pair (dm2_set_exact_clip) the forward images are the reference's bit for bit; with the
+    polygon-free overlap area (the default) they are within a few ulp."""
     ref = load_reference()
     if ref is None:
         pytest.skip("baseline/_ref not present on this box")
     import dmesh2_renderer_b200 as dm
     from dmesh2_renderer_b200 import scenes
     dev = _dev()
+    prev = dm.set_exact_clip(exact_clip)
+    try:
+        _live_reference_mid_size(dm, ref, scenes, dev, exact_clip)
+    finally:
+        dm.set_exact_clip(prev)
+
+
+def _live_reference_mid_size(dm, ref, scenes, dev, exact_clip):
     sc = scenes.triangle_soup("mid", 200_000, 512, 0.02, seed=12)
     st = scene_tensors(sc, dev)
     pm = torch.zeros((1, 2), dtype=torch.int32, device=dev)
@@ -584,6 +595,10 @@ def test_live_reference_mid_size(built):
     (c0, d0, g0), (c1, d1, g1) = outs
     assert np.mean(np.abs(c0 - c1) > 1e-4 * (1 + np.abs(c1))) == 0.0
     assert np.mean(np.abs(d0 - d1) > 1e-4 * (1 + np.abs(d1))) == 0.0
+    if exact_clip:
+        assert np.array_equal(c0, c1) and np.array_equal(d0, d1), float(np.abs(c0 - c1).max())
+    else:
+        assert float(np.abs(c0 - c1).max()) <= 2e-6 and float(np.abs(d0 - d1).max()) <= 2e-6
     for k in g0:
         e = np.abs(g0[k] - g1[k]).max() / (np.abs(g1[k]).max() + 1e-30)
         assert e <= BWD_RTOL, (k, e)

@@ -18,6 +18,23 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_balanced_shards():
+    from dmesh2_renderer_b200.multiview import balanced_shards
+    import random
+    rng = random.Random(3)
+    for n, g in [(64, 8), (64, 4), (10, 4), (3, 8), (0, 2)]:
+        costs = [1.0 + rng.random() * (3.0 if i % 5 == 0 else 0.3) for i in range(n)]
+        sh = balanced_shards(costs, g)
+        assert sorted(v for s in sh for v in s) == list(range(n))            # a partition
+        assert max(len(s) for s in sh) - min(len(s) for s in sh) <= 1        # same number of views per rank
+        assert sh == balanced_shards(list(costs), g)                         # deterministic
+        if n >= 2 * g:
+            load = [sum(costs[v] for v in s) for s in sh]
+            rr = [sum(costs[v] for v in range(r, n, g)) for r in range(g)]
+            assert max(load) <= max(rr) + 1e-9                               # never worse than round-robin here
+    assert balanced_shards([5, 1, 1, 1], 2) == [[0], [1, 2, 3]] or balanced_shards([5, 1, 1, 1], 2) == [[0, 3], [1, 2]]
+
+
 def test_shard_views_partition():
     from dmesh2_renderer_b200.multiview import micro_batches, shard_views
     for n, g in ((64, 8), (64, 4), (7, 2), (3, 4), (0, 2)):
