@@ -171,7 +171,8 @@ def check(status):
 def set_exact_clip(on=True):
     """True: every partially covered (pixel, face) pair takes the reference's polygon construction (forward images
     bit-identical to the reference's); False (default): the polygon-free overlap area of csrc/dm2_aa_fast.cuh where it
-    provably yields the same value to ~1e-7, the construction elsewhere.  Process-wide.  Returns the previous setting."""
+    yields the same value to ~1e-7 (pairs far from every rounding-dependent decision of the reference, thresholds
+    measured against the oracle: tests/test_aa_fast.py), the construction elsewhere.  Process-wide.  Returns the previous setting."""
     lib = load_library()
     prev = bool(lib.dm2_get_exact_clip())
     lib.dm2_set_exact_clip(1 if on else 0)

@@ -350,7 +350,7 @@ static __device__ __noinline__ bool aa_clip_exact(const float* __restrict__ rec,
 }
 
 // Overlap area (+ gradient) of one partially covered (pixel, face) pair: the polygon-free evaluation where it is
-// provably the reference's result (dm2_aa_fast.cuh), the exact construction otherwise.  inmask_of(): the 4-bit
+// the reference's result to ~1e-7 (dm2_aa_fast.cuh: pairs far from each of its rounding-dependent decisions), the exact construction otherwise.  inmask_of(): the 4-bit
 // inside-corner mask, only evaluated on the exact path.  Returns false = the reference skips the face for this pixel.
 template <bool GRAD, typename InMask>
 __device__ __forceinline__ bool aa_overlap(const float* __restrict__ rec, float pxmin, float pymin, bool exact_only,

@@ -383,9 +383,10 @@ void dm2_profile_enable(int32_t on);
  * thread safe against running calls. */
 void dm2_set_forward_rounds(int64_t round_len, int64_t threshold);
 /* Overlap area of a partially covered (pixel, face) pair (reference aa.h:151-441).  Default (0): the polygon-free
- * evaluation of dm2_aa_fast.cuh wherever it provably yields the reference's value (same rounded polygon vertices, area
+ * evaluation of dm2_aa_fast.cuh wherever the pair is far - by thresholds measured against the oracle, tests/test_aa_fast.py - from every
+ * rounding-dependent decision of the reference, so that it yields the reference's value (same rounded polygon vertices, area
  * equal to ~1e-7), the reference's polygon construction for the other ~0.5 % of the pairs.  1: the polygon construction
- * for every pair - forward images then are bit-identical to the reference's (tests), at ~0.3 ms per 1 M-triangle frame.
+ * for every pair - forward images then are bit-identical to the reference's (tests), at +0.46 ms per 1 M-triangle frame.
  * Process-wide; DM2_EXACT_CLIP=1 in the environment sets the initial value. */
 void dm2_set_exact_clip(int32_t on);
 int32_t dm2_get_exact_clip(void);

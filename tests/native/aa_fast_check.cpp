@@ -83,7 +83,7 @@ int main(int argc, char** argv) {
     long long total = 0, partial = 0, answered = 0, viol = 0, declined_ok = 0, declined_err = 0;
     double max_da = 0, max_dg = 0, max_dfd = 0;
     long long grad_vs_truth = 0;
-    const int kModes = 10;
+    const int kModes = 12;
     long long mode_partial[kModes] = {0}, mode_answered[kModes] = {0};
     static long long reasons[kModes][5];
     for (int mode = 0; mode < kModes; mode++) {
@@ -96,7 +96,13 @@ int main(int argc, char** argv) {
             for (int k = 0; k < 6; k++) p[k] = ((k & 1) ? py : px) + 0.5f + s * N(rng);
             const float tiny[8] = {0.0f, 6e-5f, 1.3e-4f, 3e-4f, 1e-3f, 3e-3f, 1e-2f, -1.0f};
             auto small = [&]() { float d = tiny[(int)(U(rng) * 8) % 8]; if (d < 0) d = U(rng) * 0.1f; return (U(rng) < 0.5f ? -d : d) * U(rng) * 2.0f; };
-            if (mode >= 8) {            // the benchmark scenes: cfg2-like (1024^2, sigma 4.7 px), cfg5-like (2048^2, sigma 6.6 px)
+            if (mode == 10) {           // huge triangles, vertices far off screen (negative coordinates included)
+                for (int k = 0; k < 6; k++) p[k] = ((k & 1) ? py : px) + 0.5f + 3000.0f * N(rng);
+            } else if (mode == 11) {    // a patch far from the origin of a large frame (coordinates 4096 .. 16384)
+                const float ox = 4096.0f + (float)(int)(U(rng) * 12288.0f), oy = 4096.0f + (float)(int)(U(rng) * 12288.0f);
+                for (int k = 0; k < 6; k++) p[k] = ((k & 1) ? oy : ox) + 0.5f + s * N(rng);
+                px = ox; py = oy;
+            } else if (mode >= 8) {            // the benchmark scenes: cfg2-like (1024^2, sigma 4.7 px), cfg5-like (2048^2, sigma 6.6 px)
                 const int sp = mode == 8 ? 1024 : 2048;
                 const float sg = mode == 8 ? 4.7f : 6.6f;
                 const float qx = (float)(int)(U(rng) * sp), qy = (float)(int)(U(rng) * sp);
