@@ -850,7 +850,7 @@ int launch_classify(const uint64_t* keys, long long capacity, long long longest_
 
 int launch_classify_round(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr,
                           const TileMaskArgs& tm, const uint2* ranges, const uint8_t* warp_done, int num_tiles,
-                          int round_begin, int round_len, const RoundWork& work, cudaStream_t s) {
+                          int round_begin, int round_len, const RoundWork& work, const RoundSort& sort, cudaStream_t s) {
     if (capacity <= 0 || num_tiles <= 0) return 0;
     const BinGuard guard{hdr, (uint32_t)capacity, (uint32_t)longest_cap};
     const bool listed = round_begin > 0;
@@ -860,6 +860,9 @@ int launch_classify_round(const uint64_t* keys, long long capacity, long long lo
         k_round_worklist<<<cdiv(num_tiles, 256), 256, 0, s>>>(ranges, warp_done, num_tiles, guard, (uint32_t)round_begin,
                                                               work.n, work.cls_list, work.fwd_list);
         DM2_LAUNCH_CHECK();
+        // lazy sort: the listed tiles whose sorted prefix ends inside this round's window are sorted to the end
+        if (launch_tile_sort_finish(num_tiles, ranges, sort.cursor, sort.keys_unsorted, sort.vals_unsorted, sort.keys, sort.vals,
+                                    capacity, work.cls_list, work.n, (long long)round_begin + round_len, sort.lazy, s)) return 1;
     }
     ProfScope _ps("classify", s);
     const int chunks = cdiv(round_len, kClsThreads);

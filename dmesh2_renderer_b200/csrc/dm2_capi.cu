@@ -92,7 +92,7 @@ static void face_layout(long long BF, bool layered, DM2FaceLayout* L) {
 // u32[4 + 3 nt]: the work lists of a round (RoundWork)
 static size_t cursor_words(size_t nt) { return (nt + 3 + 3) / 4 * 4; }
 static size_t cursor_zero_bytes(size_t nt) { return cursor_words(nt) * 4 + nt * 8; }     // zeroed every frame
-static size_t cursor_area_bytes(size_t nt) { return cursor_zero_bytes(nt) + (4 + 3 * nt) * 4; }
+static size_t cursor_area_bytes(size_t nt) { return cursor_zero_bytes(nt) + (4 + 4 * nt) * 4; }   // + work lists, sorted_upto
 
 static void image_layout(long long B, int H, int W, bool layered, DM2ImageLayout* L) {
     size_t off = 0;
@@ -144,6 +144,7 @@ static ImageWs carve_image(void* ws, long long B, int H, int W, bool layered) {
     const size_t nt = (size_t)B * cdiv(W, kTile) * cdiv(H, kTile);
     i.warp_done = (uint8_t*)(i.tile_cursor + cursor_words(nt));
     i.round_work = (uint32_t*)(i.warp_done + nt * 8);
+    i.sorted_upto = i.round_work + 4 + 3 * nt;
     i.final_prev_T = (float*)(p + L.final_prev_T); i.n_contrib = (uint32_t*)(p + L.n_contrib);
     i.first_face = (int*)(p + L.first_face); i.first_tet = (int*)(p + L.first_tet);
     return i;
@@ -236,10 +237,10 @@ static int zero_ranges(void* image_ws, int B, int H, int W, bool layered, cudaSt
 // shared middle of both pipelines: scatter into the tile segments + per-segment sort.  capacity: instances
 // the binning workspace was laid out for; longest: longest tile segment (-1 = unknown: every sort tier runs).
 static int bin_faces(long long BF, int B, int F, int gx, int gy, const float* key_depths, const FaceWs& fw,
-                     const BinWs& bw, const ImageWs& iw, long long longest, cudaStream_t s) {
+                     const BinWs& bw, const ImageWs& iw, long long longest, const LazySort& lazy, cudaStream_t s) {
     if (bw.R <= 0) return 0;
     return launch_tile_sort(BF, F, gx, gy, B * gx * gy, key_depths, fw.tiles_touched, fw.rects, iw.ranges,
-                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, bw.R, longest, s);
+                            iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, bw.R, longest, lazy, s);
 }
 
 }  // namespace dm2
@@ -366,6 +367,17 @@ static long long tail_longest_cap(long long longest, long long basis, bool sort_
     if (rounds > 1) cap = std::min(cap, round_end(rounds - 1));
     return cap;
 }
+// Lazy segment sort (dm2_tilesort.cu): a frame that runs in rounds sorts only the first two rounds' worth of every
+// tile list at once; tiles that run deeper are sorted to the end before the round that needs it.  DM2_LAZY_SORT=0: off.
+static bool lazy_sort_enabled() {
+    static std::once_flag once;
+    static bool on = true;
+    std::call_once(once, [] { if (const char* e = getenv("DM2_LAZY_SORT")) on = atoi(e) != 0; });
+    return on;
+}
+static LazySort lazy_for(const ImageWs& iw, long long rounds) {
+    return LazySort{iw.sorted_upto, rounds > 1 && lazy_sort_enabled() ? (uint32_t)round_end(1) : 0xFFFFFFFFu};
+}
 static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, BinWs bw, const ImageWs& iw, long long longest,
                         long long basis, float* out_color, float* out_depth, void* shade_cache,
                         long long shade_cache_bytes, bool sort_too, cudaStream_t s) {
@@ -374,9 +386,10 @@ static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, BinWs bw, c
     const long long BF = (long long)in->B * in->F;
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
     const TileMaskArgs tm{bw.vals, fw.records, in->patch_min, bw.imask, bw.meta, in->F, gx, gy, in->aa_temperature > 0.0f ? 1 : 0};
-    if (sort_too && bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, longest, s)) return 1;
-    const uint32_t* hdr = iw.tile_cursor + (size_t)in->B * gx * gy;
     const long long rounds = rounds_for(longest, basis);
+    const LazySort lazy = lazy_for(iw, rounds);
+    if (sort_too && bin_faces(BF, in->B, in->F, gx, gy, fw.depths, fw, bw, iw, longest, lazy, s)) return 1;
+    const uint32_t* hdr = iw.tile_cursor + (size_t)in->B * gx * gy;
     if (rounds == 1) {
         if (launch_classify(bw.keys, bw.R, bw.longest_cap, hdr, tm, s)) return 1;
         return launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0,
@@ -384,10 +397,11 @@ static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, BinWs bw, c
     }
     const long long nt = (long long)in->B * gx * gy;
     const RoundWork work{iw.round_work, iw.round_work + 4, iw.round_work + 4 + nt};
+    const RoundSort rsort{bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, iw.tile_cursor, lazy};
     for (long long k = 0; k < rounds; k++) {
         const int rb = k ? (int)round_end(k - 1) : 0, re = (int)round_end(k);
         if (launch_classify_round(bw.keys, bw.R, bw.longest_cap, hdr, tm, iw.ranges, iw.warp_done, (int)nt,
-                                  rb, re - rb, work, s)) return 1;
+                                  rb, re - rb, work, rsort, s)) return 1;
         if (launch_raster_forward(*in, fw, bw, iw, out_color, out_depth, shade_cache, shade_cache ? shade_cache_bytes : 0,
                                   rb, re, work, s)) return 1;
     }
@@ -544,7 +558,8 @@ int dm2_fused_forward_pipelined(const DM2FusedInputs* in, void* face_ws, void* b
         // twice) - sort the long segments now and redo classification + compositing on the same workspace
         const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
         if (missing && launch_tile_sort_tiers(in->B * gx * gy, iw.ranges, iw.tile_cursor, bw.keys_unsorted, bw.vals_unsorted,
-                                              bw.keys, bw.vals, bw.R, missing, s)) return 1;
+                                              bw.keys, bw.vals, bw.R, missing,
+                                              lazy_for(iw, rounds_for(*longest_host, *longest_host)), s)) return 1;
         DM2_CHECK(cudaMemsetAsync(iw.warp_done, 0, (size_t)in->B * gx * gy * 8, s));
         if (forward_tail(&r, fw, bw, iw, *longest_host, *longest_host, out_color, out_depth, shade_cache, shade_cache_bytes, false, s))
             return 1;
@@ -648,7 +663,7 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
     BinWs bw = carve_bin(binning_ws, num_rendered);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     // key = min depth (reference renderer.cu:603)
-    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, longest, s)) return 1;
+    if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, longest, LazySort{nullptr, 0xFFFFFFFFu}, s)) return 1;
     return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, false, s);
 }
 

@@ -288,6 +288,7 @@ struct ImageWs {
     uint2* ranges; uint32_t* tile_cursor; float* final_T; float* final_prev_T; uint32_t* n_contrib;
     uint8_t* warp_done;           // u8[8 * tiles]: footprint finished (forward pass in rounds)
     uint32_t* round_work;         // u32[4 + 3 * tiles]: work lists of a round (RoundWork)
+    uint32_t* sorted_upto;        // u32[tiles]: sorted prefix of every tile segment (lazy sort of deep scenes)
     int* first_face; int* first_tet;
 };
 // tiles (cls_list, n[0] entries) and half tiles (tile * 2 + half: fwd_list, n[1] entries) still running in a round;
@@ -311,22 +312,32 @@ int launch_scan(const uint32_t* in, uint32_t* out, long long n, uint32_t* partia
 long long scan_partials_count(long long n);
 int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, const uint32_t* tiles_touched,
                            const uint2* rects, uint2* ranges, uint32_t* cursor, cudaStream_t s);
+// lazy segment sort of deep scenes (dm2_tilesort.cu): sorted_upto u32[num_tiles] receives the length of every tile's
+// sorted prefix (nullptr: everything is sorted and nothing is recorded); prefix: list positions to sort at once
+struct LazySort { uint32_t* sorted_upto; uint32_t prefix; };
 int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
                      const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
                      uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
-                     long long capacity, long long longest, cudaStream_t s);
+                     long long capacity, long long longest, const LazySort& lazy, cudaStream_t s);
 int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
-                           cudaStream_t s);
+                           const LazySort& lazy, cudaStream_t s);
+int launch_tile_sort_finish(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
+                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity,
+                            const uint32_t* work, const uint32_t* work_n, long long need_end, const LazySort& lazy,
+                            cudaStream_t s);
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
                       long long n, int end_bit, void* temp, size_t temp_bytes, cudaStream_t s);
 size_t sort_temp_bytes(long long n);
 int launch_classify(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr, const TileMaskArgs& tm,
                     cudaStream_t s);
 long long sort_tiers_longest_cap(long long longest_hint);
+// sort: (listed rounds only) the lazy sort's second phase runs between the work list and the classification
+struct RoundSort { const uint64_t* keys_unsorted; const uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
+                   const uint32_t* cursor; LazySort lazy; };
 int launch_classify_round(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr,
                           const TileMaskArgs& tm, const uint2* ranges, const uint8_t* warp_done, int num_tiles,
-                          int round_begin, int round_len, const RoundWork& work, cudaStream_t s);
+                          int round_begin, int round_len, const RoundWork& work, const RoundSort& sort, cudaStream_t s);
 // round_end == 0: one pass over the whole lists; else list entries [round_begin, round_end) of every tile, resuming
 // from / leaving the per-pixel state in out_color / out_depth / final_T / final_prev_T / n_contrib (iw.warp_done)
 int launch_raster_forward(const DM2RenderInputs& in, const FaceWs& fw, const BinWs& bw,

@@ -247,9 +247,16 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) { return n <= 1u ? 1u 
 // sorts its bins with the bitonic network on its own, without block barriers - O(n) + small sorts
 // instead of log^2(n) block-wide stages.  A segment whose keys crowd into one bin (> n / 4) falls back
 // to the block-wide network.
+// LAZY sort (deep scenes, dm2_capi.cu forward_tail): `prefix` < n sorts only the bins that start before list
+// position `prefix` - the rest of the segment stays in bin order (every key of a later bin is behind every key of an
+// earlier one, the bins themselves unsorted).  The forward pass of such scenes terminates within the first few hundred
+// entries of lists of ~10 000 (10 M triangles @2048^2: 94.5 % of the instances lie behind the deepest position any
+// pixel of their tile visits), and the per-bin networks are ~85 % of this kernel's work; a tile that does run deeper
+// gets the rest of its segment sorted before the round that needs it (k_tile_sort_finish).  Returns the length of the
+// sorted prefix (n: everything).
 template <int THREADS>
-__device__ __forceinline__ void sort_segment_smem(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                                                  uint64_t* __restrict__ s, uint32_t n) {
+__device__ __forceinline__ uint32_t sort_segment_smem(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                      uint64_t* __restrict__ s, uint32_t n, uint32_t prefix) {
     constexpr int NW = THREADS / 32, NB = 2 * NW;
     __shared__ uint32_t s_bin[NB + 1];
     __shared__ uint32_t s_red[2 * NW];
@@ -299,29 +306,36 @@ __device__ __forceinline__ void sort_segment_smem(const uint64_t* __restrict__ k
             }
             __syncthreads();
             // s_bin[b] now holds the END of bin b; every warp sorts bins warp, warp + NW
+            uint32_t upto = n;
+            if (prefix < n) {                    // end of the last bin that starts before `prefix` (uniform)
+                for (int b = NB - 1; b >= 0; b--)
+                    if (s_bin[b] >= prefix) upto = s_bin[b];
+            }
             for (uint32_t b = warp; b < (uint32_t)NB; b += NW) {
                 const uint32_t e = s_bin[b], st0 = b == 0 ? 0u : s_bin[b - 1];
                 const uint32_t m = e - st0;
-                if (m > 1u) {
+                if (m > 1u && st0 < prefix) {
                     uint64_t* sb = s + st0;
                     bitonic_ascending(m, next_pow2(m), lane, 32u, [&](uint32_t i) { return sb[i]; },
                                       [&](uint32_t i, uint64_t x) { sb[i] = x; }, [] { __syncwarp(); });
                 }
             }
             __syncthreads();
-            return;
+            return upto;
         }
     }
     for (uint32_t i = tid; i < n; i += THREADS) s[i] = (kin[i] << 32) | vin[i];          // depth bits << 32 | face id
     __syncthreads();
     bitonic_ascending(n, next_pow2(n), tid, (uint32_t)THREADS, [&](uint32_t i) { return s[i]; },
                       [&](uint32_t i, uint64_t x) { s[i] = x; }, [] { __syncthreads(); });
+    return n;
 }
 
 template <int TIER>
 __global__ void __launch_bounds__(TIER == 0 ? 256 : 1024)
 k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, BinGuard guard) {
+            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, BinGuard guard, uint32_t prefix,
+            uint32_t* __restrict__ sorted_upto) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
     if (bin_invalid(guard)) return;
     constexpr int THREADS = TIER == 0 ? 256 : 1024;
@@ -333,13 +347,15 @@ k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_
     if (n == 0u || n <= LO || n > HI) return;
     const uint64_t tile_hi = (uint64_t)blockIdx.x << 32;
     if (TIER < 2 || n <= kSortCap2) {
-        sort_segment_smem<THREADS>(keys_in + rg.x, vals_in + rg.x, s, n);
+        const uint32_t upto = sort_segment_smem<THREADS>(keys_in + rg.x, vals_in + rg.x, s, n, prefix);
         for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
             const uint64_t v = s[i];
             keys[rg.x + i] = tile_hi | (v >> 32);
             vals[rg.x + i] = (uint32_t)v;
         }
+        if (sorted_upto && threadIdx.x == 0) sorted_upto[blockIdx.x] = upto;
     } else {
+        if (sorted_upto && threadIdx.x == 0) sorted_upto[blockIdx.x] = n;
         // rare: a segment longer than kSortCap2 instances - block-wide network on the output key buffer
         uint64_t* g = keys + rg.x;
         for (uint32_t i = threadIdx.x; i < n; i += THREADS) g[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];
@@ -351,6 +367,36 @@ k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_
             g[i] = tile_hi | (v >> 32);
             vals[rg.x + i] = (uint32_t)v;
         }
+    }
+}
+
+// Second phase of the lazy sort: the tiles of a round's work list (k_round_worklist) whose sorted prefix ends before
+// the round's window get their WHOLE segment sorted from the unsorted scatter output, which is still in the
+// workspace.  Positions below the old prefix receive the values they already hold (the order is a total one), so the
+// classification words and cache offsets recorded for them stay valid.  Persistent grid, one 1024-thread CTA at a
+// time per tile; after the first rounds the list holds a handful of tiles.
+__global__ void __launch_bounds__(1024)
+k_tile_sort_finish(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, BinGuard guard, const uint32_t* __restrict__ work,
+                   const uint32_t* __restrict__ work_n, uint32_t need_end, uint32_t* __restrict__ sorted_upto) {
+    extern __shared__ __align__(16) unsigned char tsort_smem[];
+    if (bin_invalid(guard)) return;
+    uint64_t* s = reinterpret_cast<uint64_t*>(tsort_smem);
+    const uint32_t n_items = *work_n;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t tile = work[item];
+        const uint2 rg = ranges[tile];
+        const uint32_t n = rg.y - rg.x;
+        if (n == 0u || n > kSortCap2 || sorted_upto[tile] >= min(need_end, n)) continue;      // (uniform per CTA)
+        sort_segment_smem<1024>(keys_in + rg.x, vals_in + rg.x, s, n, 0xFFFFFFFFu);
+        const uint64_t tile_hi = (uint64_t)tile << 32;
+        for (uint32_t i = threadIdx.x; i < n; i += 1024u) {
+            const uint64_t v = s[i];
+            keys[rg.x + i] = tile_hi | (v >> 32);
+            vals[rg.x + i] = (uint32_t)v;
+        }
+        if (threadIdx.x == 0) sorted_upto[tile] = n;
+        __syncthreads();
     }
 }
 
@@ -397,7 +443,7 @@ int launch_tile_count_scan(long long BF, int F, int gx, int gy, int num_tiles, c
 int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const float* key_depths,
                      const uint32_t* tiles_touched, const uint2* rects, const uint2* ranges, uint32_t* cursor,
                      uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals,
-                     long long capacity, long long longest, cudaStream_t s) {
+                     long long capacity, long long longest, const LazySort& lazy, cudaStream_t s) {
     if (BF == 0 || num_tiles == 0) return 0;
     const BinGuard guard{cursor + num_tiles, (uint32_t)capacity, 0xFFFFFFFFu};
     if (longest < 0) longest = 1ll << 40;            // unknown: launch every tier
@@ -415,7 +461,8 @@ int launch_tile_sort(long long BF, int F, int gx, int gy, int num_tiles, const f
         DM2_LAUNCH_CHECK();
     }
     const int tiers = 1 | (longest > kSortCap0 ? 2 : 0) | (longest > kSortCap1 ? 4 : 0);
-    return launch_tile_sort_tiers(num_tiles, ranges, cursor, keys_unsorted, vals_unsorted, keys, vals, capacity, tiers, s);
+    if (lazy.sorted_upto) DM2_CHECK(cudaMemsetAsync(lazy.sorted_upto, 0, (size_t)num_tiles * sizeof(uint32_t), s));
+    return launch_tile_sort_tiers(num_tiles, ranges, cursor, keys_unsorted, vals_unsorted, keys, vals, capacity, tiers, lazy, s);
 }
 
 // longest segment covered by the tiers launch_tile_sort enqueues for a given hint (-1: all of them)
@@ -427,7 +474,7 @@ long long sort_tiers_longest_cap(long long longest_hint) {
 // the per-segment sort alone; tiers: bit t = run tier t (segments of <= 2048 / <= 8192 / more instances)
 int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
-                           cudaStream_t s) {
+                           const LazySort& lazy, cudaStream_t s) {
     if (num_tiles == 0 || tiers == 0) return 0;
     const BinGuard guard{cursor + num_tiles, (uint32_t)capacity, 0xFFFFFFFFu};
     static PerDeviceOnce attr_set;
@@ -436,21 +483,49 @@ int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* c
                                        (int)(kSortCap1 * sizeof(uint64_t))));
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap2 * sizeof(uint64_t))));
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortCap2 * sizeof(uint64_t))));
         attr_set.done();
     }
+    const uint32_t prefix = lazy.sorted_upto ? lazy.prefix : 0xFFFFFFFFu;
     ProfScope _ps("tile_sort", s);
     if (tiers & 1) {
-        k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard);
+        k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard, prefix,
+                                                                            lazy.sorted_upto);
         DM2_LAUNCH_CHECK();
     }
     if (tiers & 2) {
-        k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard);
+        k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard, prefix,
+                                                                            lazy.sorted_upto);
         DM2_LAUNCH_CHECK();
     }
     if (tiers & 4) {
-        k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard);
+        k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard, prefix,
+                                                                            lazy.sorted_upto);
         DM2_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+// the lazy sort's second phase for the tiles of a round's work list (list + count on the device)
+int launch_tile_sort_finish(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
+                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity,
+                            const uint32_t* work, const uint32_t* work_n, long long need_end, const LazySort& lazy,
+                            cudaStream_t s) {
+    if (num_tiles == 0 || !lazy.sorted_upto) return 0;
+    const BinGuard guard{cursor + num_tiles, (uint32_t)capacity, 0xFFFFFFFFu};
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortCap2 * sizeof(uint64_t))));
+        attr_set.done();
+    }
+    ProfScope _ps("tile_sort", s);
+    const unsigned grid = (unsigned)std::min(num_tiles, sm_count());
+    k_tile_sort_finish<<<grid, 1024, kSortCap2 * sizeof(uint64_t), s>>>(
+        ranges, keys_unsorted, vals_unsorted, keys, vals, guard, work, work_n,
+        (uint32_t)std::min<long long>(need_end, 0xFFFFFFFFll), lazy.sorted_upto);
+    DM2_LAUNCH_CHECK();
     return 0;
 }
 

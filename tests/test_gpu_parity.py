@@ -1024,12 +1024,16 @@ def test_pipelined_forward_repairs_a_longer_segment_than_hinted(built):
     assert rel_err(l2["verts"].grad.cpu().numpy(), l1["verts"].grad.cpu().numpy()) <= 1e-5
 
 
-@pytest.mark.parametrize("round_len,pool_bytes", [(256, None), (512, None), (1024, 1 << 20)])
-def test_forward_in_rounds_equals_single_pass(built, round_len, pool_bytes):
+@pytest.mark.parametrize("round_len,pool_bytes,opacity_scale", [(256, None, 1.0), (512, None, 1.0), (1024, 1 << 20, 1.0),
+                                                                 (256, None, 0.02), (1024, None, 0.02)])
+def test_forward_in_rounds_equals_single_pass(built, round_len, pool_bytes, opacity_scale):
     """Deep scenes composite in rounds of `round_len` list entries per tile with classification only for the tiles
     that are still running (dm2_set_forward_rounds): images bit-identical to the single pass, same gradients -
     synchronous first call, pipelined second call, repaired call (hint shorter than the rounds needed), and with
-    a shading cache too small for the frame (blocks that do not fit fall back to recomputation)."""
+    a shading cache too small for the frame (blocks that do not fit fall back to recomputation).  In rounds the tile
+    segments are sorted lazily (the first two rounds' worth at once, the rest of a tile's list before the round that
+    reaches it): opacity_scale 0.02 keeps every pixel running to the end of its list, so every long segment goes
+    through the second phase."""
     import dmesh2_renderer_b200 as dm
     from dmesh2_renderer_b200 import scenes, _lib
     from dmesh2_renderer_b200 import fused as _C
@@ -1037,6 +1041,7 @@ def test_forward_in_rounds_equals_single_pass(built, round_len, pool_bytes):
     dev = _dev()
     sc = scenes.triangle_soup("deep", 80_000, 64, 0.02, seed=77)
     st = scene_tensors(sc, dev)
+    st["faces_opacity"] = st["faces_opacity"] * opacity_scale
     r = dm.Renderer(st["mv"], st["proj"], sc.width, sc.height, dev)
     lib = _lib.load_library()
     real_alloc = _C.shade_cache_alloc
