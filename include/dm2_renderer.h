@@ -380,7 +380,11 @@ void dm2_profile_enable(int32_t on);
  * (round_len a multiple of 256) - and tiles whose pixels have all terminated are not classified any further.  The
  * reference classifies nothing ahead of time (forward.cu:139-432); this is where its early termination is recovered
  * for the classification pre-pass.  Results do not depend on these values.  Defaults 512 / 4096; process-wide; not
- * thread safe against running calls. */
+ * thread safe against running calls.
+ * A frame that runs in rounds also sorts its tile segments lazily: list positions [0, 2 round_len) of every tile at once,
+ * the rest of a tile's segment only if a round reaches it - behind a tile's sorted prefix the `keys` / `vals` arrays of the
+ * binning workspace are binned by depth but not sorted (the reference sorts everything, renderer.cu:202-207; no pixel
+ * reads those entries).  DM2_LAZY_SORT=0 in the environment sorts everything. */
 void dm2_set_forward_rounds(int64_t round_len, int64_t threshold);
 /* Overlap area of a partially covered (pixel, face) pair (reference aa.h:151-441).  Default (0): the polygon-free
  * evaluation of dm2_aa_fast.cuh wherever the pair is far - by thresholds measured against the oracle, tests/test_aa_fast.py - from every
