@@ -110,8 +110,9 @@ constexpr int kRedWords = 8 * kRedGroup;
 // Candidates per sub-chunk.  Measured at cfg2 (ms): 8 candidates / 6 CTAs of 4 warps per SM 1.86;
 // 16 / 4 CTAs 1.69; 12 / 5 CTAs 1.66 - the dense passes want many pairs per sub-chunk (~110 here, 4
 // batches), the latency-bound walk wants warps.
+// (same-box A/B with the final kernels: 11 candidates 1.271, 12 1.251, 13 1.240 - 41.5 KB per CTA still fit 5 times)
 #ifndef DM2_BSUB
-#define DM2_BSUB 12
+#define DM2_BSUB 13
 #endif
 #ifndef DM2_BWD_MINBLOCKS
 #define DM2_BWD_MINBLOCKS 5
