@@ -274,7 +274,7 @@ def render_backward_cuda(num_rendered, background, patch_min, patch_width, patch
 
 def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, tet_faces, face_existence, verts_ndc,
                                 verts_image, image_ray_o, image_ray_d, num_layers, return_taps=False, fused=None,
-                                reuse=None, ray_spec=None):
+                                reuse=None, ray_spec=None, overlap_geometry=True):
     """reference render.h:101-119 / render.cu:378-476.  Returns (render_layers, render_layers_cnt).
 
     fused = (mv [B,4,4], proj [B,4,4], ray_view [B] int32): the fused host prep - the preprocess kernel
@@ -286,7 +286,11 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
     (dm2_regenerate_render_layers).  The caller vouches for the condition.
 
     ray_spec = (recipe, params [V,32], (V, H, W)) (fused only): the kernels generate the rays themselves;
-    image_ray_o / image_ray_d may then be None."""
+    image_ray_o / image_ray_d may then be None.
+
+    overlap_geometry: build the geometry / link records while the host waits for num_rendered
+    (dm2_layers_preprocess_with_geometry + dm2_generate_render_layers_prepared) instead of after it
+    (dm2_layers_preprocess + dm2_generate_render_layers); same results."""
     lib = _lib.load_library()
     use_ray_spec = ray_spec is not None and fused is not None
     if use_ray_spec and image_ray_o is None:        # shape-only placeholders (never dereferenced)
@@ -371,13 +375,20 @@ def generate_render_layers_cuda(width, height, verts, faces, tets, face_tets, te
         _lib.check(lib.dm2_layers_geo_bytes(F, T, C.byref(geo_bytes)))
         geo_buffer = torch.empty((geo_bytes.value,), dtype=torch.uint8, device=dev)
         num_rendered, longest = C.c_int64(0), C.c_int64(0)
-        _lib.check(lib.dm2_layers_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
-                                             C.byref(num_rendered), C.byref(longest), stream))
+        if overlap_geometry:
+            # the geometry / link records are enqueued behind the header read-back: the GPU builds them while the
+            # host waits for num_rendered and allocates the binning workspace
+            _lib.check(lib.dm2_layers_preprocess_with_geometry(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
+                                                               _ptr(geo_buffer), C.byref(num_rendered),
+                                                               C.byref(longest), stream))
+        else:
+            _lib.check(lib.dm2_layers_preprocess(C.byref(s), _ptr(face_buffer), _ptr(image_buffer),
+                                                 C.byref(num_rendered), C.byref(longest), stream))
         R = int(num_rendered.value)
         binning_buffer = torch.empty((binning_layout(R).total,), dtype=torch.uint8, device=dev)
-        _lib.check(lib.dm2_generate_render_layers(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer),
-                                                  _ptr(image_buffer), _ptr(geo_buffer), R, int(longest.value),
-                                                  _ptr(render_layers), _ptr(render_layers_cnt), stream))
+        gen = lib.dm2_generate_render_layers_prepared if overlap_geometry else lib.dm2_generate_render_layers
+        _lib.check(gen(C.byref(s), _ptr(face_buffer), _ptr(binning_buffer), _ptr(image_buffer), _ptr(geo_buffer), R,
+                       int(longest.value), _ptr(render_layers), _ptr(render_layers_cnt), stream))
     if return_taps:
         return render_layers, render_layers_cnt, dict(num_rendered=R, face_buffer=face_buffer,
                                                       binning_buffer=binning_buffer, image_buffer=image_buffer,

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdm2_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 RAY_RECIPES = 36        # DM2_RAY_RECIPES
 
 c_f32p = C.c_void_p   # all device pointers travel as integers
@@ -119,6 +119,10 @@ SYMBOLS = {
     "dm2_layers_geo_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "dm2_generate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dm2_layers_preprocess_with_geometry": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      _P(C.c_int64), _P(C.c_int64), C.c_void_p]),
+    "dm2_generate_render_layers_prepared": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dm2_regenerate_render_layers": (C.c_int, [_P(DM2LayerInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p]),
     "dm2_layers_composite_forward": (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 9),

@@ -623,8 +623,19 @@ static int check_layer_inputs(const DM2LayerInputs* in) {
     return 0;
 }
 
+static int layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws, void* geo_ws,
+                             int64_t* num_rendered_host, int64_t* longest_host, void* stream);
 int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws, int64_t* num_rendered_host,
                           int64_t* longest_host, void* stream) {
+    return layers_preprocess(in, face_ws, image_ws, nullptr, num_rendered_host, longest_host, stream);
+}
+int dm2_layers_preprocess_with_geometry(const DM2LayerInputs* in, void* face_ws, void* image_ws, void* geo_ws,
+                                        int64_t* num_rendered_host, int64_t* longest_host, void* stream) {
+    DM2_REQUIRE(geo_ws, "dm2_layers_preprocess_with_geometry: null geometry workspace");
+    return layers_preprocess(in, face_ws, image_ws, geo_ws, num_rendered_host, longest_host, stream);
+}
+static int layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_ws, void* geo_ws,
+                             int64_t* num_rendered_host, int64_t* longest_host, void* stream) {
     if (check_layer_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && image_ws && num_rendered_host, "dm2_layers_preprocess: null workspace");
     cudaStream_t s = (cudaStream_t)stream;
@@ -638,6 +649,8 @@ int dm2_layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* image_w
     if (zero_cursor(iw, in->B, gx, gy, s)) return 1;
     if (launch_layers_preprocess(*in, fw, iw.tile_cursor + (size_t)in->B * gx * gy + 1, s)) return 1;
     if (count_and_scan(fw, iw, BF, in->B, in->F, gx, gy, s)) return 1;
+    // the geometry / link records do not depend on the binning: they run while the host waits for the header
+    if (geo_ws && launch_layers_geometry(*in, geo_ws, true, s)) return 1;
     uint32_t flags = 0;
     if (wait_header(num_rendered_host, &flags, longest_host)) return 1;
     return check_flags(flags);
@@ -649,9 +662,24 @@ int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes) {
     return 0;
 }
 
+static int generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                                  void* geo_ws, int64_t num_rendered, int64_t longest, int32_t* render_layers,
+                                  int32_t* render_layers_cnt, bool geometry_ready, void* stream);
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws, void* image_ws,
                                void* geo_ws, int64_t num_rendered, int64_t longest, int32_t* render_layers,
                                int32_t* render_layers_cnt, void* stream) {
+    return generate_render_layers(in, face_ws, binning_ws, image_ws, geo_ws, num_rendered, longest, render_layers,
+                                  render_layers_cnt, false, stream);
+}
+int dm2_generate_render_layers_prepared(const DM2LayerInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                                        void* geo_ws, int64_t num_rendered, int64_t longest, int32_t* render_layers,
+                                        int32_t* render_layers_cnt, void* stream) {
+    return generate_render_layers(in, face_ws, binning_ws, image_ws, geo_ws, num_rendered, longest, render_layers,
+                                  render_layers_cnt, true, stream);
+}
+static int generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws, void* image_ws,
+                                  void* geo_ws, int64_t num_rendered, int64_t longest, int32_t* render_layers,
+                                  int32_t* render_layers_cnt, bool geometry_ready, void* stream) {
     if (check_layer_inputs(in)) return 2;
     DM2_REQUIRE(face_ws && binning_ws && image_ws && geo_ws && render_layers_cnt, "dm2_generate_render_layers: null buffer");
     DM2_REQUIRE(render_layers || in->num_layers == 0, "dm2_generate_render_layers: null render_layers");
@@ -664,7 +692,7 @@ int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* bi
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     // key = min depth (reference renderer.cu:603)
     if (bin_faces(BF, in->B, in->F, gx, gy, fw.min_depths, fw, bw, iw, longest, LazySort{nullptr, 0xFFFFFFFFu}, s)) return 1;
-    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, false, s);
+    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, false, geometry_ready, s);
 }
 
 int dm2_regenerate_render_layers(const DM2LayerInputs* in, void* image_ws, void* geo_ws, int32_t* render_layers,
@@ -675,7 +703,7 @@ int dm2_regenerate_render_layers(const DM2LayerInputs* in, void* image_ws, void*
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     FaceWs fw{};
     BinWs bw{};
-    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, true, (cudaStream_t)stream);
+    return launch_layers(*in, fw, bw, iw, geo_ws, render_layers, render_layers_cnt, true, false, (cudaStream_t)stream);
 }
 
 int dm2_layers_composite_forward(int32_t B, int32_t H, int32_t W, int32_t L, int32_t F, const int32_t* render_layers,

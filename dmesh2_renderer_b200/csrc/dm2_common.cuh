@@ -357,7 +357,9 @@ int launch_fused_grad_scatter(const DM2FusedInputs& in, const FaceWs& fw, const 
                               cudaStream_t s);
 size_t backward_ws_bytes(long long BF);
 int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw,
-                  void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, cudaStream_t s);
+                  void* geo_ws, int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, bool geometry_ready,
+                  cudaStream_t s);
+int launch_layers_geometry(const DM2LayerInputs& in, void* geo_ws, bool links_too, cudaStream_t s);
 size_t layers_geo_bytes(int F, int T);
 int launch_layers_composite_forward(int B, int H, int W, int L, int F, const int32_t* layers, const int32_t* cnt,
                                     const float* color, const float* opacity, const float* intense, const float* background,

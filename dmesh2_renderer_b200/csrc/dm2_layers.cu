@@ -586,19 +586,19 @@ int launch_generate_rays(const float* ray_params, int V, int H, int W, int recip
     return 0;
 }
 
-int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, void* geo_ws,
-                  int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, cudaStream_t s) {
-    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
-    const long long nblk = (long long)in.B * gx * gy;
-    if (nblk == 0) return 0;
+// The per-geometry records (face / tet geometry, link records, existence flags): they depend on the geometry tensors
+// only, not on the binning - dm2_layers_preprocess_with_geometry enqueues them behind the header read-back, so that
+// they run while the host waits for num_rendered instead of after it.  links_too = false: existence flags only
+// (incremental re-generation).
+int launch_layers_geometry(const DM2LayerInputs& in, void* geo_ws, bool links_too, cudaStream_t s) {
     float* fgeo = reinterpret_cast<float*>(geo_ws);
     float* tgeo = reinterpret_cast<float*>(reinterpret_cast<char*>(geo_ws) + align_up((size_t)in.F * kFGeoWords * 4, 256));
-    ProfScope _ps(walk_only ? "layers_geo+walk" : "layers_geo+first_hit+walk", s);
+    ProfScope _ps("layers_geometry", s);
     if (in.F > 0) {
         k_face_geo<<<cdiv(in.F, 256), 256, 0, s>>>(in.F, in.verts, in.faces, in.face_tets, in.face_existence, fgeo);
         DM2_LAUNCH_CHECK();
     }
-    if (in.T > 0 && !walk_only) {
+    if (in.T > 0 && links_too) {
         k_tet_geo<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.verts, in.tets, in.faces, in.tet_faces, in.face_tets, fgeo, in.F, in.P, tgeo);
         DM2_LAUNCH_CHECK();
         k_tet_link<<<cdiv(in.T, 256), 256, 0, s>>>(in.T, in.F, in.face_tets, tgeo);
@@ -608,6 +608,18 @@ int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, c
         k_tet_exist<<<cdiv(4ll * in.T, 256), 256, 0, s>>>(in.T, in.F, in.face_existence, tgeo);
         DM2_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+int launch_layers(const DM2LayerInputs& in, const FaceWs& fw, const BinWs& bw, const ImageWs& iw, void* geo_ws,
+                  int32_t* render_layers, int32_t* render_layers_cnt, bool walk_only, bool geometry_ready, cudaStream_t s) {
+    const int gx = cdiv(in.W, kTile), gy = cdiv(in.H, kTile);
+    const long long nblk = (long long)in.B * gx * gy;
+    if (nblk == 0) return 0;
+    float* fgeo = reinterpret_cast<float*>(geo_ws);
+    float* tgeo = reinterpret_cast<float*>(reinterpret_cast<char*>(geo_ws) + align_up((size_t)in.F * kFGeoWords * 4, 256));
+    if (!geometry_ready && launch_layers_geometry(in, geo_ws, !walk_only, s)) return 1;
+    ProfScope _ps(walk_only ? "layers_walk" : "layers_first_hit+walk", s);
     if (!walk_only) {
         k_layers_first_hit<<<(unsigned)nblk, 256, 0, s>>>(in, fw.records, bw.vals, iw.ranges, fgeo, tgeo, iw.first_face,
                                                           iw.first_tet, gx, gy);

@@ -313,7 +313,8 @@ class LayeredRenderer(Renderer):
                 verts.to(dtype=f32), faces.to(dtype=i32), tets.to(dtype=i32), face_tets.to(dtype=i32),
                 tet_faces.to(dtype=i32), faces_existence.to(dtype=i32), None, None, self.ray_o, self.ray_d, num_layers,
                 fused=(self.mv.index_select(0, view_idx).to(dtype=f32), self.proj.index_select(0, view_idx).to(dtype=f32),
-                       ray_view), return_taps=True, reuse=reuse, ray_spec=self._ray_spec())
+                       ray_view), return_taps=True, reuse=reuse, ray_spec=self._ray_spec(),
+                overlap_geometry=getattr(self, "overlap_geometry", True))
             self.__dict__["_layer_cache"] = dict(sig=sig, versions=vers, geo=geo, taps=taps)
             return layers, cnt
         verts_ndc, verts_image = self.compute_verts_ndc_image(verts, self.mv[batch_mvp_idx], self.proj[batch_mvp_idx])

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define DM2_TILE 16              /* BLOCK_X = BLOCK_Y of reference cuda_impl/config.h:4-5 */
-#define DM2_ABI_VERSION 16
+#define DM2_ABI_VERSION 17
 
 /* Inputs of RenderFunction (reference dmesh2_renderer/__init__.py:13-47). */
 typedef struct DM2RenderInputs {
@@ -218,6 +218,15 @@ int dm2_layers_geo_bytes(int32_t F, int32_t T, size_t* bytes);
 int dm2_generate_render_layers(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
                                void* image_ws, void* geo_ws, int64_t num_rendered, int64_t longest,
                                int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
+/* The same pair with the geometry / link records of geo_ws built INSIDE the preprocess call, behind the header
+ * read-back: they depend on the geometry tensors only, so the GPU computes them while the host waits for
+ * num_rendered (the reference idles there, renderer.cu:571-580).  dm2_generate_render_layers_prepared then runs the
+ * binning, the first hit and the walk on the records it finds. */
+int dm2_layers_preprocess_with_geometry(const DM2LayerInputs* in, void* face_ws, void* image_ws, void* geo_ws,
+                                        int64_t* num_rendered_host, int64_t* longest_host, void* stream);
+int dm2_generate_render_layers_prepared(const DM2LayerInputs* in, void* face_ws, void* binning_ws,
+                                        void* image_ws, void* geo_ws, int64_t num_rendered, int64_t longest,
+                                        int32_t* render_layers, int32_t* render_layers_cnt, void* stream);
 
 /* Incremental re-generation: when ONLY face_existence changed since a
  * dm2_generate_render_layers call on the same image_ws / geo_ws (same geometry, views and rays),

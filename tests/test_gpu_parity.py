@@ -383,6 +383,11 @@ def _layers_both(sc, views=None):
                                                   t(sc.face_tets), t(sc.tet_faces), t(sc.face_existence), ndc, img,
                                                   ro, rd, sc.num_layers, return_taps=True)
     assert torch.equal(_l, layers) and torch.equal(_c, cnt)
+    # the plain C-ABI pair (geometry records built after the header read-back instead of during it): same result
+    _l2, _c2 = _C.generate_render_layers_cuda(sc.width, sc.height, t(sc.verts), t(sc.faces), t(sc.tets),
+                                              t(sc.face_tets), t(sc.tet_faces), t(sc.face_existence), ndc, img,
+                                              ro, rd, sc.num_layers, overlap_geometry=False)
+    assert torch.equal(_l2, layers) and torch.equal(_c2, cnt)
     B = len(views)
     img_t = _C.image_taps(taps["image_buffer"], B, sc.height, sc.width, layered=True)
     bin_t = _C.binning_taps(taps["binning_buffer"], taps["num_rendered"])

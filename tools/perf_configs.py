@@ -65,9 +65,10 @@ def run_soup(pkg, sc, dev, views, iters):
     return ms, out
 
 
-def run_layers(pkg, sc, dev, iters, incremental=True):
+def run_layers(pkg, sc, dev, iters, incremental=True, overlap=True):
     lr = pkg.LayeredRenderer(t(sc.mv, dev), t(sc.proj, dev), sc.width, sc.height, dev)
     lr.incremental = incremental            # this package only: False = binning + first hit + geometry records every call
+    lr.overlap_geometry = overlap           # this package only: geometry records built while the host waits for num_rendered
     a = [t(getattr(sc, k), dev) for k in ("verts", "faces", "tets", "face_tets", "tet_faces", "face_existence")]
     out = {}
 
@@ -121,7 +122,9 @@ def main():
                     unit = 1000.0 / ms
                     if name == "b200":      # the reference has no incremental path: its number is a full generate
                         ms_full, _ = run_layers(pkg, sc, dev, args.iters, incremental=False)
+                        ms_full_seq, _ = run_layers(pkg, sc, dev, args.iters, incremental=False, overlap=False)
                         print(json.dumps({"config": sc.name, "impl": name, "ms_full_generate": ms_full,
+                                          "ms_full_generate_geometry_after_the_readback": ms_full_seq,
                                           "ms_walk_only_regenerate": ms}), flush=True)
             except Exception as ex:          # e.g. the reference running out of memory at cfg5
                 print(json.dumps({"config": cfg, "impl": name, "error": str(ex)[:200]}), flush=True)
