@@ -294,6 +294,18 @@ def main():
             sink = GradSink(bucket.dverts, bucket.dverts_color, bucket.dfaces_opacity)
             renderer.grad_sink = sink
 
+    # cfg4: the per-micro-batch constants (device index tensor of the views, their loss weights) are built once:
+    # indexing with a Python list inside the step costs a pageable host->device copy per use, which drains the
+    # queue three times per micro-batch (tools/step_trace.py --cfg4: 6 % GPU idle) - harness work, both arms
+    _vbc = {}
+
+    def view_batch_constants(vb):
+        k = tuple(vb)
+        if k not in _vbc:
+            idx = torch.tensor(list(vb), dtype=torch.long, device=dev)
+            _vbc[k] = (idx, wc.index_select(0, idx).contiguous(), wd.index_select(0, idx).contiguous())
+        return _vbc[k]
+
     def compute(prm, exchange=True):
         for p in prm.values():
             p.grad = None
@@ -301,10 +313,14 @@ def main():
             bucket.flat.zero_()
         total = None
         for vb in batches:
+            if cfg4:
+                idx, wcb, wdb = view_batch_constants(vb)
+                fi = prm["faces_intense"].index_select(0, idx)
+            else:
+                wcb, wdb, fi = wc, wd, prm["faces_intense"]
             color, depth = renderer(vb, patch_min[len(vb)], W, H, prm["verts"], faces, prm["verts_color"],
-                                    prm["faces_opacity"], prm["faces_intense"][vb] if cfg4 else prm["faces_intense"],
-                                    background)
-            loss = (color * (wc[vb] if cfg4 else wc)).sum() + (depth * (wd[vb] if cfg4 else wd)).sum()
+                                    prm["faces_opacity"], fi, background)
+            loss = (color * wcb).sum() + (depth * wdb).sum()
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         if use_bucket:

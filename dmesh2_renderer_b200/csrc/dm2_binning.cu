@@ -862,7 +862,7 @@ int launch_classify_round(const uint64_t* keys, long long capacity, long long lo
         DM2_LAUNCH_CHECK();
         // lazy sort: the listed tiles whose sorted prefix ends inside this round's window are sorted to the end
         if (launch_tile_sort_finish(num_tiles, ranges, sort.cursor, sort.keys_unsorted, sort.vals_unsorted, sort.keys, sort.vals,
-                                    capacity, work.cls_list, work.n, (long long)round_begin + round_len, sort.lazy, s)) return 1;
+                                    capacity, sort.tiers, work.cls_list, work.n, (long long)round_begin + round_len, sort.lazy, s)) return 1;
     }
     ProfScope _ps("classify", s);
     const int chunks = cdiv(round_len, kClsThreads);

@@ -397,7 +397,8 @@ static int forward_tail(const DM2RenderInputs* in, const FaceWs& fw, BinWs bw, c
     }
     const long long nt = (long long)in->B * gx * gy;
     const RoundWork work{iw.round_work, iw.round_work + 4, iw.round_work + 4 + nt};
-    const RoundSort rsort{bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, iw.tile_cursor, lazy};
+    const RoundSort rsort{bw.keys_unsorted, bw.vals_unsorted, bw.keys, bw.vals, iw.tile_cursor, lazy,
+                          1 | (longest < 0 ? 6 : (longest > 2048 ? 2 : 0) | (longest > 8192 ? 4 : 0))};
     for (long long k = 0; k < rounds; k++) {
         const int rb = k ? (int)round_end(k - 1) : 0, re = (int)round_end(k);
         if (launch_classify_round(bw.keys, bw.R, bw.longest_cap, hdr, tm, iw.ranges, iw.warp_done, (int)nt,

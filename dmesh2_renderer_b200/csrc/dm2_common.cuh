@@ -323,7 +323,7 @@ int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* c
                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
                            const LazySort& lazy, cudaStream_t s);
 int launch_tile_sort_finish(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
-                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity,
+                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
                             const uint32_t* work, const uint32_t* work_n, long long need_end, const LazySort& lazy,
                             cudaStream_t s);
 int launch_sort_pairs(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout,
@@ -334,7 +334,7 @@ int launch_classify(const uint64_t* keys, long long capacity, long long longest_
 long long sort_tiers_longest_cap(long long longest_hint);
 // sort: (listed rounds only) the lazy sort's second phase runs between the work list and the classification
 struct RoundSort { const uint64_t* keys_unsorted; const uint32_t* vals_unsorted; uint64_t* keys; uint32_t* vals;
-                   const uint32_t* cursor; LazySort lazy; };
+                   const uint32_t* cursor; LazySort lazy; int tiers; };
 int launch_classify_round(const uint64_t* keys, long long capacity, long long longest_cap, const uint32_t* hdr,
                           const TileMaskArgs& tm, const uint2* ranges, const uint8_t* warp_done, int num_tiles,
                           int round_begin, int round_len, const RoundWork& work, const RoundSort& sort, cudaStream_t s);

@@ -331,71 +331,54 @@ __device__ __forceinline__ uint32_t sort_segment_smem(const uint64_t* __restrict
     return n;
 }
 
+// work == nullptr: one CTA per tile (blockIdx.x), first phase (`prefix`: see sort_segment_smem).  work != nullptr: the
+// SECOND phase of the lazy sort - a persistent grid over a round's work list (k_round_worklist): the listed tiles of
+// this tier whose sorted prefix ends before min(need_end, n) get their WHOLE segment sorted from the unsorted scatter
+// output, which is still in the workspace.  Positions below the old prefix receive the values they already hold (the
+// order is a total one), so the classification words and cache offsets recorded for them stay valid.
 template <int TIER>
 __global__ void __launch_bounds__(TIER == 0 ? 256 : 1024)
 k_tile_sort(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, BinGuard guard, uint32_t prefix,
-            uint32_t* __restrict__ sorted_upto) {
+            uint32_t* __restrict__ sorted_upto, const uint32_t* __restrict__ work, const uint32_t* __restrict__ work_n,
+            uint32_t need_end) {
     extern __shared__ __align__(16) unsigned char tsort_smem[];
     if (bin_invalid(guard)) return;
     constexpr int THREADS = TIER == 0 ? 256 : 1024;
     constexpr uint32_t LO = TIER == 0 ? 0u : (TIER == 1 ? kSortCap0 : kSortCap1);
     constexpr uint32_t HI = TIER == 0 ? kSortCap0 : (TIER == 1 ? kSortCap1 : 0xFFFFFFFFu);
     uint64_t* s = reinterpret_cast<uint64_t*>(tsort_smem);
-    const uint2 rg = ranges[blockIdx.x];
-    const uint32_t n = rg.y - rg.x;
-    if (n == 0u || n <= LO || n > HI) return;
-    const uint64_t tile_hi = (uint64_t)blockIdx.x << 32;
-    if (TIER < 2 || n <= kSortCap2) {
-        const uint32_t upto = sort_segment_smem<THREADS>(keys_in + rg.x, vals_in + rg.x, s, n, prefix);
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
-            const uint64_t v = s[i];
-            keys[rg.x + i] = tile_hi | (v >> 32);
-            vals[rg.x + i] = (uint32_t)v;
-        }
-        if (sorted_upto && threadIdx.x == 0) sorted_upto[blockIdx.x] = upto;
-    } else {
-        if (sorted_upto && threadIdx.x == 0) sorted_upto[blockIdx.x] = n;
-        // rare: a segment longer than kSortCap2 instances - block-wide network on the output key buffer
-        uint64_t* g = keys + rg.x;
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) g[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];
-        __syncthreads();
-        bitonic_ascending(n, next_pow2(n), threadIdx.x, (uint32_t)THREADS, [&](uint32_t i) { return g[i]; },
-                          [&](uint32_t i, uint64_t v) { g[i] = v; }, [] { __syncthreads(); });
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
-            const uint64_t v = g[i];
-            g[i] = tile_hi | (v >> 32);
-            vals[rg.x + i] = (uint32_t)v;
-        }
-    }
-}
-
-// Second phase of the lazy sort: the tiles of a round's work list (k_round_worklist) whose sorted prefix ends before
-// the round's window get their WHOLE segment sorted from the unsorted scatter output, which is still in the
-// workspace.  Positions below the old prefix receive the values they already hold (the order is a total one), so the
-// classification words and cache offsets recorded for them stay valid.  Persistent grid, one 1024-thread CTA at a
-// time per tile; after the first rounds the list holds a handful of tiles.
-__global__ void __launch_bounds__(1024)
-k_tile_sort_finish(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, BinGuard guard, const uint32_t* __restrict__ work,
-                   const uint32_t* __restrict__ work_n, uint32_t need_end, uint32_t* __restrict__ sorted_upto) {
-    extern __shared__ __align__(16) unsigned char tsort_smem[];
-    if (bin_invalid(guard)) return;
-    uint64_t* s = reinterpret_cast<uint64_t*>(tsort_smem);
-    const uint32_t n_items = *work_n;
+    const bool listed = work != nullptr;
+    const uint32_t n_items = listed ? *work_n : gridDim.x;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t tile = work[item];
+        const uint32_t tile = listed ? work[item] : item;
         const uint2 rg = ranges[tile];
         const uint32_t n = rg.y - rg.x;
-        if (n == 0u || n > kSortCap2 || sorted_upto[tile] >= min(need_end, n)) continue;      // (uniform per CTA)
-        sort_segment_smem<1024>(keys_in + rg.x, vals_in + rg.x, s, n, 0xFFFFFFFFu);
+        if (n == 0u || n <= LO || n > HI) continue;
+        if (listed && sorted_upto[tile] >= min(need_end, n)) continue;             // (uniform per CTA)
         const uint64_t tile_hi = (uint64_t)tile << 32;
-        for (uint32_t i = threadIdx.x; i < n; i += 1024u) {
-            const uint64_t v = s[i];
-            keys[rg.x + i] = tile_hi | (v >> 32);
-            vals[rg.x + i] = (uint32_t)v;
+        if (TIER < 2 || n <= kSortCap2) {
+            const uint32_t upto = sort_segment_smem<THREADS>(keys_in + rg.x, vals_in + rg.x, s, n, listed ? 0xFFFFFFFFu : prefix);
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+                const uint64_t v = s[i];
+                keys[rg.x + i] = tile_hi | (v >> 32);
+                vals[rg.x + i] = (uint32_t)v;
+            }
+            if (sorted_upto && threadIdx.x == 0) sorted_upto[tile] = upto;
+        } else {
+            if (sorted_upto && threadIdx.x == 0) sorted_upto[tile] = n;
+            // rare: a segment longer than kSortCap2 instances - block-wide network on the output key buffer
+            uint64_t* g = keys + rg.x;
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) g[i] = (keys_in[rg.x + i] << 32) | vals_in[rg.x + i];
+            __syncthreads();
+            bitonic_ascending(n, next_pow2(n), threadIdx.x, (uint32_t)THREADS, [&](uint32_t i) { return g[i]; },
+                              [&](uint32_t i, uint64_t v) { g[i] = v; }, [] { __syncthreads(); });
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+                const uint64_t v = g[i];
+                g[i] = tile_hi | (v >> 32);
+                vals[rg.x + i] = (uint32_t)v;
+            }
         }
-        if (threadIdx.x == 0) sorted_upto[tile] = n;
         __syncthreads();
     }
 }
@@ -483,49 +466,63 @@ int launch_tile_sort_tiers(int num_tiles, const uint2* ranges, const uint32_t* c
                                        (int)(kSortCap1 * sizeof(uint64_t))));
         DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap2 * sizeof(uint64_t))));
-        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kSortCap2 * sizeof(uint64_t))));
         attr_set.done();
     }
     const uint32_t prefix = lazy.sorted_upto ? lazy.prefix : 0xFFFFFFFFu;
     ProfScope _ps("tile_sort", s);
     if (tiers & 1) {
         k_tile_sort<0><<<num_tiles, 256, kSortCap0 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard, prefix,
-                                                                            lazy.sorted_upto);
+                                                                            lazy.sorted_upto, nullptr, nullptr, 0u);
         DM2_LAUNCH_CHECK();
     }
     if (tiers & 2) {
         k_tile_sort<1><<<num_tiles, 1024, kSortCap1 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard, prefix,
-                                                                            lazy.sorted_upto);
+                                                                            lazy.sorted_upto, nullptr, nullptr, 0u);
         DM2_LAUNCH_CHECK();
     }
     if (tiers & 4) {
         k_tile_sort<2><<<num_tiles, 1024, kSortCap2 * sizeof(uint64_t), s>>>(ranges, keys_unsorted, vals_unsorted, keys, vals, guard, prefix,
-                                                                            lazy.sorted_upto);
+                                                                            lazy.sorted_upto, nullptr, nullptr, 0u);
         DM2_LAUNCH_CHECK();
     }
     return 0;
 }
 
-// the lazy sort's second phase for the tiles of a round's work list (list + count on the device)
+// the lazy sort's second phase for the tiles of a round's work list (list + count on the device): the tier kernels as
+// persistent grids over the list; tiers: as launch_tile_sort_tiers
 int launch_tile_sort_finish(int num_tiles, const uint2* ranges, const uint32_t* cursor, const uint64_t* keys_unsorted,
-                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity,
+                            const uint32_t* vals_unsorted, uint64_t* keys, uint32_t* vals, long long capacity, int tiers,
                             const uint32_t* work, const uint32_t* work_n, long long need_end, const LazySort& lazy,
                             cudaStream_t s) {
-    if (num_tiles == 0 || !lazy.sorted_upto) return 0;
+    // (every segment is sorted at least up to min(prefix, n): rounds that end there need nothing)
+    if (num_tiles == 0 || !lazy.sorted_upto || lazy.prefix == 0xFFFFFFFFu || need_end <= (long long)lazy.prefix) return 0;
     const BinGuard guard{cursor + num_tiles, (uint32_t)capacity, 0xFFFFFFFFu};
     static PerDeviceOnce attr_set;
     if (attr_set.first()) {
-        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortCap1 * sizeof(uint64_t))));
+        DM2_CHECK(cudaFuncSetAttribute(k_tile_sort<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kSortCap2 * sizeof(uint64_t))));
         attr_set.done();
     }
     ProfScope _ps("tile_sort", s);
-    const unsigned grid = (unsigned)std::min(num_tiles, sm_count());
-    k_tile_sort_finish<<<grid, 1024, kSortCap2 * sizeof(uint64_t), s>>>(
-        ranges, keys_unsorted, vals_unsorted, keys, vals, guard, work, work_n,
-        (uint32_t)std::min<long long>(need_end, 0xFFFFFFFFll), lazy.sorted_upto);
-    DM2_LAUNCH_CHECK();
+    const uint32_t need = (uint32_t)std::min<long long>(need_end, 0xFFFFFFFFll);
+    const int sms = sm_count();
+    if (tiers & 1) {
+        k_tile_sort<0><<<(unsigned)std::min(num_tiles, 8 * sms), 256, kSortCap0 * sizeof(uint64_t), s>>>(
+            ranges, keys_unsorted, vals_unsorted, keys, vals, guard, 0xFFFFFFFFu, lazy.sorted_upto, work, work_n, need);
+        DM2_LAUNCH_CHECK();
+    }
+    if (tiers & 2) {
+        k_tile_sort<1><<<(unsigned)std::min(num_tiles, 2 * sms), 1024, kSortCap1 * sizeof(uint64_t), s>>>(
+            ranges, keys_unsorted, vals_unsorted, keys, vals, guard, 0xFFFFFFFFu, lazy.sorted_upto, work, work_n, need);
+        DM2_LAUNCH_CHECK();
+    }
+    if (tiers & 4) {
+        k_tile_sort<2><<<(unsigned)std::min(num_tiles, sms), 1024, kSortCap2 * sizeof(uint64_t), s>>>(
+            ranges, keys_unsorted, vals_unsorted, keys, vals, guard, 0xFFFFFFFFu, lazy.sorted_upto, work, work_n, need);
+        DM2_LAUNCH_CHECK();
+    }
     return 0;
 }
 

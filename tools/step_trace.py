@@ -21,12 +21,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--faces", type=int, default=1_000_000)
     ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--cfg4", action="store_true", help="one multi-view step: 64 views @512^2, 8 views per Renderer call")
     a = ap.parse_args()
     import dmesh2_renderer_b200 as pkg
     from dmesh2_renderer_b200 import scenes
     pkg.load_library()
     dev = torch.device("cuda", 0)
     sc = scenes.cfg2() if (a.faces == 1_000_000 and a.size == 1024) else scenes.cfg2(n_faces=a.faces, size=a.size)
+    if a.cfg4:
+        sc = scenes.cfg4()
     t = torch.from_numpy
     r = pkg.Renderer(t(sc.mv).to(dev), t(sc.proj).to(dev), sc.width, sc.height, dev)
     faces, bg = t(sc.faces).to(dev), t(sc.background).to(dev)
@@ -35,7 +38,25 @@ def main():
     p = {k: t(getattr(sc, k)).to(dev).requires_grad_(True)
          for k in ("verts", "verts_color", "faces_opacity", "faces_intense")}
 
+    pm8 = torch.zeros((8, 2), dtype=torch.int32, device=dev)
+    consts = {}
+
+    def step4():
+        for x in p.values():
+            x.grad = None
+        for b0 in range(0, sc.mv.shape[0], 8):
+            vb = list(range(b0, b0 + 8))
+            if b0 not in consts:         # (indexing with a Python list = a pageable H2D copy that drains the queue)
+                idx = torch.tensor(vb, dtype=torch.long, device=dev)
+                consts[b0] = (idx, wc.index_select(0, idx), wd.index_select(0, idx))
+            idx, wcb, wdb = consts[b0]
+            color, depth = r(vb, pm8, sc.width, sc.height, p["verts"], faces, p["verts_color"], p["faces_opacity"],
+                             p["faces_intense"].index_select(0, idx), bg)
+            ((color * wcb).sum() + (depth * wdb).sum()).backward()
+
     def step():
+        if a.cfg4:
+            return step4()
         for x in p.values():
             x.grad = None
         color, depth = r([0], pm, sc.width, sc.height, p["verts"], faces, p["verts_color"], p["faces_opacity"],
