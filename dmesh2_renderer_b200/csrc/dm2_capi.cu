@@ -268,9 +268,11 @@ void dm2_set_exact_clip(int32_t on) { g_exact_clip.store(on != 0 ? 1 : 0, std::m
 int32_t dm2_get_exact_clip(void) { return exact_clip_requested() ? 1 : 0; }
 const char* dm2_last_error(void) { return g_err; }
 // Measured (tools/perf_configs.py --rounds-ab, profiles/r02_forward_rounds.md): doubling rounds beat equal ones (the
-// launches of rounds in which every tile has finished are not free); 512 / 4096 keeps the 8-view 512^2 micro-batch
-// (longest list 3 824, almost no early termination) on the single pass, where rounds cost 3 %.
-static long long kRoundLen = 512, kRoundThreshold = 4096;
+// launches of rounds in which every tile has finished are not free); 512 / 6144 keeps the 8-view 512^2 micro-batches
+// (longest lists 3 800 .. 4 400 depending on the cameras, almost no early termination) on the single pass, where
+// rounds cost 3-8 % - and, since the lazy segment sort, a second sort of every tile that runs to the end of its list.
+// Known points: lists of <= 4 400 without early termination lose, lists of 11 400 with it (10 M triangles) gain 30 %.
+static long long kRoundLen = 512, kRoundThreshold = 6144;
 static void round_knobs() {             // DM2_ROUND_LEN (multiple of 256) / DM2_ROUND_THRESHOLD: measurement knobs
     static std::once_flag once;
     std::call_once(once, [] {

@@ -388,7 +388,7 @@ void dm2_profile_enable(int32_t on);
  * in rounds - list entries [0, round_len), [round_len, 2 round_len), [2 round_len, 4 round_len), ... of every tile
  * (round_len a multiple of 256) - and tiles whose pixels have all terminated are not classified any further.  The
  * reference classifies nothing ahead of time (forward.cu:139-432); this is where its early termination is recovered
- * for the classification pre-pass.  Results do not depend on these values.  Defaults 512 / 4096; process-wide; not
+ * for the classification pre-pass.  Results do not depend on these values.  Defaults 512 / 6144; process-wide; not
  * thread safe against running calls.
  * A frame that runs in rounds also sorts its tile segments lazily: list positions [0, 2 round_len) of every tile at once,
  * the rest of a tile's segment only if a round reaches it - behind a tile's sorted prefix the `keys` / `vals` arrays of the

@@ -1074,7 +1074,7 @@ def test_forward_in_rounds_equals_single_pass(built, round_len, pool_bytes, opac
             assert rel_err(f.grad.cpu().numpy(), f0.grad.cpu().numpy()) <= 1e-5
     finally:
         _C.shade_cache_alloc = real_alloc
-        lib.dm2_set_forward_rounds(512, 4096)
+        lib.dm2_set_forward_rounds(512, 6144)
         FusedRenderFunction._size_hint.clear()
 
 

@@ -149,7 +149,7 @@ def main():
                         lib.dm2_set_forward_rounds(L, thr)
                         ms_ab, _ = run_soup(pkg, sc, dev, views, args.iters)
                         print(json.dumps({"config": sc.name, "round_len": L, "threshold": thr, "rep": rep, "ms": round(ms_ab, 4)}), flush=True)
-                lib.dm2_set_forward_rounds(512, 4096)
+                lib.dm2_set_forward_rounds(512, 6144)
             print(json.dumps({"config": sc.name, "impl": name, "ms": ms, "views_or_frames_per_s": unit,
                               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                               "peak_mem_first_calls_gb": PEAKS.get("first_calls"), "scene_gen_s": gen_s}),
