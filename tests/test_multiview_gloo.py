@@ -110,7 +110,17 @@ def _worker(rank, world, port, q):
         loss, bucket = multiview_step(fn, list(range(4)), v, c, o, bucket, micro_batch=1)
         total = loss.clone()
         dist.all_reduce(total)
-        q.put((rank, bucket.flat.numpy().copy(), float(total)))
+        first = bucket.flat.numpy().copy()
+        # cost-aware ownership (balanced_shards): an uneven table - rank 0 renders view 3 only - must give the same sum
+        from dmesh2_renderer_b200.multiview import balanced_shards
+        shards = balanced_shards([1.0, 1.0, 1.0, 3.0], world)
+        assert sorted(sum(shards, [])) == [0, 1, 2, 3]
+        loss2, bucket = multiview_step(fn, list(range(4)), v, c, o, bucket, micro_batch=1, shards=shards)
+        total2 = loss2.clone()
+        dist.all_reduce(total2)
+        assert np.allclose(bucket.flat.numpy(), first, rtol=1e-5, atol=1e-6 * np.abs(first).max())
+        assert abs(float(total2) - float(total)) <= 1e-5 * abs(float(total))
+        q.put((rank, first, float(total)))
     finally:
         dist.destroy_process_group()
 
