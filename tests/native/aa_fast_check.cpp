@@ -74,7 +74,44 @@ static void setup(Tri& t, float p0x, float p0y, float p1x, float p1y, float p2x,
     t.flags |= dm2::aaf_face_safety(t.v, t.e, t.r, t.flags, &t.safe);
 }
 
+// unit checks of the per-face safety word (aaf_face_safety): thresholds packed as bf16 never round DOWN, faces the fast
+// path must never answer for are flagged, a near-integer coordinate raises the flag that switches the vertex test on
+static int unit_checks() {
+    std::mt19937_64 rng(7);
+    std::uniform_real_distribution<float> U(0.0f, 1.0f);
+    int bad = 0;
+    for (int i = 0; i < 2000000; i++) {
+        const float x = ldexpf(U(rng) + 1e-9f, (int)(U(rng) * 40) - 30);
+        const float up = aaf_float_host(dm2::aaf_bf16_up(x) << 16);
+        if (!(up >= x) || !(up <= x * 1.0079f)) bad |= 1;                       // one bf16 ulp = 2^-7
+    }
+    auto flags_of = [&](float p0x, float p0y, float p1x, float p1y, float p2x, float p2y, uint32_t* sw) {
+        Tri t; setup(t, p0x, p0y, p1x, p1y, p2x, p2y); *sw = t.safe; return t.flags;
+    };
+    uint32_t sw;
+    if (!(flags_of(10.3f, 10.2f, 14.7f, 10.2004f, 12.1f, 15.9f, &sw) & dm2::kAafNever)) bad |= 2;          // |e.y| < 1e-3
+    if (!(flags_of(10.3f, 10.2f, 14.7f, NAN, 12.1f, 15.9f, &sw) & dm2::kAafNever)) bad |= 4;               // NaN
+    if (!(flags_of(10.3f, 10.2f, 2.0e6f, 11.0f, 12.1f, 15.9f, &sw) & dm2::kAafNever)) bad |= 8;            // huge
+    if (!(flags_of(10.3f, 10.2f, 1010.3f, 1010.2001f, 510.3f, 510.7f, &sw) & dm2::kAafNever)) bad |= 1 << 10;   // needle (wedge factor < 2e-3)
+    unsigned f = flags_of(10.3f, 10.2f, 14.7f, 11.4f, 12.1f, 15.9f, &sw);
+    if (f & (dm2::kAafNever | dm2::kAafNearInt)) bad |= 16;                                                  // ordinary face
+    if (!(sw >> 16) || !(sw & 0xFFFFu)) bad |= 32;
+    f = flags_of(10.3f, 10.2f, 14.0000001f, 11.4f, 12.1f, 15.9f, &sw);
+    if (!(f & dm2::kAafNearInt) || (f & dm2::kAafNever)) bad |= 64;                                          // x = 14 (+ 1e-7)
+    // edge data that is not v[i+1] - v[i] (a caller of the 21-argument function could pass anything): never
+    {
+        Tri t; setup(t, 10.3f, 10.2f, 14.7f, 11.4f, 12.1f, 15.9f);
+        t.e[0] += 0.25f;
+        unsigned fl = 0; for (int k = 0; k < 6; k++) fl |= (unsigned)t.z[k] << k;
+        uint32_t w;
+        if (!(dm2::aaf_face_safety(t.v, t.e, t.r, fl, &w) & dm2::kAafNever)) bad |= 128;
+    }
+    printf("{\"unit_failures\": %d}\n", bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "--unit")) return unit_checks();
     const long long n_per_mode = argc > 1 ? atoll(argv[1]) : 1000000;
     const uint64_t seed = argc > 2 ? strtoull(argv[2], nullptr, 10) : 1;
     std::mt19937_64 rng(seed);

@@ -37,3 +37,11 @@ def test_fast_overlap_area_contract(checker, seed):
     fr = rep["answered_frac_by_mode"]
     assert fr[8] > 0.99 and fr[9] > 0.985 and fr[0] > 0.95, rep
     assert rep["answered"] > 300000, rep
+
+
+def test_face_safety_word(checker):
+    """Per-face thresholds and flags of the fast path (aaf_face_safety): bf16 packing rounds up, parallel / non-finite /
+    huge / needle faces and inconsistent edge data are never answered for, a near-integer coordinate switches the
+    per-pair vertex test on."""
+    out = subprocess.run([checker, "--unit"], capture_output=True, text=True)
+    assert out.returncode == 0 and json.loads(out.stdout.strip().splitlines()[-1])["unit_failures"] == 0, out.stdout
