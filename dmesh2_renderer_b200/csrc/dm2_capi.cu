@@ -645,7 +645,11 @@ static int layers_preprocess(const DM2LayerInputs* in, void* face_ws, void* imag
     const long long BF = (long long)in->B * in->F;
     *num_rendered_host = 0;
     if (longest_host) *longest_host = 0;
-    if (BF == 0) return zero_ranges(image_ws, in->B, in->H, in->W, true, s);
+    if (BF == 0) {
+        // (no faces: nothing is binned, but a caller of the *_prepared entry point still finds its tet records built)
+        if (geo_ws && launch_layers_geometry(*in, geo_ws, true, s)) return 1;
+        return zero_ranges(image_ws, in->B, in->H, in->W, true, s);
+    }
     FaceWs fw = carve_face(face_ws, BF, true);
     ImageWs iw = carve_image(image_ws, in->B, in->H, in->W, true);
     const int gx = cdiv(in->W, kTile), gy = cdiv(in->H, kTile);
