@@ -110,8 +110,29 @@ static int unit_checks() {
     return bad ? 1 : 0;
 }
 
+// --pairs <file>: one record of 26 floats per pair (verts 6, edges 6, recip 6, iszero 6 as 0 / 1, pxmin, pymin), as
+// tests/test_aa_fast.py writes them from tests/golden/aa_overlap_golden.npz (the reference's own pyrenderer.py);
+// prints "answered area g0 .. g5" per pair
+static int eval_pairs(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return 2;
+    float r[26];
+    while (fread(r, sizeof(float), 26, f) == 26) {
+        unsigned flags = 0;
+        for (int k = 0; k < 6; k++) flags |= (r[18 + k] != 0.0f ? 1u : 0u) << k;
+        uint32_t sw = 0;
+        flags |= dm2::aaf_face_safety(r, r + 6, r + 12, flags, &sw);
+        float area = 0, g[6] = {0, 0, 0, 0, 0, 0};
+        const bool ok = dm2::aa_area_fast<true>(r, r + 6, r + 12, flags, sw, r[24], r[25], area, g);
+        printf("%d %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", ok ? 1 : 0, area, g[0], g[1], g[2], g[3], g[4], g[5]);
+    }
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && !strcmp(argv[1], "--unit")) return unit_checks();
+    if (argc > 2 && !strcmp(argv[1], "--pairs")) return eval_pairs(argv[2]);
     const long long n_per_mode = argc > 1 ? atoll(argv[1]) : 1000000;
     const uint64_t seed = argc > 2 ? strtoull(argv[2], nullptr, 10) : 1;
     std::mt19937_64 rng(seed);
