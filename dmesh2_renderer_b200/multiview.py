@@ -217,7 +217,13 @@ def multiview_step(render_view_batch: Callable, all_views: Sequence[int], verts:
     if bucket is None:
         bucket = GradBucket(verts.shape[0], faces_opacity.shape[0], verts.device)
     bucket.zero_()
-    mine = list(shards[rank]) if shards is not None else shard_views(len(all_views), world_size, rank)
+    if shards is not None:
+        # an ownership table that is not a partition of the views would silently drop or double gradients
+        if len(shards) != world_size or sorted(v for sh in shards for v in sh) != list(range(len(all_views))):
+            raise ValueError("shards must hold one list of view positions per rank that together cover every view once")
+        mine = list(shards[rank])
+    else:
+        mine = shard_views(len(all_views), world_size, rank)
     local_loss = torch.zeros((), dtype=torch.float32, device=verts.device)
     sink_on = False
     if renderer is not None and verts.is_cuda and getattr(renderer, "fused", True):

@@ -35,6 +35,17 @@ def test_balanced_shards():
     assert balanced_shards([5, 1, 1, 1], 2) == [[0], [1, 2, 3]] or balanced_shards([5, 1, 1, 1], 2) == [[0, 3], [1, 2]]
 
 
+def test_multiview_step_rejects_a_bad_ownership_table():
+    from dmesh2_renderer_b200.multiview import multiview_step
+    v, c, o = torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(2)
+    fn = lambda views, a, b, d: (a.sum() + b.sum() + d.sum()) * float(len(views))
+    for bad in ([[0, 1], [1, 2]], [[0, 1, 2]], [[0], [1], [2]]):
+        with pytest.raises(ValueError):
+            multiview_step(fn, [0, 1, 2], v, c, o, world_size=2, rank=0, shards=bad)
+    loss, b = multiview_step(fn, [0, 1, 2], v, c, o, world_size=1, rank=0, shards=[[0, 1, 2]])
+    assert float(b.dverts.sum()) == 3.0 * 12
+
+
 def test_shard_views_partition():
     from dmesh2_renderer_b200.multiview import micro_batches, shard_views
     for n, g in ((64, 8), (64, 4), (7, 2), (3, 4), (0, 2)):
